@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+from theiasfm_b200 import _abi
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reprojection_golden.npz")
+
+
+def golden_problem():
+    """All golden cases as ONE problem: case i = camera i, group i, point i, observation i."""
+    g = np.load(GOLDEN)
+    n = len(g["model"])
+    prob = _abi.Problem(g["ext"], np.zeros(n, np.uint8), np.arange(n, dtype=np.int32), g["model"], g["intr"],
+                        np.zeros(n, np.uint32), g["pt"], np.zeros(n, np.uint8), np.arange(n, dtype=np.int32),
+                        np.arange(n, dtype=np.int32), g["xy"])
+    return prob, g
+
+
+def rel_err(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def free_masks(p):
+    """(free_cam [n_cam,6], free_intr [n_group,10], free_pt [n_pt,4]) booleans."""
+    fc = np.ones((p.n_cam, 6), bool)
+    fc[:, :3] = (p.ext_const & _abi.EXT_POSITION_CONST)[:, None] == 0
+    fc[:, 3:] = (p.ext_const & _abi.EXT_ORIENTATION_CONST)[:, None] == 0
+    fi = np.zeros((p.n_group, 10), bool)
+    for g in range(p.n_group):
+        K = _abi.MODEL_NUM_PARAMS[int(p.group_model[g])]
+        for j in range(K):
+            fi[g, j] = not ((int(p.group_const_mask[g]) >> j) & 1)
+    fp = np.repeat((p.pt_const == 0)[:, None], 4, axis=1)
+    return fc, fi, fp
+
+
+def dense_jacobian(p, J_obs):
+    """Assemble the dense (masked, unscaled) Jacobian [2*n_obs, 6*n_cam + 10*n_group + 4*n_pt]."""
+    fc, fi, fp = free_masks(p)
+    nc, ng, npt, no = p.n_cam, p.n_group, p.n_pt, p.n_obs
+    J = np.zeros((2 * no, 6 * nc + 10 * ng + 4 * npt))
+    for k in range(no):
+        c, q = int(p.obs_cam[k]), int(p.obs_pt[k]); g = int(p.cam_group[c])
+        J[2 * k:2 * k + 2, 6 * c:6 * c + 6] = J_obs[k][:, 0:6] * fc[c]
+        J[2 * k:2 * k + 2, 6 * nc + 10 * g:6 * nc + 10 * g + 10] = J_obs[k][:, 6:16] * fi[g]
+        J[2 * k:2 * k + 2, 6 * nc + 10 * ng + 4 * q:6 * nc + 10 * ng + 4 * q + 4] = J_obs[k][:, 16:20] * fp[q]
+    return J
