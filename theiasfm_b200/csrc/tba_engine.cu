@@ -1,0 +1,996 @@
+// tba_engine.cu -- host side of the B200 bundle-adjustment engine + the C-ABI of
+// include/theia_ba_b200.h.  Replaces ceres::Solve at
+// src/theia/sfm/bundle_adjustment/bundle_adjuster.cc:205: a Levenberg-Marquardt
+// trust-region loop (Ceres 1.14 TrustRegionMinimizer control flow)
+// whose every numerical stage is a CUDA kernel from tba_kernels.cuh.  The host
+// only moves scalars.  No CPU fallback: every entry point fails with
+// TBA_ERR_NO_DEVICE / TBA_ERR_CUDA when there is no usable GPU.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/theia_ba_b200.h"
+#include "tba_kernels.cuh"
+
+namespace tba {
+
+// ------------------------------------------------------------------ NCCL (dlopen'ed)
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string* err) {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { *err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { *err = "libnccl is missing symbols"; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+// ------------------------------------------------------------------ device buffers
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+}  // namespace tba
+
+using namespace tba;
+
+struct tba_context {
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  std::string err;
+  bool uploaded = false;
+  tba_options opt;
+  uint32_t imask = 0;  // instantiated intrinsics column set
+  int NI = 0, NJ = 14;
+  DevProblem P;
+  int n_cam = 0, n_group = 0, n_pt = 0, n_tiles = 0;
+  int64_t n_obs = 0, n_slots = 0;
+  std::vector<int64_t> slot_orig;  // slot -> caller observation index (-1 padding)
+  int64_t launches = 0;
+  double h2d_bytes = 0, d2h_bytes = 0;
+  double setup_seconds = 0;
+  int64_t n_free_cs = 0;  // free camera-space coordinates (global)
+  int64_t n_free_pt = 0;  // free points on this rank
+  int64_t n_free_pt_global = 0;
+  int n_pt_caller = 0;
+  std::vector<int> pk2caller;  // packed point -> caller point id
+  // parameters and packed problem
+  DevBuf<double> ext, intr, pt, ext_c, intr_c, pt_c, cam_rec, cam_rec_c, xy, J, res, Hpp, gp, Mp, sp, dpt;
+  DevBuf<int> cam_group, group_model, slot_cam, slot_pt, tile_pt_begin, tile_nruns;
+  DevBuf<uint8_t> slot_flags, pt_const;
+  DevBuf<int16_t> slot_run;
+  // camera space: [g | cn | scal(16)] is one allreduce buffer
+  DevBuf<double> lin;       // g_cs[ncs] | cn_cs[ncs] | scal[16]
+  DevBuf<double> mask, blk_free, sm, D2, Sblk /*[n_cam*21 | n_group*55]*/, Minv_c, Minv_i;
+  DevBuf<double> b, x, r, p, z, xs, y, part /*3 x VB*/, gmax, flag, scal2 /*16*/;
+  DevBuf<PcgState> st;      // [2]
+  DevBuf<int> done_flag;
+  bool have_scale = false;
+  double x_cost = 0, fixed_cost = 0;
+  // host mirrors
+  double* h_scal = nullptr;  // pinned [64]
+  PcgState* h_st = nullptr;  // pinned
+};
+
+namespace {
+
+void set_err(tba_context* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  c->err = buf;
+}
+
+#define CUDA_OK(c, expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      set_err(c, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #expr); \
+      return TBA_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define NCCL_OK(c, expr)                                                                        \
+  do {                                                                                          \
+    ncclResult_t r__ = (expr);                                                                  \
+    if (r__ != ncclSuccess) {                                                                   \
+      set_err(c, "NCCL error %s at %s:%d", g_nccl.GetErrorString(r__), __FILE__, __LINE__);     \
+      return TBA_ERR_NCCL;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define LAUNCH(c, kern, grid, block, smem, ...)                      \
+  do {                                                               \
+    kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);     \
+    (c)->launches++;                                                 \
+  } while (0)
+
+const uint32_t kMasks[] = {0x000u, 0x001u, 0x061u, 0x0E1u, 0x07Fu, 0x3FFu};
+
+#define DISPATCH_IMASK(mask, F) \
+  switch (mask) {               \
+    case 0x000u: F(0x000u); break; \
+    case 0x001u: F(0x001u); break; \
+    case 0x061u: F(0x061u); break; \
+    case 0x0E1u: F(0x0E1u); break; \
+    case 0x07Fu: F(0x07Fu); break; \
+    default: F(0x3FFu); break;  \
+  }
+
+int allreduce_sum(tba_context* c, double* buf, size_t n) {
+  if (c->world == 1) return TBA_OK;
+  NCCL_OK(c, g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, c->stream));
+  return TBA_OK;
+}
+int allreduce_max(tba_context* c, double* buf, size_t n) {
+  if (c->world == 1) return TBA_OK;
+  NCCL_OK(c, g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclMax, c->comm, c->stream));
+  return TBA_OK;
+}
+
+double* lin_g(tba_context* c) { return c->lin.p; }
+double* lin_cn(tba_context* c) { return c->lin.p + c->P.ncs; }
+double* lin_scal(tba_context* c) { return c->lin.p + 2 * (size_t)c->P.ncs; }
+
+// scal layout: 0 cost, 1 fixed cost, 2 failed evals, 3 model cost change, 4 |delta_cs|^2, 5 |delta_pt|^2,
+//              6 |x_cs|^2, 7 |x_pt|^2
+int read_scal(tba_context* c, const double* dev, int n, double* out) {
+  CUDA_OK(c, cudaMemcpyAsync(c->h_scal, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_scal, n * sizeof(double));
+  return TBA_OK;
+}
+
+// ---- stages ---------------------------------------------------------------------------------
+// Evaluate cost / residuals / compact Jacobian / gradient / column norms at x (and Jacobi scale at iteration 0).
+int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
+  DevProblem& P = c->P;
+  CUDA_OK(c, cudaMemsetAsync(c->lin.p, 0, (2 * (size_t)P.ncs + 16) * sizeof(double), c->stream));
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  if (P.n_tiles > 0) {
+#define F(M) LAUNCH(c, k_linearize<M>, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), lin_scal(c))
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+  }
+  int rc = allreduce_sum(c, c->lin.p, 2 * (size_t)P.ncs + 16);
+  if (rc) return rc;
+  if (!c->have_scale) {
+    LAUNCH(c, k_cs_scale, VB, VT, 0, P.ncs, lin_cn(c), c->mask.p, c->opt.jacobi_scaling, c->sm.p);
+    if (P.n_pt > 0) LAUNCH(c, k_point_scale, (P.n_pt + 255) / 256, 256, 0, P, c->opt.jacobi_scaling);
+    c->have_scale = true;
+  }
+  double s[3];
+  rc = read_scal(c, lin_scal(c), 3, s);
+  if (rc) return rc;
+  *cost = s[0]; *fixed = s[1]; *ok = s[2] == 0.0;
+  return TBA_OK;
+}
+
+int stage_gradient_max_norm(tba_context* c, double* gmax) {
+  DevProblem& P = c->P;
+  CUDA_OK(c, cudaMemsetAsync(c->gmax.p, 0, 2 * sizeof(double), c->stream));
+  LAUNCH(c, k_gradmax, 128, 256, 0, P, lin_g(c), c->mask.p, c->gmax.p);
+  int rc = allreduce_max(c, c->gmax.p, 2);
+  if (rc) return rc;
+  double g[2];
+  rc = read_scal(c, c->gmax.p, 2, g);
+  if (rc) return rc;
+  *gmax = std::max(g[0], g[1]);
+  return TBA_OK;
+}
+
+// LM diagonal, per-point (E'E + D^2)^-1, SCHUR_JACOBI blocks, reduced rhs.  *ok=false if a block is not PD.
+int stage_prepare(tba_context* c, double radius, bool* ok) {
+  DevProblem& P = c->P;
+  const tba_options& o = c->opt;
+  CUDA_OK(c, cudaMemsetAsync(c->flag.p, 0, sizeof(double), c->stream));
+  LAUNCH(c, k_cs_diag, VB, VT, 0, P.ncs, lin_cn(c), c->sm.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, c->D2.p);
+  if (P.n_pt > 0) LAUNCH(c, k_point_blocks, (P.n_pt + 255) / 256, 256, 0, P, radius, o.min_lm_diagonal, o.max_lm_diagonal, c->flag.p);
+  const size_t nS = (size_t)P.n_cam * 21 + (size_t)P.n_group * 55;
+  if (o.preconditioner_type != TBA_PRECOND_IDENTITY) {
+    CUDA_OK(c, cudaMemsetAsync(c->Sblk.p, 0, nS * sizeof(double), c->stream));
+    if (P.n_tiles > 0) {
+#define F(M) LAUNCH(c, k_precond_ext<M>, P.n_tiles, TILE, 0, P, c->Sblk.p)
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+      if (c->NI > 0) {
+        const size_t smem = (size_t)TILE * 4 * c->NI * sizeof(double) + 2 * TILE * sizeof(int);
+#define F(M) LAUNCH(c, k_precond_intr<M>, P.n_tiles, TILE, smem, P, c->Sblk.p + (size_t)P.n_cam * 21)
+        DISPATCH_IMASK(c->imask, F)
+#undef F
+      }
+    }
+    int rc = allreduce_sum(c, c->Sblk.p, nS);
+    if (rc) return rc;
+    LAUNCH(c, k_precond_finish, (P.n_cam + P.n_group + 63) / 64, 64, 0, P, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->sm.p,
+           c->D2.p, c->Minv_c.p, c->Minv_i.p, c->flag.p);
+  }
+  // reduced rhs: y = F'(I - E M E') r, then b = sm .* y (k_pcg_init)
+  CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
+  if (P.n_tiles > 0) {
+#define F(M) { auto kfn = k_schur<M, 1>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, nullptr, c->y.p, nullptr, nullptr); }
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+  }
+  int rc = allreduce_sum(c, c->y.p, P.ncs);
+  if (rc) return rc;
+  LAUNCH(c, k_pcg_init, VB, VT, 0, P.ncs, c->y.p, c->sm.p, c->b.p, c->x.p, c->r.p, c->part.p);
+  // the PD flag is summed over ranks so that every rank takes the same branch
+  rc = allreduce_sum(c, c->flag.p, 1);
+  if (rc) return rc;
+  double f;
+  rc = read_scal(c, c->flag.p, 1, &f);
+  if (rc) return rc;
+  *ok = f == 0.0;
+  return TBA_OK;
+}
+
+const int* st_done(const PcgState* st) { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(st) + offsetof(PcgState, done)); }
+
+int launch_matvec(tba_context* c, const int* done) {
+  DevProblem& P = c->P;
+  if (P.n_tiles > 0) {
+#define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->xs.p, c->y.p, nullptr, done); }
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+  }
+  return allreduce_sum(c, c->y.p, P.ncs);
+}
+
+// ConjugateGradientsSolver::Solve on the reduced system; control flow on the device (PcgState),
+// the host enqueues iterations in batches and polls the done flag.
+int stage_pcg(tba_context* c, int* iters, int* status) {
+  DevProblem& P = c->P;
+  const tba_options& o = c->opt;
+  double* part_rho = c->part.p;
+  double* part_pq = c->part.p + VB;
+  double* part_Q = c->part.p + 2 * VB;
+  PcgState* st = c->st.p;
+  LAUNCH(c, k_pcg_init_state, 1, 1, 0, st, c->part.p, o.min_linear_solver_iterations, o.max_linear_solver_iterations, o.eta);
+  LAUNCH(c, k_set_flag, 1, 1, 0, c->done_flag.p, 0);
+  if (c->n_free_cs == 0) {  // no reduced system: back-substitution only
+    *iters = 0; *status = 0;
+    CUDA_OK(c, cudaMemsetAsync(c->x.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
+    return TBA_OK;
+  }
+  const int ident = o.preconditioner_type == TBA_PRECOND_IDENTITY;
+  int cur = 0;  // index of the valid state
+  int it = 0;
+  const int batch = 8;
+  for (;;) {
+    for (int k = 0; k < batch; ++k) {
+      ++it;
+      LAUNCH(c, k_pcg_v1, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_Q, c->Minv_c.p, c->Minv_i.p, c->r.p, c->z.p, part_rho, ident);
+      cur ^= 1;
+      LAUNCH(c, k_pcg_v2, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_rho, c->z.p, c->sm.p, c->p.p, c->xs.p, c->y.p);
+      cur ^= 1;
+      // every kernel of an iteration (matvec included) early-exits through the device-side state
+      int rc = launch_matvec(c, st_done(st + cur));
+      if (rc) return rc;
+      LAUNCH(c, k_pcg_v3, VB, VT, 0, P.ncs, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq);
+      LAUNCH(c, k_pcg_v4, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, part_Q);
+      cur ^= 1;
+      if (o.cg_residual_reset_period > 0 && it % o.cg_residual_reset_period == 0) {
+        LAUNCH(c, k_pcg_reset_a, VB, VT, 0, P.ncs, st + cur, c->x.p, c->sm.p, c->xs.p, c->y.p);
+        rc = launch_matvec(c, st_done(st + cur));
+        if (rc) return rc;
+        LAUNCH(c, k_pcg_reset_b, VB, VT, 0, P.ncs, st + cur, c->y.p, c->sm.p, c->D2.p, c->x.p, c->b.p, c->r.p, part_Q);
+      }
+    }
+    LAUNCH(c, k_pcg_finalize, 1, 32, 0, st + cur, st + (cur ^ 1), part_Q, c->done_flag.p);
+    cur ^= 1;
+    CUDA_OK(c, cudaMemcpyAsync(c->h_st, st + cur, sizeof(PcgState), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (c->h_st->done) break;
+    if (it > o.max_linear_solver_iterations + batch) { set_err(c, "PCG did not terminate"); return TBA_ERR_CUDA; }
+  }
+  *iters = c->h_st->iters;
+  *status = c->h_st->status;
+  return TBA_OK;
+}
+
+// BackSubstitute + model cost change.
+int stage_backsub(tba_context* c) {
+  DevProblem& P = c->P;
+  LAUNCH(c, k_cs_mul, VB, VT, 0, P.ncs, c->sm.p, c->x.p, c->xs.p);
+  CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 16 * sizeof(double), c->stream));
+  if (P.n_tiles > 0) {
+#define F(M) { auto kfn = k_schur<M, 2>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->xs.p, nullptr, c->scal2.p, nullptr); }
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+  }
+  // candidate = x + delta, step norm
+  LAUNCH(c, k_candidate_cs, VB, VT, 0, P, c->xs.p, c->scal2.p, c->rank == 0 ? 1 : 0);
+  if (P.n_pt > 0) LAUNCH(c, k_candidate_pt, 256, 256, 0, P, c->scal2.p);
+  return TBA_OK;
+}
+
+// Cost at the candidate; scal2 then holds [cost, fixed, failed, mcc, |d_cs|^2, |d_pt|^2].
+int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, double* step_norm, bool* ok) {
+  DevProblem& P = c->P;
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
+  if (P.n_tiles > 0) LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->scal2.p);
+  int rc = allreduce_sum(c, c->scal2.p, 8);
+  if (rc) return rc;
+  double s[8];
+  rc = read_scal(c, c->scal2.p, 8, s);
+  if (rc) return rc;
+  *ok = s[2] == 0.0;
+  *cand_cost = s[0];
+  *mcc = s[3];
+  *step_norm = std::sqrt(s[4] + s[5]);
+  return TBA_OK;
+}
+
+int stage_xnorm(tba_context* c, double* xn) {
+  DevProblem& P = c->P;
+  CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 16 * sizeof(double), c->stream));
+  LAUNCH(c, k_xnorm, 256, 256, 0, P, P.ext, P.intr, P.pt, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
+  int rc = allreduce_sum(c, c->scal2.p + 6, 2);
+  if (rc) return rc;
+  double s[2];
+  rc = read_scal(c, c->scal2.p + 6, 2, s);
+  if (rc) return rc;
+  *xn = std::sqrt(s[0] + s[1]);
+  return TBA_OK;
+}
+
+void accept_candidate(tba_context* c) {
+  DevProblem& P = c->P;
+  std::swap(P.ext, P.ext_c);
+  std::swap(P.intr, P.intr_c);
+  std::swap(P.pt, P.pt_c);
+  std::swap(P.cam_rec, P.cam_rec_c);
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void push_iter(tba_summary* s, const tba_iteration& it) {
+  if (s->iterations && s->num_iterations < s->iterations_capacity) s->iterations[s->num_iterations] = it;
+  s->num_iterations++;
+}
+
+int check_options(tba_context* c, const tba_options* o) {
+  if (o->use_inner_iterations) { set_err(c, "use_inner_iterations=true is not implemented by the GPU engine (set it to false, as Theia's incremental/hybrid estimators do)"); return TBA_ERR_UNSUPPORTED; }
+  if (o->linear_solver_type != TBA_ITERATIVE_SCHUR) { set_err(c, "linear_solver_type %d unsupported: the GPU engine implements ITERATIVE_SCHUR", o->linear_solver_type); return TBA_ERR_UNSUPPORTED; }
+  if (o->preconditioner_type != TBA_PRECOND_SCHUR_JACOBI && o->preconditioner_type != TBA_PRECOND_IDENTITY) { set_err(c, "preconditioner_type %d unsupported (SCHUR_JACOBI or IDENTITY)", o->preconditioner_type); return TBA_ERR_UNSUPPORTED; }
+  if (o->loss_function_type < 0 || o->loss_function_type > 5) { set_err(c, "invalid loss function type %d", o->loss_function_type); return TBA_ERR_INVALID_ARGUMENT; }
+  return TBA_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C-ABI
+extern "C" {
+
+void tba_options_init(tba_options* o) {
+  memset(o, 0, sizeof *o);
+  o->loss_function_type = TBA_LOSS_TRIVIAL; o->robust_loss_width = 2.0;
+  o->linear_solver_type = TBA_SPARSE_SCHUR; o->preconditioner_type = TBA_PRECOND_SCHUR_JACOBI;
+  o->intrinsics_to_optimize = TBA_INTR_FOCAL_LENGTH | TBA_INTR_RADIAL_DISTORTION;
+  o->num_threads = 1; o->max_num_iterations = 100; o->max_solver_time_in_seconds = 3600.0;
+  o->use_inner_iterations = 1; o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8; o->max_trust_region_radius = 1e12;
+  o->initial_trust_region_radius = 1e4; o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->eta = 1e-1;
+  o->min_linear_solver_iterations = 0; o->max_linear_solver_iterations = 500; o->jacobi_scaling = 1;
+  o->max_num_consecutive_invalid_steps = 5; o->cg_residual_reset_period = 10;
+}
+
+int tba_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void tba_abi_sizes(int32_t* out /*[4]*/) {
+  out[0] = (int32_t)sizeof(tba_options); out[1] = (int32_t)sizeof(tba_problem);
+  out[2] = (int32_t)sizeof(tba_summary); out[3] = (int32_t)sizeof(tba_iteration);
+}
+
+int tba_nccl_unique_id(void* out_128_bytes) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  std::string err;
+  if (!g_nccl.load(&err)) return TBA_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return TBA_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out_128_bytes, &id, 128);
+  return TBA_OK;
+}
+
+int tba_create(int device, int rank, int world_size, const void* nccl_unique_id, tba_context** out) {
+  if (!out || world_size < 1 || rank < 0 || rank >= world_size) return TBA_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = tba_device_count();
+  if (n <= 0 || device < 0 || device >= n) return TBA_ERR_NO_DEVICE;
+  tba_context* c = new tba_context();
+  c->device = device; c->rank = rank; c->world = world_size;
+  tba_options_init(&c->opt);
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&c->h_scal, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->h_st, sizeof(PcgState)) != cudaSuccess) {
+    delete c;
+    return TBA_ERR_CUDA;
+  }
+  if (world_size > 1) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    std::string err;
+    if (!nccl_unique_id || !g_nccl.load(&err)) { tba_destroy(c); return TBA_ERR_NCCL; }
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    if (g_nccl.CommInitRank(&c->comm, world_size, id, rank) != ncclSuccess) { tba_destroy(c); return TBA_ERR_NCCL; }
+  }
+  *out = c;
+  return TBA_OK;
+}
+
+void tba_destroy(tba_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->h_st) cudaFreeHost(c->h_st);
+  delete c;
+}
+
+const char* tba_last_error(tba_context* c) { return c ? c->err.c_str() : "null context"; }
+
+void tba_shard_points(const int32_t* pt_num_obs, int32_t n_pt, int world_size, int rank, int32_t* begin, int32_t* end) {
+  int64_t total = 0;
+  for (int32_t i = 0; i < n_pt; ++i) total += pt_num_obs[i];
+  auto cut = [&](int r) -> int32_t {
+    if (r <= 0) return 0;
+    if (r >= world_size) return n_pt;
+    const int64_t target = total * r / world_size;
+    int64_t cum = 0;
+    for (int32_t i = 0; i < n_pt; ++i) { if (cum >= target) return i; cum += pt_num_obs[i]; }
+    return n_pt;
+  };
+  *begin = cut(rank);
+  *end = cut(rank + 1);
+}
+
+// --------------------------------------------------------------------------- upload / pack
+int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p) {
+  if (!c || !options || !p) return TBA_ERR_INVALID_ARGUMENT;
+  const double t0 = now_s();
+  c->uploaded = false;
+  int rc = check_options(c, options);
+  if (rc) return rc;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  c->opt = *options;
+  const int nc = p->n_cam, ng = p->n_group, np = p->n_pt;
+  const int64_t no = p->n_obs;
+  if (nc < 0 || ng < 0 || np < 0 || no < 0) { set_err(c, "negative sizes"); return TBA_ERR_INVALID_ARGUMENT; }
+  for (int g = 0; g < ng; ++g)
+    if (p->group_model[g] != TBA_MODEL_PINHOLE && p->group_model[g] != TBA_MODEL_PINHOLE_RADIAL_TANGENTIAL) {
+      set_err(c, "camera intrinsics model %d of group %d is not supported by the GPU engine (PINHOLE, PINHOLE_RADIAL_TANGENTIAL)", p->group_model[g], g);
+      return TBA_ERR_UNSUPPORTED;
+    }
+  for (int i = 0; i < nc; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= ng) { set_err(c, "cam_group out of range"); return TBA_ERR_INVALID_ARGUMENT; }
+  // ---- counting sort by point, (group, camera) order inside a point
+  std::vector<int64_t> off((size_t)np + 1, 0);
+  for (int64_t i = 0; i < no; ++i) {
+    const int q = p->obs_pt[i], cam = p->obs_cam[i];
+    if (q < 0 || q >= np || cam < 0 || cam >= nc) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)i, cam, q); return TBA_ERR_INVALID_ARGUMENT; }
+    off[(size_t)q + 1]++;
+  }
+  int64_t maxlen = 0;
+  for (int q = 0; q < np; ++q) { maxlen = std::max(maxlen, off[(size_t)q + 1]); off[(size_t)q + 1] += off[q]; }
+  if (maxlen > TILE) { set_err(c, "track with %lld observations exceeds the engine limit of %d per track", (long long)maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
+  std::vector<int64_t> order(no);
+  {
+    std::vector<int64_t> cur(off.begin(), off.end() - 1);
+    for (int64_t i = 0; i < no; ++i) order[cur[p->obs_pt[i]]++] = i;
+  }
+  for (int q = 0; q < np; ++q) {
+    auto b = order.begin() + off[q], e = order.begin() + off[(size_t)q + 1];
+    if (e - b > 1)
+      std::sort(b, e, [&](int64_t a, int64_t bb) {
+        const int ga = p->cam_group[p->obs_cam[a]], gb = p->cam_group[p->obs_cam[bb]];
+        if (ga != gb) return ga < gb;
+        if (p->obs_cam[a] != p->obs_cam[bb]) return p->obs_cam[a] < p->obs_cam[bb];
+        return a < bb;
+      });
+  }
+  // ---- which blocks take part (blocks without residuals are not in the Ceres program)
+  std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
+  for (int64_t i = 0; i < no; ++i) { cnt_c[p->obs_cam[i]] += 1.0; cnt_g[p->cam_group[p->obs_cam[i]]] += 1.0; }
+  // packed points = points that have observations, caller order (zero-observation points are left untouched)
+  c->pk2caller.clear();
+  c->n_free_pt = 0;
+  for (int q = 0; q < np; ++q)
+    if (off[(size_t)q + 1] > off[q]) { c->pk2caller.push_back(q); c->n_free_pt += p->pt_const[q] ? 0 : 1; }
+  const int npk = (int)c->pk2caller.size();
+  c->n_free_pt_global = c->n_free_pt;
+  if (c->world > 1) {  // counts are global properties
+    std::vector<double> tmp(cnt_c);
+    tmp.insert(tmp.end(), cnt_g.begin(), cnt_g.end());
+    tmp.push_back((double)c->n_free_pt);
+    rc = [&]() -> int {
+      CUDA_OK(c, c->scal2.alloc(std::max<size_t>(tmp.size(), 16)));
+      CUDA_OK(c, cudaMemcpyAsync(c->scal2.p, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      int r2 = allreduce_sum(c, c->scal2.p, tmp.size());
+      if (r2) return r2;
+      CUDA_OK(c, cudaMemcpyAsync(tmp.data(), c->scal2.p, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      return TBA_OK;
+    }();
+    if (rc) return rc;
+    std::copy(tmp.begin(), tmp.begin() + nc, cnt_c.begin());
+    std::copy(tmp.begin() + nc, tmp.begin() + nc + ng, cnt_g.begin());
+    c->n_free_pt_global = (int64_t)tmp.back();
+  }
+  const int ne = nc * 6, ncs = ne + ng * 10;
+  std::vector<double> mask(ncs, 0.0), blk_free(nc + ng, 0.0);
+  uint32_t union_free = 0;
+  c->n_free_cs = 0;
+  for (int i = 0; i < nc; ++i) {
+    if (cnt_c[i] == 0.0) continue;
+    for (int j = 0; j < 6; ++j) {
+      const bool fr = j < 3 ? !(p->ext_const[i] & TBA_EXT_POSITION_CONST) : !(p->ext_const[i] & TBA_EXT_ORIENTATION_CONST);
+      if (fr) { mask[i * 6 + j] = 1.0; blk_free[i] = 1.0; c->n_free_cs++; }
+    }
+  }
+  for (int g = 0; g < ng; ++g) {
+    if (cnt_g[g] == 0.0) continue;
+    const int K = p->group_model[g] == TBA_MODEL_PINHOLE ? 7 : 10;
+    for (int j = 0; j < K; ++j)
+      if (!((p->group_const_mask[g] >> j) & 1u)) { mask[ne + g * 10 + j] = 1.0; blk_free[nc + g] = 1.0; union_free |= 1u << j; c->n_free_cs++; }
+  }
+  c->imask = 0x3FFu;
+  for (uint32_t m : kMasks) if ((union_free & ~m) == 0) { c->imask = m; break; }
+  c->NI = popcount10(c->imask);
+  c->NJ = 14 + 2 * c->NI;
+  std::vector<uint8_t> pt_const(npk);
+  std::vector<double> pt_packed((size_t)npk * 4);
+  for (int k = 0; k < npk; ++k) {
+    const int q = c->pk2caller[k];
+    pt_const[k] = p->pt_const[q] ? 1 : 0;
+    memcpy(&pt_packed[(size_t)k * 4], p->pt + (size_t)q * 4, 32);
+  }
+  // ---- tiles: whole points per tile of TILE slots
+  std::vector<int> tile_pt_begin, tile_nruns;
+  std::vector<int> slot_cam, slot_pt;
+  std::vector<int16_t> slot_run;
+  std::vector<uint8_t> slot_flags;
+  c->slot_orig.clear();
+  {
+    int used = TILE, npts_in_tile = MAXP;  // force a new tile at the first point
+    int run = 0;
+    auto pad_tile = [&](size_t pad) {
+      slot_cam.insert(slot_cam.end(), pad, -1); slot_pt.insert(slot_pt.end(), pad, 0);
+      slot_run.insert(slot_run.end(), pad, (int16_t)-1); slot_flags.insert(slot_flags.end(), pad, (uint8_t)0);
+      c->slot_orig.insert(c->slot_orig.end(), pad, (int64_t)-1);
+    };
+    for (int k = 0; k < npk; ++k) {
+      const int q = c->pk2caller[k];
+      const int len = (int)(off[(size_t)q + 1] - off[q]);
+      if (used + len > TILE || npts_in_tile + 1 > MAXP) {
+        if (!tile_pt_begin.empty()) { tile_nruns.push_back(run); pad_tile((size_t)(TILE - used)); }
+        tile_pt_begin.push_back(k);
+        used = 0; npts_in_tile = 0; run = 0;
+      }
+      int last_grp = -1;
+      for (int64_t kk = off[q]; kk < off[(size_t)q + 1]; ++kk) {
+        const int64_t oi = order[kk];
+        const int cam = p->obs_cam[oi], g = p->cam_group[cam];
+        if (g != last_grp) { ++run; last_grp = g; }
+        slot_cam.push_back(cam); slot_pt.push_back(k); slot_run.push_back((int16_t)(run - 1));
+        const bool any_free = blk_free[cam] != 0.0 || blk_free[nc + g] != 0.0 || !pt_const[k];
+        slot_flags.push_back(any_free ? 0 : 1);
+        c->slot_orig.push_back(oi);
+      }
+      used += len; npts_in_tile++;
+    }
+    if (!tile_pt_begin.empty()) { tile_nruns.push_back(run); pad_tile((size_t)(TILE - used)); }
+  }
+  const int n_tiles = (int)tile_pt_begin.size();
+  tile_pt_begin.push_back(npk);
+  const int64_t n_slots = (int64_t)n_tiles * TILE;
+  // xy in [tile][2][TILE]
+  std::vector<double> xy((size_t)n_slots * 2, 0.0);
+  for (int64_t s = 0; s < n_slots; ++s) {
+    const int64_t oi = c->slot_orig[s];
+    if (oi < 0) continue;
+    const int64_t t = s / TILE, l = s % TILE;
+    xy[(size_t)(t * 2 + 0) * TILE + l] = p->obs_xy[2 * oi];
+    xy[(size_t)(t * 2 + 1) * TILE + l] = p->obs_xy[2 * oi + 1];
+  }
+  // ---- device allocation + H2D
+  c->n_cam = nc; c->n_group = ng; c->n_pt = npk; c->n_pt_caller = np; c->n_tiles = n_tiles; c->n_obs = no; c->n_slots = n_slots;
+  const int npd = npk;  // points on the device
+  c->h2d_bytes = 0; c->d2h_bytes = 0; c->launches = 0;
+#define ALLOC(buf, n) CUDA_OK(c, c->buf.alloc(n))
+  ALLOC(ext, (size_t)ne); ALLOC(ext_c, (size_t)ne); ALLOC(intr, (size_t)ng * 10); ALLOC(intr_c, (size_t)ng * 10);
+  ALLOC(pt, (size_t)npd * 4); ALLOC(pt_c, (size_t)npd * 4); ALLOC(cam_rec, (size_t)nc * kCamRec); ALLOC(cam_rec_c, (size_t)nc * kCamRec);
+  ALLOC(xy, (size_t)n_slots * 2); ALLOC(J, (size_t)n_slots * c->NJ); ALLOC(res, (size_t)n_slots * 2);
+  ALLOC(Hpp, (size_t)npd * 10); ALLOC(gp, (size_t)npd * 4); ALLOC(Mp, (size_t)npd * 10); ALLOC(sp, (size_t)npd * 4); ALLOC(dpt, (size_t)npd * 4);
+  ALLOC(cam_group, (size_t)nc); ALLOC(group_model, (size_t)ng); ALLOC(slot_cam, (size_t)n_slots); ALLOC(slot_pt, (size_t)n_slots);
+  ALLOC(tile_pt_begin, (size_t)n_tiles + 1); ALLOC(tile_nruns, (size_t)n_tiles); ALLOC(slot_flags, (size_t)n_slots);
+  ALLOC(slot_run, (size_t)n_slots); ALLOC(pt_const, (size_t)npd);
+  ALLOC(lin, 2 * (size_t)ncs + 16); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
+  ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
+  ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
+  ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1);
+#undef ALLOC
+#define H2D(buf, src, n)                                                                                      \
+  do {                                                                                                        \
+    CUDA_OK(c, cudaMemcpyAsync(c->buf.p, (src), (n) * sizeof(*c->buf.p), cudaMemcpyHostToDevice, c->stream)); \
+    c->h2d_bytes += (double)((n) * sizeof(*c->buf.p));                                                        \
+  } while (0)
+  H2D(ext, p->ext, (size_t)ne); H2D(intr, p->intr, (size_t)ng * 10); H2D(pt, pt_packed.data(), (size_t)npd * 4);
+  H2D(ext_c, p->ext, (size_t)ne); H2D(intr_c, p->intr, (size_t)ng * 10); H2D(pt_c, pt_packed.data(), (size_t)npd * 4);
+  H2D(cam_group, p->cam_group, (size_t)nc); H2D(group_model, p->group_model, (size_t)ng);
+  H2D(slot_cam, slot_cam.data(), (size_t)n_slots); H2D(slot_pt, slot_pt.data(), (size_t)n_slots);
+  H2D(slot_flags, slot_flags.data(), (size_t)n_slots); H2D(slot_run, slot_run.data(), (size_t)n_slots);
+  H2D(tile_pt_begin, tile_pt_begin.data(), (size_t)n_tiles + 1); H2D(tile_nruns, tile_nruns.data(), (size_t)n_tiles);
+  H2D(xy, xy.data(), (size_t)n_slots * 2); H2D(pt_const, pt_const.data(), (size_t)npd);
+  H2D(mask, mask.data(), (size_t)ncs); H2D(blk_free, blk_free.data(), (size_t)nc + ng);
+#undef H2D
+  CUDA_OK(c, cudaMemsetAsync(c->J.p, 0, (size_t)n_slots * c->NJ * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->dpt.p, 0, (size_t)npd * 4 * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->Mp.p, 0, (size_t)npd * 10 * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->Hpp.p, 0, (size_t)npd * 10 * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->gp.p, 0, (size_t)npd * 4 * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->Minv_c.p, 0, (size_t)nc * 36 * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->Minv_i.p, 0, (size_t)ng * 100 * sizeof(double), c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  DevProblem& P = c->P;
+  P.n_cam = nc; P.n_group = ng; P.n_pt = npd; P.n_tiles = n_tiles; P.ne = ne; P.ncs = ncs; P.single_group = ng == 1;
+  P.loss_type = options->loss_function_type; P.loss_width = options->robust_loss_width;
+  P.ext = c->ext.p; P.intr = c->intr.p; P.pt = c->pt.p; P.ext_c = c->ext_c.p; P.intr_c = c->intr_c.p; P.pt_c = c->pt_c.p;
+  P.cam_group = c->cam_group.p; P.group_model = c->group_model.p; P.cam_rec = c->cam_rec.p; P.cam_rec_c = c->cam_rec_c.p;
+  P.slot_cam = c->slot_cam.p; P.slot_pt = c->slot_pt.p; P.slot_flags = c->slot_flags.p; P.slot_run = c->slot_run.p;
+  P.tile_pt_begin = c->tile_pt_begin.p; P.tile_nruns = c->tile_nruns.p; P.xy = c->xy.p; P.J = c->J.p; P.res = c->res.p;
+  P.Hpp = c->Hpp.p; P.gp = c->gp.p; P.Mp = c->Mp.p; P.sp = c->sp.p; P.dpt = c->dpt.p; P.pt_const = c->pt_const.p;
+  if (c->NI > 0) {
+    const int smem = TILE * 4 * c->NI * (int)sizeof(double) + 2 * TILE * (int)sizeof(int);
+#define F(M) CUDA_OK(c, cudaFuncSetAttribute(k_precond_intr<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+  }
+  c->have_scale = false;
+  c->uploaded = true;
+  c->setup_seconds = now_s() - t0;
+  return TBA_OK;
+}
+
+int tba_download(tba_context* c, tba_problem* p) {
+  if (!c || !p || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (p->n_cam != c->n_cam || p->n_group != c->n_group || p->n_pt != c->n_pt_caller) { set_err(c, "download: problem shape differs from the uploaded one"); return TBA_ERR_INVALID_ARGUMENT; }
+  std::vector<double> ptk((size_t)c->n_pt * 4);
+  CUDA_OK(c, cudaMemcpyAsync(p->ext, c->P.ext, (size_t)c->n_cam * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(p->intr, c->P.intr, (size_t)c->n_group * 10 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(ptk.data(), c->P.pt, (size_t)c->n_pt * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < c->n_pt; ++k) memcpy(p->pt + (size_t)c->pk2caller[k] * 4, &ptk[(size_t)k * 4], 32);
+  c->d2h_bytes += (double)c->n_cam * 48 + (double)c->n_group * 80 + (double)c->n_pt * 32;
+  return TBA_OK;
+}
+
+// --------------------------------------------------------------------------- minimise
+int tba_minimize(tba_context* c, tba_summary* s) {
+  if (!c || !s || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const tba_options& opt = c->opt;
+  tba_iteration* itbuf = s->iterations;
+  const int itcap = s->iterations_capacity;
+  memset(s, 0, sizeof *s);
+  s->iterations = itbuf; s->iterations_capacity = itcap;
+  s->setup_time_in_seconds = c->setup_seconds;
+  const double t1 = now_s();
+  const int64_t launches0 = c->launches;
+  cudaEvent_t ev0, ev1;
+  CUDA_OK(c, cudaEventCreate(&ev0));
+  CUDA_OK(c, cudaEventCreate(&ev1));
+  int term = TBA_NO_CONVERGENCE;
+  const char* msg = "";
+  int rc = TBA_OK;
+  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+  double x_cost = 0, fixed = 0, xn = 0;
+  bool ok = true;
+  tba_iteration it;
+  memset(&it, 0, sizeof it);
+  int consecutive_invalid = 0;
+#define RC(expr) do { rc = (expr); if (rc) goto fail; } while (0)
+  cudaEventRecord(ev0, c->stream);
+  RC(stage_linearize(c, &x_cost, &fixed, &ok));
+  if (!ok) { term = TBA_FAILURE; msg = "Residual and Jacobian evaluation failed."; s->initial_cost = s->final_cost = -1; goto done; }
+  s->initial_cost = x_cost + fixed;
+  if (c->n_free_cs == 0 && c->n_free_pt_global == 0) {
+    term = TBA_CONVERGENCE; msg = "Function tolerance reached. No non-constant parameter blocks found.";
+    it.iteration = 0; it.cost = x_cost + fixed; it.step_is_valid = 1; it.step_is_successful = 1;
+    push_iter(s, it);
+    goto done;
+  }
+  RC(stage_xnorm(c, &xn));
+  it.iteration = 0; it.step_is_valid = 1; it.step_is_successful = 1; it.cost = x_cost + fixed; it.trust_region_radius = radius;
+  RC(stage_gradient_max_norm(c, &it.gradient_max_norm));
+  for (;;) {
+    // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (it.step_is_successful) s->num_successful_steps++; else s->num_unsuccessful_steps++;
+    it.trust_region_radius = radius;
+    cudaEventRecord(ev1, c->stream);
+    cudaEventSynchronize(ev1);
+    { float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); it.iteration_time_in_seconds = ms * 1e-3; }
+    push_iter(s, it);
+    if (opt.verbose && c->rank == 0)
+      fprintf(stderr, "tba % 4d: f:% 3.12e d:% 3.2e g:% 3.2e h:% 3.2e rho:% 3.2e mu:% 3.2e li:% 3d t:% 3.2e\n", it.iteration, it.cost,
+              it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius,
+              it.linear_solver_iterations, it.iteration_time_in_seconds);
+    if (now_s() - t1 > opt.max_solver_time_in_seconds) { term = TBA_NO_CONVERGENCE; msg = "Maximum solver time reached."; break; }
+    if (it.iteration >= opt.max_num_iterations) { term = TBA_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
+    if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) { term = TBA_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
+    if (radius <= opt.min_trust_region_radius) { term = TBA_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
+    cudaEventRecord(ev0, c->stream);
+    const double prev_gmax = it.gradient_max_norm;
+    const int prev_iter = it.iteration;
+    memset(&it, 0, sizeof it);
+    it.iteration = prev_iter + 1;
+    // ComputeTrustRegionStep
+    bool valid = true;
+    int cg_iters = 0, cg_status = 0;
+    double mcc = 0, cand = 0, step_norm = 0;
+    bool cand_ok = true;
+    RC(stage_prepare(c, radius, &valid));
+    if (valid) {
+      RC(stage_pcg(c, &cg_iters, &cg_status));
+      if (cg_status == 2) valid = false;
+    }
+    it.linear_solver_iterations = cg_iters;
+    s->num_linear_solver_iterations += cg_iters;
+    if (valid) {
+      RC(stage_backsub(c));
+      RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok));
+      if (!std::isfinite(mcc) || !std::isfinite(step_norm)) valid = false;
+      else valid = mcc > 0.0;
+    }
+    it.step_is_valid = valid;
+    if (!valid) {  // HandleInvalidStep
+      if (++consecutive_invalid >= opt.max_num_consecutive_invalid_steps) { term = TBA_FAILURE; msg = "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps"; break; }
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      it.cost = x_cost + fixed; it.gradient_max_norm = prev_gmax; it.step_is_successful = 0;
+      continue;
+    }
+    consecutive_invalid = 0;
+    if (!cand_ok) cand = 1.7976931348623157e308;
+    it.step_norm = step_norm;
+    if (it.step_norm <= opt.parameter_tolerance * (xn + opt.parameter_tolerance)) { term = TBA_CONVERGENCE; msg = "Parameter tolerance reached."; break; }
+    it.cost_change = x_cost - cand;
+    if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) { term = TBA_CONVERGENCE; msg = "Function tolerance reached."; break; }
+    it.relative_decrease = it.cost_change / mcc;
+    if (it.relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
+      accept_candidate(c);
+      RC(stage_xnorm(c, &xn));
+      RC(stage_linearize(c, &x_cost, &fixed, &ok));
+      if (!ok) { term = TBA_FAILURE; msg = "Residual and Jacobian evaluation failed."; break; }
+      it.cost = x_cost + fixed;
+      RC(stage_gradient_max_norm(c, &it.gradient_max_norm));
+      it.step_is_successful = 1;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+      radius = std::min(opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+    } else {  // HandleUnsuccessfulStep
+      it.step_is_successful = 0; it.gradient_max_norm = prev_gmax;
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      it.cost = cand + fixed;
+    }
+  }
+  s->final_cost = x_cost + fixed;
+done:
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  s->termination_type = term;
+  s->success = term != TBA_FAILURE;
+  snprintf(s->message, sizeof s->message, "%s", msg);
+  s->solve_time_in_seconds = now_s() - t1;
+  s->num_kernel_launches = c->launches - launches0;
+  s->h2d_bytes = c->h2d_bytes; s->d2h_bytes = c->d2h_bytes;
+  c->x_cost = x_cost; c->fixed_cost = fixed;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  return TBA_OK;
+fail:
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  s->termination_type = TBA_FAILURE; s->success = 0;
+  snprintf(s->message, sizeof s->message, "%s", c->err.c_str());
+  return rc;
+#undef RC
+}
+
+int tba_solve(tba_context* c, const tba_options* options, tba_problem* problem, tba_summary* summary) {
+  if (!c || !options || !problem || !summary) return TBA_ERR_INVALID_ARGUMENT;
+  int rc = tba_upload(c, options, problem);
+  if (rc) { summary->success = 0; summary->termination_type = TBA_FAILURE; snprintf(summary->message, sizeof summary->message, "%s", c->err.c_str()); return rc; }
+  rc = tba_minimize(c, summary);
+  if (rc) return rc;
+  const double t0 = now_s();
+  rc = tba_download(c, problem);
+  summary->solve_time_in_seconds += now_s() - t0;
+  summary->d2h_bytes = c->d2h_bytes;
+  return rc;
+}
+
+// --------------------------------------------------------------------------- debug / test hooks
+int tba_debug_linearize(tba_context* c, double* cost) {
+  if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  bool ok;
+  double x, f;
+  int rc = stage_linearize(c, &x, &f, &ok);
+  if (rc) return rc;
+  c->x_cost = x; c->fixed_cost = f;
+  if (cost) *cost = x + f;
+  return ok ? TBA_OK : TBA_ERR_INVALID_ARGUMENT;
+}
+
+int tba_debug_prepare_linear_system(tba_context* c, double radius) {
+  if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  bool ok;
+  int rc = stage_prepare(c, radius, &ok);
+  if (rc) return rc;
+  return ok ? TBA_OK : TBA_ERR_INVALID_ARGUMENT;
+}
+
+int tba_debug_schur_matvec(tba_context* c, const double* x_cam, const double* x_intr, double* y_cam, double* y_intr) {
+  if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevProblem& P = c->P;
+  // y = sm .* S_unscaled (sm .* x) + D2 .* x, using p as the input buffer
+  CUDA_OK(c, cudaMemcpyAsync(c->p.p, x_cam, (size_t)P.ne * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->p.p + P.ne, x_intr, (size_t)P.n_group * 10 * 8, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_cs_mul, VB, VT, 0, P.ncs, c->sm.p, c->p.p, c->xs.p);
+  CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * 8, c->stream));
+  LAUNCH(c, k_set_flag, 1, 1, 0, c->done_flag.p, 0);
+  int rc = launch_matvec(c, c->done_flag.p);
+  if (rc) return rc;
+  LAUNCH(c, k_set_flag, 1, 1, 0, const_cast<int*>(st_done(c->st.p)), 0);
+  LAUNCH(c, k_pcg_v3, VB, VT, 0, P.ncs, c->st.p, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, c->part.p + VB);
+  CUDA_OK(c, cudaMemcpyAsync(y_cam, c->z.p, (size_t)P.ne * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(y_intr, c->z.p + P.ne, (size_t)P.n_group * 10 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return TBA_OK;
+}
+
+int tba_debug_solve_linear_system(tba_context* c, int32_t* cg_iterations, double* model_cost_change) {
+  if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  int iters = 0, status = 0;
+  int rc = stage_pcg(c, &iters, &status);
+  if (rc) return rc;
+  rc = stage_backsub(c);
+  if (rc) return rc;
+  int r2 = allreduce_sum(c, c->scal2.p + 3, 1);
+  if (r2) return r2;
+  double s[8];
+  rc = read_scal(c, c->scal2.p, 8, s);
+  if (rc) return rc;
+  if (cg_iterations) *cg_iterations = iters;
+  if (model_cost_change) *model_cost_change = s[3];
+  return status == 2 ? TBA_ERR_INVALID_ARGUMENT : TBA_OK;
+}
+
+int tba_debug_evaluate_step(tba_context* c, double* candidate_cost) {
+  if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevProblem& P = c->P;
+  CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
+  if (P.n_tiles > 0) LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->scal2.p);
+  int rc = allreduce_sum(c, c->scal2.p, 3);
+  if (rc) return rc;
+  double s[3];
+  rc = read_scal(c, c->scal2.p, 3, s);
+  if (rc) return rc;
+  if (candidate_cost) *candidate_cost = s[0] + s[1];
+  return s[2] == 0.0 ? TBA_OK : TBA_ERR_INVALID_ARGUMENT;
+}
+
+int tba_debug_read(tba_context* c, int which, double* out, int64_t n) {
+  if (!c || !c->uploaded || !out) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevProblem& P = c->P;
+  const int64_t ne = P.ne, ni = (int64_t)P.n_group * 10, np4 = (int64_t)P.n_pt * 4;
+  std::vector<double> tmp, tmp2;
+  auto fetch = [&](const double* dev, int64_t len, std::vector<double>& v) -> int {
+    v.resize((size_t)len);
+    CUDA_OK(c, cudaMemcpyAsync(v.data(), dev, (size_t)len * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return TBA_OK;
+  };
+  int rc = TBA_OK;
+  switch (which) {
+    case TBA_VEC_GRADIENT_CAM: case TBA_VEC_GRADIENT_INTR: case TBA_VEC_COLNORM2_CAM: case TBA_VEC_COLNORM2_INTR: {
+      const bool grad = which == TBA_VEC_GRADIENT_CAM || which == TBA_VEC_GRADIENT_INTR;
+      const bool cam = which == TBA_VEC_GRADIENT_CAM || which == TBA_VEC_COLNORM2_CAM;
+      const int64_t len = cam ? ne : ni;
+      if (n != len) return TBA_ERR_INVALID_ARGUMENT;
+      if ((rc = fetch((grad ? lin_g(c) : lin_cn(c)) + (cam ? 0 : ne), len, tmp))) return rc;
+      if ((rc = fetch(c->mask.p + (cam ? 0 : ne), len, tmp2))) return rc;
+      for (int64_t i = 0; i < len; ++i) out[i] = tmp[i] * tmp2[i];
+      return TBA_OK; }
+    case TBA_VEC_GRADIENT_PT: case TBA_VEC_COLNORM2_PT: case TBA_VEC_STEP_PT: {
+      if (n != (int64_t)c->n_pt_caller * 4) return TBA_ERR_INVALID_ARGUMENT;
+      std::vector<uint8_t> pc((size_t)P.n_pt);
+      CUDA_OK(c, cudaMemcpyAsync(pc.data(), c->pt_const.p, (size_t)P.n_pt, cudaMemcpyDeviceToHost, c->stream));
+      memset(out, 0, (size_t)n * 8);
+      if (which == TBA_VEC_COLNORM2_PT) {
+        if ((rc = fetch(P.Hpp, (int64_t)P.n_pt * 10, tmp))) return rc;
+        const int dg[4] = {0, 4, 7, 9};
+        for (int64_t k = 0; k < P.n_pt; ++k) for (int j = 0; j < 4; ++j) out[(int64_t)c->pk2caller[k] * 4 + j] = pc[k] ? 0.0 : tmp[k * 10 + dg[j]];
+      } else {
+        if ((rc = fetch(which == TBA_VEC_GRADIENT_PT ? P.gp : P.dpt, np4, tmp))) return rc;
+        for (int64_t k = 0; k < P.n_pt; ++k) for (int j = 0; j < 4; ++j) out[(int64_t)c->pk2caller[k] * 4 + j] = pc[k] ? 0.0 : tmp[k * 4 + j];
+      }
+      return TBA_OK; }
+    case TBA_VEC_RESIDUALS: {
+      if (n != c->n_obs * 2) return TBA_ERR_INVALID_ARGUMENT;
+      if ((rc = fetch(P.res, c->n_slots * 2, tmp))) return rc;
+      for (int64_t s = 0; s < c->n_slots; ++s) {
+        const int64_t oi = c->slot_orig[s];
+        if (oi < 0) continue;
+        const int64_t t = s / TILE, l = s % TILE;
+        out[2 * oi] = tmp[(size_t)(t * 2 + 0) * TILE + l];
+        out[2 * oi + 1] = tmp[(size_t)(t * 2 + 1) * TILE + l];
+      }
+      return TBA_OK; }
+    case TBA_VEC_SCHUR_RHS_CAM: if (n != ne) return TBA_ERR_INVALID_ARGUMENT; if ((rc = fetch(c->b.p, ne, tmp))) return rc; break;
+    case TBA_VEC_SCHUR_RHS_INTR: if (n != ni) return TBA_ERR_INVALID_ARGUMENT; if ((rc = fetch(c->b.p + ne, ni, tmp))) return rc; break;
+    case TBA_VEC_PRECOND_CAM: if (n != (int64_t)P.n_cam * 36) return TBA_ERR_INVALID_ARGUMENT; if ((rc = fetch(c->Minv_c.p, n, tmp))) return rc; break;
+    case TBA_VEC_PRECOND_INTR: if (n != (int64_t)P.n_group * 100) return TBA_ERR_INVALID_ARGUMENT; if ((rc = fetch(c->Minv_i.p, n, tmp))) return rc; break;
+    case TBA_VEC_STEP_CAM: case TBA_VEC_STEP_INTR: {
+      const bool cam = which == TBA_VEC_STEP_CAM;
+      const int64_t len = cam ? ne : ni;
+      if (n != len) return TBA_ERR_INVALID_ARGUMENT;
+      if ((rc = fetch(c->xs.p + (cam ? 0 : ne), len, tmp))) return rc;
+      for (int64_t i = 0; i < len; ++i) out[i] = -tmp[i];
+      return TBA_OK; }
+    default: return TBA_ERR_INVALID_ARGUMENT;
+  }
+  memcpy(out, tmp.data(), (size_t)n * 8);
+  return TBA_OK;
+}
+
+}  // extern "C"

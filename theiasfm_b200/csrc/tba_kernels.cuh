@@ -1,0 +1,994 @@
+// tba_kernels.cuh -- sm_100a kernels of the bundle-adjustment engine.
+//
+// Replaces the arithmetic that ceres::Solve (called at
+// src/theia/sfm/bundle_adjustment/bundle_adjuster.cc:205) performs for Theia's
+// reprojection-error problem: residual/Jacobian evaluation, block accumulation,
+// Schur elimination of the point blocks, SCHUR_JACOBI preconditioner and the
+// implicit-Schur PCG matvec.  Layout and roofline per kernel: DESIGN.md section 4-5.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tba_camera_models.cuh"
+
+namespace tba {
+
+constexpr int TILE = 256;   // observation slots per tile == threads per CTA
+constexpr int MAXP = 256;   // max points per tile
+constexpr int VB = 64;      // CTAs of the camera-space vector kernels (deterministic reductions)
+constexpr int VT = 256;
+
+// Device view of the packed problem.
+struct DevProblem {
+  int n_cam, n_group, n_pt, n_tiles;
+  int ne;                      // n_cam * 6
+  int ncs;                     // n_cam*6 + n_group*10 (camera-space vector length)
+  int single_group;            // n_group == 1: block-reduce the intrinsics accumulations
+  int loss_type; double loss_width;
+  // parameters: current x and candidate
+  double *ext, *intr, *pt, *ext_c, *intr_c, *pt_c;
+  const int* cam_group; const int* group_model;
+  double* cam_rec;             // [n_cam][kCamRec] for x
+  double* cam_rec_c;           // ... for the candidate
+  // observation slots (tile-major, point-sorted)
+  const int* slot_cam;         // -1 = padding
+  const int* slot_pt;          // packed point id
+  const uint8_t* slot_flags;   // bit0: all parameter blocks constant (Ceres fixed_cost)
+  const int16_t* slot_run;     // (point, group) run index inside the tile
+  const int* tile_pt_begin;    // [n_tiles + 1]
+  const int* tile_nruns;       // [n_tiles]
+  const double* xy;            // [tile][2][TILE]
+  double* J;                   // [tile][NJ][TILE], NJ = 14 + 2 NI
+  double* res;                 // [tile][2][TILE] robustified residuals
+  // per point
+  double* Hpp;                 // [n_pt][10] sym J_p^T J_p (unscaled)
+  double* gp;                  // [n_pt][4]  J_p^T r
+  double* Mp;                  // [n_pt][10] S_p (S_p Hpp S_p + D_p^2)^-1 S_p
+  double* sp;                  // [n_pt][4] masked Jacobi scale
+  double* dpt;                 // [n_pt][4] unscaled point delta
+  const uint8_t* pt_const;
+};
+
+// ---------------------------------------------------------------- utilities
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA (VT or TILE threads); result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double* s_red /*[32]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_red[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (wid == 0) {
+    t = lane < (blockDim.x >> 5) ? s_red[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;
+}
+
+// Segmented (by contiguous equal key) inclusive-from-the-right warp reduction:
+// the FIRST lane of every run ends up holding the run's sum.
+__device__ __forceinline__ double seg_reduce(double v, int key, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, v, o);
+    const int ok = __shfl_down_sync(0xffffffffu, key, o);
+    if (lane + o < 32 && ok == key) v += ov;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
+
+// ------------------------------------------------------------ camera prep
+__global__ void k_cam_prep(int n_cam, const double* __restrict__ ext, double* __restrict__ rec) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_cam) cam_prep(ext + (size_t)c * 6 + 3, rec + (size_t)c * kCamRec);
+}
+
+// ---------------------------------------------------------- K1 linearise
+// One thread per observation slot.  Writes the compact linearisation and the
+// robustified residual, accumulates the per-point blocks (tile-local in shared
+// memory, points never straddle tiles) and the camera-side gradient / squared
+// column norms (global fp64 reductions), the cost and the failure flag.
+//   scal[0] += cost (non-fixed), scal[1] += fixed cost, scal[2] += #failed evaluations
+template <uint32_t IMASK>
+__global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
+                                                    double* __restrict__ scal) {
+  constexpr int NI = popcount10(IMASK);
+  constexpr int NJ = 14 + 2 * NI;
+  __shared__ double s_acc[MAXP][14];
+  __shared__ double s_red[32];
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int p0 = P.tile_pt_begin[tile], npt = P.tile_pt_begin[tile + 1] - p0;
+  for (int i = tid; i < npt * 14; i += TILE) (&s_acc[0][0])[i] = 0.0;
+  __syncthreads();
+  const size_t slot = (size_t)tile * TILE + tid;
+  const int cam = P.slot_cam[slot];
+  const bool valid = cam >= 0;
+  double cost = 0.0, fixed = 0.0, failed = 0.0;
+  double Ja[6] = {0, 0, 0, 0, 0, 0}, Jw[6] = {0, 0, 0, 0, 0, 0}, Jh[2] = {0, 0}, r[2] = {0, 0};
+  double Ji[2 * NI + 1];
+#pragma unroll
+  for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
+  int pl = -1, grp = 0;
+  double h = 0.0;
+  if (valid) {
+    const int pt = P.slot_pt[slot];
+    pl = pt - p0;
+    grp = P.cam_group[cam];
+    const double4 X = *reinterpret_cast<const double4*>(P.pt + (size_t)pt * 4);
+    h = X.w;
+    const double x = P.xy[((size_t)tile * 2 + 0) * TILE + tid], y = P.xy[((size_t)tile * 2 + 1) * TILE + tid];
+    double rho0 = 0.0;
+    const bool ok = linearize_obs<IMASK>(P.group_model[grp], P.ext + (size_t)cam * 6, P.cam_rec + (size_t)cam * kCamRec,
+                                         P.intr + (size_t)grp * 10, X.x, X.y, X.z, X.w, x, y, P.loss_type, P.loss_width,
+                                         r, rho0, Ja, Jw, Jh, Ji);
+    if (!ok) {
+      failed = 1.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { Ja[j] = 0.0; Jw[j] = 0.0; }
+      Jh[0] = Jh[1] = 0.0; r[0] = r[1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
+    } else if (P.slot_flags[slot] & 1) {
+      fixed = 0.5 * rho0;
+    } else {
+      cost = 0.5 * rho0;
+    }
+  }
+  // store the compact linearisation (coalesced: consecutive threads -> consecutive doubles)
+  double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) Jt[(size_t)j * TILE] = Ja[j];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) Jt[(size_t)(6 + j) * TILE] = Jw[j];
+  Jt[(size_t)12 * TILE] = Jh[0];
+  Jt[(size_t)13 * TILE] = Jh[1];
+#pragma unroll
+  for (int j = 0; j < 2 * NI; ++j) Jt[(size_t)(14 + j) * TILE] = Ji[j];
+  P.res[((size_t)tile * 2 + 0) * TILE + tid] = r[0];
+  P.res[((size_t)tile * 2 + 1) * TILE + tid] = r[1];
+  // per-point blocks: H_pp = J_p^T J_p (10, row-major upper), g_p = J_p^T r with J_p = [Ja | Jh]
+  {
+    const double jp0[4] = {Ja[0], Ja[1], Ja[2], Jh[0]}, jp1[4] = {Ja[3], Ja[4], Ja[5], Jh[1]};
+    double acc[14];
+    int n = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = a; b < 4; ++b) acc[n++] = jp0[a] * jp0[b] + jp1[a] * jp1[b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc[10 + a] = jp0[a] * r[0] + jp1[a] * r[1];
+    const int prev = __shfl_up_sync(0xffffffffu, pl, 1);
+    const bool head = valid && (lane == 0 || prev != pl);
+#pragma unroll
+    for (int j = 0; j < 14; ++j) {
+      const double v = seg_reduce(acc[j], pl, lane);
+      if (head) atomicAdd(&s_acc[pl][j], v);
+    }
+  }
+  // camera-side gradient and squared column norms: J_c = [-h Ja | Jw]
+  if (valid) {
+    double* gc = g_cs + (size_t)cam * 6;
+    double* cc = cn_cs + (size_t)cam * 6;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double c0 = -h * Ja[j], c1 = -h * Ja[3 + j];
+      red_add(gc + j, c0 * r[0] + c1 * r[1]);
+      red_add(cc + j, c0 * c0 + c1 * c1);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      red_add(gc + 3 + j, Jw[j] * r[0] + Jw[3 + j] * r[1]);
+      red_add(cc + 3 + j, Jw[j] * Jw[j] + Jw[3 + j] * Jw[3 + j]);
+    }
+  }
+  if (NI > 0) {
+    if (P.single_group) {
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const double gsum = block_sum(Ji[j] * r[0] + Ji[NI + j] * r[1], s_red);
+        const double csum = block_sum(Ji[j] * Ji[j] + Ji[NI + j] * Ji[NI + j], s_red);
+        if (tid == 0) {
+          red_add(g_cs + P.ne + nth_bit(IMASK, j), gsum);
+          red_add(cn_cs + P.ne + nth_bit(IMASK, j), csum);
+        }
+      }
+    } else if (valid) {
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        red_add(g_cs + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), Ji[j] * r[0] + Ji[NI + j] * r[1]);
+        red_add(cn_cs + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), Ji[j] * Ji[j] + Ji[NI + j] * Ji[NI + j]);
+      }
+    }
+  }
+  // scalars
+  {
+    const double c = block_sum(cost, s_red);
+    const double f = block_sum(fixed, s_red);
+    const double e = block_sum(failed, s_red);
+    if (tid == 0) {
+      red_add(scal + 0, c);
+      if (f != 0.0) red_add(scal + 1, f);
+      if (e != 0.0) red_add(scal + 2, e);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < npt * 14; i += TILE) {
+    const int p = i / 14, j = i - p * 14;
+    if (j < 10) P.Hpp[(size_t)(p0 + p) * 10 + j] = s_acc[p][j];
+    else P.gp[(size_t)(p0 + p) * 4 + (j - 10)] = s_acc[p][j];
+  }
+}
+
+// ------------------------------------------------------- K3 cost at candidate
+__global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __restrict__ ext, const double* __restrict__ rec,
+                                               const double* __restrict__ intr, const double* __restrict__ pt,
+                                               double* __restrict__ scal) {
+  __shared__ double s_red[32];
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const size_t slot = (size_t)tile * TILE + tid;
+  const int cam = P.slot_cam[slot];
+  double cost = 0.0, fixed = 0.0, failed = 0.0;
+  if (cam >= 0) {
+    const int p = P.slot_pt[slot], grp = P.cam_group[cam];
+    const double4 X = *reinterpret_cast<const double4*>(pt + (size_t)p * 4);
+    const double x = P.xy[((size_t)tile * 2 + 0) * TILE + tid], y = P.xy[((size_t)tile * 2 + 1) * TILE + tid];
+    double r0, r1;
+    if (!reproject(P.group_model[grp], ext + (size_t)cam * 6, rec + (size_t)cam * kCamRec, intr + (size_t)grp * 10, X.x, X.y,
+                   X.z, X.w, x, y, r0, r1)) {
+      failed = 1.0;
+    } else {
+      double rho[3];
+      loss_evaluate(P.loss_type, P.loss_width, r0 * r0 + r1 * r1, rho);
+      if (P.slot_flags[slot] & 1) fixed = 0.5 * rho[0]; else cost = 0.5 * rho[0];
+    }
+  }
+  const double c = block_sum(cost, s_red);
+  const double f = block_sum(fixed, s_red);
+  const double e = block_sum(failed, s_red);
+  if (tid == 0) {
+    red_add(scal + 0, c);
+    if (f != 0.0) red_add(scal + 1, f);
+    if (e != 0.0) red_add(scal + 2, e);
+  }
+}
+
+// --------------------------------------------------------- per-point blocks
+// 4x4 SPD inverse through Cholesky (Ceres: InvertPSDMatrix, llt().solve(I)); returns false if not PD.
+__device__ inline bool spd4_inverse(const double* A /*10 upper*/, double* Ainv /*10 upper*/) {
+  // A index: (0,0)=0 (0,1)=1 (0,2)=2 (0,3)=3 (1,1)=4 (1,2)=5 (1,3)=6 (2,2)=7 (2,3)=8 (3,3)=9
+  const double a00 = A[0], a01 = A[1], a02 = A[2], a03 = A[3], a11 = A[4], a12 = A[5], a13 = A[6], a22 = A[7], a23 = A[8], a33 = A[9];
+  if (!(a00 > 0.0)) return false;
+  const double l00 = sqrt(a00), i00 = 1.0 / l00;
+  const double l10 = a01 * i00, l20 = a02 * i00, l30 = a03 * i00;
+  const double d1 = a11 - l10 * l10;
+  if (!(d1 > 0.0)) return false;
+  const double l11 = sqrt(d1), i11 = 1.0 / l11;
+  const double l21 = (a12 - l20 * l10) * i11, l31 = (a13 - l30 * l10) * i11;
+  const double d2 = a22 - l20 * l20 - l21 * l21;
+  if (!(d2 > 0.0)) return false;
+  const double l22 = sqrt(d2), i22 = 1.0 / l22;
+  const double l32 = (a23 - l30 * l20 - l31 * l21) * i22;
+  const double d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
+  if (!(d3 > 0.0)) return false;
+  const double l33 = sqrt(d3), i33 = 1.0 / l33;
+  // M = L^-1 (lower)
+  const double m10 = -l10 * i00 * i11;
+  const double m21 = -l21 * i11 * i22;
+  const double m32 = -l32 * i22 * i33;
+  const double m20 = -(l20 * i00 + l21 * m10) * i22;
+  const double m31 = -(l31 * i11 + l32 * m21) * i33;
+  const double m30 = -(l30 * i00 + l31 * m10 + l32 * m20) * i33;
+  // A^-1 = M^T M
+  Ainv[0] = i00 * i00 + m10 * m10 + m20 * m20 + m30 * m30;
+  Ainv[1] = m10 * i11 + m20 * m21 + m30 * m31;
+  Ainv[2] = m20 * i22 + m30 * m32;
+  Ainv[3] = m30 * i33;
+  Ainv[4] = i11 * i11 + m21 * m21 + m31 * m31;
+  Ainv[5] = m21 * i22 + m31 * m32;
+  Ainv[6] = m31 * i33;
+  Ainv[7] = i22 * i22 + m32 * m32;
+  Ainv[8] = m32 * i33;
+  Ainv[9] = i33 * i33;
+  return true;
+}
+
+// Jacobi scale of the point columns (iteration 0): s = 1 / (1 + sqrt(colnorm2)), 0 on constant points.
+__global__ void k_point_scale(DevProblem P, int use_scaling) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.n_pt) return;
+  const bool c = P.pt_const[p] != 0;
+  const double* H = P.Hpp + (size_t)p * 10;
+  const double d[4] = {H[0], H[4], H[7], H[9]};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) P.sp[(size_t)p * 4 + j] = c ? 0.0 : (use_scaling ? 1.0 / (1.0 + sqrt(d[j])) : 1.0);
+}
+
+// M_p = S (S Hpp S + D^2)^-1 S with D^2 = clamp(s^2 diag(Hpp), lo, hi) / radius; flag[0] += 1 if a block is not PD.
+// Also the max-norm of the (masked) point gradient into gmax partials.
+__global__ void k_point_blocks(DevProblem P, double radius, double lo, double hi, double* __restrict__ flag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.n_pt) return;
+  double* M = P.Mp + (size_t)p * 10;
+  if (P.pt_const[p]) {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) M[j] = 0.0;
+    return;
+  }
+  const double* H = P.Hpp + (size_t)p * 10;
+  const double4 s4 = *reinterpret_cast<const double4*>(P.sp + (size_t)p * 4);
+  const double s[4] = {s4.x, s4.y, s4.z, s4.w};
+  double A[10], Ai[10];
+  int n = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a; b < 4; ++b) { A[n] = s[a] * H[n] * s[b]; ++n; }
+  const int dg[4] = {0, 4, 7, 9};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) A[dg[a]] += fmin(fmax(A[dg[a]], lo), hi) / radius;
+  if (!spd4_inverse(A, Ai)) {
+    atomicAdd(flag, 1.0);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) M[j] = 0.0;
+    return;
+  }
+  n = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a; b < 4; ++b) { M[n] = s[a] * Ai[n] * s[b]; ++n; }
+}
+
+__device__ __forceinline__ void sym4_mul(const double* __restrict__ M, const double t[4], double u[4]) {
+  u[0] = M[0] * t[0] + M[1] * t[1] + M[2] * t[2] + M[3] * t[3];
+  u[1] = M[1] * t[0] + M[4] * t[1] + M[5] * t[2] + M[6] * t[3];
+  u[2] = M[2] * t[0] + M[5] * t[1] + M[7] * t[2] + M[8] * t[3];
+  u[3] = M[3] * t[0] + M[6] * t[1] + M[8] * t[2] + M[9] * t[3];
+}
+
+// --------------------------------------------- K2 implicit Schur complement
+// MODE 0: y += F^T (I - E M E^T) F xs                (PCG matvec; ImplicitSchurComplement::RightMultiply)
+// MODE 1: y += F^T (I - E M E^T) r                   (reduced rhs; ImplicitSchurComplement::ComputeRHS)
+// MODE 2: dpt = -M E^T (r - F xs);  scal[3] += model cost change  (BackSubstitute + ComputeTrustRegionStep)
+// All with the UNSCALED stored Jacobian; the Jacobi scaling lives in xs (= s .* x), M and the
+// post-scaling of y (k_vec_* kernels).  xs: camera-space vector [n_cam*6 | n_group*10].
+template <uint32_t IMASK, int MODE>
+__global__ void __launch_bounds__(TILE) k_schur(DevProblem P, const double* __restrict__ xs, double* __restrict__ y,
+                                                double* __restrict__ scal, const int* __restrict__ done_flag) {
+  constexpr int NI = popcount10(IMASK);
+  constexpr int NJ = 14 + 2 * NI;
+  if (done_flag != nullptr && *done_flag) return;
+  __shared__ double s_t[MAXP][4];
+  __shared__ double s_red[32];
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int p0 = P.tile_pt_begin[tile], npt = P.tile_pt_begin[tile + 1] - p0;
+  for (int i = tid; i < npt * 4; i += TILE) (&s_t[0][0])[i] = 0.0;
+  __syncthreads();
+  const size_t slot = (size_t)tile * TILE + tid;
+  const int cam = P.slot_cam[slot];
+  const bool valid = cam >= 0;
+  const double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+  double Ja[6], Jw[6], Jh[2], Ji[2 * NI + 1];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) Ja[j] = Jt[(size_t)j * TILE];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) Jw[j] = Jt[(size_t)(6 + j) * TILE];
+  Jh[0] = Jt[(size_t)12 * TILE];
+  Jh[1] = Jt[(size_t)13 * TILE];
+#pragma unroll
+  for (int j = 0; j < 2 * NI; ++j) Ji[j] = Jt[(size_t)(14 + j) * TILE];
+  int pl = -1, grp = 0;
+  double h = 0.0, w0 = 0.0, w1 = 0.0, r0 = 0.0, r1 = 0.0;
+  if (valid) {
+    pl = P.slot_pt[slot] - p0;
+    grp = P.cam_group[cam];
+    h = P.pt[(size_t)(p0 + pl) * 4 + 3];
+    if (MODE != 0) {
+      r0 = P.res[((size_t)tile * 2 + 0) * TILE + tid];
+      r1 = P.res[((size_t)tile * 2 + 1) * TILE + tid];
+    }
+    if (MODE != 1) {
+      const double* xc = xs + (size_t)cam * 6;
+      const double x0 = xc[0], x1 = xc[1], x2 = xc[2], x3 = xc[3], x4 = xc[4], x5 = xc[5];
+      w0 = -h * (Ja[0] * x0 + Ja[1] * x1 + Ja[2] * x2) + Jw[0] * x3 + Jw[1] * x4 + Jw[2] * x5;
+      w1 = -h * (Ja[3] * x0 + Ja[4] * x1 + Ja[5] * x2) + Jw[3] * x3 + Jw[4] * x4 + Jw[5] * x5;
+      if (NI > 0) {
+        const double* xi = xs + P.ne + (size_t)grp * 10;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const double xv = xi[nth_bit(IMASK, j)];
+          w0 += Ji[j] * xv;
+          w1 += Ji[NI + j] * xv;
+        }
+      }
+    }
+    if (MODE == 1) { w0 = r0; w1 = r1; }
+    if (MODE == 2) { w0 = r0 - w0; w1 = r1 - w1; }
+  }
+  // t_p = sum_o J_p^T w
+  {
+    double t[4] = {Ja[0] * w0 + Ja[3] * w1, Ja[1] * w0 + Ja[4] * w1, Ja[2] * w0 + Ja[5] * w1, Jh[0] * w0 + Jh[1] * w1};
+    const int prev = __shfl_up_sync(0xffffffffu, pl, 1);
+    const bool head = valid && (lane == 0 || prev != pl);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double v = seg_reduce(t[j], pl, lane);
+      if (head) atomicAdd(&s_t[pl][j], v);
+    }
+  }
+  __syncthreads();
+  if (tid < npt) {
+    const double t[4] = {s_t[tid][0], s_t[tid][1], s_t[tid][2], s_t[tid][3]};
+    double u[4];
+    sym4_mul(P.Mp + (size_t)(p0 + tid) * 10, t, u);
+    s_t[tid][0] = u[0]; s_t[tid][1] = u[1]; s_t[tid][2] = u[2]; s_t[tid][3] = u[3];
+    if (MODE == 2) {
+      double* d = P.dpt + (size_t)(p0 + tid) * 4;
+      d[0] = -u[0]; d[1] = -u[1]; d[2] = -u[2]; d[3] = -u[3];
+    }
+  }
+  __syncthreads();
+  double z0 = 0.0, z1 = 0.0;
+  if (valid) {
+    const double u0 = s_t[pl][0], u1 = s_t[pl][1], u2 = s_t[pl][2], u3 = s_t[pl][3];
+    const double e0 = Ja[0] * u0 + Ja[1] * u1 + Ja[2] * u2 + Jh[0] * u3;
+    const double e1 = Ja[3] * u0 + Ja[4] * u1 + Ja[5] * u2 + Jh[1] * u3;
+    z0 = w0 - e0;
+    z1 = w1 - e1;
+  }
+  if (MODE == 2) {
+    // model residual m = J * step = -(F xs + E u) = -(r - z); contribution -m.(r + m/2)
+    double mcc = 0.0;
+    if (valid && !(P.slot_flags[slot] & 1)) {
+      const double m0 = -(r0 - z0), m1 = -(r1 - z1);
+      mcc = -(m0 * (r0 + 0.5 * m0) + m1 * (r1 + 0.5 * m1));
+    }
+    const double s = block_sum(mcc, s_red);
+    if (tid == 0) red_add(scal + 3, s);
+    return;
+  }
+  if (valid) {
+    double* yc = y + (size_t)cam * 6;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) red_add(yc + j, -h * (Ja[j] * z0 + Ja[3 + j] * z1));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) red_add(yc + 3 + j, Jw[j] * z0 + Jw[3 + j] * z1);
+  }
+  if (NI > 0) {
+    if (P.single_group) {
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const double v = block_sum(Ji[j] * z0 + Ji[NI + j] * z1, s_red);
+        if (tid == 0) red_add(y + P.ne + nth_bit(IMASK, j), v);
+      }
+    } else if (valid) {
+#pragma unroll
+      for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), Ji[j] * z0 + Ji[NI + j] * z1);
+    }
+  }
+}
+
+// ------------------------------------------- SCHUR_JACOBI preconditioner blocks
+// Extrinsics blocks: S_cc = sum_o J_c^T Q_o J_c with Q_o = I_2 - J_p M_p J_p^T (a view observes a track once).
+// Sc: [n_cam][21] upper triangle, unscaled (scaling + D^2 + inversion in k_precond_finish).
+template <uint32_t IMASK>
+__global__ void __launch_bounds__(TILE) k_precond_ext(DevProblem P, double* __restrict__ Sc) {
+  constexpr int NI = popcount10(IMASK);
+  constexpr int NJ = 14 + 2 * NI;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const size_t slot = (size_t)tile * TILE + tid;
+  const int cam = P.slot_cam[slot];
+  if (cam < 0) return;
+  const double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+  double Ja[6], Jw[6], Jh[2];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) Ja[j] = Jt[(size_t)j * TILE];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) Jw[j] = Jt[(size_t)(6 + j) * TILE];
+  Jh[0] = Jt[(size_t)12 * TILE];
+  Jh[1] = Jt[(size_t)13 * TILE];
+  const int pt = P.slot_pt[slot];
+  const double h = P.pt[(size_t)pt * 4 + 3];
+  const double* M = P.Mp + (size_t)pt * 10;
+  const double jp0[4] = {Ja[0], Ja[1], Ja[2], Jh[0]}, jp1[4] = {Ja[3], Ja[4], Ja[5], Jh[1]};
+  double m0[4], m1[4];
+  sym4_mul(M, jp0, m0);
+  sym4_mul(M, jp1, m1);
+  const double q00 = 1.0 - (jp0[0] * m0[0] + jp0[1] * m0[1] + jp0[2] * m0[2] + jp0[3] * m0[3]);
+  const double q01 = -(jp0[0] * m1[0] + jp0[1] * m1[1] + jp0[2] * m1[2] + jp0[3] * m1[3]);
+  const double q11 = 1.0 - (jp1[0] * m1[0] + jp1[1] * m1[1] + jp1[2] * m1[2] + jp1[3] * m1[3]);
+  double c0[6], c1[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { c0[j] = -h * Ja[j]; c1[j] = -h * Ja[3 + j]; c0[3 + j] = Jw[j]; c1[3 + j] = Jw[3 + j]; }
+  double* S = Sc + (size_t)cam * 21;
+  int n = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const double qa0 = q00 * c0[a] + q01 * c1[a], qa1 = q01 * c0[a] + q11 * c1[a];
+#pragma unroll
+    for (int b = a; b < 6; ++b) { red_add(S + n, qa0 * c0[b] + qa1 * c1[b]); ++n; }
+  }
+}
+
+// Intrinsics blocks: S_gg = sum_o J_i^T J_i - sum_(p,g) W^T M_p W, W = sum_{o in p and g} J_p^T J_i.
+// Si: [n_group][55] upper triangle over the padded 10 parameter indices.  Dynamic smem: runs x 4 x NI doubles.
+template <uint32_t IMASK>
+__global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __restrict__ Si) {
+  constexpr int NI = popcount10(IMASK);
+  constexpr int NJ = 14 + 2 * NI;
+  constexpr int NW = 4 * NI;
+  constexpr int NS = NI * (NI + 1) / 2;
+  extern __shared__ double s_w[];  // [nruns][NW] then [nruns] group ids (as int) and points
+  __shared__ double s_red[32];
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int nruns = P.tile_nruns[tile];
+  int* s_grp = reinterpret_cast<int*>(s_w + (size_t)TILE * NW);
+  int* s_pt = s_grp + TILE;
+  for (int i = tid; i < nruns * NW; i += TILE) s_w[i] = 0.0;
+  __syncthreads();
+  const size_t slot = (size_t)tile * TILE + tid;
+  const int cam = P.slot_cam[slot];
+  const bool valid = cam >= 0;
+  double acc[NS + 1];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) acc[j] = 0.0;
+  int grp = 0;
+  if (valid) {
+    const double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+    double jp0[4], jp1[4], Ji[2 * NI + 1];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { jp0[j] = Jt[(size_t)j * TILE]; jp1[j] = Jt[(size_t)(3 + j) * TILE]; }
+    jp0[3] = Jt[(size_t)12 * TILE];
+    jp1[3] = Jt[(size_t)13 * TILE];
+#pragma unroll
+    for (int j = 0; j < 2 * NI; ++j) Ji[j] = Jt[(size_t)(14 + j) * TILE];
+    grp = P.cam_group[cam];
+    const int run = P.slot_run[slot];
+    if (run >= 0) {
+      s_grp[run] = grp;
+      s_pt[run] = P.slot_pt[slot];
+      double* W = s_w + (size_t)run * NW;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) atomicAdd(W + a * NI + j, jp0[a] * Ji[j] + jp1[a] * Ji[NI + j]);
+    }
+    int n = 0;
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+      for (int b = a; b < NI; ++b) { acc[n] = Ji[a] * Ji[b] + Ji[NI + a] * Ji[NI + b]; ++n; }
+  }
+  __syncthreads();
+  // per-run Schur term, handled by thread `run`
+  int rgrp = grp;
+  double sub[NS + 1];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) sub[j] = 0.0;
+  const bool has_run = tid < nruns;
+  if (has_run) {
+    rgrp = s_grp[tid];
+    const double* W = s_w + (size_t)tid * NW;
+    const double* M = P.Mp + (size_t)s_pt[tid] * 10;
+    double MW[4][NI + 1];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const double t[4] = {W[0 * NI + j], W[1 * NI + j], W[2 * NI + j], W[3 * NI + j]};
+      double u[4];
+      sym4_mul(M, t, u);
+      MW[0][j] = u[0]; MW[1][j] = u[1]; MW[2][j] = u[2]; MW[3][j] = u[3];
+    }
+    int n = 0;
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+      for (int b = a; b < NI; ++b) {
+        sub[n] = W[0 * NI + a] * MW[0][b] + W[1 * NI + a] * MW[1][b] + W[2 * NI + a] * MW[2][b] + W[3 * NI + a] * MW[3][b];
+        ++n;
+      }
+  }
+  // accumulate into Si at padded parameter indices
+  int n = 0;
+#pragma unroll
+  for (int a = 0; a < NI; ++a)
+#pragma unroll
+    for (int b = a; b < NI; ++b) {
+      const int ia = nth_bit(IMASK, a), ib = nth_bit(IMASK, b);
+      const int idx = ia * 10 - ia * (ia - 1) / 2 + (ib - ia);  // upper-triangle offset in a 10x10
+      if (P.single_group) {
+        const double v = block_sum(acc[n] - sub[n], s_red);
+        if (tid == 0) red_add(Si + idx, v);
+      } else {
+        if (valid) red_add(Si + (size_t)grp * 55 + idx, acc[n]);
+        if (has_run) red_add(Si + (size_t)rgrp * 55 + idx, -sub[n]);
+      }
+      ++n;
+    }
+}
+
+// In-place Cholesky inverse of an n x n SPD matrix held in registers/local (row-major, n <= 10).
+template <int N>
+__device__ inline bool spd_inverse_n(double* A) {
+  double L[N * N], Li[N * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i * N + j];
+      for (int k = 0; k < j; ++k) s -= L[i * N + k] * L[j * N + k];
+      if (i == j) { if (!(s > 0.0)) return false; L[i * N + i] = sqrt(s); }
+      else L[i * N + j] = s / L[j * N + j];
+    }
+  for (int i = 0; i < N * N; ++i) Li[i] = 0.0;
+  for (int j = 0; j < N; ++j) {
+    Li[j * N + j] = 1.0 / L[j * N + j];
+    for (int i = j + 1; i < N; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s -= L[i * N + k] * Li[k * N + j];
+      Li[i * N + j] = s / L[i * N + i];
+    }
+  }
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int k = (i > j ? i : j); k < N; ++k) s += Li[k * N + i] * Li[k * N + j];
+      A[i * N + j] = s;
+    }
+  return true;
+}
+
+// Minv_c[c] = (s S_cc s + D^2)^-1 (identity on non-free coordinates); same for groups.
+__global__ void k_precond_finish(DevProblem P, const double* __restrict__ Sc, const double* __restrict__ Si,
+                                 const double* __restrict__ sm, const double* __restrict__ D2, double* __restrict__ Minv_c,
+                                 double* __restrict__ Minv_i, double* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n_cam) {
+    double A[36];
+    const double* S = Sc + (size_t)i * 21;
+    const double* s = sm + (size_t)i * 6;
+    const double* d = D2 + (size_t)i * 6;
+    int n = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int b = a; b < 6; ++b) { const double v = s[a] * S[n] * s[b]; A[a * 6 + b] = v; A[b * 6 + a] = v; ++n; }
+    for (int a = 0; a < 6; ++a) { if (s[a] != 0.0) A[a * 6 + a] += d[a]; else A[a * 6 + a] = 1.0; }
+    if (!spd_inverse_n<6>(A)) { atomicAdd(flag, 1.0); for (int a = 0; a < 36; ++a) A[a] = (a % 7 == 0) ? 1.0 : 0.0; }
+    for (int a = 0; a < 36; ++a) Minv_c[(size_t)i * 36 + a] = A[a];
+  } else if (i < P.n_cam + P.n_group) {
+    const int g = i - P.n_cam;
+    double A[100];
+    const double* S = Si + (size_t)g * 55;
+    const double* s = sm + P.ne + (size_t)g * 10;
+    const double* d = D2 + P.ne + (size_t)g * 10;
+    int n = 0;
+    for (int a = 0; a < 10; ++a)
+      for (int b = a; b < 10; ++b) { const double v = s[a] * S[n] * s[b]; A[a * 10 + b] = v; A[b * 10 + a] = v; ++n; }
+    for (int a = 0; a < 10; ++a) { if (s[a] != 0.0) A[a * 10 + a] += d[a]; else A[a * 10 + a] = 1.0; }
+    if (!spd_inverse_n<10>(A)) { atomicAdd(flag, 1.0); for (int a = 0; a < 100; ++a) A[a] = (a % 11 == 0) ? 1.0 : 0.0; }
+    for (int a = 0; a < 100; ++a) Minv_i[(size_t)g * 100 + a] = A[a];
+  }
+}
+
+// ------------------------------------------------ camera-space vector kernels
+// Jacobi scale (iteration 0) and LM diagonal; gradient max-norm partial.
+//   sm = mask / (1 + sqrt(cn));  D2 = clamp(sm^2 cn, lo, hi) / radius on free coordinates.
+__global__ void k_cs_scale(int ncs, const double* __restrict__ cn, const double* __restrict__ mask, int use_scaling,
+                           double* __restrict__ sm) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncs; i += gridDim.x * blockDim.x)
+    sm[i] = mask[i] != 0.0 ? (use_scaling ? 1.0 / (1.0 + sqrt(cn[i])) : 1.0) : 0.0;
+}
+__global__ void k_cs_diag(int ncs, const double* __restrict__ cn, const double* __restrict__ sm, double radius, double lo,
+                          double hi, double* __restrict__ D2) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncs; i += gridDim.x * blockDim.x)
+    D2[i] = sm[i] != 0.0 ? fmin(fmax(sm[i] * sm[i] * cn[i], lo), hi) / radius : 0.0;
+}
+
+// PCG state (ping-pong between kernels).
+struct PcgState {
+  double rho, last_rho, beta, alpha, pq, Q0, Q1, norm_b2;
+  int iters;        // current (1-based) iteration
+  int done;
+  int status;       // 0 success/converged, 1 no convergence (max iters / indefinite: x still usable), 2 failure
+  int pending_q;    // a Q-test is pending (part_Q holds x.(b+r) of iteration `iters`)
+  int min_iters, max_iters;
+  double eta;
+};
+
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, double* s_red) {
+  // every CTA sums the VB partials in the same fixed order -> identical on all CTAs and all ranks
+  double v = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < VB; ++i) v += part[i];
+    s_red[0] = v;
+  }
+  __syncthreads();
+  v = s_red[0];
+  __syncthreads();
+  return v;
+}
+
+__device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x); }
+
+// b = sm .* y_rhs ; x = 0 ; r = b ; partial |b|^2
+__global__ void __launch_bounds__(VT) k_pcg_init(int ncs, const double* __restrict__ yrhs, const double* __restrict__ sm,
+                                                 double* __restrict__ b, double* __restrict__ x, double* __restrict__ r,
+                                                 double* __restrict__ part) {
+  __shared__ double s_red[32];
+  double acc = 0.0;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double v = sm[i] * yrhs[i];
+    b[i] = v; x[i] = 0.0; r[i] = v;
+    acc += v * v;
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void k_pcg_init_state(PcgState* st, const double* __restrict__ part, int min_iters, int max_iters, double eta) {
+  double v = 0.0;
+  for (int i = 0; i < VB; ++i) v += part[i];
+  PcgState s;
+  s.rho = 1.0; s.last_rho = 1.0; s.beta = 0.0; s.alpha = 0.0; s.pq = 0.0; s.Q0 = 0.0; s.Q1 = 0.0; s.norm_b2 = v;
+  s.iters = 1; s.done = (v == 0.0) ? 1 : 0; s.status = 0; s.pending_q = 0;
+  if (v == 0.0) s.iters = 0;
+  s.min_iters = min_iters; s.max_iters = max_iters; s.eta = eta;
+  *st = s;
+}
+
+// V1: [Q-test of the previous iteration]; z = Minv r; partial rho = r.z
+__global__ void __launch_bounds__(VT) k_pcg_v1(DevProblem P, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                               const double* __restrict__ part_Q, const double* __restrict__ Minv_c,
+                                               const double* __restrict__ Minv_i, const double* __restrict__ r,
+                                               double* __restrict__ z, double* __restrict__ part_rho, int identity_precond) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  if (!st.done && st.pending_q) {
+    const double Q1 = -sum_partials(part_Q, s_red);
+    const double zeta = st.iters * (Q1 - st.Q0) / Q1;
+    st.Q1 = Q1;
+    st.pending_q = 0;
+    if (zeta < st.eta && st.iters >= st.min_iters) { st.done = 1; st.status = 0; }
+    else {
+      st.Q0 = Q1;
+      if (st.iters >= st.max_iters) { st.done = 1; st.status = 1; }
+      else st.iters += 1;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
+  if (st.done) return;
+  double acc = 0.0;
+  const int nblk = P.n_cam + P.n_group;
+  for (int blk = blockIdx.x * VT + threadIdx.x; blk < nblk; blk += VB * VT) {
+    if (blk < P.n_cam) {
+      const double* M = Minv_c + (size_t)blk * 36;
+      const double* rr = r + (size_t)blk * 6;
+      double* zz = z + (size_t)blk * 6;
+      double rv[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) rv[a] = rr[a];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = rv[a];
+        if (!identity_precond) {
+          s = 0.0;
+#pragma unroll
+          for (int b = 0; b < 6; ++b) s += M[a * 6 + b] * rv[b];
+        }
+        zz[a] = s;
+        acc += rv[a] * s;
+      }
+    } else {
+      const int g = blk - P.n_cam;
+      const double* M = Minv_i + (size_t)g * 100;
+      const double* rr = r + P.ne + (size_t)g * 10;
+      double* zz = z + P.ne + (size_t)g * 10;
+      double rv[10];
+#pragma unroll
+      for (int a = 0; a < 10; ++a) rv[a] = rr[a];
+#pragma unroll
+      for (int a = 0; a < 10; ++a) {
+        double s = rv[a];
+        if (!identity_precond) {
+          s = 0.0;
+#pragma unroll
+          for (int b = 0; b < 10; ++b) s += M[a * 10 + b] * rv[b];
+        }
+        zz[a] = s;
+        acc += rv[a] * s;
+      }
+    }
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part_rho[blockIdx.x] = s;
+}
+
+// V2: rho, beta; p = z + beta p; xs = sm .* p; y = 0
+__global__ void __launch_bounds__(VT) k_pcg_v2(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                               const double* __restrict__ part_rho, const double* __restrict__ z,
+                                               const double* __restrict__ sm, double* __restrict__ p, double* __restrict__ xs,
+                                               double* __restrict__ y) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  if (!st.done) {
+    const double rho = sum_partials(part_rho, s_red);
+    st.last_rho = st.rho;
+    st.rho = rho;
+    if (zero_or_inf(rho)) { st.done = 1; st.status = 2; }
+    else if (st.iters > 1) {
+      st.beta = rho / st.last_rho;
+      if (zero_or_inf(st.beta)) { st.done = 1; st.status = 2; }
+    } else st.beta = 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
+  if (st.done) return;
+  const bool first = st.iters == 1;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double pv = first ? z[i] : z[i] + st.beta * p[i];
+    p[i] = pv;
+    xs[i] = sm[i] * pv;
+    y[i] = 0.0;
+  }
+}
+
+// V3: q = sm .* y + D2 .* p (stored in z); partial pq = p.q
+__global__ void __launch_bounds__(VT) k_pcg_v3(int ncs, const PcgState* __restrict__ in, const double* __restrict__ y,
+                                               const double* __restrict__ sm, const double* __restrict__ D2,
+                                               const double* __restrict__ p, double* __restrict__ q,
+                                               double* __restrict__ part_pq) {
+  __shared__ double s_red[32];
+  if (in->done) return;
+  double acc = 0.0;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double qv = sm[i] * y[i] + D2[i] * p[i];
+    q[i] = qv;
+    acc += p[i] * qv;
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part_pq[blockIdx.x] = s;
+}
+
+// V4: alpha = rho / pq; x += alpha p; r -= alpha q; partial x.(b + r)
+__global__ void __launch_bounds__(VT) k_pcg_v4(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                               const double* __restrict__ part_pq, const double* __restrict__ p,
+                                               const double* __restrict__ q, const double* __restrict__ b,
+                                               double* __restrict__ x, double* __restrict__ r, double* __restrict__ part_Q) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  if (!st.done) {
+    const double pq = sum_partials(part_pq, s_red);
+    st.pq = pq;
+    if (pq <= 0.0 || isinf(pq)) { st.done = 1; st.status = 1; }
+    else {
+      st.alpha = st.rho / pq;
+      if (isinf(st.alpha)) { st.done = 1; st.status = 2; }
+      else st.pending_q = 1;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
+  if (st.done) return;
+  double acc = 0.0;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double xv = x[i] + st.alpha * p[i];
+    const double rv = r[i] - st.alpha * q[i];
+    x[i] = xv; r[i] = rv;
+    acc += xv * (b[i] + rv);
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part_Q[blockIdx.x] = s;
+}
+
+// Residual reset (every cg_residual_reset_period iterations): xs = sm .* x, y = 0 ... matvec ... r = b - (sm.*y + D2.*x)
+__global__ void __launch_bounds__(VT) k_pcg_reset_a(int ncs, const PcgState* __restrict__ in, const double* __restrict__ x,
+                                                    const double* __restrict__ sm, double* __restrict__ xs, double* __restrict__ y) {
+  if (in->done) return;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) { xs[i] = sm[i] * x[i]; y[i] = 0.0; }
+}
+__global__ void __launch_bounds__(VT) k_pcg_reset_b(int ncs, const PcgState* __restrict__ in, const double* __restrict__ y,
+                                                    const double* __restrict__ sm, const double* __restrict__ D2,
+                                                    const double* __restrict__ x, const double* __restrict__ b,
+                                                    double* __restrict__ r, double* __restrict__ part_Q) {
+  __shared__ double s_red[32];
+  if (in->done) return;
+  double acc = 0.0;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double rv = b[i] - (sm[i] * y[i] + D2[i] * x[i]);
+    r[i] = rv;
+    acc += x[i] * (b[i] + rv);
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part_Q[blockIdx.x] = s;
+}
+
+// Finalise a batch: run the pending Q-test so that `done`/`iters` are current, publish the flag.
+__global__ void k_pcg_finalize(const PcgState* __restrict__ in, PcgState* __restrict__ out, const double* __restrict__ part_Q,
+                               int* __restrict__ done_flag) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  if (!st.done && st.pending_q) {
+    const double Q1 = -sum_partials(part_Q, s_red);
+    const double zeta = st.iters * (Q1 - st.Q0) / Q1;
+    st.Q1 = Q1;
+    st.pending_q = 0;
+    if (zeta < st.eta && st.iters >= st.min_iters) { st.done = 1; st.status = 0; }
+    else {
+      st.Q0 = Q1;
+      if (st.iters >= st.max_iters) { st.done = 1; st.status = 1; }
+      else st.iters += 1;
+    }
+  }
+  if (threadIdx.x == 0) { *out = st; *done_flag = st.done; }
+}
+__global__ void k_set_flag(int* f, int v) { *f = v; }
+
+// xs = sm .* x (scaled solution -> unscaled), used before back-substitution
+__global__ void k_cs_mul(int ncs, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ o) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncs; i += gridDim.x * blockDim.x) o[i] = a[i] * b[i];
+}
+
+// ------------------------------------------------- candidate / norms / gradient
+// candidate = x + delta: cameras/intrinsics delta = -xs (xs = sm .* x_sol, zero on constant coordinates);
+// points delta = dpt.  scal[4] += |delta|^2 (camera side, rank 0 only counts), scal[5] += |delta_pt|^2.
+__global__ void k_candidate_cs(DevProblem P, const double* __restrict__ xs, double* __restrict__ scal, int count_norm) {
+  __shared__ double s_red[32];
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.ncs; i += gridDim.x * blockDim.x) {
+    const double d = -xs[i];
+    if (i < P.ne) P.ext_c[i] = P.ext[i] + d; else P.intr_c[i - P.ne] = P.intr[i - P.ne] + d;
+    acc += d * d;
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0 && count_norm) red_add(scal + 4, s);
+}
+__global__ void k_candidate_pt(DevProblem P, double* __restrict__ scal) {
+  __shared__ double s_red[32];
+  double acc = 0.0;
+  const size_t n = (size_t)P.n_pt * 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double d = P.pt_const[i >> 2] ? 0.0 : P.dpt[i];
+    P.pt_c[i] = P.pt[i] + d;
+    acc += d * d;
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) red_add(scal + 5, s);
+}
+
+// |x|^2 over non-constant parameter blocks (ambient coordinates): scal[6] (camera side), scal[7] (points)
+__global__ void k_xnorm(DevProblem P, const double* __restrict__ ext, const double* __restrict__ intr,
+                        const double* __restrict__ pt, const double* __restrict__ blk_free /*[n_cam + n_group]*/,
+                        double* __restrict__ scal, int count_cs) {
+  __shared__ double s_red[32];
+  double a_cs = 0.0, a_pt = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < (size_t)P.ne; i += stride) if (blk_free[i / 6] != 0.0) a_cs += ext[i] * ext[i];
+  for (size_t i = t0; i < (size_t)P.n_group * 10; i += stride) if (blk_free[P.n_cam + i / 10] != 0.0) a_cs += intr[i] * intr[i];
+  for (size_t i = t0; i < (size_t)P.n_pt * 4; i += stride) if (!P.pt_const[i >> 2]) a_pt += pt[i] * pt[i];
+  const double s1 = block_sum(a_cs, s_red);
+  const double s2 = block_sum(a_pt, s_red);
+  if (threadIdx.x == 0) { if (count_cs) red_add(scal + 6, s1); red_add(scal + 7, s2); }
+}
+
+// max |g| over masked camera-space gradient -> gmax[0]; over free points -> gmax[1] (as ordered ints of the bit pattern)
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  // v >= 0: the IEEE bit pattern is monotone
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__global__ void k_gradmax(DevProblem P, const double* __restrict__ g_cs, const double* __restrict__ mask, double* __restrict__ gmax) {
+  double m_cs = 0.0, m_pt = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < (size_t)P.ncs; i += stride) if (mask[i] != 0.0) m_cs = fmax(m_cs, fabs(g_cs[i]));
+  for (size_t i = t0; i < (size_t)P.n_pt * 4; i += stride) if (!P.pt_const[i >> 2]) m_pt = fmax(m_pt, fabs(P.gp[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m_cs = fmax(m_cs, __shfl_down_sync(0xffffffffu, m_cs, o));
+    m_pt = fmax(m_pt, __shfl_down_sync(0xffffffffu, m_pt, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomic_max_double(gmax + 0, m_cs); atomic_max_double(gmax + 1, m_pt); }
+}
+
+}  // namespace tba

@@ -1,0 +1,212 @@
+"""ctypes binding of the C-ABI (include/theia_ba_b200.h) -> theiasfm_b200/libtheia_ba_b200.so.
+
+There is NO CPU fallback: if the CUDA library is missing, or no B200 is visible, construction
+of an ``Engine`` raises.  The product path never touches ``oracle/``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtheia_ba_b200.so")
+_LIB = None
+
+# every symbol include/theia_ba_b200.h declares
+EXPORTED_SYMBOLS = [
+    "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
+    "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
+    "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
+    "tba_debug_evaluate_step", "tba_debug_read",
+]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("tba error %d: %s" % (code, message))
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C theiasfm_b200/csrc). There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        L.tba_options_init.argtypes = [C.POINTER(_abi.tba_options)]
+        L.tba_device_count.restype = C.c_int
+        L.tba_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.tba_destroy.argtypes = [C.c_void_p]
+        L.tba_nccl_unique_id.argtypes = [C.c_void_p]
+        L.tba_last_error.restype = C.c_char_p
+        L.tba_last_error.argtypes = [C.c_void_p]
+        L.tba_solve.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.POINTER(_abi.tba_summary)]
+        L.tba_upload.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem)]
+        L.tba_minimize.argtypes = [C.c_void_p, C.POINTER(_abi.tba_summary)]
+        L.tba_download.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
+        L.tba_shard_points.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.tba_debug_linearize.argtypes = [C.c_void_p, dp]
+        L.tba_debug_prepare_linear_system.argtypes = [C.c_void_p, C.c_double]
+        L.tba_debug_schur_matvec.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.tba_debug_solve_linear_system.argtypes = [C.c_void_p, C.POINTER(C.c_int32), dp]
+        L.tba_debug_evaluate_step.argtypes = [C.c_void_p, dp]
+        L.tba_debug_read.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64]
+        L.tba_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def default_options(**kw):
+    """theia::BundleAdjustmentOptions defaults (bundle_adjustment.h:78-122) + Ceres' defaults."""
+    o = _abi.tba_options()
+    lib().tba_options_init(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def device_count():
+    return lib().tba_device_count()
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = lib().tba_nccl_unique_id(buf)
+    if rc != 0:
+        raise EngineError(rc, "ncclGetUniqueId failed")
+    return buf.raw
+
+
+def shard_points(pt_num_obs, world_size, rank):
+    a = np.ascontiguousarray(pt_num_obs, dtype=np.int32)
+    b, e = C.c_int32(), C.c_int32()
+    lib().tba_shard_points(a.ctypes.data_as(C.POINTER(C.c_int32)), len(a), world_size, rank, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+class Summary:
+    def __init__(self, s, iters):
+        for f, _ in _abi.tba_summary._fields_:
+            if f not in ("iterations", "message"):
+                setattr(self, f, getattr(s, f))
+        self.message = s.message.decode(errors="replace")
+        n = min(s.num_iterations, len(iters))
+        self.iterations = [{f: getattr(iters[i], f) for f, _ in _abi.tba_iteration._fields_} for i in range(n)]
+
+    @property
+    def costs(self):
+        return np.array([it["cost"] for it in self.iterations])
+
+
+class Engine:
+    """One GPU's engine context (tba_create / tba_destroy)."""
+
+    def __init__(self, device=0, rank=0, world_size=1, nccl_id=None, max_iterations_logged=2048):
+        L = lib()
+        if L.tba_device_count() <= 0:
+            raise EngineError(_abi.ERR_NO_DEVICE, "no CUDA device visible; the engine has no CPU fallback")
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        rc = L.tba_create(device, rank, world_size, idbuf, C.byref(h))
+        if rc != 0:
+            raise EngineError(rc, "tba_create failed")
+        self._h = h
+        self.rank, self.world_size = rank, world_size
+        self._iters = (_abi.tba_iteration * max_iterations_logged)()
+        self._problem = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().tba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(rc, lib().tba_last_error(self._h).decode(errors="replace"))
+
+    def _new_summary(self):
+        s = _abi.tba_summary()
+        s.iterations = C.cast(self._iters, C.POINTER(_abi.tba_iteration))
+        s.iterations_capacity = len(self._iters)
+        return s
+
+    # ---- whole solve: host buffers in, host buffers out (the drop-in call)
+    def solve(self, problem, options=None):
+        options = options or default_options()
+        s = self._new_summary()
+        st = problem.as_struct()
+        rc = lib().tba_solve(self._h, C.byref(options), C.byref(st), C.byref(s))
+        out = Summary(s, self._iters)
+        out.rc = rc
+        if rc != 0:
+            out.message = lib().tba_last_error(self._h).decode(errors="replace")
+        return out
+
+    # ---- split phase
+    def upload(self, problem, options=None):
+        options = options or default_options()
+        self._problem = problem
+        self._st = problem.as_struct()
+        self._check(lib().tba_upload(self._h, C.byref(options), C.byref(self._st)))
+
+    def minimize(self):
+        s = self._new_summary()
+        self._check(lib().tba_minimize(self._h, C.byref(s)))
+        return Summary(s, self._iters)
+
+    def download(self, problem=None):
+        problem = problem or self._problem
+        st = problem.as_struct()
+        self._check(lib().tba_download(self._h, C.byref(st)))
+
+    # ---- stage hooks (kernel-level parity tests)
+    def linearize(self):
+        c = C.c_double()
+        rc = lib().tba_debug_linearize(self._h, C.byref(c))
+        return rc == 0, c.value
+
+    def prepare_linear_system(self, radius):
+        return lib().tba_debug_prepare_linear_system(self._h, radius) == 0
+
+    def schur_matvec(self, x_cam, x_intr):
+        x_cam = np.ascontiguousarray(x_cam, np.float64); x_intr = np.ascontiguousarray(x_intr, np.float64)
+        y_cam = np.zeros_like(x_cam); y_intr = np.zeros_like(x_intr)
+        self._check(lib().tba_debug_schur_matvec(self._h, _dp(x_cam), _dp(x_intr), _dp(y_cam), _dp(y_intr)))
+        return y_cam, y_intr
+
+    def solve_linear_system(self):
+        it, m = C.c_int32(), C.c_double()
+        rc = lib().tba_debug_solve_linear_system(self._h, C.byref(it), C.byref(m))
+        return rc == 0, it.value, m.value
+
+    def evaluate_step(self):
+        c = C.c_double()
+        rc = lib().tba_debug_evaluate_step(self._h, C.byref(c))
+        return rc == 0, c.value
+
+    def read(self, which):
+        p = self._problem
+        n = {_abi.VEC_GRADIENT_CAM: p.n_cam * 6, _abi.VEC_GRADIENT_INTR: p.n_group * 10, _abi.VEC_GRADIENT_PT: p.n_pt * 4,
+             _abi.VEC_COLNORM2_CAM: p.n_cam * 6, _abi.VEC_COLNORM2_INTR: p.n_group * 10, _abi.VEC_COLNORM2_PT: p.n_pt * 4,
+             _abi.VEC_RESIDUALS: p.n_obs * 2, _abi.VEC_SCHUR_RHS_CAM: p.n_cam * 6, _abi.VEC_SCHUR_RHS_INTR: p.n_group * 10,
+             _abi.VEC_PRECOND_CAM: p.n_cam * 36, _abi.VEC_PRECOND_INTR: p.n_group * 100, _abi.VEC_STEP_CAM: p.n_cam * 6,
+             _abi.VEC_STEP_INTR: p.n_group * 10, _abi.VEC_STEP_PT: p.n_pt * 4}[which]
+        out = np.zeros(n)
+        self._check(lib().tba_debug_read(self._h, which, _dp(out), n))
+        return out
