@@ -203,6 +203,15 @@ int tba_upload(tba_context* ctx, const tba_options* options, const tba_problem* 
 int tba_minimize(tba_context* ctx, tba_summary* summary);
 int tba_download(tba_context* ctx, tba_problem* problem);
 
+/* Re-load ext / intr / pt of an uploaded problem (same shape) without re-packing. */
+int tba_reset_parameters(tba_context* ctx, const tba_problem* problem);
+
+/* Per-kernel device timing (CUDA events on the engine stream) for the roofline report:
+ * out[0..3] = {ms in the Schur matvec kernel, launches, ms in the linearise kernel, launches},
+ * out[4..7] = {observation slots, observations, packed points, doubles stored per observation}. */
+int tba_set_profiling(tba_context* ctx, int enable);
+int tba_get_profile(tba_context* ctx, double* out8);
+
 /* Contiguous point range [begin,end) owned by `rank` of `world_size`
  * (balanced by observation count given per-point counts). */
 void tba_shard_points(const int32_t* pt_num_obs, int32_t n_pt, int world_size,

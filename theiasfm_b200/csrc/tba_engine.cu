@@ -104,6 +104,10 @@ struct tba_context {
   DevBuf<PcgState> st;      // [2]
   DevBuf<int> done_flag;
   bool have_scale = false;
+  // optional per-kernel timing (CUDA events on the engine stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_spans[2];  // 0: matvec, 1: linearize ; indices into ev_pool
   double x_cost = 0, fixed_cost = 0;
   // host mirrors
   double* h_scal = nullptr;  // pinned [64]
@@ -144,6 +148,23 @@ void set_err(tba_context* c, const char* fmt, ...) {
     kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);     \
     (c)->launches++;                                                 \
   } while (0)
+
+int prof_begin(tba_context* c) {
+  if (!c->profiling) return -1;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return -1;
+  c->ev_pool.push_back(e);
+  cudaEventRecord(e, c->stream);
+  return (int)c->ev_pool.size() - 1;
+}
+void prof_end(tba_context* c, int which, int begin) {
+  if (begin < 0) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  c->ev_pool.push_back(e);
+  cudaEventRecord(e, c->stream);
+  c->ev_spans[which].push_back({begin, (int)c->ev_pool.size() - 1});
+}
 
 const uint32_t kMasks[] = {0x000u, 0x001u, 0x061u, 0x0E1u, 0x07Fu, 0x3FFu};
 
@@ -188,9 +209,11 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
   CUDA_OK(c, cudaMemsetAsync(c->lin.p, 0, (2 * (size_t)P.ncs + 16) * sizeof(double), c->stream));
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
   if (P.n_tiles > 0) {
+    const int pb = prof_begin(c);
 #define F(M) LAUNCH(c, k_linearize<M>, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), lin_scal(c))
     DISPATCH_IMASK(c->imask, F)
 #undef F
+    prof_end(c, 1, pb);
   }
   int rc = allreduce_sum(c, c->lin.p, 2 * (size_t)P.ncs + 16);
   if (rc) return rc;
@@ -270,9 +293,11 @@ const int* st_done(const PcgState* st) { return reinterpret_cast<const int*>(rei
 int launch_matvec(tba_context* c, const int* done) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
+    const int pb = prof_begin(c);
 #define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->xs.p, c->y.p, nullptr, done); }
     DISPATCH_IMASK(c->imask, F)
 #undef F
+    prof_end(c, 0, pb);
   }
   return allreduce_sum(c, c->y.p, P.ncs);
 }
@@ -744,6 +769,8 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     term = TBA_CONVERGENCE; msg = "Function tolerance reached. No non-constant parameter blocks found.";
     it.iteration = 0; it.cost = x_cost + fixed; it.step_is_valid = 1; it.step_is_successful = 1;
     push_iter(s, it);
+    s->num_successful_steps = 1;
+    s->final_cost = x_cost + fixed;
     goto done;
   }
   RC(stage_xnorm(c, &xn));
@@ -850,6 +877,47 @@ int tba_solve(tba_context* c, const tba_options* options, tba_problem* problem, 
   summary->solve_time_in_seconds += now_s() - t0;
   summary->d2h_bytes = c->d2h_bytes;
   return rc;
+}
+
+int tba_reset_parameters(tba_context* c, const tba_problem* p) {
+  if (!c || !p || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (p->n_cam != c->n_cam || p->n_group != c->n_group || p->n_pt != c->n_pt_caller) { set_err(c, "reset: problem shape differs from the uploaded one"); return TBA_ERR_INVALID_ARGUMENT; }
+  std::vector<double> ptk((size_t)c->n_pt * 4);
+  for (int k = 0; k < c->n_pt; ++k) memcpy(&ptk[(size_t)k * 4], p->pt + (size_t)c->pk2caller[k] * 4, 32);
+  CUDA_OK(c, cudaMemcpyAsync(c->P.ext, p->ext, (size_t)c->n_cam * 48, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->P.intr, p->intr, (size_t)c->n_group * 80, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->P.pt, ptk.data(), (size_t)c->n_pt * 32, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->P.ext_c, p->ext, (size_t)c->n_cam * 48, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->P.intr_c, p->intr, (size_t)c->n_group * 80, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->P.pt_c, ptk.data(), (size_t)c->n_pt * 32, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->have_scale = false;
+  return TBA_OK;
+}
+
+int tba_set_profiling(tba_context* c, int enable) {
+  if (!c) return TBA_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(c->device);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  c->ev_pool.clear(); c->ev_spans[0].clear(); c->ev_spans[1].clear();
+  c->profiling = enable != 0;
+  return TBA_OK;
+}
+
+// out[0] = total ms in the Schur matvec kernel, out[1] = #launches, out[2] = total ms in linearize, out[3] = #launches,
+// out[4] = observation slots, out[5] = valid observations, out[6] = packed points, out[7] = doubles stored per observation
+int tba_get_profile(tba_context* c, double* out) {
+  if (!c || !out) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < 2; ++w) {
+    double tot = 0;
+    for (auto& sp : c->ev_spans[w]) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_pool[sp.first], c->ev_pool[sp.second]); tot += ms; }
+    out[2 * w] = tot; out[2 * w + 1] = (double)c->ev_spans[w].size();
+  }
+  out[4] = (double)c->n_slots; out[5] = (double)c->n_obs; out[6] = (double)c->n_pt; out[7] = (double)c->NJ;
+  return TBA_OK;
 }
 
 // --------------------------------------------------------------------------- debug / test hooks

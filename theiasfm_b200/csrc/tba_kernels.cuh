@@ -137,7 +137,13 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
 #pragma unroll
       for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
     } else if (P.slot_flags[slot] & 1) {
+      // every parameter block of this residual is constant: Ceres removes it from the program (fixed_cost)
       fixed = 0.5 * rho0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { Ja[j] = 0.0; Jw[j] = 0.0; }
+      Jh[0] = Jh[1] = 0.0; r[0] = r[1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
     } else {
       cost = 0.5 * rho0;
     }

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile",
 ]
 
 
@@ -56,6 +56,9 @@ def lib():
         L.tba_debug_evaluate_step.argtypes = [C.c_void_p, dp]
         L.tba_debug_read.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64]
         L.tba_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
+        L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
+        L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.tba_get_profile.argtypes = [C.c_void_p, dp]
         _LIB = L
     return _LIB
 
@@ -174,6 +177,19 @@ class Engine:
         problem = problem or self._problem
         st = problem.as_struct()
         self._check(lib().tba_download(self._h, C.byref(st)))
+
+    def reset_parameters(self, problem):
+        st = problem.as_struct()
+        self._check(lib().tba_reset_parameters(self._h, C.byref(st)))
+
+    def set_profiling(self, enable=True):
+        self._check(lib().tba_set_profiling(self._h, int(enable)))
+
+    def profile(self):
+        out = np.zeros(8)
+        self._check(lib().tba_get_profile(self._h, _dp(out)))
+        return dict(matvec_ms=out[0], matvec_launches=int(out[1]), linearize_ms=out[2], linearize_launches=int(out[3]),
+                    slots=int(out[4]), observations=int(out[5]), points=int(out[6]), doubles_per_obs=int(out[7]))
 
     # ---- stage hooks (kernel-level parity tests)
     def linearize(self):

@@ -7,9 +7,18 @@ observations = exact projection + pixel noise, initial estimate = ground truth +
 Everything is float64 numpy; the projection here is an independent vectorised restatement of
 Camera::ProjectPoint (camera.cc:204-213) used only to synthesise measurements.
 """
+import ctypes
+
 import numpy as np
 
 from . import _abi
+
+try:  # keep freed large blocks in the heap: re-faulting fresh pages for every numpy temporary dominates generation
+    _libc = ctypes.CDLL("libc.so.6")
+    _libc.mallopt(-3, (1 << 31) - 1)  # M_MMAP_THRESHOLD
+    _libc.mallopt(-1, (1 << 31) - 1)  # M_TRIM_THRESHOLD
+except OSError:  # pragma: no cover
+    pass
 
 CONFIGS = {
     # BASELINE.json configs[0..3]
@@ -31,7 +40,8 @@ def rotation_from_angle_axis(w):
     K[:, 1, 0], K[:, 1, 2] = k[:, 2], -k[:, 0]
     K[:, 2, 0], K[:, 2, 1] = -k[:, 1], k[:, 0]
     s, c = np.sin(theta)[:, None, None], np.cos(theta)[:, None, None]
-    R = np.eye(3)[None] + s * K + (1.0 - c) * (K @ K)
+    KK = np.einsum("nij,njk->nik", K, K)  # einsum, not @: batched 3x3 matmul through BLAS is pathologically slow
+    R = np.eye(3)[None] + s * K + (1.0 - c) * KK
     R[small] = np.eye(3)
     return R
 
@@ -47,11 +57,13 @@ def angle_axis_from_rotation(R):
     return v * f[:, None]
 
 
-def project(model, ext, intr, pt):
-    """Vectorised Camera::ProjectPoint: ext [n,6], intr [n,10], pt [n,4] -> pix [n,2], depth [n]."""
+def project(model, ext, intr, pt, R=None):
+    """Vectorised Camera::ProjectPoint: ext [n,6], intr [n,10], pt [n,4] -> pix [n,2], depth [n].
+    R: optional precomputed world->camera rotations [n,3,3]."""
     a = pt[:, :3] - pt[:, 3:4] * ext[:, :3]
-    R = rotation_from_angle_axis(ext[:, 3:6])
-    q = np.einsum("nij,nj->ni", R, a)
+    if R is None:
+        R = rotation_from_angle_axis(ext[:, 3:6])
+    q = np.stack([(R[:, i, :] * a).sum(axis=1) for i in range(3)], axis=1)
     u, v = q[:, 0] / q[:, 2], q[:, 1] / q[:, 2]
     r2 = u * u + v * v
     if model == _abi.MODEL_PINHOLE:
@@ -113,7 +125,9 @@ def make_scene(n_cam, n_pt, obs_per_pt=10, model=_abi.MODEL_PINHOLE, shared_intr
     offs = base[None, :-1] + np.floor(rng.uniform(0, 1, (n_pt, L)) * size).astype(np.int64) - half
     obs_cam = order[(i0[:, None] + offs) % n_cam].astype(np.int32).reshape(-1)
     obs_pt = np.repeat(np.arange(n_pt, dtype=np.int32), L)
-    pix, depth = project(model, ext_gt[obs_cam], intr_gt[cam_group[obs_cam]], pt_gt[obs_pt])
+    R_cam = rotation_from_angle_axis(ext_gt[:, 3:6])
+    pix, depth = project(model, ext_gt[obs_cam], intr_gt[cam_group[obs_cam]], pt_gt[obs_pt], R=R_cam[obs_cam])
+    del R_cam
     keep = (depth > 0) & (pix[:, 0] >= 0) & (pix[:, 0] <= 1000) & (pix[:, 1] >= 0) & (pix[:, 1] <= 1000)
     obs_cam, obs_pt, pix = obs_cam[keep], obs_pt[keep], pix[keep]
     obs_xy = pix + noise_px * rng.normal(size=pix.shape)
