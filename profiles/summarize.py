@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Turns the raw ncu outputs brought back in gpurun_out/ into the committed text summaries under profiles/.
+  python profiles/summarize.py launches <launches.csv> > profiles/<name>.txt
+  python profiles/summarize.py full <report.ncu-rep>   > profiles/<name>.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    tot, cnt = collections.defaultdict(float), collections.Counter()
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(row["Metric Unit"], 1.0)
+        k = row["Kernel Name"].split("(")[0]
+        tot[k] += v
+        cnt[k] += 1
+    T = sum(tot.values())
+    print("# per-kernel device time (ncu --metrics gpu__time_duration.sum --clock-control none); cold-cache, serialised: compare SHARES")
+    print("%-44s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "avg_us", "share"))
+    for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+        print("%-44s %6d %12.1f %10.1f %6.1f%%" % (k[:44], cnt[k], v, v / cnt[k], 100 * v / T))
+    print("%-44s %6d %12.1f" % ("TOTAL", sum(cnt.values()), T))
+
+
+def full(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print("# ncu --set full --clock-control none; one block per captured launch")
+    for r in rows[2:]:
+        print("## %s  grid=%s block=%s" % (r[idx["Kernel Name"]], r[idx.get("launch__grid_size", 0)], r[idx.get("launch__block_size", 0)]))
+        for k in KEYS:
+            if k in idx and r[idx[k]] != "":
+                print("  %-78s %18s %s" % (k, r[idx[k]], units[idx[k]]))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

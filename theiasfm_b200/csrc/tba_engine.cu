@@ -108,6 +108,7 @@ struct tba_context {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_spans[2];  // 0: matvec, 1: linearize ; indices into ev_pool
+  int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
   // host mirrors
   double* h_scal = nullptr;  // pinned [64]
@@ -351,6 +352,7 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
   }
   *iters = c->h_st->iters;
   *status = c->h_st->status;
+  c->real_matvecs += c->h_st->iters + (o.cg_residual_reset_period > 0 ? c->h_st->iters / o.cg_residual_reset_period : 0);
   return TBA_OK;
 }
 
@@ -901,6 +903,7 @@ int tba_set_profiling(tba_context* c, int enable) {
   cudaSetDevice(c->device);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   c->ev_pool.clear(); c->ev_spans[0].clear(); c->ev_spans[1].clear();
+  c->real_matvecs = 0;
   c->profiling = enable != 0;
   return TBA_OK;
 }
@@ -916,6 +919,7 @@ int tba_get_profile(tba_context* c, double* out) {
     for (auto& sp : c->ev_spans[w]) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_pool[sp.first], c->ev_pool[sp.second]); tot += ms; }
     out[2 * w] = tot; out[2 * w + 1] = (double)c->ev_spans[w].size();
   }
+  out[1] = (double)c->real_matvecs;  // early-exited launches (after convergence inside a batch) cost ~2 us and do no work
   out[4] = (double)c->n_slots; out[5] = (double)c->n_obs; out[6] = (double)c->n_pt; out[7] = (double)c->NJ;
   return TBA_OK;
 }
