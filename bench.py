@@ -42,8 +42,9 @@ def solver_kwargs(max_iters):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line).
+    Started before the warm-up (nvidia-smi takes ~1 s to come up); samples are filtered to the timed window."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -51,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -59,19 +60,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [r for t, r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit() and t_begin - 0.02 <= t <= t_end + 0.05]
+        rows = inside if inside else ok
+        sm = [float(r[2]) for r in rows]
+        mx = [float(r[3]) for r in rows]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[6:10]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": "timed region" if inside else "whole run (timed region shorter than the sampling period)",
+                "power_w_max": max([float(r[4]) for r in rows if r[4].replace(".", "").isdigit()], default=None)}
 
 
 def load_peaks():
@@ -177,6 +182,8 @@ def main():
         shard = full
     init = shard.copy()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up: W LM iterations, then restore the initial estimate
     eng.upload(shard, engine.default_options(**solver_kwargs(max(W, 1))))
     if W > 0:
@@ -186,14 +193,13 @@ def main():
     eng.upload(shard, engine.default_options(**solver_kwargs(K)))  # same packing, K iterations
     eng.reset_parameters(init)
     eng.set_profiling(True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    tw0 = time.time()
     t0 = time.perf_counter()
     s = eng.minimize()
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(tw0, time.time())
     prof = eng.profile()
     eng.set_profiling(False)
     iters = s.num_iterations - 1

@@ -240,6 +240,30 @@ def test_edge_cases(eng, oracle):
     assert s.rc == _abi.ERR_UNSUPPORTED
 
 
+def test_long_tracks_use_the_cta_level_path(eng, oracle):
+    """Tracks with more than 32 observations live in 'long' tiles (per-point sums combined across warps in shared
+    memory); mixed with short tracks and exactly-32 / 33-observation tracks at the boundary."""
+    p = synthetic.make_scene(n_cam=120, n_pt=260, obs_per_pt=48, seed=41)
+    rng = np.random.default_rng(1)
+    keep = np.ones(p.n_obs, bool)
+    target = {q: int(rng.choice([3, 7, 31, 32, 33, 48])) for q in range(p.n_pt)}
+    seen = np.zeros(p.n_pt, int)
+    for i in range(p.n_obs):
+        q = int(p.obs_pt[i])
+        seen[q] += 1
+        keep[i] = seen[q] <= target[q]
+    p = _abi.Problem(p.ext, p.ext_const, p.cam_group, p.group_model, p.intr, p.group_const_mask, p.pt, p.pt_const,
+                     p.obs_cam[keep], p.obs_pt[keep], p.obs_xy[keep])
+    counts = np.bincount(p.obs_pt, minlength=p.n_pt)
+    assert (counts > 32).sum() > 20 and (counts == 32).sum() > 5 and (counts < 32).sum() > 20
+    po, pg = p.copy(), p.copy()
+    so = oracle.solve(po, _opts(oracle, max_num_iterations=12))
+    sg = eng.solve(pg, _opts(engine, max_num_iterations=12))
+    assert sg.rc == 0 and sg.num_iterations == so.num_iterations
+    assert np.all(np.abs(sg.costs - so.costs) <= 1e-8 * so.costs)
+    assert rel_err(pg.pt, po.pt) < 1e-6 and rel_err(pg.ext, po.ext) < 1e-6
+
+
 def test_schur_operator_properties_at_scale(eng):
     """Size-independent properties on a 200k-observation scene: S is symmetric positive definite and linear."""
     p = synthetic.make_scene(n_cam=200, n_pt=20_000, obs_per_pt=10, seed=9)

@@ -14,7 +14,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -95,12 +97,15 @@ struct tba_context {
   // parameters and packed problem
   DevBuf<double> ext, intr, pt, ext_c, intr_c, pt_c, cam_rec, cam_rec_c, xy, J, res, Hpp, gp, Mp, sp, dpt;
   DevBuf<int> cam_group, group_model, slot_cam, slot_pt, tile_pt_begin, tile_nruns;
-  DevBuf<uint8_t> slot_flags, pt_const;
+  DevBuf<uint8_t> slot_flags, pt_const, tile_flags;
+  void* stage = nullptr;  // pinned host staging for the packed observation arrays
+  size_t stage_cap = 0;
+  int n_long_points = 0;
   DevBuf<int16_t> slot_run;
   // camera space: [g | cn | scal(16)] is one allreduce buffer
   DevBuf<double> lin;       // g_cs[ncs] | cn_cs[ncs] | scal[16]
   DevBuf<double> mask, blk_free, sm, D2, Sblk /*[n_cam*21 | n_group*55]*/, Minv_c, Minv_i;
-  DevBuf<double> b, x, r, p, z, xs, y, part /*3 x VB*/, gmax, flag, scal2 /*16*/;
+  DevBuf<double> b, x, r, p, z, xs, y, part /*3 x VB*/, gmax, flag, scal2 /*16*/, rep /*NREP x REPW*/;
   DevBuf<PcgState> st;      // [2]
   DevBuf<int> done_flag;
   bool have_scale = false;
@@ -190,6 +195,8 @@ int allreduce_max(tba_context* c, double* buf, size_t n) {
   return TBA_OK;
 }
 
+size_t schur_smem(const tba_context* c) { return (size_t)(c->NJ + 2) * TILE * sizeof(double); }
+
 double* lin_g(tba_context* c) { return c->lin.p; }
 double* lin_cn(tba_context* c) { return c->lin.p + c->P.ncs; }
 double* lin_scal(tba_context* c) { return c->lin.p + 2 * (size_t)c->P.ncs; }
@@ -211,10 +218,11 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-#define F(M) LAUNCH(c, k_linearize<M>, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), lin_scal(c))
+#define F(M) LAUNCH(c, k_linearize<M>, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p)
     DISPATCH_IMASK(c->imask, F)
 #undef F
     prof_end(c, 1, pb);
+    LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, lin_g(c) + P.ne, lin_cn(c) + P.ne, lin_scal(c));
   }
   int rc = allreduce_sum(c, c->lin.p, 2 * (size_t)P.ncs + 16);
   if (rc) return rc;
@@ -272,9 +280,10 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
   // reduced rhs: y = F'(I - E M E') r, then b = sm .* y (k_pcg_init)
   CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
-#define F(M) { auto kfn = k_schur<M, 1>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, nullptr, c->y.p, nullptr, nullptr); }
+#define F(M) { auto kfn = k_schur<M, 1>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr); }
     DISPATCH_IMASK(c->imask, F)
 #undef F
+    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   int rc = allreduce_sum(c, c->y.p, P.ncs);
   if (rc) return rc;
@@ -295,10 +304,11 @@ int launch_matvec(tba_context* c, const int* done) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-#define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->xs.p, c->y.p, nullptr, done); }
+#define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
     DISPATCH_IMASK(c->imask, F)
 #undef F
     prof_end(c, 0, pb);
+    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   return allreduce_sum(c, c->y.p, P.ncs);
 }
@@ -362,9 +372,10 @@ int stage_backsub(tba_context* c) {
   LAUNCH(c, k_cs_mul, VB, VT, 0, P.ncs, c->sm.p, c->x.p, c->xs.p);
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 16 * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
-#define F(M) { auto kfn = k_schur<M, 2>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->xs.p, nullptr, c->scal2.p, nullptr); }
+#define F(M) { auto kfn = k_schur<M, 2>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, nullptr, c->rep.p, nullptr); }
     DISPATCH_IMASK(c->imask, F)
 #undef F
+    LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   // candidate = x + delta, step norm
   LAUNCH(c, k_candidate_cs, VB, VT, 0, P, c->xs.p, c->scal2.p, c->rank == 0 ? 1 : 0);
@@ -376,7 +387,10 @@ int stage_backsub(tba_context* c) {
 int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, double* step_norm, bool* ok) {
   DevProblem& P = c->P;
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
-  if (P.n_tiles > 0) LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->scal2.p);
+  if (P.n_tiles > 0) {
+    LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p);
+    LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
+  }
   int rc = allreduce_sum(c, c->scal2.p, 8);
   if (rc) return rc;
   double s[8];
@@ -408,6 +422,21 @@ void accept_candidate(tba_context* c) {
   std::swap(P.intr, P.intr_c);
   std::swap(P.pt, P.pt_c);
   std::swap(P.cam_rec, P.cam_rec_c);
+}
+
+template <class F>
+void parallel_for(int64_t n, int nthreads, F f) {
+  if (n <= 0) return;
+  const int T = (int)std::min<int64_t>(nthreads, (n + 8191) / 8192);
+  if (T <= 1) { f((int64_t)0, n, 0); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + T - 1) / T;
+  for (int t = 0; t < T; ++t) {
+    const int64_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=, &f] { f(b, e, t); });
+  }
+  for (auto& x : th) x.join();
 }
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -498,6 +527,7 @@ void tba_destroy(tba_context* c) {
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->h_st) cudaFreeHost(c->h_st);
+  if (c->stage) cudaFreeHost(c->stage);
   delete c;
 }
 
@@ -536,40 +566,62 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
       return TBA_ERR_UNSUPPORTED;
     }
   for (int i = 0; i < nc; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= ng) { set_err(c, "cam_group out of range"); return TBA_ERR_INVALID_ARGUMENT; }
-  // ---- counting sort by point, (group, camera) order inside a point
+  // ---- host packing, multi-threaded (phases A-E below), into pinned staging memory
+  const int T = std::max(1, std::min<int>(32, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
+  // A: validate, per-point / per-camera observation counts
+  std::vector<int> cnt_pt((size_t)np, 0), cnt_cam((size_t)nc, 0);
+  std::atomic<int64_t> bad(-1);
+  parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t i = b0; i < e0; ++i) {
+      const int q = p->obs_pt[i], cam = p->obs_cam[i];
+      if (q < 0 || q >= np || cam < 0 || cam >= nc) { bad.store(i); return; }
+      __atomic_fetch_add(&cnt_pt[q], 1, __ATOMIC_RELAXED);
+      __atomic_fetch_add(&cnt_cam[cam], 1, __ATOMIC_RELAXED);
+    }
+  });
+  if (bad.load() >= 0) { const int64_t i = bad.load(); set_err(c, "observation %lld references camera %d / point %d out of range", (long long)i, p->obs_cam[i], p->obs_pt[i]); return TBA_ERR_INVALID_ARGUMENT; }
+  // B: offsets
   std::vector<int64_t> off((size_t)np + 1, 0);
-  for (int64_t i = 0; i < no; ++i) {
-    const int q = p->obs_pt[i], cam = p->obs_cam[i];
-    if (q < 0 || q >= np || cam < 0 || cam >= nc) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)i, cam, q); return TBA_ERR_INVALID_ARGUMENT; }
-    off[(size_t)q + 1]++;
-  }
-  int64_t maxlen = 0;
-  for (int q = 0; q < np; ++q) { maxlen = std::max(maxlen, off[(size_t)q + 1]); off[(size_t)q + 1] += off[q]; }
-  if (maxlen > TILE) { set_err(c, "track with %lld observations exceeds the engine limit of %d per track", (long long)maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
-  std::vector<int64_t> order(no);
+  int maxlen = 0;
+  for (int q = 0; q < np; ++q) { maxlen = std::max(maxlen, cnt_pt[q]); off[(size_t)q + 1] = off[q] + cnt_pt[q]; }
+  if (maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
+  // C: observations grouped by point, (group, camera, index) order inside a point; runs = distinct groups of a point
+  std::vector<int64_t> order((size_t)no);
   {
     std::vector<int64_t> cur(off.begin(), off.end() - 1);
-    for (int64_t i = 0; i < no; ++i) order[cur[p->obs_pt[i]]++] = i;
+    parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
+      for (int64_t i = b0; i < e0; ++i) order[(size_t)__atomic_fetch_add(&cur[p->obs_pt[i]], (int64_t)1, __ATOMIC_RELAXED)] = i;
+    });
   }
-  for (int q = 0; q < np; ++q) {
-    auto b = order.begin() + off[q], e = order.begin() + off[(size_t)q + 1];
-    if (e - b > 1)
-      std::sort(b, e, [&](int64_t a, int64_t bb) {
-        const int ga = p->cam_group[p->obs_cam[a]], gb = p->cam_group[p->obs_cam[bb]];
-        if (ga != gb) return ga < gb;
-        if (p->obs_cam[a] != p->obs_cam[bb]) return p->obs_cam[a] < p->obs_cam[bb];
-        return a < bb;
-      });
-  }
+  std::vector<uint8_t> pt_nruns((size_t)np, 0);
+  parallel_for(np, T, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t q = b0; q < e0; ++q) {
+      auto bb = order.begin() + off[q], ee = order.begin() + off[(size_t)q + 1];
+      if (ee - bb > 1)
+        std::sort(bb, ee, [&](int64_t a, int64_t d) {
+          const int ga = p->cam_group[p->obs_cam[a]], gb = p->cam_group[p->obs_cam[d]];
+          if (ga != gb) return ga < gb;
+          if (p->obs_cam[a] != p->obs_cam[d]) return p->obs_cam[a] < p->obs_cam[d];
+          return a < d;
+        });
+      int runs = 0, last = -1;
+      for (auto it2 = bb; it2 != ee; ++it2) { const int g = p->cam_group[p->obs_cam[*it2]]; if (g != last) { ++runs; last = g; } }
+      pt_nruns[q] = (uint8_t)std::min(runs, 255);
+    }
+  });
   // ---- which blocks take part (blocks without residuals are not in the Ceres program)
   std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
-  for (int64_t i = 0; i < no; ++i) { cnt_c[p->obs_cam[i]] += 1.0; cnt_g[p->cam_group[p->obs_cam[i]]] += 1.0; }
-  // packed points = points that have observations, caller order (zero-observation points are left untouched)
+  for (int i = 0; i < nc; ++i) { cnt_c[i] = cnt_cam[i]; cnt_g[p->cam_group[i]] += cnt_cam[i]; }
+  // packed points = points that have observations (zero-observation points are left untouched): first the points
+  // whose track fits one warp (<= 32 observations) in caller order, then the long tracks (their own tiles)
   c->pk2caller.clear();
+  c->pk2caller.reserve((size_t)np);
   c->n_free_pt = 0;
-  for (int q = 0; q < np; ++q)
-    if (off[(size_t)q + 1] > off[q]) { c->pk2caller.push_back(q); c->n_free_pt += p->pt_const[q] ? 0 : 1; }
+  int n_long = 0;
+  for (int q = 0; q < np; ++q) if (cnt_pt[q] > 0 && cnt_pt[q] <= 32) c->pk2caller.push_back(q);
+  for (int q = 0; q < np; ++q) if (cnt_pt[q] > 32) { c->pk2caller.push_back(q); ++n_long; }
   const int npk = (int)c->pk2caller.size();
+  for (int k = 0; k < npk; ++k) c->n_free_pt += p->pt_const[c->pk2caller[k]] ? 0 : 1;
   c->n_free_pt_global = c->n_free_pt;
   if (c->world > 1) {  // counts are global properties
     std::vector<double> tmp(cnt_c);
@@ -610,61 +662,86 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   for (uint32_t m : kMasks) if ((union_free & ~m) == 0) { c->imask = m; break; }
   c->NI = popcount10(c->imask);
   c->NJ = 14 + 2 * c->NI;
-  std::vector<uint8_t> pt_const(npk);
-  std::vector<double> pt_packed((size_t)npk * 4);
-  for (int k = 0; k < npk; ++k) {
-    const int q = c->pk2caller[k];
-    pt_const[k] = p->pt_const[q] ? 1 : 0;
-    memcpy(&pt_packed[(size_t)k * 4], p->pt + (size_t)q * 4, 32);
-  }
-  // ---- tiles: whole points per tile of TILE slots
+  // D: tiles (serial, light).  A tile is TILE slots = 8 warps of 32; in a normal tile a point never straddles a warp
+  // (so every warp is autonomous); long tracks (> 32 observations) go to "long" tiles handled at CTA level.
   std::vector<int> tile_pt_begin, tile_nruns;
-  std::vector<int> slot_cam, slot_pt;
-  std::vector<int16_t> slot_run;
-  std::vector<uint8_t> slot_flags;
-  c->slot_orig.clear();
+  std::vector<uint8_t> tile_flags;
+  std::vector<int64_t> pt_slot((size_t)npk);  // first slot of each packed point
+  std::vector<int> pt_runbase((size_t)npk);   // run index (inside its tile) of the point's first run
   {
-    int used = TILE, npts_in_tile = MAXP;  // force a new tile at the first point
-    int run = 0;
-    auto pad_tile = [&](size_t pad) {
-      slot_cam.insert(slot_cam.end(), pad, -1); slot_pt.insert(slot_pt.end(), pad, 0);
-      slot_run.insert(slot_run.end(), pad, (int16_t)-1); slot_flags.insert(slot_flags.end(), pad, (uint8_t)0);
-      c->slot_orig.insert(c->slot_orig.end(), pad, (int64_t)-1);
-    };
+    int used = TILE, npts_in_tile = MAXP, run = 0;
+    bool in_long = false;
     for (int k = 0; k < npk; ++k) {
       const int q = c->pk2caller[k];
-      const int len = (int)(off[(size_t)q + 1] - off[q]);
-      if (used + len > TILE || npts_in_tile + 1 > MAXP) {
-        if (!tile_pt_begin.empty()) { tile_nruns.push_back(run); pad_tile((size_t)(TILE - used)); }
+      const int len = cnt_pt[q];
+      const bool is_long = len > 32;
+      int start = used;
+      if (!is_long && (start % 32) + len > 32) start = (start / 32 + 1) * 32;  // next warp
+      if (start + len > TILE || npts_in_tile + 1 > MAXP || is_long != in_long) {
+        if (!tile_pt_begin.empty()) tile_nruns.push_back(run);
         tile_pt_begin.push_back(k);
-        used = 0; npts_in_tile = 0; run = 0;
+        tile_flags.push_back(is_long ? 1 : 0);
+        in_long = is_long;
+        start = 0; npts_in_tile = 0; run = 0;
       }
-      int last_grp = -1;
-      for (int64_t kk = off[q]; kk < off[(size_t)q + 1]; ++kk) {
-        const int64_t oi = order[kk];
-        const int cam = p->obs_cam[oi], g = p->cam_group[cam];
-        if (g != last_grp) { ++run; last_grp = g; }
-        slot_cam.push_back(cam); slot_pt.push_back(k); slot_run.push_back((int16_t)(run - 1));
-        const bool any_free = blk_free[cam] != 0.0 || blk_free[nc + g] != 0.0 || !pt_const[k];
-        slot_flags.push_back(any_free ? 0 : 1);
-        c->slot_orig.push_back(oi);
-      }
-      used += len; npts_in_tile++;
+      pt_slot[k] = (int64_t)(tile_pt_begin.size() - 1) * TILE + start;
+      pt_runbase[k] = run;
+      run += pt_nruns[q];
+      used = start + len;
+      npts_in_tile++;
     }
-    if (!tile_pt_begin.empty()) { tile_nruns.push_back(run); pad_tile((size_t)(TILE - used)); }
+    if (!tile_pt_begin.empty()) tile_nruns.push_back(run);
   }
   const int n_tiles = (int)tile_pt_begin.size();
   tile_pt_begin.push_back(npk);
   const int64_t n_slots = (int64_t)n_tiles * TILE;
-  // xy in [tile][2][TILE]
-  std::vector<double> xy((size_t)n_slots * 2, 0.0);
-  for (int64_t s = 0; s < n_slots; ++s) {
-    const int64_t oi = c->slot_orig[s];
-    if (oi < 0) continue;
-    const int64_t t = s / TILE, l = s % TILE;
-    xy[(size_t)(t * 2 + 0) * TILE + l] = p->obs_xy[2 * oi];
-    xy[(size_t)(t * 2 + 1) * TILE + l] = p->obs_xy[2 * oi + 1];
+  // E: fill the slot arrays (pinned staging), parallel over packed points
+  const size_t stage_bytes = (size_t)n_slots * (4 + 4 + 2 + 1 + 16) + (size_t)npk * (32 + 1) + 1024;
+  if (c->stage_cap < stage_bytes) {
+    if (c->stage) cudaFreeHost(c->stage);
+    c->stage = nullptr; c->stage_cap = 0;
+    CUDA_OK(c, cudaMallocHost(&c->stage, stage_bytes + stage_bytes / 8));
+    c->stage_cap = stage_bytes + stage_bytes / 8;
   }
+  uint8_t* sp8 = (uint8_t*)c->stage;
+  auto carve = [&](size_t bytes) { uint8_t* r0 = sp8; sp8 += (bytes + 255) / 256 * 256; return r0; };
+  double* h_xy = (double*)carve((size_t)n_slots * 16);
+  double* h_pt = (double*)carve((size_t)npk * 32);
+  int* h_slot_cam = (int*)carve((size_t)n_slots * 4);
+  int* h_slot_pt = (int*)carve((size_t)n_slots * 4);
+  int16_t* h_slot_run = (int16_t*)carve((size_t)n_slots * 2);
+  uint8_t* h_slot_flags = carve((size_t)n_slots);
+  uint8_t* h_pt_const = carve((size_t)npk);
+  c->slot_orig.assign((size_t)n_slots, (int64_t)-1);
+  parallel_for(n_slots, T, [&](int64_t b0, int64_t e0, int) {
+    memset(h_slot_cam + b0, 0xFF, (size_t)(e0 - b0) * 4);
+    memset(h_slot_pt + b0, 0, (size_t)(e0 - b0) * 4);
+    memset(h_slot_run + b0, 0xFF, (size_t)(e0 - b0) * 2);
+    memset(h_slot_flags + b0, 0, (size_t)(e0 - b0));
+  });
+  parallel_for((int64_t)n_tiles * 2, T, [&](int64_t b0, int64_t e0, int) { memset(h_xy + b0 * TILE, 0, (size_t)(e0 - b0) * TILE * 8); });
+  parallel_for(npk, T, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t k = b0; k < e0; ++k) {
+      const int q = c->pk2caller[k];
+      h_pt_const[k] = p->pt_const[q] ? 1 : 0;
+      memcpy(h_pt + (size_t)k * 4, p->pt + (size_t)q * 4, 32);
+      int64_t s0 = pt_slot[k];
+      int run = pt_runbase[k] - 1, last_grp = -1;
+      for (int64_t kk = off[q]; kk < off[(size_t)q + 1]; ++kk, ++s0) {
+        const int64_t oi = order[kk];
+        const int cam = p->obs_cam[oi], g = p->cam_group[cam];
+        if (g != last_grp) { ++run; last_grp = g; }
+        h_slot_cam[s0] = cam; h_slot_pt[s0] = (int)k; h_slot_run[s0] = (int16_t)run;
+        const bool any_free = blk_free[cam] != 0.0 || blk_free[nc + g] != 0.0 || !h_pt_const[k];
+        h_slot_flags[s0] = any_free ? 0 : 1;
+        c->slot_orig[(size_t)s0] = oi;
+        const int64_t wq = s0 / 32, l = s0 % 32;  // [tile][warp][2][32]
+        h_xy[(size_t)(wq * 2 + 0) * 32 + l] = p->obs_xy[2 * oi];
+        h_xy[(size_t)(wq * 2 + 1) * 32 + l] = p->obs_xy[2 * oi + 1];
+      }
+    }
+  });
+  c->n_long_points = n_long;
   // ---- device allocation + H2D
   c->n_cam = nc; c->n_group = ng; c->n_pt = npk; c->n_pt_caller = np; c->n_tiles = n_tiles; c->n_obs = no; c->n_slots = n_slots;
   const int npd = npk;  // points on the device
@@ -676,26 +753,28 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(Hpp, (size_t)npd * 10); ALLOC(gp, (size_t)npd * 4); ALLOC(Mp, (size_t)npd * 10); ALLOC(sp, (size_t)npd * 4); ALLOC(dpt, (size_t)npd * 4);
   ALLOC(cam_group, (size_t)nc); ALLOC(group_model, (size_t)ng); ALLOC(slot_cam, (size_t)n_slots); ALLOC(slot_pt, (size_t)n_slots);
   ALLOC(tile_pt_begin, (size_t)n_tiles + 1); ALLOC(tile_nruns, (size_t)n_tiles); ALLOC(slot_flags, (size_t)n_slots);
-  ALLOC(slot_run, (size_t)n_slots); ALLOC(pt_const, (size_t)npd);
+  ALLOC(slot_run, (size_t)n_slots); ALLOC(pt_const, (size_t)npd); ALLOC(tile_flags, (size_t)n_tiles);
   ALLOC(lin, 2 * (size_t)ncs + 16); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
   ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
   ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
-  ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1);
+  ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(rep, (size_t)NREP * REPW);
 #undef ALLOC
 #define H2D(buf, src, n)                                                                                      \
   do {                                                                                                        \
     CUDA_OK(c, cudaMemcpyAsync(c->buf.p, (src), (n) * sizeof(*c->buf.p), cudaMemcpyHostToDevice, c->stream)); \
     c->h2d_bytes += (double)((n) * sizeof(*c->buf.p));                                                        \
   } while (0)
-  H2D(ext, p->ext, (size_t)ne); H2D(intr, p->intr, (size_t)ng * 10); H2D(pt, pt_packed.data(), (size_t)npd * 4);
-  H2D(ext_c, p->ext, (size_t)ne); H2D(intr_c, p->intr, (size_t)ng * 10); H2D(pt_c, pt_packed.data(), (size_t)npd * 4);
+  H2D(ext, p->ext, (size_t)ne); H2D(intr, p->intr, (size_t)ng * 10); H2D(pt, h_pt, (size_t)npd * 4);
+  H2D(ext_c, p->ext, (size_t)ne); H2D(intr_c, p->intr, (size_t)ng * 10); H2D(pt_c, h_pt, (size_t)npd * 4);
   H2D(cam_group, p->cam_group, (size_t)nc); H2D(group_model, p->group_model, (size_t)ng);
-  H2D(slot_cam, slot_cam.data(), (size_t)n_slots); H2D(slot_pt, slot_pt.data(), (size_t)n_slots);
-  H2D(slot_flags, slot_flags.data(), (size_t)n_slots); H2D(slot_run, slot_run.data(), (size_t)n_slots);
+  H2D(slot_cam, h_slot_cam, (size_t)n_slots); H2D(slot_pt, h_slot_pt, (size_t)n_slots);
+  H2D(slot_flags, h_slot_flags, (size_t)n_slots); H2D(slot_run, h_slot_run, (size_t)n_slots);
   H2D(tile_pt_begin, tile_pt_begin.data(), (size_t)n_tiles + 1); H2D(tile_nruns, tile_nruns.data(), (size_t)n_tiles);
-  H2D(xy, xy.data(), (size_t)n_slots * 2); H2D(pt_const, pt_const.data(), (size_t)npd);
+  H2D(xy, h_xy, (size_t)n_slots * 2); H2D(pt_const, h_pt_const, (size_t)npd);
+  H2D(tile_flags, tile_flags.data(), (size_t)n_tiles);
   H2D(mask, mask.data(), (size_t)ncs); H2D(blk_free, blk_free.data(), (size_t)nc + ng);
 #undef H2D
+  CUDA_OK(c, cudaMemsetAsync(c->rep.p, 0, (size_t)NREP * REPW * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->J.p, 0, (size_t)n_slots * c->NJ * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->dpt.p, 0, (size_t)npd * 4 * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->Mp.p, 0, (size_t)npd * 10 * sizeof(double), c->stream));
@@ -710,11 +789,20 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   P.ext = c->ext.p; P.intr = c->intr.p; P.pt = c->pt.p; P.ext_c = c->ext_c.p; P.intr_c = c->intr_c.p; P.pt_c = c->pt_c.p;
   P.cam_group = c->cam_group.p; P.group_model = c->group_model.p; P.cam_rec = c->cam_rec.p; P.cam_rec_c = c->cam_rec_c.p;
   P.slot_cam = c->slot_cam.p; P.slot_pt = c->slot_pt.p; P.slot_flags = c->slot_flags.p; P.slot_run = c->slot_run.p;
-  P.tile_pt_begin = c->tile_pt_begin.p; P.tile_nruns = c->tile_nruns.p; P.xy = c->xy.p; P.J = c->J.p; P.res = c->res.p;
+  P.tile_pt_begin = c->tile_pt_begin.p; P.tile_nruns = c->tile_nruns.p; P.tile_flags = c->tile_flags.p; P.xy = c->xy.p; P.J = c->J.p; P.res = c->res.p;
   P.Hpp = c->Hpp.p; P.gp = c->gp.p; P.Mp = c->Mp.p; P.sp = c->sp.p; P.dpt = c->dpt.p; P.pt_const = c->pt_const.p;
   if (c->NI > 0) {
     const int smem = TILE * 4 * c->NI * (int)sizeof(double) + 2 * TILE * (int)sizeof(int);
 #define F(M) CUDA_OK(c, cudaFuncSetAttribute(k_precond_intr<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+  }
+  {
+    const int smem = (int)schur_smem(c);
+#define F(M)                                                                                                        \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DISPATCH_IMASK(c->imask, F)
 #undef F
   }
@@ -990,7 +1078,10 @@ int tba_debug_evaluate_step(tba_context* c, double* candidate_cost) {
   DevProblem& P = c->P;
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
-  if (P.n_tiles > 0) LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->scal2.p);
+  if (P.n_tiles > 0) {
+    LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p);
+    LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
+  }
   int rc = allreduce_sum(c, c->scal2.p, 3);
   if (rc) return rc;
   double s[3];
@@ -1043,9 +1134,9 @@ int tba_debug_read(tba_context* c, int which, double* out, int64_t n) {
       for (int64_t s = 0; s < c->n_slots; ++s) {
         const int64_t oi = c->slot_orig[s];
         if (oi < 0) continue;
-        const int64_t t = s / TILE, l = s % TILE;
-        out[2 * oi] = tmp[(size_t)(t * 2 + 0) * TILE + l];
-        out[2 * oi + 1] = tmp[(size_t)(t * 2 + 1) * TILE + l];
+        const int64_t wq = s / 32, l = s % 32;  // [tile][warp][2][32]
+        out[2 * oi] = tmp[(size_t)(wq * 2 + 0) * 32 + l];
+        out[2 * oi + 1] = tmp[(size_t)(wq * 2 + 1) * 32 + l];
       }
       return TBA_OK; }
     case TBA_VEC_SCHUR_RHS_CAM: if (n != ne) return TBA_ERR_INVALID_ARGUMENT; if ((rc = fetch(c->b.p, ne, tmp))) return rc; break;

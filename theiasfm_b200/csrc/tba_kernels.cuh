@@ -37,6 +37,7 @@ struct DevProblem {
   const int16_t* slot_run;     // (point, group) run index inside the tile
   const int* tile_pt_begin;    // [n_tiles + 1]
   const int* tile_nruns;       // [n_tiles]
+  const uint8_t* tile_flags;   // [n_tiles] bit0: long tile (tracks > 32 observations; points may straddle warps)
   const double* xy;            // [tile][2][TILE]
   double* J;                   // [tile][NJ][TILE], NJ = 14 + 2 NI
   double* res;                 // [tile][2][TILE] robustified residuals
@@ -91,23 +92,51 @@ __global__ void k_cam_prep(int n_cam, const double* __restrict__ ext, double* __
   if (c < n_cam) cam_prep(ext + (size_t)c * 6 + 3, rec + (size_t)c * kCamRec);
 }
 
+// ---------------------------------------------------- replicated scalar accumulators
+// Sums that every warp of every tile adds into the SAME few addresses (shared-intrinsics gradient / matvec output,
+// cost, ...) go to one of NREP replicas (row = warp id mod NREP) and are folded by k_fold afterwards: avoids the
+// same-address serialisation of fp64 RED at L2 and keeps warps free of block-level barriers.
+constexpr int NREP = 256;
+constexpr int REPW = 32;  // columns: 0..9 intrinsics (a), 10..19 intrinsics (b), 20 cost, 21 fixed cost, 22 failed, 23 model cost change
+__device__ __forceinline__ double* rep_row(double* rep) {
+  return rep + (size_t)((blockIdx.x * (TILE / 32) + (threadIdx.x >> 5)) & (NREP - 1)) * REPW;
+}
+// dst_a[0..9] += column sums 0..9, dst_b[0..9] += columns 10..19, dst_s[0..3] += columns 20..23; replicas re-zeroed.
+__global__ void k_fold(double* __restrict__ rep, double* __restrict__ dst_a, double* __restrict__ dst_b, double* __restrict__ dst_s) {
+  const int j = threadIdx.x;
+  if (j >= REPW) return;
+  double v = 0.0;
+  for (int r = 0; r < NREP; ++r) { v += rep[(size_t)r * REPW + j]; rep[(size_t)r * REPW + j] = 0.0; }
+  if (j < 10) { if (dst_a) dst_a[j] += v; }
+  else if (j < 20) { if (dst_b) dst_b[j - 10] += v; }
+  else if (j < 24) { if (dst_s) dst_s[j - 20] += v; }
+}
+
+// Index of the first lane of the run (contiguous equal key) that `lane` belongs to, from the ballot of run heads.
+__device__ __forceinline__ int run_head_lane(unsigned heads, int lane) { return 31 - __clz(heads & (0xffffffffu >> (31 - lane))); }
+
+// Element (row k, lane) of the per-warp slice of a [tile][warp][rows][32] array.
+__device__ __forceinline__ size_t wslice(int tile, int warp, int rows) { return ((size_t)tile * (TILE / 32) + warp) * rows * 32; }
+
 // ---------------------------------------------------------- K1 linearise
-// One thread per observation slot.  Writes the compact linearisation and the
-// robustified residual, accumulates the per-point blocks (tile-local in shared
-// memory, points never straddle tiles) and the camera-side gradient / squared
-// column norms (global fp64 reductions), the cost and the failure flag.
-//   scal[0] += cost (non-fixed), scal[1] += fixed cost, scal[2] += #failed evaluations
+// One thread per observation slot.  Writes the compact linearisation and the robustified residual
+// ([tile][warp][NJ][32] / [tile][warp][2][32]: a warp's slice is contiguous), the per-point blocks, the camera-side
+// gradient / squared column norms (fp64 RED to global) and cost / failure counters (replicas).
+// Normal tiles: a point never straddles a warp -> per-point sums by warp-shuffle segmented reduction only, no
+// block barrier.  Long tiles (tracks > 32 observations): combined across warps in shared memory.
 template <uint32_t IMASK>
 __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
-                                                    double* __restrict__ scal) {
+                                                    double* __restrict__ rep) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
   __shared__ double s_acc[MAXP][14];
-  __shared__ double s_red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool long_tile = (P.tile_flags[tile] & 1) != 0;
   const int p0 = P.tile_pt_begin[tile], npt = P.tile_pt_begin[tile + 1] - p0;
-  for (int i = tid; i < npt * 14; i += TILE) (&s_acc[0][0])[i] = 0.0;
-  __syncthreads();
+  if (long_tile) {
+    for (int i = tid; i < npt * 14; i += TILE) (&s_acc[0][0])[i] = 0.0;
+    __syncthreads();
+  }
   const size_t slot = (size_t)tile * TILE + tid;
   const int cam = P.slot_cam[slot];
   const bool valid = cam >= 0;
@@ -116,7 +145,7 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
   double Ji[2 * NI + 1];
 #pragma unroll
   for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
-  int pl = -1, grp = 0;
+  int pl = -1 - lane, grp = 0;  // padding lanes: unique negative keys (each its own run)
   double h = 0.0;
   if (valid) {
     const int pt = P.slot_pt[slot];
@@ -124,42 +153,39 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
     grp = P.cam_group[cam];
     const double4 X = *reinterpret_cast<const double4*>(P.pt + (size_t)pt * 4);
     h = X.w;
-    const double x = P.xy[((size_t)tile * 2 + 0) * TILE + tid], y = P.xy[((size_t)tile * 2 + 1) * TILE + tid];
+    const double* xyw = P.xy + wslice(tile, warp, 2) + lane;
+    const double x = xyw[0], y = xyw[32];
     double rho0 = 0.0;
     const bool ok = linearize_obs<IMASK>(P.group_model[grp], P.ext + (size_t)cam * 6, P.cam_rec + (size_t)cam * kCamRec,
                                          P.intr + (size_t)grp * 10, X.x, X.y, X.z, X.w, x, y, P.loss_type, P.loss_width,
                                          r, rho0, Ja, Jw, Jh, Ji);
-    if (!ok) {
-      failed = 1.0;
+    const bool is_fixed = (P.slot_flags[slot] & 1) != 0;
+    if (!ok) failed = 1.0;
+    else if (is_fixed) fixed = 0.5 * rho0;  // every block constant: Ceres removes the residual (fixed_cost)
+    else cost = 0.5 * rho0;
+    if (!ok || is_fixed) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) { Ja[j] = 0.0; Jw[j] = 0.0; }
       Jh[0] = Jh[1] = 0.0; r[0] = r[1] = 0.0;
 #pragma unroll
       for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
-    } else if (P.slot_flags[slot] & 1) {
-      // every parameter block of this residual is constant: Ceres removes it from the program (fixed_cost)
-      fixed = 0.5 * rho0;
-#pragma unroll
-      for (int j = 0; j < 6; ++j) { Ja[j] = 0.0; Jw[j] = 0.0; }
-      Jh[0] = Jh[1] = 0.0; r[0] = r[1] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 2 * NI; ++j) Ji[j] = 0.0;
-    } else {
-      cost = 0.5 * rho0;
     }
   }
-  // store the compact linearisation (coalesced: consecutive threads -> consecutive doubles)
-  double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+  // store the compact linearisation (each warp writes 256-byte rows of its own slice)
+  {
+    double* Jt = P.J + wslice(tile, warp, NJ) + lane;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) Jt[(size_t)j * TILE] = Ja[j];
+    for (int j = 0; j < 6; ++j) Jt[j * 32] = Ja[j];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) Jt[(size_t)(6 + j) * TILE] = Jw[j];
-  Jt[(size_t)12 * TILE] = Jh[0];
-  Jt[(size_t)13 * TILE] = Jh[1];
+    for (int j = 0; j < 6; ++j) Jt[(6 + j) * 32] = Jw[j];
+    Jt[12 * 32] = Jh[0];
+    Jt[13 * 32] = Jh[1];
 #pragma unroll
-  for (int j = 0; j < 2 * NI; ++j) Jt[(size_t)(14 + j) * TILE] = Ji[j];
-  P.res[((size_t)tile * 2 + 0) * TILE + tid] = r[0];
-  P.res[((size_t)tile * 2 + 1) * TILE + tid] = r[1];
+    for (int j = 0; j < 2 * NI; ++j) Jt[(14 + j) * 32] = Ji[j];
+    double* rt = P.res + wslice(tile, warp, 2) + lane;
+    rt[0] = r[0];
+    rt[32] = r[1];
+  }
   // per-point blocks: H_pp = J_p^T J_p (10, row-major upper), g_p = J_p^T r with J_p = [Ja | Jh]
   {
     const double jp0[4] = {Ja[0], Ja[1], Ja[2], Jh[0]}, jp1[4] = {Ja[3], Ja[4], Ja[5], Jh[1]};
@@ -174,9 +200,19 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
     const int prev = __shfl_up_sync(0xffffffffu, pl, 1);
     const bool head = valid && (lane == 0 || prev != pl);
 #pragma unroll
-    for (int j = 0; j < 14; ++j) {
-      const double v = seg_reduce(acc[j], pl, lane);
-      if (head) atomicAdd(&s_acc[pl][j], v);
+    for (int j = 0; j < 14; ++j) acc[j] = seg_reduce(acc[j], pl, lane);
+    if (head) {
+      if (long_tile) {
+#pragma unroll
+        for (int j = 0; j < 14; ++j) atomicAdd(&s_acc[pl][j], acc[j]);
+      } else {
+        double2* H2 = reinterpret_cast<double2*>(P.Hpp + (size_t)(p0 + pl) * 10);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) H2[j] = make_double2(acc[2 * j], acc[2 * j + 1]);
+        double2* G2 = reinterpret_cast<double2*>(P.gp + (size_t)(p0 + pl) * 4);
+        G2[0] = make_double2(acc[10], acc[11]);
+        G2[1] = make_double2(acc[12], acc[13]);
+      }
     }
   }
   // camera-side gradient and squared column norms: J_c = [-h Ja | Jw]
@@ -195,16 +231,14 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
       red_add(cc + 3 + j, Jw[j] * Jw[j] + Jw[3 + j] * Jw[3 + j]);
     }
   }
+  double* rr = rep_row(rep);
   if (NI > 0) {
     if (P.single_group) {
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
-        const double gsum = block_sum(Ji[j] * r[0] + Ji[NI + j] * r[1], s_red);
-        const double csum = block_sum(Ji[j] * Ji[j] + Ji[NI + j] * Ji[NI + j], s_red);
-        if (tid == 0) {
-          red_add(g_cs + P.ne + nth_bit(IMASK, j), gsum);
-          red_add(cn_cs + P.ne + nth_bit(IMASK, j), csum);
-        }
+        const double gsum = warp_sum(Ji[j] * r[0] + Ji[NI + j] * r[1]);
+        const double csum = warp_sum(Ji[j] * Ji[j] + Ji[NI + j] * Ji[NI + j]);
+        if (lane == 0) { red_add(rr + nth_bit(IMASK, j), gsum); red_add(rr + 10 + nth_bit(IMASK, j), csum); }
       }
     } else if (valid) {
 #pragma unroll
@@ -214,41 +248,39 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
       }
     }
   }
-  // scalars
   {
-    const double c = block_sum(cost, s_red);
-    const double f = block_sum(fixed, s_red);
-    const double e = block_sum(failed, s_red);
-    if (tid == 0) {
-      red_add(scal + 0, c);
-      if (f != 0.0) red_add(scal + 1, f);
-      if (e != 0.0) red_add(scal + 2, e);
+    const double c = warp_sum(cost), f = warp_sum(fixed), e = warp_sum(failed);
+    if (lane == 0) {
+      red_add(rr + 20, c);
+      if (f != 0.0) red_add(rr + 21, f);
+      if (e != 0.0) red_add(rr + 22, e);
     }
   }
-  __syncthreads();
-  for (int i = tid; i < npt * 14; i += TILE) {
-    const int p = i / 14, j = i - p * 14;
-    if (j < 10) P.Hpp[(size_t)(p0 + p) * 10 + j] = s_acc[p][j];
-    else P.gp[(size_t)(p0 + p) * 4 + (j - 10)] = s_acc[p][j];
+  if (long_tile) {
+    __syncthreads();
+    for (int i = tid; i < npt * 14; i += TILE) {
+      const int p = i / 14, j = i - p * 14;
+      if (j < 10) P.Hpp[(size_t)(p0 + p) * 10 + j] = s_acc[p][j];
+      else P.gp[(size_t)(p0 + p) * 4 + (j - 10)] = s_acc[p][j];
+    }
   }
 }
 
 // ------------------------------------------------------- K3 cost at candidate
 __global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __restrict__ ext, const double* __restrict__ rec,
                                                const double* __restrict__ intr, const double* __restrict__ pt,
-                                               double* __restrict__ scal) {
-  __shared__ double s_red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x;
+                                               double* __restrict__ rep) {
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t slot = (size_t)tile * TILE + tid;
   const int cam = P.slot_cam[slot];
   double cost = 0.0, fixed = 0.0, failed = 0.0;
   if (cam >= 0) {
     const int p = P.slot_pt[slot], grp = P.cam_group[cam];
     const double4 X = *reinterpret_cast<const double4*>(pt + (size_t)p * 4);
-    const double x = P.xy[((size_t)tile * 2 + 0) * TILE + tid], y = P.xy[((size_t)tile * 2 + 1) * TILE + tid];
+    const double* xyw = P.xy + wslice(tile, warp, 2) + lane;
     double r0, r1;
     if (!reproject(P.group_model[grp], ext + (size_t)cam * 6, rec + (size_t)cam * kCamRec, intr + (size_t)grp * 10, X.x, X.y,
-                   X.z, X.w, x, y, r0, r1)) {
+                   X.z, X.w, xyw[0], xyw[32], r0, r1)) {
       failed = 1.0;
     } else {
       double rho[3];
@@ -256,13 +288,12 @@ __global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __res
       if (P.slot_flags[slot] & 1) fixed = 0.5 * rho[0]; else cost = 0.5 * rho[0];
     }
   }
-  const double c = block_sum(cost, s_red);
-  const double f = block_sum(fixed, s_red);
-  const double e = block_sum(failed, s_red);
-  if (tid == 0) {
-    red_add(scal + 0, c);
-    if (f != 0.0) red_add(scal + 1, f);
-    if (e != 0.0) red_add(scal + 2, e);
+  const double c = warp_sum(cost), f = warp_sum(fixed), e = warp_sum(failed);
+  if (lane == 0) {
+    double* rr = rep_row(rep);
+    red_add(rr + 20, c);
+    if (f != 0.0) red_add(rr + 21, f);
+    if (e != 0.0) red_add(rr + 22, e);
   }
 }
 
@@ -360,96 +391,171 @@ __device__ __forceinline__ void sym4_mul(const double* __restrict__ M, const dou
   u[3] = M[3] * t[0] + M[6] * t[1] + M[8] * t[2] + M[9] * t[3];
 }
 
+// ---------------------------------------------------- TMA (bulk async copy) helpers
+// cp.async.bulk global -> shared::cta completing on an mbarrier (SASS: UBLKCP + SYNCS.ARRIVE.TRANS64).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // --------------------------------------------- K2 implicit Schur complement
 // MODE 0: y += F^T (I - E M E^T) F xs                (PCG matvec; ImplicitSchurComplement::RightMultiply)
 // MODE 1: y += F^T (I - E M E^T) r                   (reduced rhs; ImplicitSchurComplement::ComputeRHS)
-// MODE 2: dpt = -M E^T (r - F xs);  scal[3] += model cost change  (BackSubstitute + ComputeTrustRegionStep)
+// MODE 2: dpt = -M E^T (r - F xs);  rep[23] += model cost change  (BackSubstitute + ComputeTrustRegionStep)
 // All with the UNSCALED stored Jacobian; the Jacobi scaling lives in xs (= s .* x), M and the
-// post-scaling of y (k_vec_* kernels).  xs: camera-space vector [n_cam*6 | n_group*10].
+// post-scaling of y (k_pcg_* kernels).  xs: camera-space vector [n_cam*6 | n_group*10].
+//
+// Every WARP is autonomous on a normal tile: lane 0 issues one TMA bulk copy of the warp's contiguous slice of the
+// compact Jacobian (NJ x 32 doubles) [+ residuals] into the warp's shared-memory stage, completing on the warp's
+// own mbarrier; meanwhile all lanes gather their camera's x block (3 x 128-bit loads) and the head lanes fetch
+// M_p, so the gather latency overlaps the copy.  Per-point sums: warp-shuffle segmented reduction (a point's
+// observations are contiguous lanes of ONE warp), u_p = M_p t_p on the head lane, broadcast back by shuffle.
+// Camera-side sums: fp64 RED.ADD to global; shared-intrinsics sums: warp reduce + RED to a replica row.
+// No block barrier on this path.  Long tiles (tracks > 32 observations) combine the per-point sums across warps in
+// shared memory (two block barriers).  Dynamic shared memory: TILE * (NJ + 2) doubles.
 template <uint32_t IMASK, int MODE>
-__global__ void __launch_bounds__(TILE) k_schur(DevProblem P, const double* __restrict__ xs, double* __restrict__ y,
-                                                double* __restrict__ scal, const int* __restrict__ done_flag) {
+__global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 : 2) k_schur(DevProblem P, const double* __restrict__ xs, double* __restrict__ y,
+                                                double* __restrict__ rep, const int* __restrict__ done_flag) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
+  constexpr int WS = (NJ + 2) * 32;  // doubles per warp stage
   if (done_flag != nullptr && *done_flag) return;
+  extern __shared__ __align__(128) double s_dyn[];
   __shared__ double s_t[MAXP][4];
-  __shared__ double s_red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  __shared__ __align__(8) uint64_t s_bar[TILE / 32];
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* sJ = s_dyn + (size_t)warp * WS;  // [NJ][32]
+  double* sR = sJ + NJ * 32;               // [2][32]
+  if (lane == 0) {
+    mbar_init(&s_bar[warp], 1);
+    constexpr uint32_t jbytes = NJ * 32 * 8, rbytes = (MODE != 0) ? 2 * 32 * 8 : 0;
+    mbar_expect_tx(&s_bar[warp], jbytes + rbytes);
+    bulk_g2s(sJ, P.J + wslice(tile, warp, NJ), jbytes, &s_bar[warp]);
+    if (MODE != 0) bulk_g2s(sR, P.res + wslice(tile, warp, 2), rbytes, &s_bar[warp]);
+  }
+  const bool long_tile = (P.tile_flags[tile] & 1) != 0;
   const int p0 = P.tile_pt_begin[tile], npt = P.tile_pt_begin[tile + 1] - p0;
-  for (int i = tid; i < npt * 4; i += TILE) (&s_t[0][0])[i] = 0.0;
-  __syncthreads();
+  if (long_tile) {
+    for (int i = tid; i < npt * 4; i += TILE) (&s_t[0][0])[i] = 0.0;
+  }
   const size_t slot = (size_t)tile * TILE + tid;
   const int cam = P.slot_cam[slot];
   const bool valid = cam >= 0;
-  const double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
-  double Ja[6], Jw[6], Jh[2], Ji[2 * NI + 1];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) Ja[j] = Jt[(size_t)j * TILE];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) Jw[j] = Jt[(size_t)(6 + j) * TILE];
-  Jh[0] = Jt[(size_t)12 * TILE];
-  Jh[1] = Jt[(size_t)13 * TILE];
-#pragma unroll
-  for (int j = 0; j < 2 * NI; ++j) Ji[j] = Jt[(size_t)(14 + j) * TILE];
-  int pl = -1, grp = 0;
-  double h = 0.0, w0 = 0.0, w1 = 0.0, r0 = 0.0, r1 = 0.0;
+  int pl = -1 - lane, grp = 0;
+  double h = 0.0;
+  double2 xa = make_double2(0.0, 0.0), xb = xa, xc = xa;
+  double xi[NI + 1];
   if (valid) {
     pl = P.slot_pt[slot] - p0;
     grp = P.cam_group[cam];
     h = P.pt[(size_t)(p0 + pl) * 4 + 3];
-    if (MODE != 0) {
-      r0 = P.res[((size_t)tile * 2 + 0) * TILE + tid];
-      r1 = P.res[((size_t)tile * 2 + 1) * TILE + tid];
-    }
     if (MODE != 1) {
-      const double* xc = xs + (size_t)cam * 6;
-      const double x0 = xc[0], x1 = xc[1], x2 = xc[2], x3 = xc[3], x4 = xc[4], x5 = xc[5];
-      w0 = -h * (Ja[0] * x0 + Ja[1] * x1 + Ja[2] * x2) + Jw[0] * x3 + Jw[1] * x4 + Jw[2] * x5;
-      w1 = -h * (Ja[3] * x0 + Ja[4] * x1 + Ja[5] * x2) + Jw[3] * x3 + Jw[4] * x4 + Jw[5] * x5;
+      const double2* x2 = reinterpret_cast<const double2*>(xs + (size_t)cam * 6);
+      xa = __ldg(x2); xb = __ldg(x2 + 1); xc = __ldg(x2 + 2);
       if (NI > 0) {
-        const double* xi = xs + P.ne + (size_t)grp * 10;
+        const double* xg = xs + P.ne + (size_t)grp * 10;
 #pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const double xv = xi[nth_bit(IMASK, j)];
-          w0 += Ji[j] * xv;
-          w1 += Ji[NI + j] * xv;
-        }
+        for (int j = 0; j < NI; ++j) xi[j] = __ldg(xg + nth_bit(IMASK, j));
       }
+    }
+  }
+  const int prev = __shfl_up_sync(0xffffffffu, pl, 1);
+  const bool head = lane == 0 || prev != pl;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  // head lanes prefetch M_p (normal tiles)
+  double2 m01 = make_double2(0.0, 0.0), m23 = m01, m45 = m01, m67 = m01, m89 = m01;
+  if (!long_tile && head && valid) {
+    const double2* M2 = reinterpret_cast<const double2*>(P.Mp + (size_t)(p0 + pl) * 10);
+    m01 = __ldg(M2); m23 = __ldg(M2 + 1); m45 = __ldg(M2 + 2); m67 = __ldg(M2 + 3); m89 = __ldg(M2 + 4);
+  }
+  if (long_tile) __syncthreads();  // s_t zeroed
+  __syncwarp();
+  mbar_wait(&s_bar[warp], 0);  // this warp's slice landed in shared memory
+  const double* Jt = sJ + lane;
+#define JA(j) Jt[(j) * 32]
+#define JW(j) Jt[(6 + (j)) * 32]
+#define JH(j) Jt[(12 + (j)) * 32]
+#define JI(j) Jt[(14 + (j)) * 32]
+  double w0 = 0.0, w1 = 0.0, r0 = 0.0, r1 = 0.0;
+  if (valid) {
+    if (MODE != 0) { r0 = sR[lane]; r1 = sR[32 + lane]; }
+    if (MODE != 1) {
+      w0 = -h * (JA(0) * xa.x + JA(1) * xa.y + JA(2) * xb.x) + JW(0) * xb.y + JW(1) * xc.x + JW(2) * xc.y;
+      w1 = -h * (JA(3) * xa.x + JA(4) * xa.y + JA(5) * xb.x) + JW(3) * xb.y + JW(4) * xc.x + JW(5) * xc.y;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) { w0 += JI(j) * xi[j]; w1 += JI(NI + j) * xi[j]; }
     }
     if (MODE == 1) { w0 = r0; w1 = r1; }
     if (MODE == 2) { w0 = r0 - w0; w1 = r1 - w1; }
   }
-  // t_p = sum_o J_p^T w
-  {
-    double t[4] = {Ja[0] * w0 + Ja[3] * w1, Ja[1] * w0 + Ja[4] * w1, Ja[2] * w0 + Ja[5] * w1, Jh[0] * w0 + Jh[1] * w1};
-    const int prev = __shfl_up_sync(0xffffffffu, pl, 1);
-    const bool head = valid && (lane == 0 || prev != pl);
+  // t_p = sum_o J_p^T w,  J_p = [Ja | Jh]
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  if (valid) {
+    t[0] = JA(0) * w0 + JA(3) * w1; t[1] = JA(1) * w0 + JA(4) * w1; t[2] = JA(2) * w0 + JA(5) * w1;
+    t[3] = JH(0) * w0 + JH(1) * w1;
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double v = seg_reduce(t[j], pl, lane);
-      if (head) atomicAdd(&s_t[pl][j], v);
+  for (int j = 0; j < 4; ++j) t[j] = seg_reduce(t[j], pl, lane);
+  double u0, u1, u2, u3;
+  if (!long_tile) {
+    u0 = m01.x * t[0] + m01.y * t[1] + m23.x * t[2] + m23.y * t[3];
+    u1 = m01.y * t[0] + m45.x * t[1] + m45.y * t[2] + m67.x * t[3];
+    u2 = m23.x * t[0] + m45.y * t[1] + m67.y * t[2] + m89.x * t[3];
+    u3 = m23.y * t[0] + m67.x * t[1] + m89.x * t[2] + m89.y * t[3];
+    if (MODE == 2 && head && valid) {
+      double2* d = reinterpret_cast<double2*>(P.dpt + (size_t)(p0 + pl) * 4);
+      d[0] = make_double2(-u0, -u1);
+      d[1] = make_double2(-u2, -u3);
     }
-  }
-  __syncthreads();
-  if (tid < npt) {
-    const double t[4] = {s_t[tid][0], s_t[tid][1], s_t[tid][2], s_t[tid][3]};
-    double u[4];
-    sym4_mul(P.Mp + (size_t)(p0 + tid) * 10, t, u);
-    s_t[tid][0] = u[0]; s_t[tid][1] = u[1]; s_t[tid][2] = u[2]; s_t[tid][3] = u[3];
-    if (MODE == 2) {
-      double* d = P.dpt + (size_t)(p0 + tid) * 4;
-      d[0] = -u[0]; d[1] = -u[1]; d[2] = -u[2]; d[3] = -u[3];
+    const int hl = run_head_lane(heads, lane);
+    u0 = __shfl_sync(0xffffffffu, u0, hl); u1 = __shfl_sync(0xffffffffu, u1, hl);
+    u2 = __shfl_sync(0xffffffffu, u2, hl); u3 = __shfl_sync(0xffffffffu, u3, hl);
+  } else {
+    if (head && valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&s_t[pl][j], t[j]);
     }
+    __syncthreads();
+    if (tid < npt) {
+      const double tt[4] = {s_t[tid][0], s_t[tid][1], s_t[tid][2], s_t[tid][3]};
+      double uu[4];
+      sym4_mul(P.Mp + (size_t)(p0 + tid) * 10, tt, uu);
+      s_t[tid][0] = uu[0]; s_t[tid][1] = uu[1]; s_t[tid][2] = uu[2]; s_t[tid][3] = uu[3];
+      if (MODE == 2) {
+        double* d = P.dpt + (size_t)(p0 + tid) * 4;
+        d[0] = -uu[0]; d[1] = -uu[1]; d[2] = -uu[2]; d[3] = -uu[3];
+      }
+    }
+    __syncthreads();
+    u0 = u1 = u2 = u3 = 0.0;
+    if (valid) { u0 = s_t[pl][0]; u1 = s_t[pl][1]; u2 = s_t[pl][2]; u3 = s_t[pl][3]; }
   }
-  __syncthreads();
   double z0 = 0.0, z1 = 0.0;
   if (valid) {
-    const double u0 = s_t[pl][0], u1 = s_t[pl][1], u2 = s_t[pl][2], u3 = s_t[pl][3];
-    const double e0 = Ja[0] * u0 + Ja[1] * u1 + Ja[2] * u2 + Jh[0] * u3;
-    const double e1 = Ja[3] * u0 + Ja[4] * u1 + Ja[5] * u2 + Jh[1] * u3;
-    z0 = w0 - e0;
-    z1 = w1 - e1;
+    z0 = w0 - (JA(0) * u0 + JA(1) * u1 + JA(2) * u2 + JH(0) * u3);
+    z1 = w1 - (JA(3) * u0 + JA(4) * u1 + JA(5) * u2 + JH(1) * u3);
   }
+  double* rr = rep_row(rep);
   if (MODE == 2) {
     // model residual m = J * step = -(F xs + E u) = -(r - z); contribution -m.(r + m/2)
     double mcc = 0.0;
@@ -457,29 +563,33 @@ __global__ void __launch_bounds__(TILE) k_schur(DevProblem P, const double* __re
       const double m0 = -(r0 - z0), m1 = -(r1 - z1);
       mcc = -(m0 * (r0 + 0.5 * m0) + m1 * (r1 + 0.5 * m1));
     }
-    const double s = block_sum(mcc, s_red);
-    if (tid == 0) red_add(scal + 3, s);
+    mcc = warp_sum(mcc);
+    if (lane == 0) red_add(rr + 23, mcc);
     return;
   }
   if (valid) {
     double* yc = y + (size_t)cam * 6;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) red_add(yc + j, -h * (Ja[j] * z0 + Ja[3 + j] * z1));
+    for (int j = 0; j < 3; ++j) red_add(yc + j, -h * (JA(j) * z0 + JA(3 + j) * z1));
 #pragma unroll
-    for (int j = 0; j < 3; ++j) red_add(yc + 3 + j, Jw[j] * z0 + Jw[3 + j] * z1);
+    for (int j = 0; j < 3; ++j) red_add(yc + 3 + j, JW(j) * z0 + JW(3 + j) * z1);
   }
   if (NI > 0) {
     if (P.single_group) {
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
-        const double v = block_sum(Ji[j] * z0 + Ji[NI + j] * z1, s_red);
-        if (tid == 0) red_add(y + P.ne + nth_bit(IMASK, j), v);
+        const double v = warp_sum(valid ? JI(j) * z0 + JI(NI + j) * z1 : 0.0);
+        if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
       }
     } else if (valid) {
 #pragma unroll
-      for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), Ji[j] * z0 + Ji[NI + j] * z1);
+      for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), JI(j) * z0 + JI(NI + j) * z1);
     }
   }
+#undef JA
+#undef JW
+#undef JH
+#undef JI
 }
 
 // ------------------------------------------- SCHUR_JACOBI preconditioner blocks
@@ -489,18 +599,18 @@ template <uint32_t IMASK>
 __global__ void __launch_bounds__(TILE) k_precond_ext(DevProblem P, double* __restrict__ Sc) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
-  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t slot = (size_t)tile * TILE + tid;
   const int cam = P.slot_cam[slot];
   if (cam < 0) return;
-  const double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+  const double* Jt = P.J + wslice(tile, warp, NJ) + lane;
   double Ja[6], Jw[6], Jh[2];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) Ja[j] = Jt[(size_t)j * TILE];
+  for (int j = 0; j < 6; ++j) Ja[j] = Jt[j * 32];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) Jw[j] = Jt[(size_t)(6 + j) * TILE];
-  Jh[0] = Jt[(size_t)12 * TILE];
-  Jh[1] = Jt[(size_t)13 * TILE];
+  for (int j = 0; j < 6; ++j) Jw[j] = Jt[(6 + j) * 32];
+  Jh[0] = Jt[12 * 32];
+  Jh[1] = Jt[13 * 32];
   const int pt = P.slot_pt[slot];
   const double h = P.pt[(size_t)pt * 4 + 3];
   const double* M = P.Mp + (size_t)pt * 10;
@@ -534,7 +644,7 @@ __global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __r
   constexpr int NS = NI * (NI + 1) / 2;
   extern __shared__ double s_w[];  // [nruns][NW] then [nruns] group ids (as int) and points
   __shared__ double s_red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nruns = P.tile_nruns[tile];
   int* s_grp = reinterpret_cast<int*>(s_w + (size_t)TILE * NW);
   int* s_pt = s_grp + TILE;
@@ -548,14 +658,14 @@ __global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __r
   for (int j = 0; j < NS; ++j) acc[j] = 0.0;
   int grp = 0;
   if (valid) {
-    const double* Jt = P.J + (size_t)tile * NJ * TILE + tid;
+    const double* Jt = P.J + wslice(tile, warp, NJ) + lane;
     double jp0[4], jp1[4], Ji[2 * NI + 1];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { jp0[j] = Jt[(size_t)j * TILE]; jp1[j] = Jt[(size_t)(3 + j) * TILE]; }
-    jp0[3] = Jt[(size_t)12 * TILE];
-    jp1[3] = Jt[(size_t)13 * TILE];
+    for (int j = 0; j < 3; ++j) { jp0[j] = Jt[j * 32]; jp1[j] = Jt[(3 + j) * 32]; }
+    jp0[3] = Jt[12 * 32];
+    jp1[3] = Jt[13 * 32];
 #pragma unroll
-    for (int j = 0; j < 2 * NI; ++j) Ji[j] = Jt[(size_t)(14 + j) * TILE];
+    for (int j = 0; j < 2 * NI; ++j) Ji[j] = Jt[(14 + j) * 32];
     grp = P.cam_group[cam];
     const int run = P.slot_run[slot];
     if (run >= 0) {
