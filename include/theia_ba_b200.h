@@ -196,6 +196,13 @@ int tba_solve(tba_context* ctx, const tba_options* options,
               tba_problem* problem, tba_summary* summary);
 
 /*
+ * Single-process multi-GPU form of tba_solve for callers that, like Theia's estimators, run BA from one host
+ * thread: shards points + observations over n_devices GPUs of the box (0 = all visible), one rank per device on
+ * its own host thread, NCCL all-reduce of the camera-space sums.  Contexts are created once per process.
+ */
+int tba_solve_multi(const tba_options* options, tba_problem* problem, tba_summary* summary, int n_devices);
+
+/*
  * Split-phase variant used by the benchmark and tests: upload+pack once,
  * iterate on device-resident data, download.
  */

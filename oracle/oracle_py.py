@@ -58,6 +58,7 @@ def lib():
         L.oracle_constant_intrinsics_mask.argtypes = [C.c_int, C.c_int]
         L.oracle_loss.argtypes = [C.c_int, C.c_double, C.c_double, dp]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -78,6 +79,10 @@ def default_options(**kw):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(n)
 
 
 def residual_jacobian(problem):

@@ -1,0 +1,233 @@
+// adapter_test.cc -- test driver for adapter/bundle_adjuster_b200.{h,cc} (built by adapter/Makefile, run by
+// tests/test_adapter.py).  `adapter_test flatten` checks, without a GPU, that AddView / AddTrack / Optimize's
+// parameterisation decisions reproduce bundle_adjuster.cc:102-180,223-287.  `adapter_test solve` (GPU) runs
+// BundleAdjustReconstructionB200 / BundleAdjustPartialReconstructionB200 end to end and compares with the CPU
+// oracle (dlopen'ed from oracle/libba_oracle.so; test infrastructure only).
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+
+#include "bundle_adjuster_b200.h"
+
+using namespace theia;
+
+#define EXPECT(cond)                                                                      \
+  do {                                                                                    \
+    if (!(cond)) { std::fprintf(stderr, "FAILED: %s (%s:%d)\n", #cond, __FILE__, __LINE__); std::exit(1); } \
+  } while (0)
+
+// plain-double Camera::ProjectPoint for a PINHOLE camera with identity-ish intrinsics (test data synthesis only)
+static void Project(const double* ext, const double* k, const double* X, double* pix) {
+  const double a[3] = {X[0] - X[3] * ext[0], X[1] - X[3] * ext[1], X[2] - X[3] * ext[2]};
+  const double* w = ext + 3;
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double q[3];
+  if (th2 > 1e-16) {
+    const double th = std::sqrt(th2), c = std::cos(th), s = std::sin(th);
+    const double kx = w[0] / th, ky = w[1] / th, kz = w[2] / th;
+    const double cr[3] = {ky * a[2] - kz * a[1], kz * a[0] - kx * a[2], kx * a[1] - ky * a[0]};
+    const double d = (kx * a[0] + ky * a[1] + kz * a[2]) * (1 - c);
+    q[0] = a[0] * c + cr[0] * s + kx * d; q[1] = a[1] * c + cr[1] * s + ky * d; q[2] = a[2] * c + cr[2] * s + kz * d;
+  } else { q[0] = a[0]; q[1] = a[1]; q[2] = a[2]; }
+  const double u = q[0] / q[2], v = q[1] / q[2], r2 = u * u + v * v, d = 1 + r2 * (k[5] + k[6] * r2);
+  pix[0] = k[0] * u * d + k[2] * v * d + k[3];
+  pix[1] = k[0] * k[1] * v * d + k[4];
+}
+
+struct Scene {
+  Reconstruction rec;
+  std::vector<ViewId> views;
+  std::vector<TrackId> tracks;
+};
+
+// n_views cameras in front of a point cloud; views 0..n_shared-1 share one intrinsics group, the others own theirs.
+static void BuildScene(Scene* sc, int n_views, int n_tracks, int obs_per_track, int n_shared, unsigned seed) {
+  std::mt19937 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  std::normal_distribution<double> N(0.0, 1.0);
+  std::vector<std::vector<double>> gt_ext(n_views, std::vector<double>(6));
+  for (int i = 0; i < n_views; ++i) {
+    const ViewId id = i < n_shared ? sc->rec.AddView("v" + std::to_string(i), 7) : sc->rec.AddView("v" + std::to_string(i));
+    sc->views.push_back(id);
+    View* v = sc->rec.MutableView(id);
+    v->SetEstimated(true);
+    double* e = v->MutableCamera()->mutable_extrinsics();
+    for (int j = 0; j < 3; ++j) gt_ext[i][j] = 2.0 * U(rng);
+    for (int j = 3; j < 6; ++j) gt_ext[i][j] = 0.1 * U(rng);
+    for (int j = 0; j < 6; ++j) e[j] = gt_ext[i][j] + (j < 3 ? 0.02 : 0.004) * N(rng);
+    double* k = v->MutableCamera()->mutable_intrinsics();
+    k[0] = 800.0 * (i < n_shared ? 1.01 : 1.0 + 0.01 * U(rng)); k[1] = 1.0; k[2] = 0.0; k[3] = 500.0; k[4] = 500.0; k[5] = 0.0; k[6] = 0.0;
+  }
+  const double kgt[7] = {800.0, 1.0, 0.0, 500.0, 500.0, -0.05, 0.01};
+  for (int t = 0; t < n_tracks; ++t) {
+    double X[4] = {1.5 * U(rng), 1.5 * U(rng), 12.0 + 2.0 * U(rng), 1.0};
+    std::vector<std::pair<ViewId, Feature>> obs;
+    for (int o = 0; o < obs_per_track; ++o) {
+      const int vi = (t * 3 + o * 5) % n_views;
+      bool dup = false;
+      for (auto& ob : obs) dup |= ob.first == sc->views[vi];
+      if (dup) continue;
+      double pix[2];
+      Project(gt_ext[vi].data(), kgt, X, pix);
+      obs.emplace_back(sc->views[vi], Feature(pix[0] + 0.3 * N(rng), pix[1] + 0.3 * N(rng)));
+    }
+    const TrackId id = sc->rec.AddTrack(obs);
+    sc->tracks.push_back(id);
+    Track* tr = sc->rec.MutableTrack(id);
+    tr->SetEstimated(true);
+    for (int j = 0; j < 3; ++j) (*tr->MutablePoint())[j] = X[j] + 0.03 * N(rng);
+  }
+}
+
+static BundleAdjustmentOptions IterativeOptions() {
+  BundleAdjustmentOptions o;
+  o.linear_solver_type = ceres::ITERATIVE_SCHUR;
+  o.use_inner_iterations = false;
+  return o;
+}
+
+static int TestFlatten() {
+  Scene sc;
+  BuildScene(&sc, 10, 60, 4, 4, 11);
+  // one un-estimated view and one un-estimated track must be skipped everywhere
+  sc.rec.MutableView(sc.views[9])->SetEstimated(false);
+  sc.rec.MutableTrack(sc.tracks[5])->SetEstimated(false);
+  {
+    // --- full BA (bundle_adjustment.cc:66-80): every estimated view and track
+    BundleAdjusterB200 ba(IterativeOptions(), &sc.rec);
+    for (ViewId v : sc.rec.ViewIds()) ba.AddView(v);
+    for (TrackId t : sc.rec.TrackIds()) ba.AddTrack(t);
+    BundleAdjusterB200::Flat f; tba_options o;
+    ba.Flatten(&f, &o);
+    EXPECT(o.linear_solver_type == TBA_ITERATIVE_SCHUR && o.use_inner_iterations == 0 && o.max_num_iterations == 100);
+    EXPECT(o.intrinsics_to_optimize == (TBA_INTR_FOCAL_LENGTH | TBA_INTR_RADIAL_DISTORTION));
+    EXPECT(f.view_of_cam.size() == 9);
+    for (size_t i = 0; i < f.view_of_cam.size(); ++i) { EXPECT(f.view_of_cam[i] != sc.views[9]); EXPECT(f.ext_const[i] == 0); }
+    for (size_t q = 0; q < f.track_of_pt.size(); ++q) { EXPECT(f.track_of_pt[q] != sc.tracks[5]); EXPECT(f.pt_const[q] == 0); }
+    for (size_t g = 0; g < f.id_of_group.size(); ++g) { EXPECT(f.group_model[g] == TBA_MODEL_PINHOLE); EXPECT(f.group_const_mask[g] == 0x1Eu); }
+    EXPECT(f.id_of_group.size() == 1 + 5);  // the shared group + 5 estimated single-view groups
+    // every residual appears exactly once
+    std::unordered_set<uint64_t> seen;
+    for (size_t k = 0; k < f.obs_cam.size(); ++k) EXPECT(seen.insert((uint64_t)f.obs_cam[k] << 32 | (uint32_t)f.obs_pt[k]).second);
+    size_t expected = 0;
+    for (TrackId t : sc.rec.TrackIds()) { Track* tr = sc.rec.MutableTrack(t); if (!tr->IsEstimated()) continue; for (ViewId v : tr->ViewIds()) expected += sc.rec.MutableView(v)->IsEstimated(); }
+    EXPECT(f.obs_cam.size() == expected);
+  }
+  {
+    // --- partial BA (bundle_adjustment.cc:47-63): views {0,1}, tracks = a few tracks
+    BundleAdjustmentOptions opt = IterativeOptions();
+    opt.constant_camera_position = true;
+    opt.intrinsics_to_optimize = OptimizeIntrinsicsType::FOCAL_LENGTH | OptimizeIntrinsicsType::PRINCIPAL_POINTS;
+    BundleAdjusterB200 ba(opt, &sc.rec);
+    ba.AddView(sc.views[0]);
+    ba.AddView(sc.views[5]);
+    ba.AddView(sc.views[0]);  // idempotent (:106-108)
+    std::unordered_set<TrackId> opt_tracks = {sc.tracks[0], sc.tracks[1], sc.tracks[2]};
+    for (TrackId t : opt_tracks) ba.AddTrack(t);
+    BundleAdjusterB200::Flat f; tba_options o;
+    ba.Flatten(&f, &o);
+    EXPECT(o.constant_camera_position == 1);
+    for (size_t i = 0; i < f.view_of_cam.size(); ++i) {
+      const bool optimised = f.view_of_cam[i] == sc.views[0] || f.view_of_cam[i] == sc.views[5];
+      EXPECT(f.ext_const[i] == (optimised ? TBA_EXT_POSITION_CONST : TBA_EXT_ALL_CONST));
+      const CameraIntrinsicsGroupId gid = sc.rec.CameraIntrinsicsGroupIdFromViewId(f.view_of_cam[i]);
+      const bool group_optimised = gid == sc.rec.CameraIntrinsicsGroupIdFromViewId(sc.views[0]) || gid == sc.rec.CameraIntrinsicsGroupIdFromViewId(sc.views[5]);
+      // FOCAL_LENGTH | PRINCIPAL_POINTS free -> constant {1,2,5,6} = 0x66; groups seen only through constant cameras: all 7 constant
+      EXPECT(f.group_const_mask[f.cam_group[i]] == (group_optimised ? 0x66u : 0x7Fu));
+    }
+    for (size_t q = 0; q < f.track_of_pt.size(); ++q) EXPECT(f.pt_const[q] == (opt_tracks.count(f.track_of_pt[q]) ? 0 : 1));
+    // a view of the shared group that is NOT optimised still shares the optimised group's block (view 1 shares with view 0)
+    bool found_shared_const_cam = false;
+    for (size_t i = 0; i < f.view_of_cam.size(); ++i)
+      if (f.view_of_cam[i] == sc.views[1] || f.view_of_cam[i] == sc.views[2] || f.view_of_cam[i] == sc.views[3]) {
+        found_shared_const_cam = true;
+        EXPECT(f.ext_const[i] == TBA_EXT_ALL_CONST && f.group_const_mask[f.cam_group[i]] == 0x66u);
+      }
+    EXPECT(found_shared_const_cam);
+  }
+  std::printf("flatten ok\n");
+  return 0;
+}
+
+typedef int (*oracle_solve_fn)(const tba_options*, tba_problem*, tba_summary*);
+
+static int TestSolve(const char* oracle_path) {
+  Scene sc;
+  BuildScene(&sc, 12, 400, 5, 5, 21);
+  // default Theia options (SPARSE_SCHUR + inner iterations) are refused loudly, parameters untouched
+  {
+    Scene copy = sc;
+    const double before = copy.rec.MutableTrack(copy.tracks[3])->Point().v[0];
+    BundleAdjustmentSummary s = BundleAdjustReconstructionB200(BundleAdjustmentOptions(), &copy.rec);
+    EXPECT(!s.success);
+    EXPECT(copy.rec.MutableTrack(copy.tracks[3])->Point().v[0] == before);
+  }
+  // oracle on the same flattened problem
+  double oracle_final = -1, oracle_initial = -1;
+  {
+    Scene copy = sc;
+    BundleAdjusterB200 ba(IterativeOptions(), &copy.rec);
+    for (ViewId v : copy.rec.ViewIds()) ba.AddView(v);
+    for (TrackId t : copy.rec.TrackIds()) ba.AddTrack(t);
+    BundleAdjusterB200::Flat f; tba_options o;
+    ba.Flatten(&f, &o);
+    void* h = dlopen(oracle_path, RTLD_NOW);
+    EXPECT(h != nullptr);
+    oracle_solve_fn solve = (oracle_solve_fn)dlsym(h, "oracle_solve");
+    EXPECT(solve != nullptr);
+    tba_problem p = f.AsProblem();
+    tba_summary s; std::memset(&s, 0, sizeof s);
+    EXPECT(solve(&o, &p, &s) == 0 && s.success);
+    oracle_final = s.final_cost; oracle_initial = s.initial_cost;
+  }
+  BundleAdjustmentSummary s = BundleAdjustReconstructionB200(IterativeOptions(), &sc.rec);
+  EXPECT(s.success);
+  EXPECT(std::fabs(s.initial_cost - oracle_initial) <= 1e-10 * oracle_initial);
+  EXPECT(std::fabs(s.final_cost - oracle_final) <= 1e-6 * oracle_final);
+  EXPECT(s.final_cost < 0.05 * s.initial_cost);
+  // the in-place update happened: reprojection with the refined parameters reproduces final_cost
+  double cost = 0;
+  for (TrackId t : sc.rec.TrackIds()) {
+    Track* tr = sc.rec.MutableTrack(t);
+    for (ViewId v : tr->ViewIds()) {
+      View* view = sc.rec.MutableView(v);
+      double pix[2];
+      Project(view->MutableCamera()->extrinsics(), view->MutableCamera()->intrinsics(), tr->Point().data(), pix);
+      const Feature* f = view->GetFeature(t);
+      cost += 0.5 * ((pix[0] - f->x()) * (pix[0] - f->x()) + (pix[1] - f->y()) * (pix[1] - f->y()));
+    }
+  }
+  EXPECT(std::fabs(cost - s.final_cost) <= 1e-9 * cost);
+  // partial BA: two views + their tracks; everything else bit-identical
+  {
+    Scene copy = sc;
+    std::unordered_set<ViewId> vs = {copy.views[2], copy.views[7]};
+    std::unordered_set<TrackId> ts;
+    for (ViewId v : vs) for (TrackId t : copy.rec.MutableView(v)->TrackIds()) ts.insert(t);
+    for (ViewId v : vs) { double* e = copy.rec.MutableView(v)->MutableCamera()->mutable_extrinsics(); e[0] += 0.05; e[4] -= 0.01; }
+    BundleAdjustmentSummary ps = BundleAdjustPartialReconstructionB200(IterativeOptions(), vs, ts, &copy.rec);
+    EXPECT(ps.success && ps.final_cost < ps.initial_cost);
+    for (ViewId v : copy.views) {
+      if (vs.count(v)) continue;
+      EXPECT(std::memcmp(copy.rec.MutableView(v)->MutableCamera()->extrinsics(), sc.rec.MutableView(v)->MutableCamera()->extrinsics(), 48) == 0);
+    }
+    for (TrackId t : copy.tracks) {
+      if (ts.count(t)) continue;
+      EXPECT(std::memcmp(copy.rec.MutableTrack(t)->Point().data(), sc.rec.MutableTrack(t)->Point().data(), 32) == 0);
+    }
+  }
+  std::printf("solve ok: cost %.6e -> %.6e (oracle %.6e), setup %.3f s, solve %.3f s\n", s.initial_cost, s.final_cost, oracle_final, s.setup_time_in_seconds, s.solve_time_in_seconds);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "flatten") return TestFlatten();
+  if (argc >= 3 && std::string(argv[1]) == "solve") return TestSolve(argv[2]);
+  std::fprintf(stderr, "usage: adapter_test flatten | solve <path to libba_oracle.so>\n");
+  return 2;
+}

@@ -1,0 +1,28 @@
+"""The C++ adapter (adapter/bundle_adjuster_b200.{h,cc}: drop-in for Theia's BundleAdjuster / BundleAdjust*Reconstruction)
+compiled against the theia_compat stand-in headers."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ADAPTER = os.path.join(ROOT, "adapter")
+
+
+@pytest.fixture(scope="module")
+def adapter_test_bin(oracle):
+    subprocess.check_call(["make", "-C", ADAPTER], stdout=subprocess.DEVNULL)
+    return os.path.join(ADAPTER, "adapter_test")
+
+
+def test_problem_construction_matches_reference_rules(adapter_test_bin):
+    out = subprocess.run([adapter_test_bin, "flatten"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "flatten ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_adapter_end_to_end_against_oracle(adapter_test_bin):
+    out = subprocess.run([adapter_test_bin, "solve", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "solve ok" in out.stdout

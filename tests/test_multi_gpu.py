@@ -60,3 +60,21 @@ def test_sharded_solve_matches_single_gpu(world, scene):
     # replicated state is bit-identical across ranks (deterministic reductions + NCCL all-reduce)
     for r in res[1:]:
         assert np.array_equal(r[8], res[0][8]) and np.array_equal(r[9], res[0][9]) and r[3] == res[0][3]
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_single_process_multi_gpu_entry_point(world):
+    """tba_solve_multi: the form the C++ adapter uses (one host thread per device inside the library)."""
+    if engine.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    p = synthetic.make_scene(n_cam=40, n_pt=6000, obs_per_pt=8, seed=31)
+    e1 = engine.Engine()
+    ref = p.copy()
+    s1 = e1.solve(ref, engine.default_options(**KW))
+    e1.close()
+    got = p.copy()
+    sm = engine.solve_multi(got, engine.default_options(**KW), n_devices=world)
+    assert sm.rc == 0 and sm.success, sm.message
+    assert len(sm.costs) == len(s1.costs) and np.all(np.abs(sm.costs - s1.costs) <= 1e-9 * s1.costs)
+    assert np.abs(got.pt - ref.pt).max() <= 1e-7 * np.abs(ref.pt).max()
+    assert np.abs(got.ext - ref.ext).max() <= 1e-7 * np.abs(ref.ext).max()

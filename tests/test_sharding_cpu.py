@@ -40,6 +40,7 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle_py
+    oracle_py.set_num_threads(1)  # forked child: libgomp's thread pool of the parent does not exist here
     p = synthetic.make_scene(n_cam=12, n_pt=300, obs_per_pt=5, seed=21)
     shard, b, e = p.shard(rank, world)
     opt = oracle_py.default_options(use_inner_iterations=0, linear_solver_type=_abi.ITERATIVE_SCHUR)

@@ -1012,6 +1012,82 @@ int tba_get_profile(tba_context* c, double* out) {
   return TBA_OK;
 }
 
+// --------------------------------------------------------------------------- single-process multi-GPU
+// The drop-in is called from ONE host thread (Theia's estimators); this entry point shards points + observations over
+// n_devices GPUs of the box, runs one rank per device on its own host thread (each with its own context, stream and
+// NCCL communicator) and gathers the result.  Contexts are cached for the life of the process.
+namespace {
+std::mutex g_multi_mu;
+std::vector<tba_context*> g_multi_ctx;
+}  // namespace
+
+int tba_solve_multi(const tba_options* options, tba_problem* problem, tba_summary* summary, int n_devices) {
+  if (!options || !problem || !summary) return TBA_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(g_multi_mu);
+  const int avail = tba_device_count();
+  if (avail <= 0) return TBA_ERR_NO_DEVICE;
+  if (n_devices <= 0 || n_devices > avail) n_devices = avail;
+  if ((int)g_multi_ctx.size() != n_devices) {
+    for (tba_context* cx : g_multi_ctx) tba_destroy(cx);
+    g_multi_ctx.assign((size_t)n_devices, nullptr);
+    unsigned char id[128];
+    if (n_devices > 1 && tba_nccl_unique_id(id) != TBA_OK) { g_multi_ctx.clear(); return TBA_ERR_NCCL; }
+    std::vector<int> rcs((size_t)n_devices, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_devices; ++r) th.emplace_back([&, r] { rcs[r] = tba_create(r, r, n_devices, n_devices > 1 ? id : nullptr, &g_multi_ctx[r]); });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n_devices; ++r)
+      if (rcs[r] != TBA_OK) { const int e = rcs[r]; for (tba_context* cx : g_multi_ctx) tba_destroy(cx); g_multi_ctx.clear(); return e; }
+  }
+  if (n_devices == 1) return tba_solve(g_multi_ctx[0], options, problem, summary);
+  // shard ranges balanced by observation count
+  const int np = problem->n_pt;
+  for (int64_t i = 0; i < problem->n_obs; ++i)
+    if (problem->obs_pt[i] < 0 || problem->obs_pt[i] >= np) return TBA_ERR_INVALID_ARGUMENT;
+  std::vector<int32_t> cnt((size_t)np, 0);
+  for (int64_t i = 0; i < problem->n_obs; ++i) cnt[problem->obs_pt[i]]++;
+  struct Shard { int32_t b = 0, e = 0; std::vector<double> ext, intr, pt, xy; std::vector<int32_t> cam, ptl; tba_summary s; int rc = 0; };
+  std::vector<Shard> sh((size_t)n_devices);
+  tba_iteration* itbuf = summary->iterations;
+  const int itcap = summary->iterations_capacity;
+  std::vector<std::thread> th;
+  for (int r = 0; r < n_devices; ++r)
+    th.emplace_back([&, r] {
+      Shard& S = sh[r];
+      tba_shard_points(cnt.data(), np, n_devices, r, &S.b, &S.e);
+      S.ext.assign(problem->ext, problem->ext + (size_t)problem->n_cam * 6);
+      S.intr.assign(problem->intr, problem->intr + (size_t)problem->n_group * 10);
+      S.pt.assign(problem->pt + (size_t)S.b * 4, problem->pt + (size_t)S.e * 4);
+      for (int64_t i = 0; i < problem->n_obs; ++i) {
+        const int q = problem->obs_pt[i];
+        if (q < S.b || q >= S.e) continue;
+        S.cam.push_back(problem->obs_cam[i]); S.ptl.push_back(q - S.b);
+        S.xy.push_back(problem->obs_xy[2 * i]); S.xy.push_back(problem->obs_xy[2 * i + 1]);
+      }
+      tba_problem p = *problem;
+      p.ext = S.ext.data(); p.intr = S.intr.data(); p.pt = S.pt.data(); p.n_pt = S.e - S.b; p.pt_const = problem->pt_const + S.b;
+      p.n_obs = (int64_t)S.cam.size(); p.obs_cam = S.cam.data(); p.obs_pt = S.ptl.data(); p.obs_xy = S.xy.data();
+      memset(&S.s, 0, sizeof S.s);
+      if (r == 0) { S.s.iterations = itbuf; S.s.iterations_capacity = itcap; }
+      S.rc = tba_solve(g_multi_ctx[r], options, &p, &S.s);
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < n_devices; ++r)
+    if (sh[r].rc != TBA_OK) { *summary = sh[r].s; summary->iterations = itbuf; summary->iterations_capacity = itcap; return sh[r].rc; }
+  memcpy(problem->ext, sh[0].ext.data(), (size_t)problem->n_cam * 48);
+  memcpy(problem->intr, sh[0].intr.data(), (size_t)problem->n_group * 80);
+  for (int r = 0; r < n_devices; ++r) memcpy(problem->pt + (size_t)sh[r].b * 4, sh[r].pt.data(), (size_t)(sh[r].e - sh[r].b) * 32);
+  *summary = sh[0].s;
+  for (int r = 1; r < n_devices; ++r) {
+    summary->num_kernel_launches += sh[r].s.num_kernel_launches;
+    summary->h2d_bytes += sh[r].s.h2d_bytes;
+    summary->d2h_bytes += sh[r].s.d2h_bytes;
+    summary->setup_time_in_seconds = std::max(summary->setup_time_in_seconds, sh[r].s.setup_time_in_seconds);
+    summary->solve_time_in_seconds = std::max(summary->solve_time_in_seconds, sh[r].s.solve_time_in_seconds);
+  }
+  return TBA_OK;
+}
+
 // --------------------------------------------------------------------------- debug / test hooks
 int tba_debug_linearize(tba_context* c, double* cost) {
   if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi",
 ]
 
 
@@ -56,6 +56,7 @@ def lib():
         L.tba_debug_evaluate_step.argtypes = [C.c_void_p, dp]
         L.tba_debug_read.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64]
         L.tba_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
+        L.tba_solve_multi.argtypes = [C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.POINTER(_abi.tba_summary), C.c_int]
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.tba_get_profile.argtypes = [C.c_void_p, dp]
@@ -109,6 +110,20 @@ class Summary:
     @property
     def costs(self):
         return np.array([it["cost"] for it in self.iterations])
+
+
+def solve_multi(problem, options=None, n_devices=0, max_iterations_logged=2048):
+    """tba_solve_multi: single-process multi-GPU solve (one host thread per device inside the library)."""
+    options = options or default_options()
+    iters = (_abi.tba_iteration * max_iterations_logged)()
+    s = _abi.tba_summary()
+    s.iterations = C.cast(iters, C.POINTER(_abi.tba_iteration))
+    s.iterations_capacity = max_iterations_logged
+    st = problem.as_struct()
+    rc = lib().tba_solve_multi(C.byref(options), C.byref(st), C.byref(s), n_devices)
+    out = Summary(s, iters)
+    out.rc = rc
+    return out
 
 
 class Engine:
