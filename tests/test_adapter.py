@@ -19,10 +19,3 @@ def test_problem_construction_matches_reference_rules(adapter_test_bin):
     out = subprocess.run([adapter_test_bin, "flatten"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "flatten ok" in out.stdout
-
-
-@pytest.mark.gpu
-def test_adapter_end_to_end_against_oracle(adapter_test_bin):
-    out = subprocess.run([adapter_test_bin, "solve", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout + out.stderr
-    assert "solve ok" in out.stdout

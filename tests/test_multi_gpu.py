@@ -42,13 +42,18 @@ def test_sharded_solve_matches_single_gpu(world, scene):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     nccl_id = engine.nccl_unique_id()
-    procs = [ctx.Process(target=_worker, args=(r, world, nccl_id, scene_kw, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, nccl_id, scene_kw, out), daemon=True) for r in range(world)]
     for q in procs:
         q.start()
-    res = sorted([out.get(timeout=300) for _ in range(world)])
-    for q in procs:
-        q.join(timeout=60)
-        assert q.exitcode == 0
+    try:
+        res = sorted([out.get(timeout=300) for _ in range(world)])
+        for q in procs:
+            q.join(timeout=60)
+            assert q.exitcode == 0
+    finally:
+        for q in procs:  # a hung rank must not hang the suite
+            if q.is_alive():
+                q.kill()
     for rank, rc, msg, costs, cg, b, e, pt, ext, intr in res:
         assert rc == 0, msg
         assert len(costs) == len(s1.costs) and cg == [i["linear_solver_iterations"] for i in s1.iterations]
@@ -62,19 +67,35 @@ def test_sharded_solve_matches_single_gpu(world, scene):
         assert np.array_equal(r[8], res[0][8]) and np.array_equal(r[9], res[0][9]) and r[3] == res[0][3]
 
 
+_MULTI_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+from theiasfm_b200 import _abi, engine, synthetic
+KW = dict(use_inner_iterations=0, linear_solver_type=_abi.ITERATIVE_SCHUR, max_num_iterations=12)
+world = int(sys.argv[1])
+p = synthetic.make_scene(n_cam=40, n_pt=6000, obs_per_pt=8, seed=31)
+e1 = engine.Engine()
+ref = p.copy()
+s1 = e1.solve(ref, engine.default_options(**KW))
+e1.close()
+got = p.copy()
+sm = engine.solve_multi(got, engine.default_options(**KW), n_devices=world)
+assert sm.rc == 0 and sm.success, sm.message
+assert len(sm.costs) == len(s1.costs) and np.all(np.abs(sm.costs - s1.costs) <= 1e-9 * s1.costs)
+assert np.abs(got.pt - ref.pt).max() <= 1e-7 * np.abs(ref.pt).max()
+assert np.abs(got.ext - ref.ext).max() <= 1e-7 * np.abs(ref.ext).max()
+print("solve_multi ok")
+"""
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_single_process_multi_gpu_entry_point(world):
-    """tba_solve_multi: the form the C++ adapter uses (one host thread per device inside the library)."""
+    """tba_solve_multi: the form the C++ adapter uses (one host thread per device inside the library).
+    Runs in a subprocess with a hard timeout: NOT yet exercised on hardware (the round-1 GPU budget ran out on the
+    call that first hit an NCCL-init deadlock in this path, fixed since by code inspection only)."""
     if engine.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    p = synthetic.make_scene(n_cam=40, n_pt=6000, obs_per_pt=8, seed=31)
-    e1 = engine.Engine()
-    ref = p.copy()
-    s1 = e1.solve(ref, engine.default_options(**KW))
-    e1.close()
-    got = p.copy()
-    sm = engine.solve_multi(got, engine.default_options(**KW), n_devices=world)
-    assert sm.rc == 0 and sm.success, sm.message
-    assert len(sm.costs) == len(s1.costs) and np.all(np.abs(sm.costs - s1.costs) <= 1e-9 * s1.costs)
-    assert np.abs(got.pt - ref.pt).max() <= 1e-7 * np.abs(ref.pt).max()
-    assert np.abs(got.ext - ref.ext).max() <= 1e-7 * np.abs(ref.ext).max()
+    import subprocess
+    out = subprocess.run([sys.executable, "-c", _MULTI_SCRIPT % ROOT, str(world)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "solve_multi ok" in out.stdout, out.stdout + out.stderr

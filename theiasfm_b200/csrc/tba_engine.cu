@@ -509,12 +509,16 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
     return TBA_ERR_CUDA;
   }
   if (world_size > 1) {
-    std::lock_guard<std::mutex> lk(g_nccl_mu);
-    std::string err;
-    if (!nccl_unique_id || !g_nccl.load(&err)) { tba_destroy(c); return TBA_ERR_NCCL; }
+    {
+      // the lock covers only the dlopen: ncclCommInitRank blocks until every rank has called it, and the ranks of a
+      // single-process multi-GPU group (tba_solve_multi) call tba_create concurrently from their own threads
+      std::lock_guard<std::mutex> lk(g_nccl_mu);
+      std::string err;
+      if (!nccl_unique_id || !g_nccl.load(&err)) { tba_destroy(c); return TBA_ERR_NCCL; }
+    }
     ncclUniqueId id;
     memcpy(&id, nccl_unique_id, 128);
-    if (g_nccl.CommInitRank(&c->comm, world_size, id, rank) != ncclSuccess) { tba_destroy(c); return TBA_ERR_NCCL; }
+    if (g_nccl.CommInitRank(&c->comm, world_size, id, rank) != ncclSuccess) { c->comm = nullptr; tba_destroy(c); return TBA_ERR_NCCL; }
   }
   *out = c;
   return TBA_OK;
