@@ -90,6 +90,8 @@ def load_peaks():
 def cpu_baseline(steps, warmup=0):
     """The CPU restatement (oracle/, kind 'port') on a bounded sample: a 1k-camera / 100k-point / 1M-observation scene."""
     from oracle import oracle_py
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the baseline)
+    oracle_py.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     p = synthetic.make_scene(**SAMPLE_CONFIG)
     n_obs = p.n_obs
     if warmup:
