@@ -120,9 +120,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = args.steps, max(args.warmup, 0)
     cfg = synthetic.CONFIGS[args.workload]
-    config = {"workload": "%s: %d cameras / %d points / ~%d observations, PINHOLE, one shared intrinsics group, TRIVIAL loss, "
-                          "default intrinsics mask (f,k1,k2 free), use_inner_iterations=false" %
-                          (args.workload, cfg["n_cam"], cfg["n_pt"], cfg["n_pt"] * cfg["obs_per_pt"]),
+    model_name = "PINHOLE" if cfg["model"] == _abi.MODEL_PINHOLE else "PINHOLE_RADIAL_TANGENTIAL"
+    groups = "one shared intrinsics group" if cfg["shared_intrinsics"] else "one intrinsics group per camera"
+    config = {"workload": "%s: %d cameras / %d points / ~%d observations, %s, %s, TRIVIAL loss, default intrinsics mask "
+                          "(FOCAL_LENGTH|RADIAL_DISTORTION free), use_inner_iterations=false" %
+                          (args.workload, cfg["n_cam"], cfg["n_pt"], cfg["n_pt"] * cfg["obs_per_pt"], model_name, groups),
               "parallelism": "points+observations sharded over %d GPU(s), cameras replicated, NCCL allreduce per PCG iteration" % world,
               "l2_policy": "inputs larger than L2: the stored linearisation streamed by every kernel is %.1f GB per GPU at N=1" %
                            (cfg["n_pt"] * cfg["obs_per_pt"] * 160 / 1e9)}

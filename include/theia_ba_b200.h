@@ -242,6 +242,11 @@ enum { TBA_VEC_GRADIENT_CAM = 0,  /* [n_cam*6]            J^T r, unscaled      *
        TBA_VEC_STEP_CAM = 11,     /* last LM step (unscaled delta)              */
        TBA_VEC_STEP_INTR = 12,
        TBA_VEC_STEP_PT = 13 };
+/* Host-only (no CUDA, no context): the observation packing tba_upload performs, into caller
+ * buffers of capacity cap_slots slots; sizes_out = {n_tiles, n_slots, n_packed_points, n_long_points, NI, imask}. */
+int tba_debug_pack(const tba_problem* problem, int64_t cap_slots, int64_t* sizes_out, int32_t* slot_cam, int32_t* slot_pt,
+                   int16_t* slot_run, uint8_t* slot_flags, double* xy, int64_t* slot_orig, int32_t* pk2caller,
+                   int32_t* tile_pt_begin, int32_t* tile_nruns, uint8_t* tile_flags, double* mask);
 int tba_debug_linearize(tba_context* ctx, double* cost);
 int tba_debug_prepare_linear_system(tba_context* ctx, double radius);
 int tba_debug_schur_matvec(tba_context* ctx, const double* x_cam /*[n_cam*6]*/,

@@ -22,6 +22,7 @@
 
 #include "../../include/theia_ba_b200.h"
 #include "tba_kernels.cuh"
+#include "tba_pack.h"
 
 namespace tba {
 
@@ -72,6 +73,8 @@ struct DevBuf {
 }  // namespace tba
 
 using namespace tba;
+
+static_assert(TILE == kPackTile && MAXP == kPackMaxPoints, "tba_pack.h and tba_kernels.cuh disagree on the tile shape");
 
 struct tba_context {
   int device = 0, rank = 0, world = 1;
@@ -424,21 +427,6 @@ void accept_candidate(tba_context* c) {
   std::swap(P.cam_rec, P.cam_rec_c);
 }
 
-template <class F>
-void parallel_for(int64_t n, int nthreads, F f) {
-  if (n <= 0) return;
-  const int T = (int)std::min<int64_t>(nthreads, (n + 8191) / 8192);
-  if (T <= 1) { f((int64_t)0, n, 0); return; }
-  std::vector<std::thread> th;
-  const int64_t chunk = (n + T - 1) / T;
-  for (int t = 0; t < T; ++t) {
-    const int64_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([=, &f] { f(b, e, t); });
-  }
-  for (auto& x : th) x.join();
-}
-
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void push_iter(tba_summary* s, const tba_iteration& it) {
@@ -570,62 +558,17 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
       return TBA_ERR_UNSUPPORTED;
     }
   for (int i = 0; i < nc; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= ng) { set_err(c, "cam_group out of range"); return TBA_ERR_INVALID_ARGUMENT; }
-  // ---- host packing, multi-threaded (phases A-E below), into pinned staging memory
+  // ---- host packing (tba_pack.h: phases A-E, multi-threaded), into pinned staging memory
   const int T = std::max(1, std::min<int>(32, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
-  // A: validate, per-point / per-camera observation counts
-  std::vector<int> cnt_pt((size_t)np, 0), cnt_cam((size_t)nc, 0);
-  std::atomic<int64_t> bad(-1);
-  parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
-    for (int64_t i = b0; i < e0; ++i) {
-      const int q = p->obs_pt[i], cam = p->obs_cam[i];
-      if (q < 0 || q >= np || cam < 0 || cam >= nc) { bad.store(i); return; }
-      __atomic_fetch_add(&cnt_pt[q], 1, __ATOMIC_RELAXED);
-      __atomic_fetch_add(&cnt_cam[cam], 1, __ATOMIC_RELAXED);
-    }
-  });
-  if (bad.load() >= 0) { const int64_t i = bad.load(); set_err(c, "observation %lld references camera %d / point %d out of range", (long long)i, p->obs_cam[i], p->obs_pt[i]); return TBA_ERR_INVALID_ARGUMENT; }
-  // B: offsets
-  std::vector<int64_t> off((size_t)np + 1, 0);
-  int maxlen = 0;
-  for (int q = 0; q < np; ++q) { maxlen = std::max(maxlen, cnt_pt[q]); off[(size_t)q + 1] = off[q] + cnt_pt[q]; }
-  if (maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
-  // C: observations grouped by point, (group, camera, index) order inside a point; runs = distinct groups of a point
-  std::vector<int64_t> order((size_t)no);
-  {
-    std::vector<int64_t> cur(off.begin(), off.end() - 1);
-    parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
-      for (int64_t i = b0; i < e0; ++i) order[(size_t)__atomic_fetch_add(&cur[p->obs_pt[i]], (int64_t)1, __ATOMIC_RELAXED)] = i;
-    });
-  }
-  std::vector<uint8_t> pt_nruns((size_t)np, 0);
-  parallel_for(np, T, [&](int64_t b0, int64_t e0, int) {
-    for (int64_t q = b0; q < e0; ++q) {
-      auto bb = order.begin() + off[q], ee = order.begin() + off[(size_t)q + 1];
-      if (ee - bb > 1)
-        std::sort(bb, ee, [&](int64_t a, int64_t d) {
-          const int ga = p->cam_group[p->obs_cam[a]], gb = p->cam_group[p->obs_cam[d]];
-          if (ga != gb) return ga < gb;
-          if (p->obs_cam[a] != p->obs_cam[d]) return p->obs_cam[a] < p->obs_cam[d];
-          return a < d;
-        });
-      int runs = 0, last = -1;
-      for (auto it2 = bb; it2 != ee; ++it2) { const int g = p->cam_group[p->obs_cam[*it2]]; if (g != last) { ++runs; last = g; } }
-      pt_nruns[q] = (uint8_t)std::min(runs, 255);
-    }
-  });
+  HostPack H;
+  pack_count_and_sort(p, T, &H);  // A, B, C
+  if (H.bad >= 0) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)H.bad, p->obs_cam[H.bad], p->obs_pt[H.bad]); return TBA_ERR_INVALID_ARGUMENT; }
+  if (H.maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", H.maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
+  pack_points(p, &H);
   // ---- which blocks take part (blocks without residuals are not in the Ceres program)
   std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
-  for (int i = 0; i < nc; ++i) { cnt_c[i] = cnt_cam[i]; cnt_g[p->cam_group[i]] += cnt_cam[i]; }
-  // packed points = points that have observations (zero-observation points are left untouched): first the points
-  // whose track fits one warp (<= 32 observations) in caller order, then the long tracks (their own tiles)
-  c->pk2caller.clear();
-  c->pk2caller.reserve((size_t)np);
-  c->n_free_pt = 0;
-  int n_long = 0;
-  for (int q = 0; q < np; ++q) if (cnt_pt[q] > 0 && cnt_pt[q] <= 32) c->pk2caller.push_back(q);
-  for (int q = 0; q < np; ++q) if (cnt_pt[q] > 32) { c->pk2caller.push_back(q); ++n_long; }
-  const int npk = (int)c->pk2caller.size();
-  for (int k = 0; k < npk; ++k) c->n_free_pt += p->pt_const[c->pk2caller[k]] ? 0 : 1;
+  for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
+  c->n_free_pt = H.n_free_pt;
   c->n_free_pt_global = c->n_free_pt;
   if (c->world > 1) {  // counts are global properties
     std::vector<double> tmp(cnt_c);
@@ -645,62 +588,25 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
     std::copy(tmp.begin() + nc, tmp.begin() + nc + ng, cnt_g.begin());
     c->n_free_pt_global = (int64_t)tmp.back();
   }
+  pack_masks_and_tiles(p, cnt_c, cnt_g, &H);  // masks, D
   const int ne = nc * 6, ncs = ne + ng * 10;
-  std::vector<double> mask(ncs, 0.0), blk_free(nc + ng, 0.0);
-  uint32_t union_free = 0;
-  c->n_free_cs = 0;
-  for (int i = 0; i < nc; ++i) {
-    if (cnt_c[i] == 0.0) continue;
-    for (int j = 0; j < 6; ++j) {
-      const bool fr = j < 3 ? !(p->ext_const[i] & TBA_EXT_POSITION_CONST) : !(p->ext_const[i] & TBA_EXT_ORIENTATION_CONST);
-      if (fr) { mask[i * 6 + j] = 1.0; blk_free[i] = 1.0; c->n_free_cs++; }
-    }
-  }
-  for (int g = 0; g < ng; ++g) {
-    if (cnt_g[g] == 0.0) continue;
-    const int K = p->group_model[g] == TBA_MODEL_PINHOLE ? 7 : 10;
-    for (int j = 0; j < K; ++j)
-      if (!((p->group_const_mask[g] >> j) & 1u)) { mask[ne + g * 10 + j] = 1.0; blk_free[nc + g] = 1.0; union_free |= 1u << j; c->n_free_cs++; }
-  }
+  const std::vector<double>& mask = H.mask;
+  const std::vector<double>& blk_free = H.blk_free;
+  std::vector<int>& tile_pt_begin = H.tile_pt_begin;
+  std::vector<int>& tile_nruns = H.tile_nruns;
+  std::vector<uint8_t>& tile_flags = H.tile_flags;
+  c->pk2caller = H.pk2caller;
+  c->n_free_cs = H.n_free_cs;
   c->imask = 0x3FFu;
-  for (uint32_t m : kMasks) if ((union_free & ~m) == 0) { c->imask = m; break; }
+  for (uint32_t m : kMasks) if ((H.union_free & ~m) == 0) { c->imask = m; break; }
   c->NI = popcount10(c->imask);
   c->NJ = 14 + 2 * c->NI;
-  // D: tiles (serial, light).  A tile is TILE slots = 8 warps of 32; in a normal tile a point never straddles a warp
-  // (so every warp is autonomous); long tracks (> 32 observations) go to "long" tiles handled at CTA level.
-  std::vector<int> tile_pt_begin, tile_nruns;
-  std::vector<uint8_t> tile_flags;
-  std::vector<int64_t> pt_slot((size_t)npk);  // first slot of each packed point
-  std::vector<int> pt_runbase((size_t)npk);   // run index (inside its tile) of the point's first run
-  {
-    int used = TILE, npts_in_tile = MAXP, run = 0;
-    bool in_long = false;
-    for (int k = 0; k < npk; ++k) {
-      const int q = c->pk2caller[k];
-      const int len = cnt_pt[q];
-      const bool is_long = len > 32;
-      int start = used;
-      if (!is_long && (start % 32) + len > 32) start = (start / 32 + 1) * 32;  // next warp
-      if (start + len > TILE || npts_in_tile + 1 > MAXP || is_long != in_long) {
-        if (!tile_pt_begin.empty()) tile_nruns.push_back(run);
-        tile_pt_begin.push_back(k);
-        tile_flags.push_back(is_long ? 1 : 0);
-        in_long = is_long;
-        start = 0; npts_in_tile = 0; run = 0;
-      }
-      pt_slot[k] = (int64_t)(tile_pt_begin.size() - 1) * TILE + start;
-      pt_runbase[k] = run;
-      run += pt_nruns[q];
-      used = start + len;
-      npts_in_tile++;
-    }
-    if (!tile_pt_begin.empty()) tile_nruns.push_back(run);
-  }
-  const int n_tiles = (int)tile_pt_begin.size();
-  tile_pt_begin.push_back(npk);
-  const int64_t n_slots = (int64_t)n_tiles * TILE;
+  const int npk = (int)H.pk2caller.size();
+  const int n_long = H.n_long;
+  const int n_tiles = H.n_tiles;
+  const int64_t n_slots = H.n_slots;
   // E: fill the slot arrays (pinned staging), parallel over packed points
-  const size_t stage_bytes = (size_t)n_slots * (4 + 4 + 2 + 1 + 16) + (size_t)npk * (32 + 1) + 1024;
+  const size_t stage_bytes = (size_t)n_slots * (4 + 4 + 2 + 1 + 16) + (size_t)npk * (32 + 1) + 8 * 256;
   if (c->stage_cap < stage_bytes) {
     if (c->stage) cudaFreeHost(c->stage);
     c->stage = nullptr; c->stage_cap = 0;
@@ -717,34 +623,12 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   uint8_t* h_slot_flags = carve((size_t)n_slots);
   uint8_t* h_pt_const = carve((size_t)npk);
   c->slot_orig.assign((size_t)n_slots, (int64_t)-1);
-  parallel_for(n_slots, T, [&](int64_t b0, int64_t e0, int) {
-    memset(h_slot_cam + b0, 0xFF, (size_t)(e0 - b0) * 4);
-    memset(h_slot_pt + b0, 0, (size_t)(e0 - b0) * 4);
-    memset(h_slot_run + b0, 0xFF, (size_t)(e0 - b0) * 2);
-    memset(h_slot_flags + b0, 0, (size_t)(e0 - b0));
-  });
-  parallel_for((int64_t)n_tiles * 2, T, [&](int64_t b0, int64_t e0, int) { memset(h_xy + b0 * TILE, 0, (size_t)(e0 - b0) * TILE * 8); });
-  parallel_for(npk, T, [&](int64_t b0, int64_t e0, int) {
-    for (int64_t k = b0; k < e0; ++k) {
-      const int q = c->pk2caller[k];
-      h_pt_const[k] = p->pt_const[q] ? 1 : 0;
-      memcpy(h_pt + (size_t)k * 4, p->pt + (size_t)q * 4, 32);
-      int64_t s0 = pt_slot[k];
-      int run = pt_runbase[k] - 1, last_grp = -1;
-      for (int64_t kk = off[q]; kk < off[(size_t)q + 1]; ++kk, ++s0) {
-        const int64_t oi = order[kk];
-        const int cam = p->obs_cam[oi], g = p->cam_group[cam];
-        if (g != last_grp) { ++run; last_grp = g; }
-        h_slot_cam[s0] = cam; h_slot_pt[s0] = (int)k; h_slot_run[s0] = (int16_t)run;
-        const bool any_free = blk_free[cam] != 0.0 || blk_free[nc + g] != 0.0 || !h_pt_const[k];
-        h_slot_flags[s0] = any_free ? 0 : 1;
-        c->slot_orig[(size_t)s0] = oi;
-        const int64_t wq = s0 / 32, l = s0 % 32;  // [tile][warp][2][32]
-        h_xy[(size_t)(wq * 2 + 0) * 32 + l] = p->obs_xy[2 * oi];
-        h_xy[(size_t)(wq * 2 + 1) * 32 + l] = p->obs_xy[2 * oi + 1];
-      }
-    }
-  });
+  {
+    PackDest d;
+    d.xy = h_xy; d.pt = h_pt; d.slot_cam = h_slot_cam; d.slot_pt = h_slot_pt; d.slot_run = h_slot_run; d.slot_flags = h_slot_flags;
+    d.pt_const = h_pt_const; d.slot_orig = c->slot_orig.data();
+    pack_fill(p, H, T, d);
+  }
   c->n_long_points = n_long;
   // ---- device allocation + H2D
   c->n_cam = nc; c->n_group = ng; c->n_pt = npk; c->n_pt_caller = np; c->n_tiles = n_tiles; c->n_obs = no; c->n_slots = n_slots;
@@ -1093,6 +977,41 @@ int tba_solve_multi(const tba_options* options, tba_problem* problem, tba_summar
 }
 
 // --------------------------------------------------------------------------- debug / test hooks
+// Host-only: run the packing of tba_upload (world = 1) into caller buffers of capacity `cap_slots` slots /
+// problem->n_pt points / cap_slots/256 + 1 tiles.  No CUDA call: usable (and tested) without a GPU.
+// sizes_out = {n_tiles, n_slots, n_packed_points, n_long_points, NI, imask}.
+int tba_debug_pack(const tba_problem* p, int64_t cap_slots, int64_t* sizes_out, int32_t* slot_cam, int32_t* slot_pt, int16_t* slot_run,
+                   uint8_t* slot_flags, double* xy, int64_t* slot_orig, int32_t* pk2caller, int32_t* tile_pt_begin,
+                   int32_t* tile_nruns, uint8_t* tile_flags, double* mask) {
+  if (!p || !sizes_out) return TBA_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < p->n_cam; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= p->n_group) return TBA_ERR_INVALID_ARGUMENT;
+  HostPack H;
+  pack_count_and_sort(p, 4, &H);
+  if (H.bad >= 0) return TBA_ERR_INVALID_ARGUMENT;
+  if (H.maxlen > TILE) return TBA_ERR_UNSUPPORTED;
+  pack_points(p, &H);
+  std::vector<double> cnt_c(p->n_cam, 0.0), cnt_g(p->n_group, 0.0);
+  for (int i = 0; i < p->n_cam; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
+  pack_masks_and_tiles(p, cnt_c, cnt_g, &H);
+  uint32_t imask = 0x3FFu;
+  for (uint32_t m : kMasks) if ((H.union_free & ~m) == 0) { imask = m; break; }
+  sizes_out[0] = H.n_tiles; sizes_out[1] = H.n_slots; sizes_out[2] = (int64_t)H.pk2caller.size(); sizes_out[3] = H.n_long;
+  sizes_out[4] = popcount10(imask); sizes_out[5] = imask;
+  if (H.n_slots > cap_slots) return TBA_ERR_INVALID_ARGUMENT;
+  std::vector<double> pt((size_t)H.pk2caller.size() * 4);
+  std::vector<uint8_t> ptc(H.pk2caller.size());
+  for (int64_t s = 0; s < H.n_slots; ++s) slot_orig[s] = -1;
+  PackDest d;
+  d.xy = xy; d.pt = pt.data(); d.slot_cam = slot_cam; d.slot_pt = slot_pt; d.slot_run = slot_run; d.slot_flags = slot_flags;
+  d.pt_const = ptc.data(); d.slot_orig = slot_orig;
+  pack_fill(p, H, 4, d);
+  for (size_t k = 0; k < H.pk2caller.size(); ++k) pk2caller[k] = H.pk2caller[k];
+  for (int t = 0; t <= H.n_tiles; ++t) tile_pt_begin[t] = H.tile_pt_begin[t];
+  for (int t = 0; t < H.n_tiles; ++t) { tile_nruns[t] = H.tile_nruns[t]; tile_flags[t] = H.tile_flags[t]; }
+  for (size_t i = 0; i < H.mask.size(); ++i) mask[i] = H.mask[i];
+  return TBA_OK;
+}
+
 int tba_debug_linearize(tba_context* c, double* cost) {
   if (!c || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
   CUDA_OK(c, cudaSetDevice(c->device));

@@ -1,0 +1,222 @@
+// tba_pack.h -- host-side packing of a flattened BA problem into the engine's tile layout.
+// Pure host code (no CUDA): used by tba_upload() and, for CPU-only tests of the host logic, by tba_debug_pack().
+//
+// Layout rules: observations sorted by point, (intrinsics group, camera, index) order inside a point; tiles of TILE
+// slots = 8 warp slices of 32; in a normal tile a point never straddles a warp slice; tracks with more than 32
+// observations go to "long" tiles (packed after all normal points); at most MAXP points per tile; padding slots have
+// cam = -1.  Which parameter blocks take part follows bundle_adjuster.cc:102-180 as recorded by the adapter in
+// ext_const / group_const_mask / pt_const, plus "blocks without residuals are not in the program".
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/theia_ba_b200.h"
+
+namespace tba {
+
+constexpr int kPackTile = 256;
+constexpr int kPackMaxPoints = 256;
+
+template <class F>
+void parallel_for(int64_t n, int nthreads, F f) {
+  if (n <= 0) return;
+  const int T = (int)std::min<int64_t>(nthreads, (n + 8191) / 8192);
+  if (T <= 1) { f((int64_t)0, n, 0); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + T - 1) / T;
+  for (int t = 0; t < T; ++t) {
+    const int64_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=, &f] { f(b, e, t); });
+  }
+  for (auto& x : th) x.join();
+}
+
+struct HostPack {
+  // phases A-C
+  std::vector<int> cnt_pt, cnt_cam;
+  std::vector<int64_t> off, order;
+  std::vector<uint8_t> pt_nruns;
+  int maxlen = 0;
+  int64_t bad = -1;
+  // packed points
+  std::vector<int> pk2caller;
+  int n_long = 0;
+  int64_t n_free_pt = 0, n_free_cs = 0;
+  // masks + tiles
+  std::vector<double> mask, blk_free;
+  uint32_t union_free = 0;
+  std::vector<int> tile_pt_begin, tile_nruns;
+  std::vector<uint8_t> tile_flags;
+  std::vector<int64_t> pt_slot;  // first slot of each packed point
+  std::vector<int> pt_runbase;   // run index (inside its tile) of the point's first run
+  int n_tiles = 0;
+  int64_t n_slots = 0;
+};
+
+struct PackDest {
+  double* xy;        // [tile][warp][2][32]
+  double* pt;        // [packed point][4]
+  int* slot_cam;     // -1 = padding
+  int* slot_pt;      // packed point id
+  int16_t* slot_run;
+  uint8_t* slot_flags;
+  uint8_t* pt_const;  // [packed point]
+  int64_t* slot_orig; // pre-filled with -1
+};
+
+// A: validate + per-point / per-camera counts; B: offsets; C: observations grouped by point and sorted inside a point.
+inline void pack_count_and_sort(const tba_problem* p, int T, HostPack* H) {
+  const int nc = p->n_cam, np = p->n_pt;
+  const int64_t no = p->n_obs;
+  H->cnt_pt.assign((size_t)np, 0);
+  H->cnt_cam.assign((size_t)nc, 0);
+  std::atomic<int64_t> bad(-1);
+  int* cnt_pt = H->cnt_pt.data();
+  int* cnt_cam = H->cnt_cam.data();
+  parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t i = b0; i < e0; ++i) {
+      const int q = p->obs_pt[i], cam = p->obs_cam[i];
+      if (q < 0 || q >= np || cam < 0 || cam >= nc) { bad.store(i); return; }
+      __atomic_fetch_add(&cnt_pt[q], 1, __ATOMIC_RELAXED);
+      __atomic_fetch_add(&cnt_cam[cam], 1, __ATOMIC_RELAXED);
+    }
+  });
+  H->bad = bad.load();
+  if (H->bad >= 0) return;
+  H->off.assign((size_t)np + 1, 0);
+  H->maxlen = 0;
+  for (int q = 0; q < np; ++q) { H->maxlen = std::max(H->maxlen, cnt_pt[q]); H->off[(size_t)q + 1] = H->off[q] + cnt_pt[q]; }
+  if (H->maxlen > kPackTile) return;
+  H->order.assign((size_t)no, 0);
+  {
+    std::vector<int64_t> cur(H->off.begin(), H->off.end() - 1);
+    int64_t* order = H->order.data();
+    parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
+      for (int64_t i = b0; i < e0; ++i) order[(size_t)__atomic_fetch_add(&cur[p->obs_pt[i]], (int64_t)1, __ATOMIC_RELAXED)] = i;
+    });
+  }
+  H->pt_nruns.assign((size_t)np, 0);
+  parallel_for(np, T, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t q = b0; q < e0; ++q) {
+      auto bb = H->order.begin() + H->off[q], ee = H->order.begin() + H->off[(size_t)q + 1];
+      if (ee - bb > 1)
+        std::sort(bb, ee, [&](int64_t a, int64_t d) {
+          const int ga = p->cam_group[p->obs_cam[a]], gb = p->cam_group[p->obs_cam[d]];
+          if (ga != gb) return ga < gb;
+          if (p->obs_cam[a] != p->obs_cam[d]) return p->obs_cam[a] < p->obs_cam[d];
+          return a < d;
+        });
+      int runs = 0, last = -1;
+      for (auto it2 = bb; it2 != ee; ++it2) { const int g = p->cam_group[p->obs_cam[*it2]]; if (g != last) { ++runs; last = g; } }
+      H->pt_nruns[q] = (uint8_t)std::min(runs, 255);
+    }
+  });
+}
+
+// Packed points = points that have observations (zero-observation points are left untouched): first the points whose
+// track fits one warp slice (<= 32 observations) in caller order, then the long tracks.
+inline void pack_points(const tba_problem* p, HostPack* H) {
+  const int np = p->n_pt;
+  H->pk2caller.clear();
+  H->pk2caller.reserve((size_t)np);
+  H->n_long = 0;
+  H->n_free_pt = 0;
+  for (int q = 0; q < np; ++q) if (H->cnt_pt[q] > 0 && H->cnt_pt[q] <= 32) H->pk2caller.push_back(q);
+  for (int q = 0; q < np; ++q) if (H->cnt_pt[q] > 32) { H->pk2caller.push_back(q); ++H->n_long; }
+  for (int q : H->pk2caller) H->n_free_pt += p->pt_const[q] ? 0 : 1;
+}
+
+// Free-coordinate masks (cnt_c / cnt_g are the GLOBAL observation counts per camera / group) and phase D: tiles.
+inline void pack_masks_and_tiles(const tba_problem* p, const std::vector<double>& cnt_c, const std::vector<double>& cnt_g, HostPack* H) {
+  const int nc = p->n_cam, ng = p->n_group;
+  const int ne = nc * 6, ncs = ne + ng * 10;
+  H->mask.assign((size_t)ncs, 0.0);
+  H->blk_free.assign((size_t)nc + ng, 0.0);
+  H->union_free = 0;
+  H->n_free_cs = 0;
+  for (int i = 0; i < nc; ++i) {
+    if (cnt_c[i] == 0.0) continue;
+    for (int j = 0; j < 6; ++j) {
+      const bool fr = j < 3 ? !(p->ext_const[i] & TBA_EXT_POSITION_CONST) : !(p->ext_const[i] & TBA_EXT_ORIENTATION_CONST);
+      if (fr) { H->mask[(size_t)i * 6 + j] = 1.0; H->blk_free[i] = 1.0; H->n_free_cs++; }
+    }
+  }
+  for (int g = 0; g < ng; ++g) {
+    if (cnt_g[g] == 0.0) continue;
+    const int K = p->group_model[g] == TBA_MODEL_PINHOLE ? 7 : 10;
+    for (int j = 0; j < K; ++j)
+      if (!((p->group_const_mask[g] >> j) & 1u)) { H->mask[(size_t)ne + g * 10 + j] = 1.0; H->blk_free[(size_t)nc + g] = 1.0; H->union_free |= 1u << j; H->n_free_cs++; }
+  }
+  const int npk = (int)H->pk2caller.size();
+  H->tile_pt_begin.clear(); H->tile_nruns.clear(); H->tile_flags.clear();
+  H->pt_slot.assign((size_t)npk, 0);
+  H->pt_runbase.assign((size_t)npk, 0);
+  {
+    int used = kPackTile, npts_in_tile = kPackMaxPoints, run = 0;
+    bool in_long = false;
+    for (int k = 0; k < npk; ++k) {
+      const int q = H->pk2caller[k];
+      const int len = H->cnt_pt[q];
+      const bool is_long = len > 32;
+      int start = used;
+      if (!is_long && (start % 32) + len > 32) start = (start / 32 + 1) * 32;  // next warp slice
+      if (start + len > kPackTile || npts_in_tile + 1 > kPackMaxPoints || is_long != in_long) {
+        if (!H->tile_pt_begin.empty()) H->tile_nruns.push_back(run);
+        H->tile_pt_begin.push_back(k);
+        H->tile_flags.push_back(is_long ? 1 : 0);
+        in_long = is_long;
+        start = 0; npts_in_tile = 0; run = 0;
+      }
+      H->pt_slot[k] = (int64_t)(H->tile_pt_begin.size() - 1) * kPackTile + start;
+      H->pt_runbase[k] = run;
+      run += H->pt_nruns[q];
+      used = start + len;
+      npts_in_tile++;
+    }
+    if (!H->tile_pt_begin.empty()) H->tile_nruns.push_back(run);
+  }
+  H->n_tiles = (int)H->tile_pt_begin.size();
+  H->tile_pt_begin.push_back(npk);
+  H->n_slots = (int64_t)H->n_tiles * kPackTile;
+}
+
+// E: fill the slot arrays, parallel over packed points.
+inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const PackDest& d) {
+  const int nc = p->n_cam;
+  const int npk = (int)H.pk2caller.size();
+  parallel_for(H.n_slots, T, [&](int64_t b0, int64_t e0, int) {
+    memset(d.slot_cam + b0, 0xFF, (size_t)(e0 - b0) * 4);
+    memset(d.slot_pt + b0, 0, (size_t)(e0 - b0) * 4);
+    memset(d.slot_run + b0, 0xFF, (size_t)(e0 - b0) * 2);
+    memset(d.slot_flags + b0, 0, (size_t)(e0 - b0));
+  });
+  parallel_for((int64_t)H.n_tiles * 2, T, [&](int64_t b0, int64_t e0, int) { memset(d.xy + b0 * kPackTile, 0, (size_t)(e0 - b0) * kPackTile * 8); });
+  parallel_for(npk, T, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t k = b0; k < e0; ++k) {
+      const int q = H.pk2caller[k];
+      d.pt_const[k] = p->pt_const[q] ? 1 : 0;
+      memcpy(d.pt + (size_t)k * 4, p->pt + (size_t)q * 4, 32);
+      int64_t s0 = H.pt_slot[k];
+      int run = H.pt_runbase[k] - 1, last_grp = -1;
+      for (int64_t kk = H.off[q]; kk < H.off[(size_t)q + 1]; ++kk, ++s0) {
+        const int64_t oi = H.order[kk];
+        const int cam = p->obs_cam[oi], g = p->cam_group[cam];
+        if (g != last_grp) { ++run; last_grp = g; }
+        d.slot_cam[s0] = cam; d.slot_pt[s0] = (int)k; d.slot_run[s0] = (int16_t)run;
+        const bool any_free = H.blk_free[cam] != 0.0 || H.blk_free[(size_t)nc + g] != 0.0 || !d.pt_const[k];
+        d.slot_flags[s0] = any_free ? 0 : 1;
+        d.slot_orig[(size_t)s0] = oi;
+        const int64_t wq = s0 / 32, l = s0 % 32;  // [tile][warp][2][32]
+        d.xy[(size_t)(wq * 2 + 0) * 32 + l] = p->obs_xy[2 * oi];
+        d.xy[(size_t)(wq * 2 + 1) * 32 + l] = p->obs_xy[2 * oi + 1];
+      }
+    }
+  });
+}
+
+}  // namespace tba

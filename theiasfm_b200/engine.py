@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack",
 ]
 
 
@@ -57,6 +57,7 @@ def lib():
         L.tba_debug_read.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64]
         L.tba_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
         L.tba_solve_multi.argtypes = [C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.POINTER(_abi.tba_summary), C.c_int]
+        L.tba_debug_pack.restype = C.c_int
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.tba_get_profile.argtypes = [C.c_void_p, dp]
@@ -110,6 +111,35 @@ class Summary:
     @property
     def costs(self):
         return np.array([it["cost"] for it in self.iterations])
+
+
+def debug_pack(problem):
+    """tba_debug_pack: the host-side tile packing (no GPU needed). Returns a dict of numpy arrays."""
+    cap = (problem.n_obs // 200 + problem.n_pt // 8 + 8) * 256 + problem.n_obs * 2
+    sizes = np.zeros(6, np.int64)
+    out = dict(slot_cam=np.zeros(cap, np.int32), slot_pt=np.zeros(cap, np.int32), slot_run=np.zeros(cap, np.int16),
+               slot_flags=np.zeros(cap, np.uint8), xy=np.zeros(cap * 2), slot_orig=np.zeros(cap, np.int64),
+               pk2caller=np.zeros(max(problem.n_pt, 1), np.int32), tile_pt_begin=np.zeros(cap // 256 + 2, np.int32),
+               tile_nruns=np.zeros(cap // 256 + 2, np.int32), tile_flags=np.zeros(cap // 256 + 2, np.uint8),
+               mask=np.zeros(problem.n_cam * 6 + problem.n_group * 10))
+    st = problem.as_struct()
+    P = C.POINTER
+    rc = lib().tba_debug_pack(C.byref(st), cap, sizes.ctypes.data_as(P(C.c_int64)), out["slot_cam"].ctypes.data_as(P(C.c_int32)),
+                              out["slot_pt"].ctypes.data_as(P(C.c_int32)), out["slot_run"].ctypes.data_as(P(C.c_int16)),
+                              out["slot_flags"].ctypes.data_as(P(C.c_uint8)), _dp(out["xy"]), out["slot_orig"].ctypes.data_as(P(C.c_int64)),
+                              out["pk2caller"].ctypes.data_as(P(C.c_int32)), out["tile_pt_begin"].ctypes.data_as(P(C.c_int32)),
+                              out["tile_nruns"].ctypes.data_as(P(C.c_int32)), out["tile_flags"].ctypes.data_as(P(C.c_uint8)), _dp(out["mask"]))
+    n_tiles, n_slots, npk, n_long, ni, imask = (int(v) for v in sizes)
+    out.update(rc=rc, n_tiles=n_tiles, n_slots=n_slots, n_packed_points=npk, n_long_points=n_long, NI=ni, imask=imask)
+    if rc == 0:
+        for k in ("slot_cam", "slot_pt", "slot_run", "slot_flags", "slot_orig"):
+            out[k] = out[k][:n_slots]
+        out["xy"] = out["xy"][:n_slots * 2]
+        out["pk2caller"] = out["pk2caller"][:npk]
+        out["tile_pt_begin"] = out["tile_pt_begin"][:n_tiles + 1]
+        out["tile_nruns"] = out["tile_nruns"][:n_tiles]
+        out["tile_flags"] = out["tile_flags"][:n_tiles]
+    return out
 
 
 def solve_multi(problem, options=None, n_devices=0, max_iterations_logged=2048):
