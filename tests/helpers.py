@@ -48,3 +48,33 @@ def dense_jacobian(p, J_obs):
         J[2 * k:2 * k + 2, 6 * nc + 10 * g:6 * nc + 10 * g + 10] = J_obs[k][:, 6:16] * fi[g]
         J[2 * k:2 * k + 2, 6 * nc + 10 * ng + 4 * q:6 * nc + 10 * ng + 4 * q + 4] = J_obs[k][:, 16:20] * fp[q]
     return J
+
+
+FOUNTAIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fountain11_ir.npz")
+
+
+def fountain_problem(intrinsics_to_optimize=_abi.INTR_NONE):
+    """The reference's fountain-11 reconstruction as a Problem (shared PINHOLE intrinsics; constant by default, as in
+    the run that produced it: the stored intrinsics equal the ground-truth calibration exactly)."""
+    g = np.load(FOUNTAIN)
+    n = len(g["names"])
+    mask = _abi.constant_intrinsics_mask(_abi.MODEL_PINHOLE, intrinsics_to_optimize)
+    p = _abi.Problem(g["ext"], np.zeros(n, np.uint8), np.zeros(n, np.int32), [_abi.MODEL_PINHOLE], g["intr"], [mask], g["pt"],
+                     np.zeros(len(g["pt"]), np.uint8), g["obs_cam"], g["obs_pt"], g["obs_xy"])
+    return p, g
+
+
+def umeyama_align(src, dst):
+    """Similarity transform (scale, rotation, translation) minimising |s R src + t - dst| (Umeyama 1991); what
+    AlignReconstructions (transformation/align_reconstructions.cc:97-130) applies to camera positions."""
+    src = np.asarray(src, float); dst = np.asarray(dst, float)
+    mu_s, mu_d = src.mean(0), dst.mean(0)
+    xs, xd = src - mu_s, dst - mu_d
+    U, S, Vt = np.linalg.svd(xd.T @ xs / len(src))
+    D = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        D[2, 2] = -1
+    R = U @ D @ Vt
+    scale = np.trace(np.diag(S) @ D) / (xs ** 2).sum() * len(src)
+    t = mu_d - scale * R @ mu_s
+    return (scale * (R @ src.T)).T + t, scale
