@@ -165,6 +165,9 @@ typedef struct tba_summary {
   char message[256];
 } tba_summary;
 
+/* A context is NOT re-entrant: one solve at a time per context (Theia's estimators call full BA from a single
+ * thread; bundle_adjuster.h's BundleAdjuster is not thread-safe either).  Different contexts may be used from
+ * different threads concurrently. */
 typedef struct tba_context tba_context;
 
 /* Fill *o with theia::BundleAdjustmentOptions' defaults + Ceres' defaults. */

@@ -152,10 +152,17 @@ void set_err(tba_context* c, const char* fmt, ...) {
     }                                                                                           \
   } while (0)
 
-#define LAUNCH(c, kern, grid, block, smem, ...)                      \
-  do {                                                               \
-    kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);     \
-    (c)->launches++;                                                 \
+// Every launch is checked: a rejected launch (bad configuration, missing shared-memory opt-in) must not turn into a
+// silently skipped kernel.
+#define LAUNCH(c, kern, grid, block, smem, ...)                                                              \
+  do {                                                                                                       \
+    kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);                                             \
+    const cudaError_t le__ = cudaPeekAtLastError();                                                          \
+    if (le__ != cudaSuccess) {                                                                               \
+      set_err(c, "kernel launch failed: %s at %s:%d (%s)", cudaGetErrorString(le__), __FILE__, __LINE__, #kern); \
+      return TBA_ERR_CUDA;                                                                                   \
+    }                                                                                                        \
+    (c)->launches++;                                                                                         \
   } while (0)
 
 int prof_begin(tba_context* c) {
