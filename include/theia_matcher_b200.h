@@ -1,0 +1,56 @@
+/*
+ * theia_matcher_b200.h -- C-ABI of the secondary path: batched brute-force descriptor
+ * matching behind theia::BruteForceFeatureMatcher (src/theia/matching/brute_force_feature_matcher.cc:49-117).
+ * The per-pair hook MatchImagePair (feature_matcher.h:110-113) is too fine for a GPU; a maintainer overrides the
+ * virtual FeatureMatcher::MatchImages (feature_matcher.h:97) to hand ALL image pairs to tbm_match_all and stores the
+ * returned matches with FeaturesAndMatchesDatabase::PutImagePairMatch.
+ * Semantics are MatchImagePair's, per pair: squared float L2 (distance.h:52-56), best of image 2 for every descriptor of
+ * image 1 (ties: lower index), kept if !use_lowes_ratio || best < ratio^2 * second (:78-81, double arithmetic on
+ * float distances), early "not enough matches" exits (:84-86, :116), symmetric filtering through IntersectMatches
+ * (feature_matcher_utils.cc:48-71).  Round 1: correctness-first CUDA-core kernel (bit-exact float summation order);
+ * the tcgen05 distance GEMM is round-2 work.
+ */
+#ifndef THEIA_MATCHER_B200_H_
+#define THEIA_MATCHER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* IndexedFeatureMatch, indexed_feature_match.h:40-52 */
+typedef struct tbm_match { int32_t feature1_ind, feature2_ind; float distance; } tbm_match;
+
+/* the FeatureMatcherOptions fields MatchImagePair reads (feature_matcher_options.h:45-71), same defaults */
+typedef struct tbm_options {
+  int32_t keep_only_symmetric_matches; /* 1 */
+  int32_t use_lowes_ratio;             /* 1 */
+  float lowes_ratio;                   /* 0.8f */
+  int32_t min_num_feature_matches;     /* 30 */
+} tbm_options;
+
+void tbm_options_init(tbm_options* o);
+
+/*
+ * descriptors: [img_off[n_img]][dim] float (host), image i owns rows [img_off[i], img_off[i+1]).
+ * pairs: [n_pairs][2] image indices.  For pair p the matches are written to matches[match_off[p] .. match_off[p+1])
+ * (ascending feature1_ind); pair_ok[p] = MatchImagePair's return value (0 => the pair is dropped, its matches are the
+ * ones found before the early exit, as in the reference).  Returns 0, or a negative code (-3 CUDA, -5 no device,
+ * -1 bad argument / capacity too small: then match_off[n_pairs] holds the required capacity).
+ */
+int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, int32_t n_img, int32_t dim,
+                  const int32_t* pairs, int64_t n_pairs, const tbm_options* options, tbm_match* matches,
+                  int64_t matches_capacity, int64_t* match_off /*[n_pairs+1]*/, uint8_t* pair_ok /*[n_pairs]*/);
+
+/* Host-only post-processing of the nearest-neighbour results of one pair (ratio test, early exits, intersection):
+ * exposed so that the CPU test suite can check it without a GPU.  best_j / best_d / second_d: forward [n1] and
+ * reverse [n2] results; second_valid = 0 when the other image has a single descriptor.  Returns MatchImagePair's bool. */
+int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const float* f_second_d, int32_t n1, int f_second_valid,
+                          const int32_t* r_best_j, const float* r_best_d, const float* r_second_d, int32_t n2, int r_second_valid,
+                          const tbm_options* options, tbm_match* matches /* capacity n1 */, int32_t* n_matches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,51 @@
+"""Secondary path on the GPU: tbm_match_all (CUDA-core round-1 kernel, bit-exact float summation order) against the CPU
+oracle -- identical match lists including distances -- on the reference's three matcher cases and on random unit
+descriptors (SIFT-like 128-D, ragged image sizes).  First executed by the round-end driver (GPU budget)."""
+import numpy as np
+import pytest
+
+from test_matcher_host import _oracle_match
+from theiasfm_b200 import matcher
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(v):
+    v = np.asarray(v, np.float32)
+    return v / np.linalg.norm(v)
+
+
+def test_reference_cases_on_gpu():
+    ones = np.stack([_unit(np.ones(10))] * 10)
+    a = np.ones(10, np.float32); a[0] = 0.9
+    b = np.ones(10, np.float32); b[0] = 0.89
+    c = np.ones(10, np.float32); c[0] = 0
+    d = np.ones(10, np.float32); d[1] = 0; d[2] = 0
+    sets = [ones, ones.copy(), _unit(np.ones(10))[None], np.stack([_unit(a), _unit(b)]),
+            np.stack([_unit(np.ones(10)), np.eye(10, dtype=np.float32)[0]]), np.stack([_unit(c), _unit(d)])]
+    for pair, kw in (((0, 1), dict(min_num_feature_matches=0, keep_only_symmetric_matches=0, use_lowes_ratio=0)),
+                     ((2, 3), dict(min_num_feature_matches=0, keep_only_symmetric_matches=0, use_lowes_ratio=1)),
+                     ((4, 5), dict(min_num_feature_matches=0, keep_only_symmetric_matches=1, use_lowes_ratio=0))):
+        rc, res, ok = matcher.match_all(sets, [pair], matcher.default_options(**kw))
+        ok_o, exp = _oracle_match(np.ascontiguousarray(sets[pair[0]]), np.ascontiguousarray(sets[pair[1]]), **kw)
+        assert rc == 0 and ok[0] == ok_o and res[0] == exp
+    assert len(res[0]) == 1  # the reference's SymmetricMatches expectation
+
+
+def test_random_descriptors_match_oracle_exactly():
+    rng = np.random.default_rng(77)
+    base = rng.normal(size=(700, 128)).astype(np.float32)
+    sets = []
+    for n in (700, 513, 31, 1000, 2):
+        take = base[rng.permutation(700)[:min(n, 700)]] + 0.05 * rng.normal(size=(min(n, 700), 128)).astype(np.float32)
+        extra = rng.normal(size=(max(0, n - 700), 128)).astype(np.float32)
+        s = np.concatenate([take, extra]).astype(np.float32)
+        sets.append(np.ascontiguousarray(s / np.linalg.norm(s, axis=1, keepdims=True)))
+    pairs = [(0, 1), (1, 0), (0, 3), (2, 3), (3, 4), (4, 2), (1, 1)]
+    for kw in (dict(), dict(keep_only_symmetric_matches=0), dict(use_lowes_ratio=0, min_num_feature_matches=0)):
+        rc, res, ok = matcher.match_all(sets, pairs, matcher.default_options(**kw))
+        assert rc == 0
+        for p, (i, j) in enumerate(pairs):
+            ok_o, exp = _oracle_match(sets[i], sets[j], **kw)
+            assert ok[p] == ok_o and res[p] == exp, (kw, i, j)
+    assert sum(len(r) for r in res) > 1000

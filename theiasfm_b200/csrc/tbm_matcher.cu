@@ -1,0 +1,178 @@
+// tbm_matcher.cu -- secondary path: brute-force descriptor matching on the GPU, C-ABI of
+// include/theia_matcher_b200.h.  Round-1 kernel: CUDA cores, exact float arithmetic in the reference's order (so the
+// match sets are bit-identical to the CPU restatement); NOT yet the tcgen05 distance GEMM.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/theia_matcher_b200.h"
+
+namespace {
+
+constexpr int ROWS = 32;    // query descriptors per CTA (= lanes of a warp)
+constexpr int SLICES = 8;   // warps per CTA; warp w scans candidate rows w, w+8, ... of every tile
+constexpr int TJ = 32;      // candidate descriptors per shared-memory tile
+
+struct Top2 { float bd; int bj; float sd; int has2; };
+
+// insert candidate (d, j), candidates arrive in ascending j within one scanner: strict "<" keeps the lower index
+__device__ __forceinline__ void top2_push(Top2& t, float d, int j) {
+  if (t.bj < 0 || d < t.bd) { t.sd = t.bd; t.has2 = t.bj >= 0; t.bd = d; t.bj = j; }
+  else if (!t.has2 || d < t.sd) { t.sd = d; t.has2 = 1; }
+}
+
+// For every row i of A: the nearest (squared L2, ties -> lower index) and second-nearest distance among the rows of B.
+// Distances are accumulated left to right in float WITHOUT fused multiply-add: s = s + (a-b)*(a-b), exactly
+// L2::operator() evaluated term by term (distance.h:52-56).
+__global__ void __launch_bounds__(ROWS* SLICES) k_nn2(const float* __restrict__ A, int nA, const float* __restrict__ B, int nB, int dim,
+                                                      int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d) {
+  extern __shared__ float smem[];
+  const int dimp = dim + 1;                 // padded row stride of the query tile: conflict-free column access
+  float* sA = smem;                         // [ROWS][dimp]
+  float* sB = smem + ROWS * dimp;           // [TJ][dim]
+  __shared__ Top2 s_merge[SLICES][ROWS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * ROWS;
+  for (int idx = threadIdx.x; idx < ROWS * dim; idx += ROWS * SLICES) {
+    const int r = idx / dim, k = idx - r * dim;
+    sA[r * dimp + k] = (i0 + r < nA) ? A[(size_t)(i0 + r) * dim + k] : 0.0f;
+  }
+  Top2 t;
+  t.bd = 0.0f; t.bj = -1; t.sd = 0.0f; t.has2 = 0;
+  for (int j0 = 0; j0 < nB; j0 += TJ) {
+    __syncthreads();  // previous tile consumed (and sA written, first time)
+    for (int idx = threadIdx.x; idx < TJ * dim; idx += ROWS * SLICES) {
+      const int r = idx / dim, k = idx - r * dim;
+      sB[idx] = (j0 + r < nB) ? B[(size_t)(j0 + r) * dim + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int jj = warp; jj < TJ; jj += SLICES) {
+      const int j = j0 + jj;
+      if (j >= nB) break;
+      const float* a = sA + lane * dimp;
+      const float* b = sB + jj * dim;
+      float s = 0.0f;
+      for (int k = 0; k < dim; ++k) {
+        const float d = __fsub_rn(a[k], b[k]);
+        s = __fadd_rn(s, __fmul_rn(d, d));
+      }
+      top2_push(t, s, j);
+    }
+  }
+  s_merge[warp][lane] = t;
+  __syncthreads();
+  if (warp == 0 && i0 + lane < nA) {
+    // merge the 8 scanners: best = lexicographic minimum of (distance, index); second = smallest remaining value
+    Top2 m = s_merge[0][lane];
+    for (int w = 1; w < SLICES; ++w) {
+      const Top2 o = s_merge[w][lane];
+      if (o.bj < 0) continue;
+      if (m.bj < 0) { m = o; continue; }
+      const bool o_wins = o.bd < m.bd || (o.bd == m.bd && o.bj < m.bj);
+      // candidates for the second place: the loser's best, and both seconds
+      float lose_d = o_wins ? m.bd : o.bd;
+      float sd = lose_d;
+      if (m.has2 && m.sd < sd) sd = m.sd;
+      if (o.has2 && o.sd < sd) sd = o.sd;
+      if (o_wins) { m.bd = o.bd; m.bj = o.bj; }
+      m.sd = sd; m.has2 = 1;
+    }
+    best_j[i0 + lane] = m.bj;
+    best_d[i0 + lane] = m.bd;
+    second_d[i0 + lane] = m.has2 ? m.sd : 0.0f;
+  }
+}
+
+struct DevF { float* p = nullptr; size_t n = 0; ~DevF() { if (p) cudaFree(p); } bool alloc(size_t c) { if (c <= n && p) return true; if (p) cudaFree(p); p = nullptr; n = 0; if (cudaMalloc(&p, (c ? c : 1) * sizeof(float)) != cudaSuccess) return false; n = c; return true; } };
+struct DevI { int* p = nullptr; size_t n = 0; ~DevI() { if (p) cudaFree(p); } bool alloc(size_t c) { if (c <= n && p) return true; if (p) cudaFree(p); p = nullptr; n = 0; if (cudaMalloc(&p, (c ? c : 1) * sizeof(int)) != cudaSuccess) return false; n = c; return true; } };
+
+// :58-59, :78-81: keep the best match when the ratio test is off, there is no second candidate, or it passes
+inline bool passes(const tbm_options* o, float best, float second, int second_valid) {
+  if (!o->use_lowes_ratio || !second_valid) return true;
+  const double sq = (double)o->lowes_ratio * (double)o->lowes_ratio;
+  return (double)best < sq * (double)second;
+}
+
+}  // namespace
+
+extern "C" {
+
+void tbm_options_init(tbm_options* o) { o->keep_only_symmetric_matches = 1; o->use_lowes_ratio = 1; o->lowes_ratio = 0.8f; o->min_num_feature_matches = 30; }
+
+int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const float* f_second_d, int32_t n1, int f_second_valid,
+                          const int32_t* r_best_j, const float* r_best_d, const float* r_second_d, int32_t n2, int r_second_valid,
+                          const tbm_options* o, tbm_match* matches, int32_t* n_matches) {
+  int n = 0;
+  for (int i = 0; i < n1; ++i) {  // forward matches (:63-82)
+    if (f_best_j[i] < 0) continue;
+    if (passes(o, f_best_d[i], f_second_d[i], f_second_valid)) { matches[n].feature1_ind = i; matches[n].feature2_ind = f_best_j[i]; matches[n].distance = f_best_d[i]; ++n; }
+  }
+  *n_matches = n;
+  if (n < o->min_num_feature_matches) return 0;  // :84-86
+  if (o->keep_only_symmetric_matches) {          // :89-113 + IntersectMatches
+    int kept = 0;
+    for (int k = 0; k < n; ++k) {
+      const int i = matches[k].feature1_ind, j = matches[k].feature2_ind;
+      const bool rev = j >= 0 && j < n2 && r_best_j[j] == i && passes(o, r_best_d[j], r_second_d[j], r_second_valid);
+      if (rev) matches[kept++] = matches[k];
+    }
+    n = kept;
+    *n_matches = n;
+  }
+  return n >= o->min_num_feature_matches;  // :116
+}
+
+int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, int32_t n_img, int32_t dim, const int32_t* pairs,
+                  int64_t n_pairs, const tbm_options* options, tbm_match* matches, int64_t cap, int64_t* match_off, uint8_t* pair_ok) {
+  if (!descriptors || !img_off || !pairs || !options || !match_off || !pair_ok || n_img < 0 || dim <= 0 || dim > 512 || n_pairs < 0) return -1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return -5; }
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  const int64_t total = img_off[n_img];
+  int64_t max_n = 0;
+  for (int i = 0; i < n_img; ++i) { if (img_off[i + 1] < img_off[i]) return -1; max_n = img_off[i + 1] - img_off[i] > max_n ? img_off[i + 1] - img_off[i] : max_n; }
+  DevF d_desc, d_bd[2], d_sd[2];
+  DevI d_bj[2];
+  if (!d_desc.alloc((size_t)total * dim)) return -3;
+  for (int s = 0; s < 2; ++s) if (!d_bd[s].alloc((size_t)max_n) || !d_sd[s].alloc((size_t)max_n) || !d_bj[s].alloc((size_t)max_n)) return -3;
+  if (cudaMemcpy(d_desc.p, descriptors, (size_t)total * dim * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+  const size_t smem = ((size_t)ROWS * (dim + 1) + (size_t)TJ * dim) * sizeof(float);
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(k_nn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+  std::vector<int32_t> bj[2];
+  std::vector<float> bd[2], sd[2];
+  std::vector<tbm_match> tmp;
+  int64_t written = 0;
+  bool overflow = false;
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    const int a = pairs[2 * p], b = pairs[2 * p + 1];
+    if (a < 0 || a >= n_img || b < 0 || b >= n_img) return -1;
+    const int n1 = (int)(img_off[a + 1] - img_off[a]), n2 = (int)(img_off[b + 1] - img_off[b]);
+    const float* A = d_desc.p + (size_t)img_off[a] * dim;
+    const float* B = d_desc.p + (size_t)img_off[b] * dim;
+    for (int dir = 0; dir < 2; ++dir) {
+      const int nq = dir == 0 ? n1 : n2, nc = dir == 0 ? n2 : n1;
+      bj[dir].assign((size_t)nq, -1); bd[dir].assign((size_t)nq, 0.0f); sd[dir].assign((size_t)nq, 0.0f);
+      if (nq == 0 || nc == 0) continue;
+      if (dir == 1 && !options->keep_only_symmetric_matches) continue;
+      k_nn2<<<(nq + ROWS - 1) / ROWS, ROWS * SLICES, smem>>>(dir == 0 ? A : B, nq, dir == 0 ? B : A, nc, dim, d_bj[dir].p, d_bd[dir].p, d_sd[dir].p);
+      if (cudaPeekAtLastError() != cudaSuccess) return -3;
+      if (cudaMemcpy(bj[dir].data(), d_bj[dir].p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(bd[dir].data(), d_bd[dir].p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(sd[dir].data(), d_sd[dir].p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    }
+    tmp.resize((size_t)(n1 > 0 ? n1 : 1));
+    int32_t nm = 0;
+    pair_ok[p] = (uint8_t)tbm_debug_postprocess(bj[0].data(), bd[0].data(), sd[0].data(), n1, n2 >= 2, bj[1].data(), bd[1].data(), sd[1].data(), n2,
+                                                n1 >= 2, options, tmp.data(), &nm);
+    match_off[p] = written;
+    if (written + nm > cap || !matches) overflow = true;
+    else memcpy(matches + written, tmp.data(), (size_t)nm * sizeof(tbm_match));
+    written += nm;
+  }
+  match_off[n_pairs] = written;
+  return overflow ? -1 : 0;
+}
+
+}  // extern "C"
