@@ -76,3 +76,29 @@ def test_postprocess_matches_oracle(kw):
     assert bool(ok) == ok_o and got == exp
     if not kw:
         assert len(got) > 80
+
+
+def test_top2_scan_and_merge_equal_sequential_scan_with_ties():
+    """theiasfm_b200/csrc/tbm_top2.h (used by the CUDA kernel) compiled for the host: the kernel's 8-scanner order +
+    merge gives exactly the sequential-scan answer, including heavy ties and tiny candidate counts."""
+    so = os.path.join(ROOT, "tests", "_host_top2.so")
+    src = os.path.join(ROOT, "tests", "host_top2.cc")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-O2", "-std=c++14", "-fPIC", "-shared", src, "-o", so])
+    L = C.CDLL(so)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    rng = np.random.default_rng(0)
+    for trial in range(3000):
+        n = int(rng.integers(0, 140))
+        levels = int(rng.choice([1, 2, 3, 5, 1000]))
+        d = rng.integers(0, levels, n).astype(np.float32) * np.float32(0.25) if levels < 1000 else rng.random(n).astype(np.float32)
+        d = np.ascontiguousarray(d if n else np.zeros(1, np.float32))
+        outs = []
+        for fn in (L.emulate_kernel, L.sequential):
+            bj, h2 = C.c_int(), C.c_int(); bd, sd = C.c_float(), C.c_float()
+            fn(d.ctypes.data_as(fp), n, C.byref(bj), C.byref(bd), C.byref(sd), C.byref(h2))
+            outs.append((bj.value, bd.value, sd.value, h2.value))
+        assert outs[0] == outs[1], (trial, n, d[:n].tolist(), outs)
+        if n >= 2:  # and the sequential scan is the plain definition
+            order = np.argsort(d[:n], kind="stable")
+            assert outs[1] == (int(order[0]), float(d[order[0]]), float(d[order[1]]), 1)

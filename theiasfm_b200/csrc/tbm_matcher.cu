@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/theia_matcher_b200.h"
+#include "tbm_top2.h"
 
 namespace {
 
@@ -15,13 +16,8 @@ constexpr int ROWS = 32;    // query descriptors per CTA (= lanes of a warp)
 constexpr int SLICES = 8;   // warps per CTA; warp w scans candidate rows w, w+8, ... of every tile
 constexpr int TJ = 32;      // candidate descriptors per shared-memory tile
 
-struct Top2 { float bd; int bj; float sd; int has2; };
-
-// insert candidate (d, j), candidates arrive in ascending j within one scanner: strict "<" keeps the lower index
-__device__ __forceinline__ void top2_push(Top2& t, float d, int j) {
-  if (t.bj < 0 || d < t.bd) { t.sd = t.bd; t.has2 = t.bj >= 0; t.bd = d; t.bj = j; }
-  else if (!t.has2 || d < t.sd) { t.sd = d; t.has2 = 1; }
-}
+using tbm::Top2;
+using tbm::top2_push;
 
 // For every row i of A: the nearest (squared L2, ties -> lower index) and second-nearest distance among the rows of B.
 // Distances are accumulated left to right in float WITHOUT fused multiply-add: s = s + (a-b)*(a-b), exactly
@@ -40,7 +36,7 @@ __global__ void __launch_bounds__(ROWS* SLICES) k_nn2(const float* __restrict__ 
     sA[r * dimp + k] = (i0 + r < nA) ? A[(size_t)(i0 + r) * dim + k] : 0.0f;
   }
   Top2 t;
-  t.bd = 0.0f; t.bj = -1; t.sd = 0.0f; t.has2 = 0;
+  tbm::top2_init(t);
   for (int j0 = 0; j0 < nB; j0 += TJ) {
     __syncthreads();  // previous tile consumed (and sA written, first time)
     for (int idx = threadIdx.x; idx < TJ * dim; idx += ROWS * SLICES) {
@@ -64,21 +60,9 @@ __global__ void __launch_bounds__(ROWS* SLICES) k_nn2(const float* __restrict__ 
   s_merge[warp][lane] = t;
   __syncthreads();
   if (warp == 0 && i0 + lane < nA) {
-    // merge the 8 scanners: best = lexicographic minimum of (distance, index); second = smallest remaining value
+    // merge the 8 scanners (tbm_top2.h)
     Top2 m = s_merge[0][lane];
-    for (int w = 1; w < SLICES; ++w) {
-      const Top2 o = s_merge[w][lane];
-      if (o.bj < 0) continue;
-      if (m.bj < 0) { m = o; continue; }
-      const bool o_wins = o.bd < m.bd || (o.bd == m.bd && o.bj < m.bj);
-      // candidates for the second place: the loser's best, and both seconds
-      float lose_d = o_wins ? m.bd : o.bd;
-      float sd = lose_d;
-      if (m.has2 && m.sd < sd) sd = m.sd;
-      if (o.has2 && o.sd < sd) sd = o.sd;
-      if (o_wins) { m.bd = o.bd; m.bj = o.bj; }
-      m.sd = sd; m.has2 = 1;
-    }
+    for (int w = 1; w < SLICES; ++w) tbm::top2_merge(m, s_merge[w][lane]);
     best_j[i0 + lane] = m.bj;
     best_d[i0 + lane] = m.bd;
     second_d[i0 + lane] = m.has2 ? m.sd : 0.0f;
