@@ -210,8 +210,11 @@ def main():
     dev_s = sum(it["iteration_time_in_seconds"] for it in s.iterations)
     t_max = max_over_ranks(dev_s)
     launches = sum_over_ranks(float(s.num_kernel_launches))
-    assert iters == K, "timed region ran %d LM iterations, expected %d (%s)" % (iters, K, s.message)
-    value = n_obs_total * K / t_max
+    # exactly K iterations run unless the solver hits the fp64 floor first (tolerances are zero); the metric always uses
+    # the number of iterations that actually ran and says so
+    note = None if iters == K else "solver stopped after %d of %d LM iterations: %s" % (iters, K, s.message)
+    iters = max(iters, 1)
+    value = n_obs_total * iters / t_max
     # ---- roofline of the dominant kernel (implicit-Schur matvec)
     peak, peak_src = load_peaks()
     nj = prof["doubles_per_obs"]
@@ -242,18 +245,19 @@ def main():
         se = eng.solve(host, engine.default_options(**solver_kwargs(K)))
         barrier()
         t_e2e = max_over_ranks(time.perf_counter() - t0)
-        assert se.rc == 0 and se.num_iterations - 1 == K, se.message
-        e2e = {"value": n_obs_total * K / t_e2e, "unit": "obs/s", "h2d_bytes_per_step": sum_over_ranks(se.h2d_bytes) / K,
-               "d2h_bytes_per_step": sum_over_ranks(se.d2h_bytes) / K, "seconds": t_e2e,
+        assert se.rc == 0, se.message
+        e_iters = max(se.num_iterations - 1, 1)
+        e2e = {"value": n_obs_total * e_iters / t_e2e, "unit": "obs/s", "h2d_bytes_per_step": sum_over_ranks(se.h2d_bytes) / e_iters,
+               "d2h_bytes_per_step": sum_over_ranks(se.d2h_bytes) / e_iters, "seconds": t_e2e, "steps_run": e_iters,
                "host_pack_and_upload_seconds": max_over_ranks(se.setup_time_in_seconds), "final_cost": se.final_cost}
     cb = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         cb = cpu_baseline(3)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "obs/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": 1e3 * t_max / iters, "steps_run": iters, "note": note, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cb, "lm_iters_per_s": K / t_max,
+                "roofline": roofline, "cpu_baseline": cb, "lm_iters_per_s": iters / t_max,
                 "pcg_iterations": s.num_linear_solver_iterations, "initial_cost": s.initial_cost, "final_cost": s.final_cost,
                 "wall_seconds_timed_region": wall, "n_obs": n_obs_total}
         print(json.dumps(line))
