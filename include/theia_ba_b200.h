@@ -213,6 +213,17 @@ int tba_upload(tba_context* ctx, const tba_options* options, const tba_problem* 
 int tba_minimize(tba_context* ctx, tba_summary* summary);
 int tba_download(tba_context* ctx, tba_problem* problem);
 
+/*
+ * N1: SetOutlierTracksToUnestimated (src/theia/sfm/set_outlier_tracks_to_unestimated.cc:62-136) evaluated on
+ * the device-resident problem of this context (after tba_solve / tba_minimize), without a D2H -> hash-map -> reproject
+ * round trip.  status[q] (q = caller point index): 0 keep, 1 bad reprojection (negative depth in a view, or mean squared
+ * reprojection error > max_inlier_reprojection_error^2), 2 insufficient triangulation angle.  mean_sq_error (optional):
+ * the per-track mean squared reprojection error of ComputeStatisticsForTrack
+ * (select_good_tracks_for_bundle_adjustment.cc:79-108).  The return value of the reference = *bad + *insufficient.
+ */
+int tba_filter_tracks(tba_context* ctx, double max_inlier_reprojection_error, double min_triangulation_angle_degrees,
+                      uint8_t* status, double* mean_sq_error, int32_t* num_bad_reprojections, int32_t* num_insufficient_angles);
+
 /* Re-load ext / intr / pt of an uploaded problem (same shape) without re-packing. */
 int tba_reset_parameters(tba_context* ctx, const tba_problem* problem);
 

@@ -58,6 +58,7 @@ def lib():
         L.oracle_constant_intrinsics_mask.argtypes = [C.c_int, C.c_int]
         L.oracle_loss.argtypes = [C.c_int, C.c_double, C.c_double, dp]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_filter_tracks.argtypes = [C.POINTER(_abi.tba_problem), C.c_double, C.c_double, C.POINTER(C.c_uint8), dp]
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
@@ -111,6 +112,15 @@ def project_point(model, ext, intr, pt):
     out = np.zeros(2)
     depth = lib().oracle_project_point(model, _dp(ext), _dp(intr), _dp(pt), _dp(out))
     return out, depth
+
+
+def filter_tracks(problem, max_inlier_reprojection_error, min_triangulation_angle_degrees):
+    """oracle_filter_tracks: (status [n_pt] uint8, mean squared reprojection error [n_pt], number removed)."""
+    status = np.zeros(max(problem.n_pt, 1), np.uint8); mean = np.zeros(max(problem.n_pt, 1))
+    st = problem.as_struct()
+    removed = lib().oracle_filter_tracks(C.byref(st), max_inlier_reprojection_error, min_triangulation_angle_degrees,
+                                         status.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(mean))
+    return status[:problem.n_pt], mean[:problem.n_pt], removed
 
 
 def loss(kind, width, s):

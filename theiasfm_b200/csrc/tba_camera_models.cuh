@@ -117,15 +117,17 @@ __device__ inline void loss_evaluate(int type, double a, double s, double rho[3]
   }
 }
 
-// Projection only (the double instantiation of the functor). Returns false if ||a||^2 < 1e-8.
-__device__ inline bool reproject(int model, const double* __restrict__ C, const double* __restrict__ R,
-                                 const double* __restrict__ k, const double X0, const double X1, const double X2,
-                                 const double h, const double x, const double y, double& r0, double& r1) {
+// Camera::ProjectPoint (camera.cc:204-213) without any guard: pixel and camera-frame depth coordinate q_z
+// (the caller divides by h for the depth ProjectPoint returns).  a = X - h C is also returned for the callers' guards.
+__device__ inline void project_pixel(int model, const double* __restrict__ C, const double* __restrict__ R,
+                                     const double* __restrict__ k, const double X0, const double X1, const double X2, const double h,
+                                     double& px, double& py, double& qz, double& a_sq) {
   const double a0 = X0 - h * C[0], a1 = X1 - h * C[1], a2 = X2 - h * C[2];
-  if (a0 * a0 + a1 * a1 + a2 * a2 < 1e-8) return false;
+  a_sq = a0 * a0 + a1 * a1 + a2 * a2;
   const double q0 = R[0] * a0 + R[1] * a1 + R[2] * a2;
   const double q1 = R[3] * a0 + R[4] * a1 + R[5] * a2;
   const double q2 = R[6] * a0 + R[7] * a1 + R[8] * a2;
+  qz = q2;
   const double u = q0 / q2, v = q1 / q2;
   const double r2 = u * u + v * v;
   double ud, vd;
@@ -138,8 +140,19 @@ __device__ inline bool reproject(int model, const double* __restrict__ C, const 
     const double ty = k[8] * (r2 + 2.0 * v * v) + 2.0 * k[9] * u * v;
     ud = u * rd + tx; vd = v * rd + ty;
   }
-  r0 = k[0] * ud + k[2] * vd + k[3] - x;
-  r1 = k[0] * k[1] * vd + k[4] - y;
+  px = k[0] * ud + k[2] * vd + k[3];
+  py = k[0] * k[1] * vd + k[4];
+}
+
+// Projection only (the double instantiation of the functor). Returns false if ||a||^2 < 1e-8.
+__device__ inline bool reproject(int model, const double* __restrict__ C, const double* __restrict__ R,
+                                 const double* __restrict__ k, const double X0, const double X1, const double X2,
+                                 const double h, const double x, const double y, double& r0, double& r1) {
+  double px, py, qz, a_sq;
+  project_pixel(model, C, R, k, X0, X1, X2, h, px, py, qz, a_sq);
+  if (a_sq < 1e-8) return false;
+  r0 = px - x;
+  r1 = py - y;
   return true;
 }
 

@@ -105,6 +105,9 @@ struct tba_context {
   size_t stage_cap = 0;
   int n_long_points = 0;
   DevBuf<int16_t> slot_run;
+  DevBuf<long long> pt_slot;   // first slot of each packed point (track filter)
+  DevBuf<int> pt_len;          // observations of each packed point
+  DevBuf<double> pt_stat;      // per-point mean squared reprojection error (track filter output)
   // camera space: [g | cn | scal(16)] is one allreduce buffer
   DevBuf<double> lin;       // g_cs[ncs] | cn_cs[ncs] | scal[16]
   DevBuf<double> mask, blk_free, sm, D2, Sblk /*[n_cam*21 | n_group*55]*/, Minv_c, Minv_i;
@@ -649,6 +652,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(cam_group, (size_t)nc); ALLOC(group_model, (size_t)ng); ALLOC(slot_cam, (size_t)n_slots); ALLOC(slot_pt, (size_t)n_slots);
   ALLOC(tile_pt_begin, (size_t)n_tiles + 1); ALLOC(tile_nruns, (size_t)n_tiles); ALLOC(slot_flags, (size_t)n_slots);
   ALLOC(slot_run, (size_t)n_slots); ALLOC(pt_const, (size_t)npd); ALLOC(tile_flags, (size_t)n_tiles);
+  ALLOC(pt_slot, (size_t)npd); ALLOC(pt_len, (size_t)npd); ALLOC(pt_stat, (size_t)npd);
   ALLOC(lin, 2 * (size_t)ncs + 16); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
   ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
   ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
@@ -667,6 +671,12 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   H2D(tile_pt_begin, tile_pt_begin.data(), (size_t)n_tiles + 1); H2D(tile_nruns, tile_nruns.data(), (size_t)n_tiles);
   H2D(xy, h_xy, (size_t)n_slots * 2); H2D(pt_const, h_pt_const, (size_t)npd);
   H2D(tile_flags, tile_flags.data(), (size_t)n_tiles);
+  {
+    std::vector<long long> h_pt_slot((size_t)npd);
+    std::vector<int> h_pt_len((size_t)npd);
+    for (int k = 0; k < npd; ++k) { h_pt_slot[k] = (long long)H.pt_slot[k]; h_pt_len[k] = H.cnt_pt[H.pk2caller[k]]; }
+    H2D(pt_slot, h_pt_slot.data(), (size_t)npd); H2D(pt_len, h_pt_len.data(), (size_t)npd);
+  }
   H2D(mask, mask.data(), (size_t)ncs); H2D(blk_free, blk_free.data(), (size_t)nc + ng);
 #undef H2D
   CUDA_OK(c, cudaMemsetAsync(c->rep.p, 0, (size_t)NREP * REPW * sizeof(double), c->stream));
@@ -904,6 +914,38 @@ int tba_get_profile(tba_context* c, double* out) {
   }
   out[1] = (double)c->real_matvecs;  // early-exited launches (after convergence inside a batch) cost ~2 us and do no work
   out[4] = (double)c->n_slots; out[5] = (double)c->n_obs; out[6] = (double)c->n_pt; out[7] = (double)c->NJ;
+  return TBA_OK;
+}
+
+// --------------------------------------------------------------------------- N1: post-BA track filter
+// SetOutlierTracksToUnestimated (set_outlier_tracks_to_unestimated.cc:62-136) on the device-resident problem (after
+// tba_minimize / tba_solve on this context): status[q] for every CALLER point q: 0 keep, 1 bad reprojection (negative
+// depth in some view, or mean squared reprojection error > max^2), 2 insufficient triangulation angle (also points
+// without observations, whose ray list is empty).  mean_sq_error (optional, [n_pt]) receives the per-track mean squared
+// reprojection error that ComputeStatisticsForTrack reports (NaN for points without observations).
+int tba_filter_tracks(tba_context* c, double max_inlier_reprojection_error, double min_triangulation_angle_degrees,
+                      uint8_t* status, double* mean_sq_error, int32_t* num_bad_reprojections, int32_t* num_insufficient_angles) {
+  if (!c || !c->uploaded || !status) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevProblem& P = c->P;
+  const double max_sq = max_inlier_reprojection_error * max_inlier_reprojection_error;
+  const double cos_min = std::cos(min_triangulation_angle_degrees * 3.14159265358979323846 / 180.0);
+  DevBuf<uint8_t> d_status;
+  CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
+  // the per-camera rotation records must describe the CURRENT extrinsics
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  if (P.n_pt > 0) LAUNCH(c, k_filter_tracks, (P.n_pt + 127) / 128, 128, 0, P, c->pt_slot.p, c->pt_len.p, max_sq, cos_min, d_status.p, c->pt_stat.p);
+  std::vector<uint8_t> hs((size_t)P.n_pt);
+  std::vector<double> hm((size_t)P.n_pt);
+  CUDA_OK(c, cudaMemcpyAsync(hs.data(), d_status.p, (size_t)P.n_pt, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(hm.data(), c->pt_stat.p, (size_t)P.n_pt * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  int nb = 0, ni = 0;
+  for (int q = 0; q < c->n_pt_caller; ++q) { status[q] = 2; if (mean_sq_error) mean_sq_error[q] = std::nan(""); }
+  for (int k = 0; k < P.n_pt; ++k) { status[c->pk2caller[k]] = hs[k]; if (mean_sq_error) mean_sq_error[c->pk2caller[k]] = hm[k]; }
+  for (int q = 0; q < c->n_pt_caller; ++q) { nb += status[q] == 1; ni += status[q] == 2; }
+  if (num_bad_reprojections) *num_bad_reprojections = nb;
+  if (num_insufficient_angles) *num_insufficient_angles = ni;
   return TBA_OK;
 }
 

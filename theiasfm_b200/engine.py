@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
         L.tba_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
         L.tba_solve_multi.argtypes = [C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.POINTER(_abi.tba_summary), C.c_int]
         L.tba_debug_pack.restype = C.c_int
+        L.tba_filter_tracks.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_uint8), dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.tba_get_profile.argtypes = [C.c_void_p, dp]
@@ -199,6 +200,7 @@ class Engine:
         options = options or default_options()
         s = self._new_summary()
         st = problem.as_struct()
+        self._problem = problem
         rc = lib().tba_solve(self._h, C.byref(options), C.byref(st), C.byref(s))
         out = Summary(s, self._iters)
         out.rc = rc
@@ -222,6 +224,15 @@ class Engine:
         problem = problem or self._problem
         st = problem.as_struct()
         self._check(lib().tba_download(self._h, C.byref(st)))
+
+    def filter_tracks(self, max_inlier_reprojection_error, min_triangulation_angle_degrees):
+        """tba_filter_tracks on the device-resident problem: (status [n_pt] uint8, mean_sq_error [n_pt], n_bad, n_insufficient)."""
+        n = self._problem.n_pt
+        status = np.zeros(max(n, 1), np.uint8); mean = np.zeros(max(n, 1))
+        nb, ni = C.c_int32(), C.c_int32()
+        self._check(lib().tba_filter_tracks(self._h, max_inlier_reprojection_error, min_triangulation_angle_degrees,
+                                            status.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(mean), C.byref(nb), C.byref(ni)))
+        return status[:n], mean[:n], nb.value, ni.value
 
     def reset_parameters(self, problem):
         st = problem.as_struct()
