@@ -194,6 +194,8 @@ BundleAdjustmentSummary BundleAdjusterB200::Optimize() {
     }
     rc = tba_solve(ctx, &opts, &problem, &s);  // replaces ceres::Solve, :205
     if (rc != TBA_OK) std::snprintf(s.message, sizeof s.message, "%s", tba_last_error(ctx));
+    resident_ = rc == TBA_OK;
+    if (resident_) resident_tracks_ = flat.track_of_pt;
   }
   last_summary_ = s;
   last_summary_.iterations = nullptr;
@@ -221,6 +223,26 @@ BundleAdjustmentSummary BundleAdjusterB200::Optimize() {
   summary.final_cost = s.final_cost;
   summary.success = s.success != 0;  // IsSolutionUsable(), :218
   return summary;
+}
+
+int BundleAdjusterB200::SetOutlierTracksToUnestimated(const double max_inlier_reprojection_error,
+                                                      const double min_triangulation_angle_degrees) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!resident_ || g_ctx == nullptr) return -1;
+  std::vector<uint8_t> status(resident_tracks_.size() + 1);
+  int32_t bad = 0, insufficient = 0;
+  if (tba_filter_tracks(g_ctx, max_inlier_reprojection_error, min_triangulation_angle_degrees, status.data(), nullptr, &bad,
+                        &insufficient) != TBA_OK) {
+    std::fprintf(stderr, "theia_ba_b200: %s\n", tba_last_error(g_ctx));
+    return -1;
+  }
+  int removed = 0;
+  for (size_t q = 0; q < resident_tracks_.size(); ++q) {
+    Track* track = reconstruction_->MutableTrack(resident_tracks_[q]);
+    if (track == nullptr || !track->IsEstimated()) continue;  // :77-79: only estimated tracks are examined
+    if (status[q] != 0) { track->SetEstimated(false); ++removed; }  // :100-101,111-112,121-122
+  }
+  return removed;  // :135
 }
 
 // bundle_adjustment.cc:47-63

@@ -79,6 +79,12 @@ class BundleAdjusterB200 {
     tba_problem AsProblem();
   };
   void Flatten(Flat* flat, tba_options* options) const;
+  // N1: SetOutlierTracksToUnestimated (set_outlier_tracks_to_unestimated.cc:62-136) for the tracks of THIS problem,
+  // evaluated on the device-resident copy the last Optimize() left on the GPU (no re-flattening, no re-upload).
+  // Marks outlier tracks un-estimated in the Reconstruction and returns how many were removed, or -1 when there is
+  // no device-resident problem (Optimize() not run, failed, or ran through the multi-GPU entry point).
+  int SetOutlierTracksToUnestimated(const double max_inlier_reprojection_error, const double min_triangulation_angle_degrees);
+
   // Detail of the last Optimize() (termination, iteration count, message).
   const tba_summary& last_summary() const { return last_summary_; }
 
@@ -94,6 +100,8 @@ class BundleAdjusterB200 {
   std::unordered_set<ViewId> constant_extrinsics_views_;  // added through AddTrack only (bundle_adjuster.cc:166-168)
   std::vector<std::pair<ViewId, TrackId>> residuals_;     // in insertion order
   tba_summary last_summary_;
+  std::vector<TrackId> resident_tracks_;  // point index -> TrackId of the problem left on the device by Optimize()
+  bool resident_ = false;
 };
 
 // Drop-ins for bundle_adjustment.h:136-143 (bundle_adjustment.cc:47-80).

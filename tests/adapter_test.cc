@@ -221,6 +221,30 @@ static int TestSolve(const char* oracle_path) {
       EXPECT(std::memcmp(copy.rec.MutableTrack(t)->Point().data(), sc.rec.MutableTrack(t)->Point().data(), 32) == 0);
     }
   }
+  // N1: post-BA outlier filter on the device-resident problem (set_outlier_tracks_to_unestimated.cc:62-136)
+  {
+    Scene copy = sc;
+    // one gross outlier track: shift all its measurements
+    const TrackId bad_track = copy.tracks[10];
+    for (ViewId v : copy.rec.MutableTrack(bad_track)->ViewIds()) {
+      const Feature* f = copy.rec.MutableView(v)->GetFeature(bad_track);
+      copy.rec.MutableView(v)->AddFeature(bad_track, Feature(f->x() + 80.0, f->y() - 60.0));
+    }
+    BundleAdjustmentOptions o = IterativeOptions();
+    o.max_num_iterations = 0;  // evaluate only: parameters stay at the refined solution
+    BundleAdjusterB200 ba(o, &copy.rec);
+    for (ViewId v : copy.rec.ViewIds()) ba.AddView(v);
+    for (TrackId t : copy.rec.TrackIds()) ba.AddTrack(t);
+    EXPECT(ba.SetOutlierTracksToUnestimated(5.0, 0.0) == -1);  // nothing resident before Optimize()
+    EXPECT(ba.Optimize().success);
+    const int removed = ba.SetOutlierTracksToUnestimated(5.0, 0.0);
+    EXPECT(removed == 1);
+    EXPECT(!copy.rec.MutableTrack(bad_track)->IsEstimated());
+    int still = 0;
+    for (TrackId t : copy.tracks) still += copy.rec.MutableTrack(t)->IsEstimated();
+    EXPECT(still == (int)copy.tracks.size() - 1);
+    EXPECT(ba.SetOutlierTracksToUnestimated(5.0, 179.0) == (int)copy.tracks.size() - 1);  // impossible angle: every estimated track goes
+  }
   std::printf("solve ok: cost %.6e -> %.6e (oracle %.6e), setup %.3f s, solve %.3f s\n", s.initial_cost, s.final_cost, oracle_final, s.setup_time_in_seconds, s.solve_time_in_seconds);
   return 0;
 }
