@@ -65,3 +65,62 @@ def test_reference_reconstruction_passes_its_own_filter(oracle):
     st_np, mean_np = _numpy_filter(p, 5.0, 3.0)
     assert np.array_equal(st, st_np) and np.allclose(mean, mean_np, rtol=1e-9)
     assert np.median(np.sqrt(mean)) < 0.5
+
+
+def test_device_filter_body_on_packed_layout_matches_oracle(oracle):
+    """theiasfm_b200/csrc/tba_filter.cuh (what k_filter_tracks runs per thread) compiled for the host and executed over the
+    packed tile layout of tba_debug_pack: statuses and statistics equal the oracle's, on ragged synthetic tracks with
+    outliers and on the reference's fountain reconstruction."""
+    import ctypes as C
+    import os
+    import subprocess
+    from theiasfm_b200 import engine
+    here = os.path.dirname(os.path.abspath(__file__))
+    so, src = os.path.join(here, "_host_filter.so"), os.path.join(here, "host_filter.cc")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", src, "-o", so])
+    L = C.CDLL(so)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+    def run(p, max_err, angle):
+        k = engine.debug_pack(p)
+        assert k["rc"] == 0
+        npk = k["n_packed_points"]
+        valid = k["slot_cam"] >= 0
+        slots = np.nonzero(valid)[0]
+        pts = k["slot_pt"][valid]
+        first = np.full(npk, -1, np.int64); cnt = np.bincount(pts, minlength=npk).astype(np.int32)
+        first[pts[::-1]] = slots[::-1]
+        pt_packed = np.ascontiguousarray(p.pt[k["pk2caller"]])
+        status = np.zeros(max(npk, 1), np.uint8); mean = np.zeros(max(npk, 1))
+        slot_cam = np.ascontiguousarray(k["slot_cam"]); xy = np.ascontiguousarray(k["xy"]); first = np.ascontiguousarray(first)
+        L.host_filter(p.n_cam, p.ext.ctypes.data_as(dp), p.intr.ctypes.data_as(dp), p.cam_group.ctypes.data_as(ip), p.group_model.ctypes.data_as(ip),
+                      npk, pt_packed.ctypes.data_as(dp), xy.ctypes.data_as(dp), slot_cam.ctypes.data_as(ip),
+                      first.ctypes.data_as(C.POINTER(C.c_longlong)), cnt.ctypes.data_as(ip), C.c_double(max_err), C.c_double(angle),
+                      status.ctypes.data_as(C.POINTER(C.c_ubyte)), mean.ctypes.data_as(dp))
+        full = np.full(p.n_pt, 2, np.uint8); full[k["pk2caller"]] = status[:npk]
+        fmean = np.full(p.n_pt, np.nan); fmean[k["pk2caller"]] = mean[:npk]
+        return full, fmean
+
+    p = synthetic.make_scene(n_cam=60, n_pt=900, obs_per_pt=40, seed=5, perturb=0.3)
+    rng = np.random.default_rng(4)
+    target = rng.choice([2, 3, 9, 31, 32, 33, 40], size=p.n_pt)
+    seen = np.zeros(p.n_pt, int); keep = np.zeros(p.n_obs, bool)
+    for i in range(p.n_obs):
+        seen[p.obs_pt[i]] += 1
+        keep[i] = seen[p.obs_pt[i]] <= target[p.obs_pt[i]]
+    keep[p.obs_pt == 5] = False
+    perm = rng.permutation(int(keep.sum()))
+    p = _abi.Problem(p.ext, p.ext_const, p.cam_group, p.group_model, p.intr, p.group_const_mask, p.pt, p.pt_const,
+                     p.obs_cam[keep][perm], p.obs_pt[keep][perm], p.obs_xy[keep][perm])
+    p.obs_xy[rng.choice(p.n_obs, 200, replace=False)] += 40.0
+    p.pt[9, 3] = -1.0
+    for prob, cases in ((p, [(5.0, 3.0), (15.0, 25.0)]), (fountain_problem()[0], [(5.0, 3.0), (1.0, 8.0)])):
+        for max_err, angle in cases:
+            st, mean = run(prob, max_err, angle)
+            st_o, mean_o, _ = oracle.filter_tracks(prob, max_err, angle)
+            ok = np.isfinite(mean_o)
+            assert np.allclose(mean[ok], mean_o[ok], rtol=1e-10)
+            borderline = ok & (np.abs(mean_o - max_err ** 2) <= 1e-9 * max_err ** 2)
+            assert np.array_equal(st[~borderline], st_o[~borderline])
+    assert (st_o == 0).sum() > 1000

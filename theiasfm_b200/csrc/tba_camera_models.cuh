@@ -49,7 +49,7 @@ __host__ __device__ constexpr int nth_bit(uint32_t m, int j) {
 }
 
 // Rotation matrix and left Jacobian of SO(3) for one camera.
-__device__ inline void cam_prep(const double* __restrict__ w, double* __restrict__ rec) {
+__host__ __device__ inline void cam_prep(const double* __restrict__ w, double* __restrict__ rec) {
   const double w0 = w[0], w1 = w[1], w2 = w[2];
   const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
   double* R = rec;
@@ -119,7 +119,7 @@ __device__ inline void loss_evaluate(int type, double a, double s, double rho[3]
 
 // Camera::ProjectPoint (camera.cc:204-213) without any guard: pixel and camera-frame depth coordinate q_z
 // (the caller divides by h for the depth ProjectPoint returns).  a = X - h C is also returned for the callers' guards.
-__device__ inline void project_pixel(int model, const double* __restrict__ C, const double* __restrict__ R,
+__host__ __device__ inline void project_pixel(int model, const double* __restrict__ C, const double* __restrict__ R,
                                      const double* __restrict__ k, const double X0, const double X1, const double X2, const double h,
                                      double& px, double& py, double& qz, double& a_sq) {
   const double a0 = X0 - h * C[0], a1 = X1 - h * C[1], a2 = X2 - h * C[2];

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "tba_camera_models.cuh"
+#include "tba_filter.cuh"
 
 namespace tba {
 
@@ -309,49 +310,12 @@ __global__ void k_filter_tracks(DevProblem P, const long long* __restrict__ pt_s
                                 double cos_min_angle, uint8_t* __restrict__ status, double* __restrict__ mean_sq_err) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P.n_pt) return;
-  const double4 X = *reinterpret_cast<const double4*>(P.pt + (size_t)k * 4);
-  const long long s0 = pt_slot[k];
-  const int len = pt_len[k];
-  bool behind = false;
-  double sum = 0.0;
-  for (int o = 0; o < len; ++o) {
-    const long long s = s0 + o;
-    const int cam = P.slot_cam[s];
-    const int grp = P.cam_group[cam];
-    const long long wq = s >> 5;
-    const int l = (int)(s & 31);
-    const double x = P.xy[(size_t)(wq * 2 + 0) * 32 + l], y = P.xy[(size_t)(wq * 2 + 1) * 32 + l];
-    double px, py, qz, a_sq;
-    project_pixel(P.group_model[grp], P.ext + (size_t)cam * 6, P.cam_rec + (size_t)cam * kCamRec, P.intr + (size_t)grp * 10, X.x, X.y,
-                  X.z, X.w, px, py, qz, a_sq);
-    if (qz / X.w < 0.0) behind = true;
-    sum += (px - x) * (px - x) + (py - y) * (py - y);
-  }
-  const double mean = sum / (double)len;  // len == 0 cannot happen for a packed point
+  FilterView V;
+  V.ext = P.ext; V.cam_rec = P.cam_rec; V.intr = P.intr; V.pt = P.pt; V.xy = P.xy;
+  V.slot_cam = P.slot_cam; V.cam_group = P.cam_group; V.group_model = P.group_model;
+  double mean;
+  status[k] = filter_track(V, k, pt_slot[k], pt_len[k], max_sq_err, cos_min_angle, &mean);
   if (mean_sq_err) mean_sq_err[k] = mean;
-  uint8_t st = 0;
-  if (behind || mean > max_sq_err) st = 1;
-  else {
-    // unit rays from every camera centre to the (de-homogenised) point; sufficient if some pair is wide enough
-    const double ih = 1.0 / X.w;
-    const double Xn0 = X.x * ih, Xn1 = X.y * ih, Xn2 = X.z * ih;
-    bool wide = false;
-    for (int i = 0; i < len && !wide; ++i) {
-      const double* Ci = P.ext + (size_t)P.slot_cam[s0 + i] * 6;
-      double a0 = Xn0 - Ci[0], a1 = Xn1 - Ci[1], a2 = Xn2 - Ci[2];
-      const double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-      a0 /= na; a1 /= na; a2 /= na;
-      for (int j = i + 1; j < len; ++j) {
-        const double* Cj = P.ext + (size_t)P.slot_cam[s0 + j] * 6;
-        double b0 = Xn0 - Cj[0], b1 = Xn1 - Cj[1], b2 = Xn2 - Cj[2];
-        const double nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
-        b0 /= nb; b1 /= nb; b2 /= nb;
-        if (a0 * b0 + a1 * b1 + a2 * b2 < cos_min_angle) { wide = true; break; }
-      }
-    }
-    if (!wide) st = 2;
-  }
-  status[k] = st;
 }
 
 // --------------------------------------------------------- per-point blocks
