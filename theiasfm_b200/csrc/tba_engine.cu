@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -119,6 +120,8 @@ struct tba_context {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_spans[2];  // 0: matvec, 1: linearize ; indices into ev_pool
+  bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
+  bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
   // host mirrors
@@ -317,9 +320,15 @@ int launch_matvec(tba_context* c, const int* done) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-#define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
-    DISPATCH_IMASK(c->imask, F)
+    if (c->exp_bulkred) {
+#define F(M) { auto kfn = k_schur<M, 0, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
+      DISPATCH_IMASK(c->imask, F)
 #undef F
+    } else {
+#define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    }
     prof_end(c, 0, pb);
     if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
@@ -501,6 +510,8 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   tba_context* c = new tba_context();
   c->device = device; c->rank = rank; c->world = world_size;
   tba_options_init(&c->opt);
+  { const char* e = getenv("TBA_MATVEC_BULKRED"); c->exp_bulkred = e != nullptr && e[0] == '1'; }
+  { const char* e = getenv("TBA_PACK_SORT"); c->exp_pack_sort = e != nullptr && e[0] == '1'; }
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&c->h_scal, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->h_st, sizeof(PcgState)) != cudaSuccess) {
     delete c;
@@ -574,7 +585,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   pack_count_and_sort(p, T, &H);  // A, B, C
   if (H.bad >= 0) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)H.bad, p->obs_cam[H.bad], p->obs_pt[H.bad]); return TBA_ERR_INVALID_ARGUMENT; }
   if (H.maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", H.maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
-  pack_points(p, &H);
+  pack_points(p, &H, c->exp_pack_sort);
   // ---- which blocks take part (blocks without residuals are not in the Ceres program)
   std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
   for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
@@ -706,6 +717,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
     const int smem = (int)schur_smem(c);
 #define F(M)                                                                                                        \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DISPATCH_IMASK(c->imask, F)
@@ -1038,7 +1050,7 @@ int tba_debug_pack(const tba_problem* p, int64_t cap_slots, int64_t* sizes_out, 
   pack_count_and_sort(p, 4, &H);
   if (H.bad >= 0) return TBA_ERR_INVALID_ARGUMENT;
   if (H.maxlen > TILE) return TBA_ERR_UNSUPPORTED;
-  pack_points(p, &H);
+  { const char* e = getenv("TBA_PACK_SORT"); pack_points(p, &H, e != nullptr && e[0] == '1'); }
   std::vector<double> cnt_c(p->n_cam, 0.0), cnt_g(p->n_group, 0.0);
   for (int i = 0; i < p->n_cam; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
   pack_masks_and_tiles(p, cnt_c, cnt_g, &H);

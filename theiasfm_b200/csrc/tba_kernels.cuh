@@ -439,6 +439,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Bulk reduction shared -> global (TMA): dst[0..bytes) += src[0..bytes) element-wise in fp64, asynchronously.
+// bytes multiple of 16, both addresses 16-byte aligned.  Experimental path (TBA_MATVEC_BULKRED=1): replaces the six
+// per-observation RED.ADD.F64 of the matvec by ONE 48-byte bulk reduction issued from a staged shared-memory row.
+__device__ __forceinline__ void bulk_red_add_f64(double* dst, const double* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // --------------------------------------------- K2 implicit Schur complement
 // MODE 0: y += F^T (I - E M E^T) F xs                (PCG matvec; ImplicitSchurComplement::RightMultiply)
 // MODE 1: y += F^T (I - E M E^T) r                   (reduced rhs; ImplicitSchurComplement::ComputeRHS)
@@ -454,7 +467,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Camera-side sums: fp64 RED.ADD to global; shared-intrinsics sums: warp reduce + RED to a replica row.
 // No block barrier on this path.  Long tiles (tracks > 32 observations) combine the per-point sums across warps in
 // shared memory (two block barriers).  Dynamic shared memory: TILE * (NJ + 2) doubles.
-template <uint32_t IMASK, int MODE>
+template <uint32_t IMASK, int MODE, bool BULKRED = false>
 __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 : 2) k_schur(DevProblem P, const double* __restrict__ xs, double* __restrict__ y,
                                                 double* __restrict__ rep, const int* __restrict__ done_flag) {
   constexpr int NI = popcount10(IMASK);
@@ -586,6 +599,39 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     }
     mcc = warp_sum(mcc);
     if (lane == 0) red_add(rr + 23, mcc);
+    return;
+  }
+  if (BULKRED) {
+    // experimental: stage the lane's 6 camera-side contributions in its own 48-byte row of the (now consumed) residual /
+    // padding area of the warp stage, then one TMA bulk reduction per observation
+    double yv[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) yv[j] = valid ? -h * (JA(j) * z0 + JA(3 + j) * z1) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) yv[3 + j] = valid ? JW(j) * z0 + JW(3 + j) * z1 : 0.0;
+    double yi[NI + 1];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) yi[j] = valid ? JI(j) * z0 + JI(NI + j) * z1 : 0.0;
+    __syncwarp();  // every lane has finished reading the J slice: rows 0..5 of the slice are reused as staging [32][6]
+    double* stage = sJ + lane * 6;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) stage[j] = yv[j];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (valid) bulk_red_add_f64(y + (size_t)cam * 6, stage, 48);
+    bulk_commit_and_wait_read();
+    if (NI > 0) {
+      if (P.single_group) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const double v = warp_sum(yi[j]);
+          if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), yi[j]);
+      }
+    }
     return;
   }
   if (valid) {
