@@ -46,7 +46,7 @@ def test_sharded_solve_matches_single_gpu(world, scene):
     for q in procs:
         q.start()
     try:
-        res = sorted([out.get(timeout=300) for _ in range(world)])
+        res = sorted([out.get(timeout=150) for _ in range(world)])
         for q in procs:
             q.join(timeout=60)
             assert q.exitcode == 0
@@ -97,5 +97,5 @@ def test_single_process_multi_gpu_entry_point(world):
     if engine.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import subprocess
-    out = subprocess.run([sys.executable, "-c", _MULTI_SCRIPT % ROOT, str(world)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, "-c", _MULTI_SCRIPT % ROOT, str(world)], capture_output=True, text=True, timeout=180)
     assert out.returncode == 0 and "solve_multi ok" in out.stdout, out.stdout + out.stderr
