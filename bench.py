@@ -79,6 +79,24 @@ class ClockSampler:
                 "power_w_max": max([float(r[4]) for r in rows if r[4].replace(".", "").isdigit()], default=None)}
 
 
+def run_microbench(device):
+    """fp64 FMA peak, fp64 RED rate and 48-byte gather rate of this GPU (theiasfm_b200/csrc/tba_microbench.cu), measured
+    in a SEPARATE process before the solve so that it cannot disturb the timed region; None if anything goes wrong."""
+    code = ("import ctypes, json, sys; L = ctypes.CDLL(%r); out = (ctypes.c_double * 3)(); "
+            "rc = L.tba_microbench(%d, out); print(json.dumps({'rc': rc, 'v': list(out)}))"
+            % (os.path.join(ROOT, "theiasfm_b200", "libtheia_microbench_b200.so"), device))
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        if d["rc"] != 0:
+            return None
+        return {"fp64_fma_tflops": d["v"][0], "fp64_red_gops": d["v"][1], "gather48_grows": d["v"][2],
+                "how": "tba_microbench: 8 DFMA chains/thread; RED.ADD.F64 and 3xLDG.128 gathers over a 60k-double vector, "
+                       "32 distinct rows per warp; best of 5 after warm-up"}
+    except Exception:  # noqa: BLE001 -- the micro-benchmark is optional evidence, never a reason to fail the bench
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -175,6 +193,7 @@ def main():
         obj = [engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         nccl_id = obj[0]
+    micro = run_microbench(local_rank) if rank == 0 else None
     eng = engine.Engine(device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id)
 
     full = synthetic.make_config(args.workload)
@@ -232,6 +251,10 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": mv_ms,
                 "launches_timed": prof["matvec_launches"], "share_of_step": prof["matvec_ms"] * 1e-3 / dev_s if dev_s > 0 else None,
+                # the matvec issues 6 fp64 REDs and 1 48-byte gather per observation: floors from the measured rates
+                "atomic_floor_ms": (6.0 * prof["observations"] / (micro["fp64_red_gops"] * 1e9) * 1e3) if micro else None,
+                "gather_floor_ms": (prof["observations"] / (micro["gather48_grows"] * 1e9) * 1e3) if micro else None,
+                "hbm_floor_ms": alg_bytes / (peak * 1e9) * 1e3,
                 "linearize": {"avg_launch_ms": lin_ms, "algorithmic_bytes_per_launch": lin_bytes,
                               "achieved": lin_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0,
                               "frac": (lin_bytes / (lin_ms * 1e-3) / 1e9 / peak) if lin_ms > 0 else 0.0,
@@ -257,7 +280,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "obs/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t_max / iters, "steps_run": iters, "note": note, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cb, "lm_iters_per_s": iters / t_max,
+                "roofline": roofline, "microbench": micro, "cpu_baseline": cb, "lm_iters_per_s": iters / t_max,
                 "pcg_iterations": s.num_linear_solver_iterations, "initial_cost": s.initial_cost, "final_cost": s.final_cost,
                 "wall_seconds_timed_region": wall, "n_obs": n_obs_total}
         print(json.dumps(line))

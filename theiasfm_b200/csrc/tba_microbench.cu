@@ -1,0 +1,83 @@
+// tba_microbench.cu -- three tiny device micro-benchmarks that give the roofline denominators MEASURED_PEAKS.json
+// does not have ("fp64 peak is not in that file -- builder must measure a DFMA microbenchmark"):
+//   out[0] fp64 FMA throughput, TFLOP/s (8 independent DFMA chains per thread)
+//   out[1] fp64 RED.ADD throughput to 60 000 spread addresses (the matvec's camera vector at 10k cameras), G ops/s
+//   out[2] 48-byte gather throughput from the same vector (3 x LDG.128 per lane, 32 distinct rows per warp), G rows/s
+// Built into its own library (libtheia_microbench_b200.so) and run by bench.py in a separate process, so that nothing
+// here can disturb the measured solve.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+namespace {
+
+__global__ void k_dfma(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void k_red(double* y, unsigned n, int reps) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < reps; ++k) {
+    const unsigned idx = (gid * 2654435761u + (unsigned)k * 40503u) % n;
+    atomicAdd(y + idx, 1.0);
+  }
+}
+
+__global__ void k_gather(const double* __restrict__ x, unsigned n_rows, int reps, double* out) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  for (int k = 0; k < reps; ++k) {
+    const unsigned row = (gid * 2654435761u + (unsigned)k * 40503u) % n_rows;
+    const double2* p = reinterpret_cast<const double2*>(x + (size_t)row * 6);
+    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    acc += a.x + a.y + b.x + b.y + c.x + c.y;
+  }
+  out[gid] = acc;
+}
+
+float time_ms(cudaEvent_t e0, cudaEvent_t e1) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); return ms; }
+
+}  // namespace
+
+extern "C" int tba_microbench(int device, double* out3) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -5;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 16, threads = 256;
+  const size_t nthreads = (size_t)blocks * threads;
+  const unsigned n_y = 60000;
+  double *d_out = nullptr, *d_y = nullptr;
+  if (cudaMalloc(&d_out, nthreads * sizeof(double)) != cudaSuccess || cudaMalloc(&d_y, (size_t)n_y * sizeof(double)) != cudaSuccess) return -3;
+  cudaMemset(d_y, 0, (size_t)n_y * sizeof(double));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 4096, reps = 64;
+  double best[3] = {0, 0, 0};
+  for (int rep = 0; rep < 6; ++rep) {  // first repetition is the warm-up
+    cudaEventRecord(e0); k_dfma<<<blocks, threads>>>(d_out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double t0 = time_ms(e0, e1) * 1e-3;
+    cudaEventRecord(e0); k_red<<<blocks, threads>>>(d_y, n_y, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double t1 = time_ms(e0, e1) * 1e-3;
+    cudaEventRecord(e0); k_gather<<<blocks, threads>>>(d_y, n_y / 6, reps, d_out); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double t2 = time_ms(e0, e1) * 1e-3;
+    if (rep == 0) continue;
+    const double v0 = (double)nthreads * iters * 8 * 2 / t0 * 1e-12, v1 = (double)nthreads * reps / t1 * 1e-9, v2 = (double)nthreads * reps / t2 * 1e-9;
+    if (v0 > best[0]) best[0] = v0;
+    if (v1 > best[1]) best[1] = v1;
+    if (v2 > best[2]) best[2] = v2;
+  }
+  const cudaError_t err = cudaDeviceSynchronize();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out); cudaFree(d_y);
+  if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) return -3;
+  out3[0] = best[0]; out3[1] = best[1]; out3[2] = best[2];
+  return 0;
+}
