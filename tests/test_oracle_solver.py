@@ -179,3 +179,29 @@ def test_every_robust_loss_solves_and_resists_outliers(oracle, loss):
         return np.linalg.norm(aligned - truth["ext"][:, :3], axis=1).max()
 
     assert solve(loss) < 0.5 * solve(_abi.LOSS_TRIVIAL)
+
+
+@pytest.mark.parametrize("solver", [_abi.SPARSE_SCHUR, _abi.DENSE_SCHUR])
+def test_exact_schur_solver_types(oracle, solver):
+    """DENSE_SCHUR / SPARSE_SCHUR (Theia's default linear solver, bundle_adjustment.h:86): the oracle factorises the
+    explicit reduced camera matrix; its LM step equals the dense normal-equations step, and the solve converges to the
+    same minimum as the ITERATIVE_SCHUR restatement and scipy."""
+    p = _tiny(seed=11)
+    opt = oracle.default_options(use_inner_iterations=0, linear_solver_type=solver)
+    o = oracle.Oracle(p.copy(), opt)
+    ok, cost = o.linearize()
+    radius = 1e4
+    assert ok and o.prepare_linear_system(radius)
+    ok, iters, mcc = o.solve_linear_system()
+    assert ok and iters == 1
+    d = _dense_system(oracle, p, radius, opt)
+    Hf = d["H"] + np.diag(np.where(d["free"], 0.0, 1.0))
+    y = np.linalg.solve(Hf, d["b"])
+    got = np.concatenate([o.read(_abi.VEC_STEP_CAM), o.read(_abi.VEC_STEP_INTR), o.read(_abi.VEC_STEP_PT)])
+    assert rel_err(got, -(y * d["scale"])) < 1e-9
+    pe, pi = p.copy(), p.copy()
+    kw = dict(use_inner_iterations=0, function_tolerance=1e-12, max_num_iterations=100)
+    se = oracle.solve(pe, oracle.default_options(linear_solver_type=solver, **kw))
+    si = oracle.solve(pi, oracle.default_options(linear_solver_type=_abi.ITERATIVE_SCHUR, **kw))
+    assert se.success and abs(se.final_cost - si.final_cost) <= 1e-7 * si.final_cost
+    assert all(i["linear_solver_iterations"] in (0, 1) for i in se.iterations)

@@ -455,8 +455,11 @@ void push_iter(tba_summary* s, const tba_iteration& it) {
 
 int check_options(tba_context* c, const tba_options* o) {
   if (o->use_inner_iterations) { set_err(c, "use_inner_iterations=true is not implemented by the GPU engine (set it to false, as Theia's incremental/hybrid estimators do)"); return TBA_ERR_UNSUPPORTED; }
-  if (o->linear_solver_type != TBA_ITERATIVE_SCHUR) { set_err(c, "linear_solver_type %d unsupported: the GPU engine implements ITERATIVE_SCHUR", o->linear_solver_type); return TBA_ERR_UNSUPPORTED; }
-  if (o->preconditioner_type != TBA_PRECOND_SCHUR_JACOBI && o->preconditioner_type != TBA_PRECOND_IDENTITY) { set_err(c, "preconditioner_type %d unsupported (SCHUR_JACOBI or IDENTITY)", o->preconditioner_type); return TBA_ERR_UNSUPPORTED; }
+  if (o->linear_solver_type != TBA_ITERATIVE_SCHUR && o->linear_solver_type != TBA_DENSE_SCHUR && o->linear_solver_type != TBA_SPARSE_SCHUR) {
+    set_err(c, "linear_solver_type %d unsupported: the GPU engine implements ITERATIVE_SCHUR, and DENSE_SCHUR / SPARSE_SCHUR as the same Schur system solved to the fp64 floor", o->linear_solver_type);
+    return TBA_ERR_UNSUPPORTED;
+  }
+  if (o->linear_solver_type == TBA_ITERATIVE_SCHUR && o->preconditioner_type != TBA_PRECOND_SCHUR_JACOBI && o->preconditioner_type != TBA_PRECOND_IDENTITY) { set_err(c, "preconditioner_type %d unsupported (SCHUR_JACOBI or IDENTITY)", o->preconditioner_type); return TBA_ERR_UNSUPPORTED; }
   if (o->loss_function_type < 0 || o->loss_function_type > 5) { set_err(c, "invalid loss function type %d", o->loss_function_type); return TBA_ERR_INVALID_ARGUMENT; }
   return TBA_OK;
 }
@@ -570,6 +573,15 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   if (rc) return rc;
   CUDA_OK(c, cudaSetDevice(c->device));
   c->opt = *options;
+  if (options->linear_solver_type == TBA_DENSE_SCHUR || options->linear_solver_type == TBA_SPARSE_SCHUR) {
+    // The exact Schur solver types (Theia's default, and what SetBundleAdjustmentOptions picks below 1000 views:
+    // reconstruction_estimator_utils.cc:110-133) solve the SAME reduced system a Cholesky factorisation of S solves;
+    // here it is solved by the preconditioned CG run until the quadratic model stops changing at fp64 resolution.
+    c->opt.eta = 1e-13;
+    c->opt.min_linear_solver_iterations = 0;
+    c->opt.max_linear_solver_iterations = std::max(c->opt.max_linear_solver_iterations, 2000);
+    c->opt.preconditioner_type = TBA_PRECOND_SCHUR_JACOBI;
+  }
   const int nc = p->n_cam, ng = p->n_group, np = p->n_pt;
   const int64_t no = p->n_obs;
   if (nc < 0 || ng < 0 || np < 0 || no < 0) { set_err(c, "negative sizes"); return TBA_ERR_INVALID_ARGUMENT; }
