@@ -21,9 +21,15 @@ namespace {
 
 double NowSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+}  // namespace
+
 // One engine context per process (the estimators call BA from a single thread; concurrent callers are serialised).
+namespace b200 {
+namespace {
 std::mutex g_mu;
 tba_context* g_ctx = nullptr;
+}  // namespace
+std::mutex& Mutex() { return g_mu; }
 tba_context* AcquireContext() {
   if (g_ctx == nullptr) {
     const char* dev = std::getenv("THEIA_B200_DEVICE");
@@ -31,7 +37,34 @@ tba_context* AcquireContext() {
   }
   return g_ctx;
 }
+tba_context* CurrentContext() { return g_ctx; }
+uint64_t& Generation() { static uint64_t g = 0; return g; }
 
+// 1:1 copy of BundleAdjustmentOptions (SetSolverOptions, bundle_adjuster.cc:57-79)
+void ToEngineOptions(const BundleAdjustmentOptions& in, tba_options* o) {
+  tba_options_init(o);
+  o->loss_function_type = static_cast<int32_t>(in.loss_function_type);
+  o->robust_loss_width = in.robust_loss_width;
+  o->linear_solver_type = static_cast<int32_t>(in.linear_solver_type);
+  o->preconditioner_type = static_cast<int32_t>(in.preconditioner_type);
+  o->visibility_clustering_type = static_cast<int32_t>(in.visibility_clustering_type);
+  o->verbose = in.verbose;
+  o->constant_camera_orientation = in.constant_camera_orientation;
+  o->constant_camera_position = in.constant_camera_position;
+  o->intrinsics_to_optimize = static_cast<int32_t>(in.intrinsics_to_optimize);
+  o->num_threads = in.num_threads;
+  o->max_num_iterations = in.max_num_iterations;
+  o->max_solver_time_in_seconds = in.max_solver_time_in_seconds;
+  o->use_inner_iterations = in.use_inner_iterations;
+  o->function_tolerance = in.function_tolerance;
+  o->gradient_tolerance = in.gradient_tolerance;
+  o->parameter_tolerance = in.parameter_tolerance;
+  o->max_trust_region_radius = in.max_trust_region_radius;
+}
+}  // namespace b200
+
+namespace {
+using b200::AcquireContext;
 }  // namespace
 
 tba_problem BundleAdjusterB200::Flat::AsProblem() {
@@ -93,25 +126,7 @@ void BundleAdjusterB200::AddTrack(const TrackId track_id) {
 }
 
 void BundleAdjusterB200::Flatten(Flat* f, tba_options* o) const {
-  // ---- options: 1:1 copy (SetSolverOptions, bundle_adjuster.cc:57-79)
-  tba_options_init(o);
-  o->loss_function_type = static_cast<int32_t>(options_.loss_function_type);
-  o->robust_loss_width = options_.robust_loss_width;
-  o->linear_solver_type = static_cast<int32_t>(options_.linear_solver_type);
-  o->preconditioner_type = static_cast<int32_t>(options_.preconditioner_type);
-  o->visibility_clustering_type = static_cast<int32_t>(options_.visibility_clustering_type);
-  o->verbose = options_.verbose;
-  o->constant_camera_orientation = options_.constant_camera_orientation;
-  o->constant_camera_position = options_.constant_camera_position;
-  o->intrinsics_to_optimize = static_cast<int32_t>(options_.intrinsics_to_optimize);
-  o->num_threads = options_.num_threads;
-  o->max_num_iterations = options_.max_num_iterations;
-  o->max_solver_time_in_seconds = options_.max_solver_time_in_seconds;
-  o->use_inner_iterations = options_.use_inner_iterations;
-  o->function_tolerance = options_.function_tolerance;
-  o->gradient_tolerance = options_.gradient_tolerance;
-  o->parameter_tolerance = options_.parameter_tolerance;
-  o->max_trust_region_radius = options_.max_trust_region_radius;
+  b200::ToEngineOptions(options_, o);
   // ---- parameter blocks that appear in residual blocks, in first-use order
   std::unordered_map<ViewId, int32_t> cam_of_view;
   std::unordered_map<TrackId, int32_t> pt_of_track;
@@ -177,7 +192,7 @@ BundleAdjustmentSummary BundleAdjusterB200::Optimize() {
   Flatten(&flat, &opts);
   tba_problem problem = flat.AsProblem();
   const double internal_setup_time = NowSeconds() - start_time_;  // :203
-  std::lock_guard<std::mutex> lock(g_mu);
+  std::lock_guard<std::mutex> lock(b200::Mutex());
   tba_summary s;
   std::memset(&s, 0, sizeof s);
   int rc;
@@ -195,6 +210,7 @@ BundleAdjustmentSummary BundleAdjusterB200::Optimize() {
     rc = tba_solve(ctx, &opts, &problem, &s);  // replaces ceres::Solve, :205
     if (rc != TBA_OK) std::snprintf(s.message, sizeof s.message, "%s", tba_last_error(ctx));
     resident_ = rc == TBA_OK;
+    generation_ = ++b200::Generation();  // this problem now owns the context's device-resident state
     if (resident_) resident_tracks_ = flat.track_of_pt;
   }
   last_summary_ = s;
@@ -227,8 +243,9 @@ BundleAdjustmentSummary BundleAdjusterB200::Optimize() {
 
 int BundleAdjusterB200::SetOutlierTracksToUnestimated(const double max_inlier_reprojection_error,
                                                       const double min_triangulation_angle_degrees) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  if (!resident_ || g_ctx == nullptr) return -1;
+  std::lock_guard<std::mutex> lock(b200::Mutex());
+  tba_context* g_ctx = b200::CurrentContext();
+  if (!resident_ || g_ctx == nullptr || generation_ != b200::Generation()) return -1;
   std::vector<uint8_t> status(resident_tracks_.size() + 1);
   int32_t bad = 0, insufficient = 0;
   if (tba_filter_tracks(g_ctx, max_inlier_reprojection_error, min_triangulation_angle_degrees, status.data(), nullptr, &bad,

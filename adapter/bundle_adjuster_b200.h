@@ -7,6 +7,7 @@
 #include <ceres/types.h>
 
 #include <memory>
+#include <mutex>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -82,7 +83,8 @@ class BundleAdjusterB200 {
   // N1: SetOutlierTracksToUnestimated (set_outlier_tracks_to_unestimated.cc:62-136) for the tracks of THIS problem,
   // evaluated on the device-resident copy the last Optimize() left on the GPU (no re-flattening, no re-upload).
   // Marks outlier tracks un-estimated in the Reconstruction and returns how many were removed, or -1 when there is
-  // no device-resident problem (Optimize() not run, failed, or ran through the multi-GPU entry point).
+  // no device-resident problem (Optimize() not run, failed, ran through the multi-GPU entry point, or another
+  // BundleAdjusterB200 / TrackEstimatorB200 has used the engine context since).
   int SetOutlierTracksToUnestimated(const double max_inlier_reprojection_error, const double min_triangulation_angle_degrees);
 
   // Detail of the last Optimize() (termination, iteration count, message).
@@ -102,7 +104,18 @@ class BundleAdjusterB200 {
   tba_summary last_summary_;
   std::vector<TrackId> resident_tracks_;  // point index -> TrackId of the problem left on the device by Optimize()
   bool resident_ = false;
+  uint64_t generation_ = 0;               // b200::Generation() when that problem was uploaded
 };
+
+// Shared by the adapters of this directory: the process-wide engine context (guarded by Mutex()), a counter that
+// identifies which flattened problem currently lives on the device, and the options copy.
+namespace b200 {
+std::mutex& Mutex();
+tba_context* AcquireContext();   // creates the context on first use (THEIA_B200_DEVICE); nullptr without a usable GPU
+tba_context* CurrentContext();
+uint64_t& Generation();
+void ToEngineOptions(const BundleAdjustmentOptions& in, tba_options* out);
+}  // namespace b200
 
 // Drop-ins for bundle_adjustment.h:136-143 (bundle_adjustment.cc:47-80).
 BundleAdjustmentSummary BundleAdjustReconstructionB200(const BundleAdjustmentOptions& options, Reconstruction* reconstruction);

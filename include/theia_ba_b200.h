@@ -224,6 +224,32 @@ int tba_download(tba_context* ctx, tba_problem* problem);
 int tba_filter_tracks(tba_context* ctx, double max_inlier_reprojection_error, double min_triangulation_angle_degrees,
                       uint8_t* status, double* mean_sq_error, int32_t* num_bad_reprojections, int32_t* num_insufficient_angles);
 
+/*
+ * N3, batched micro-BA on the device-resident problem of this context (after tba_upload; read the points
+ * back with tba_download).  Every camera and intrinsics block is held constant, whatever ext_const / group_const_mask
+ * say; points with pt_const != 0 are skipped (status 255).
+ *
+ * tba_adjust_tracks = BundleAdjustTrack (src/theia/sfm/bundle_adjustment/bundle_adjustment.cc:96-107, DENSE_QR, no inner
+ * iterations) for every non-constant point at once: status[q] = ceres termination (TBA_CONVERGENCE / NO_CONVERGENCE /
+ * FAILURE; BundleAdjustmentSummary::success = status != TBA_FAILURE), initial_cost / final_cost optional [n_pt]
+ * (-1 where no solve ran).  options: loss, tolerances, max_num_iterations, trust-region fields of tba_options.
+ *
+ * tba_estimate_tracks = TrackEstimator::EstimateTrack (src/theia/sfm/estimate_track.cc:199-264) for every non-constant
+ * point at once, from the observations of the problem (the caller lists only estimated views, as
+ * GetObservationsFromTrackViews does): viewing rays -> SufficientTriangulationAngle -> TriangulateMidpoint ->
+ * BundleAdjustTrack (if bundle_adjustment) -> AcceptableReprojectionError.  The incoming point value is ignored.
+ * status[q]: 0 estimated (the reference's "return true"), 1 fewer than 2 views or insufficient angle (num_bad_angles_),
+ * 2 triangulation failed, 3 per-track BA failed, 4 unacceptable reprojection error (num_bad_reprojections_).
+ * Like the reference, a track that fails at stage n keeps the point written by stage n-1.  counts[5] (optional) =
+ * histogram of status 0..4.
+ */
+int tba_adjust_tracks(tba_context* ctx, const tba_options* options, uint8_t* status, double* initial_cost, double* final_cost,
+                      int32_t* num_failed);
+int tba_estimate_tracks(tba_context* ctx, const tba_options* ba_options, double max_acceptable_reprojection_error_pixels,
+                        double min_triangulation_angle_degrees, int32_t bundle_adjustment, uint8_t* status, int32_t counts[5]);
+enum { TBA_TRACK_ESTIMATED = 0, TBA_TRACK_BAD_ANGLE = 1, TBA_TRACK_TRIANGULATION_FAILED = 2, TBA_TRACK_BA_FAILED = 3,
+       TBA_TRACK_BAD_REPROJECTION = 4, TBA_TRACK_SKIPPED = 255 };
+
 /* Re-load ext / intr / pt of an uploaded problem (same shape) without re-packing. */
 int tba_reset_parameters(tba_context* ctx, const tba_problem* problem);
 

@@ -123,6 +123,31 @@ def filter_tracks(problem, max_inlier_reprojection_error, min_triangulation_angl
     return status[:problem.n_pt], mean[:problem.n_pt], removed
 
 
+def adjust_tracks(problem, options=None):
+    """oracle_adjust_tracks (batched BundleAdjustTrack): updates problem.pt; (status [n_pt] uint8, initial_cost, final_cost, n_failed)."""
+    options = options or default_options(use_inner_iterations=0)
+    n = max(problem.n_pt, 1)
+    status = np.zeros(n, np.uint8); ic = np.zeros(n); fc = np.zeros(n)
+    st = problem.as_struct()
+    L = lib()
+    L.oracle_adjust_tracks.argtypes = [C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    failed = L.oracle_adjust_tracks(C.byref(options), C.byref(st), status.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(ic), _dp(fc))
+    return status[:problem.n_pt], ic[:problem.n_pt], fc[:problem.n_pt], failed
+
+
+def estimate_tracks(problem, options=None, max_reprojection_error_pixels=5.0, min_triangulation_angle_degrees=3.0, bundle_adjustment=True):
+    """oracle_estimate_tracks (batched TrackEstimator::EstimateTrack): updates problem.pt; (status [n_pt] uint8, counts [5])."""
+    options = options or default_options(use_inner_iterations=0)
+    status = np.zeros(max(problem.n_pt, 1), np.uint8); counts = np.zeros(5, np.int32)
+    st = problem.as_struct()
+    L = lib()
+    L.oracle_estimate_tracks.argtypes = [C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.c_double, C.c_double, C.c_int,
+                                         C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+    L.oracle_estimate_tracks(C.byref(options), C.byref(st), max_reprojection_error_pixels, min_triangulation_angle_degrees, int(bundle_adjustment),
+                             status.ctypes.data_as(C.POINTER(C.c_uint8)), counts.ctypes.data_as(C.POINTER(C.c_int32)))
+    return status[:problem.n_pt], counts
+
+
 def loss(kind, width, s):
     rho = np.zeros(3)
     lib().oracle_loss(kind, width, s, _dp(rho))

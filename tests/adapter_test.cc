@@ -13,6 +13,7 @@
 #include <string>
 
 #include "bundle_adjuster_b200.h"
+#include "track_estimator_b200.h"
 
 using namespace theia;
 
@@ -249,9 +250,122 @@ static int TestSolve(const char* oracle_path) {
   return 0;
 }
 
+// N3: TrackEstimatorB200 (drop-in for estimate_track.h).  Without a GPU: loud refusal, reconstruction untouched.
+static int TestTracksNoGpu() {
+  Scene sc;
+  BuildScene(&sc, 8, 60, 4, 3, 5);
+  for (TrackId t : sc.tracks) sc.rec.MutableTrack(t)->SetEstimated(false);
+  sc.rec.MutableTrack(sc.tracks[0])->SetEstimated(true);
+  const double before = sc.rec.MutableTrack(sc.tracks[7])->Point().v[1];
+  TrackEstimatorB200::Options o;
+  TrackEstimatorB200 est(o, &sc.rec);
+  TrackEstimatorB200::Summary s = est.EstimateAllTracks();
+  EXPECT(s.input_num_estimated_tracks == 1 && s.num_triangulation_attempts == 59);
+  if (tba_device_count() <= 0) {
+    EXPECT(!est.engine_ok() && s.estimated_tracks.empty());
+    EXPECT(sc.rec.MutableTrack(sc.tracks[7])->Point().v[1] == before && !sc.rec.MutableTrack(sc.tracks[7])->IsEstimated());
+  }
+  // nothing to do: no engine call at all
+  for (TrackId t : sc.tracks) sc.rec.MutableTrack(t)->SetEstimated(true);
+  TrackEstimatorB200 est2(o, &sc.rec);
+  s = est2.EstimateAllTracks();
+  EXPECT(s.num_triangulation_attempts == 0 && s.input_num_estimated_tracks == 60 && est2.engine_ok());
+  std::printf("tracks-nogpu ok\n");
+  return 0;
+}
+
+typedef int (*oracle_estimate_fn)(const tba_options*, tba_problem*, double, double, int, uint8_t*, int32_t*);
+
+static int TestTracks(const char* oracle_path) {
+  Scene sc;
+  BuildScene(&sc, 12, 400, 5, 5, 21);
+  EXPECT(BundleAdjustReconstructionB200(IterativeOptions(), &sc.rec).success);  // consistent cameras + points
+  Scene refined = sc;
+  // a track with a gross outlier measurement, an un-estimated view (its features are skipped), an already estimated track
+  const TrackId outlier = sc.tracks[10], done = sc.tracks[30];
+  {
+    const ViewId v = *sc.rec.MutableTrack(outlier)->ViewIds().begin();
+    const Feature* f = sc.rec.MutableView(v)->GetFeature(outlier);
+    sc.rec.MutableView(v)->AddFeature(outlier, Feature(f->x() + 300.0, f->y()));
+  }
+  const ViewId unestimated_view = sc.views[11];
+  sc.rec.MutableView(unestimated_view)->SetEstimated(false);
+  for (TrackId t : sc.tracks) {
+    Track* tr = sc.rec.MutableTrack(t);
+    tr->SetEstimated(t == done);
+    if (t != done) for (int j = 0; j < 4; ++j) (*tr->MutablePoint())[j] = 7.0 + j;  // must be ignored
+  }
+  // oracle on an independent flattening of the same job
+  std::vector<double> ext, intr, pt, xy; std::vector<uint8_t> ec, pc; std::vector<int32_t> cg, gm, oc, op; std::vector<uint32_t> mk;
+  std::vector<TrackId> order;
+  {
+    std::vector<ViewId> vs;
+    for (ViewId v : sc.views) if (sc.rec.MutableView(v)->IsEstimated()) vs.push_back(v);
+    for (size_t i = 0; i < vs.size(); ++i) {
+      Camera* cam = sc.rec.MutableView(vs[i])->MutableCamera();
+      for (int j = 0; j < 6; ++j) ext.push_back(cam->extrinsics()[j]);
+      ec.push_back(TBA_EXT_ALL_CONST); cg.push_back((int32_t)i); gm.push_back(TBA_MODEL_PINHOLE); mk.push_back(0x7F);
+      for (int j = 0; j < TBA_INTR_STRIDE; ++j) intr.push_back(j < 7 ? cam->intrinsics()[j] : 0.0);
+    }
+    for (TrackId t : sc.tracks) {
+      if (t == done) continue;
+      Track* tr = sc.rec.MutableTrack(t);
+      for (int j = 0; j < 4; ++j) pt.push_back(tr->Point().data()[j]);
+      pc.push_back(0);
+      for (size_t i = 0; i < vs.size(); ++i) {
+        if (!tr->ViewIds().count(vs[i])) continue;
+        const Feature* f = sc.rec.MutableView(vs[i])->GetFeature(t);
+        oc.push_back((int32_t)i); op.push_back((int32_t)order.size()); xy.push_back(f->x()); xy.push_back(f->y());
+      }
+      order.push_back(t);
+    }
+  }
+  tba_problem p; std::memset(&p, 0, sizeof p);
+  p.n_cam = (int32_t)ec.size(); p.ext = ext.data(); p.ext_const = ec.data(); p.cam_group = cg.data();
+  p.n_group = p.n_cam; p.group_model = gm.data(); p.intr = intr.data(); p.group_const_mask = mk.data();
+  p.n_pt = (int32_t)order.size(); p.pt = pt.data(); p.pt_const = pc.data(); p.n_obs = (int64_t)oc.size();
+  p.obs_cam = oc.data(); p.obs_pt = op.data(); p.obs_xy = xy.data();
+  void* h = dlopen(oracle_path, RTLD_NOW);
+  EXPECT(h != nullptr);
+  oracle_estimate_fn oracle_estimate = (oracle_estimate_fn)dlsym(h, "oracle_estimate_tracks");
+  EXPECT(oracle_estimate != nullptr);
+  tba_options oo; tba_options_init(&oo); oo.use_inner_iterations = 0; oo.linear_solver_type = TBA_ITERATIVE_SCHUR;
+  std::vector<uint8_t> ost(order.size()); int32_t ocounts[5];
+  EXPECT(oracle_estimate(&oo, &p, 5.0, 3.0, 1, ost.data(), ocounts) == 0);
+
+  TrackEstimatorB200::Options o;
+  o.ba_options = IterativeOptions();
+  TrackEstimatorB200 est(o, &sc.rec);
+  TrackEstimatorB200::Summary s = est.EstimateAllTracks();
+  EXPECT(est.engine_ok());
+  EXPECT(s.input_num_estimated_tracks == 1 && s.num_triangulation_attempts == (int)order.size());
+  EXPECT((int)s.estimated_tracks.size() == ocounts[0] && est.num_bad_reprojections() == ocounts[4] && est.num_bad_angles() == ocounts[1]);
+  EXPECT(ocounts[0] >= (int)order.size() - 5 && ocounts[4] >= 1);
+  EXPECT(!s.estimated_tracks.count(outlier) && !sc.rec.MutableTrack(outlier)->IsEstimated());
+  for (size_t q = 0; q < order.size(); ++q) {
+    Track* tr = sc.rec.MutableTrack(order[q]);
+    EXPECT(tr->IsEstimated() == (ost[q] == 0) && (s.estimated_tracks.count(order[q]) == 1) == (ost[q] == 0));
+    if (ost[q] != 0) continue;
+    const double* a = tr->Point().data();
+    const double* b = &pt[q * 4];
+    const double* r = refined.rec.MutableTrack(order[q])->Point().data();
+    for (int j = 0; j < 3; ++j) {
+      EXPECT(std::fabs(a[j] / a[3] - b[j] / b[3]) <= 1e-6 * (1.0 + std::fabs(b[j] / b[3])));   // = oracle
+      EXPECT(std::fabs(a[j] / a[3] - r[j] / r[3]) <= 0.2);                                      // ~ the jointly refined point
+    }
+  }
+  // cameras untouched
+  for (ViewId v : sc.views) EXPECT(std::memcmp(sc.rec.MutableView(v)->MutableCamera()->extrinsics(), refined.rec.MutableView(v)->MutableCamera()->extrinsics(), 48) == 0);
+  std::printf("tracks ok: %d of %d estimated, %d bad reprojections, %d bad angles\n", (int)s.estimated_tracks.size(), s.num_triangulation_attempts,
+              est.num_bad_reprojections(), est.num_bad_angles());
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "flatten") return TestFlatten();
   if (argc >= 3 && std::string(argv[1]) == "solve") return TestSolve(argv[2]);
-  std::fprintf(stderr, "usage: adapter_test flatten | solve <path to libba_oracle.so>\n");
+  if (argc >= 2 && std::string(argv[1]) == "tracks-nogpu") return TestTracksNoGpu();
+  if (argc >= 3 && std::string(argv[1]) == "tracks") return TestTracks(argv[2]);
+  std::fprintf(stderr, "usage: adapter_test flatten | tracks-nogpu | solve <libba_oracle.so> | tracks <libba_oracle.so>\n");
   return 2;
 }

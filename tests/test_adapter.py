@@ -19,3 +19,11 @@ def test_problem_construction_matches_reference_rules(adapter_test_bin):
     out = subprocess.run([adapter_test_bin, "flatten"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "flatten ok" in out.stdout
+
+
+def test_track_estimator_host_logic_and_loud_refusal_without_gpu(adapter_test_bin):
+    """TrackEstimatorB200 (drop-in for estimate_track.h): bookkeeping of EstimateTracks (:142-158) and, in a container
+    without a GPU, a loud refusal that leaves the reconstruction untouched (no CPU path)."""
+    out = subprocess.run([adapter_test_bin, "tracks-nogpu"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "tracks-nogpu ok" in out.stdout

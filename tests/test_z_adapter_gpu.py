@@ -21,3 +21,11 @@ def test_adapter_end_to_end_against_oracle(adapter_test_bin):
     out = subprocess.run([adapter_test_bin, "solve", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "solve ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_track_estimator_end_to_end_against_oracle(adapter_test_bin):
+    """TrackEstimatorB200::EstimateAllTracks (batched estimate_track.cc) after a joint BA, against oracle_estimate_tracks."""
+    out = subprocess.run([adapter_test_bin, "tracks", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "tracks ok" in out.stdout

@@ -23,6 +23,13 @@
 #include <cstdint>
 #include <cfloat>
 
+// '#pragma unroll' only where the device compiler sees it (the host pass of __host__ __device__ code warns otherwise)
+#ifdef __CUDA_ARCH__
+#define TBA_UNROLL _Pragma("unroll")
+#else
+#define TBA_UNROLL
+#endif
+
 namespace tba {
 
 constexpr int kModelPinhole = 0;
@@ -89,7 +96,7 @@ __host__ __device__ inline void cam_prep(const double* __restrict__ w, double* _
 }
 
 // ceres::LossFunction::Evaluate for the six types create_loss_function.cc:42-71 maps to.
-__device__ inline void loss_evaluate(int type, double a, double s, double rho[3]) {
+__host__ __device__ inline void loss_evaluate(int type, double a, double s, double rho[3]) {
   switch (type) {
     case 1: {  // HUBER
       const double b = a * a;
@@ -145,7 +152,7 @@ __host__ __device__ inline void project_pixel(int model, const double* __restric
 }
 
 // Projection only (the double instantiation of the functor). Returns false if ||a||^2 < 1e-8.
-__device__ inline bool reproject(int model, const double* __restrict__ C, const double* __restrict__ R,
+__host__ __device__ inline bool reproject(int model, const double* __restrict__ C, const double* __restrict__ R,
                                  const double* __restrict__ k, const double X0, const double X1, const double X2,
                                  const double h, const double x, const double y, double& r0, double& r1) {
   double px, py, qz, a_sq;
@@ -161,7 +168,7 @@ __device__ inline bool reproject(int model, const double* __restrict__ C, const 
 // of the stored intrinsics columns (bits of IMASK).  r[2] is the robustified residual,
 // rho0 the loss value (cost contribution 0.5 * rho0).
 template <uint32_t IMASK>
-__device__ inline bool linearize_obs(int model, const double* __restrict__ C, const double* __restrict__ rec,
+__host__ __device__ inline bool linearize_obs(int model, const double* __restrict__ C, const double* __restrict__ rec,
                                      const double* __restrict__ k, const double X0, const double X1, const double X2,
                                      const double h, const double x, const double y, int loss_type, double loss_width,
                                      double r[2], double& rho0, double Ja[6], double Jw[6], double Jh[2], double* Ji) {
@@ -258,12 +265,12 @@ __device__ inline bool linearize_obs(int model, const double* __restrict__ C, co
     col[2][0] = vd;  col[2][1] = 0.0;       // d/ds
     col[3][0] = 1.0; col[3][1] = 0.0;       // d/dcx
     col[4][0] = 0.0; col[4][1] = 1.0;       // d/dcy
-#pragma unroll
+    TBA_UNROLL
     for (int j = 5; j < 10; ++j) {          // distortion params: K2 * d(ud,vd)/dk_j
       col[j][0] = f * dk[j][0] + sk * dk[j][1];
       col[j][1] = f * ar * dk[j][1];
     }
-#pragma unroll
+    TBA_UNROLL
     for (int j = 0; j < NI; ++j) {
       constexpr uint32_t M = IMASK;
       const int idx = nth_bit(M, j);

@@ -973,6 +973,95 @@ int tba_filter_tracks(tba_context* c, double max_inlier_reprojection_error, doub
   return TBA_OK;
 }
 
+// --------------------------------------------------------------------------- N3: batched track estimation / per-track BA
+namespace {
+PointLmOptions point_lm_options(const tba_options& o) {
+  PointLmOptions l;
+  l.loss_type = o.loss_function_type; l.loss_width = o.robust_loss_width;
+  l.max_num_iterations = o.max_num_iterations;
+  l.function_tolerance = o.function_tolerance; l.gradient_tolerance = o.gradient_tolerance; l.parameter_tolerance = o.parameter_tolerance;
+  l.initial_radius = o.initial_trust_region_radius; l.max_radius = o.max_trust_region_radius; l.min_radius = o.min_trust_region_radius;
+  l.min_relative_decrease = o.min_relative_decrease; l.min_diag = o.min_lm_diagonal; l.max_diag = o.max_lm_diagonal;
+  l.jacobi_scaling = o.jacobi_scaling; l.max_consecutive_invalid = o.max_num_consecutive_invalid_steps;
+  return l;
+}
+
+// D2H of the per-packed-point outputs and scatter to caller order (points without observations are not packed).
+int gather_track_outputs(tba_context* c, const uint8_t* d_status, const double* d_cost2, uint8_t fill, uint8_t* status, double* initial_cost,
+                         double* final_cost) {
+  const int npk = c->P.n_pt;
+  std::vector<uint8_t> hs((size_t)npk);
+  std::vector<double> hc((size_t)npk * 2);
+  if (npk > 0) {
+    CUDA_OK(c, cudaMemcpyAsync(hs.data(), d_status, (size_t)npk, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(hc.data(), d_cost2, (size_t)npk * 16, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int q = 0; q < c->n_pt_caller; ++q) {
+    status[q] = fill;
+    if (initial_cost) initial_cost[q] = -1.0;
+    if (final_cost) final_cost[q] = -1.0;
+  }
+  for (int k = 0; k < npk; ++k) {
+    const int q = c->pk2caller[k];
+    status[q] = hs[k];
+    if (initial_cost) initial_cost[q] = hc[(size_t)2 * k];
+    if (final_cost) final_cost[q] = hc[(size_t)2 * k + 1];
+  }
+  c->d2h_bytes += (double)npk * 17;
+  return TBA_OK;
+}
+}  // namespace
+
+int tba_adjust_tracks(tba_context* c, const tba_options* options, uint8_t* status, double* initial_cost, double* final_cost,
+                      int32_t* num_failed) {
+  if (!c || !c->uploaded || !options || !status) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevProblem& P = c->P;
+  DevBuf<uint8_t> d_status;
+  DevBuf<double> d_cost2;
+  CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
+  CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  if (P.n_pt > 0) LAUNCH(c, k_adjust_tracks, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, point_lm_options(*options), d_status.p, d_cost2.p);
+  const int rc = gather_track_outputs(c, d_status.p, d_cost2.p, kTrackSkipped, status, initial_cost, final_cost);
+  if (rc) return rc;
+  int nf = 0;
+  for (int q = 0; q < c->n_pt_caller; ++q) nf += status[q] == TBA_FAILURE;
+  if (num_failed) *num_failed = nf;
+  return TBA_OK;
+}
+
+int tba_estimate_tracks(tba_context* c, const tba_options* ba_options, double max_acceptable_reprojection_error_pixels,
+                        double min_triangulation_angle_degrees, int32_t bundle_adjustment, uint8_t* status, int32_t counts[5]) {
+  if (!c || !c->uploaded || !ba_options || !status) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevProblem& P = c->P;
+  TrackEstimatorOptions o;
+  o.max_sq_reprojection_error = max_acceptable_reprojection_error_pixels * max_acceptable_reprojection_error_pixels;
+  o.cos_min_angle = std::cos(min_triangulation_angle_degrees * 3.14159265358979323846 / 180.0);
+  o.bundle_adjustment = bundle_adjustment ? 1 : 0;
+  o.lm = point_lm_options(*ba_options);
+  DevBuf<uint8_t> d_status;
+  DevBuf<double> d_cost2;
+  CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
+  CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  // the rays live in the Jacobian store (NJ >= 14 doubles per slot; re-linearised by the next tba_minimize anyway)
+  double* ray = P.J;
+  if (c->n_slots > 0) LAUNCH(c, k_track_rays, (unsigned)((c->n_slots + 255) / 256), 256, 0, P, (long long)c->n_slots, ray);
+  if (P.n_pt > 0) LAUNCH(c, k_estimate_tracks, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, ray, o, d_status.p, d_cost2.p);
+  // caller points without any observation: "view_ids.size() < 2" -> bad angle bucket
+  const int rc = gather_track_outputs(c, d_status.p, d_cost2.p, kTrackBadAngle, status, nullptr, nullptr);
+  if (rc) return rc;
+  if (counts) {
+    for (int j = 0; j < 5; ++j) counts[j] = 0;
+    for (int q = 0; q < c->n_pt_caller; ++q)
+      if (status[q] < 5) ++counts[status[q]];
+  }
+  return TBA_OK;
+}
+
 // --------------------------------------------------------------------------- single-process multi-GPU
 // The drop-in is called from ONE host thread (Theia's estimators); this entry point shards points + observations over
 // n_devices GPUs of the box, runs one rank per device on its own host thread (each with its own context, stream and

@@ -11,6 +11,7 @@
 
 #include "tba_camera_models.cuh"
 #include "tba_filter.cuh"
+#include "tba_track_estimator.cuh"
 
 namespace tba {
 
@@ -316,6 +317,62 @@ __global__ void k_filter_tracks(DevProblem P, const long long* __restrict__ pt_s
   double mean;
   status[k] = filter_track(V, k, pt_slot[k], pt_len[k], max_sq_err, cos_min_angle, &mean);
   if (mean_sq_err) mean_sq_err[k] = mean;
+}
+
+// --------------------------------------------------------- N3: batched track estimation / per-track BA
+// Unit viewing ray of every observation slot (Camera::PixelToUnitDepthRay, normalised): one thread per slot, coalesced
+// reads of xy and writes of ray[slot/32][3][32]; the iterative undistortion makes this the arithmetic half of
+// TrackEstimator::EstimateTrack, and it is observation-parallel.
+__global__ void k_track_rays(DevProblem P, long long n_slots, double* __restrict__ ray) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int cam = P.slot_cam[s];
+  if (cam < 0) return;
+  const int grp = P.cam_group[cam];
+  const long long wq = s >> 5;
+  const int l = (int)(s & 31);
+  double d[3];
+  observation_ray(P.group_model[grp], P.cam_rec + (size_t)cam * kCamRec, P.intr + (size_t)grp * 10, P.xy[(size_t)(wq * 2) * 32 + l],
+                  P.xy[(size_t)(wq * 2 + 1) * 32 + l], d);
+  ray[(size_t)(wq * 3 + 0) * 32 + l] = d[0]; ray[(size_t)(wq * 3 + 1) * 32 + l] = d[1]; ray[(size_t)(wq * 3 + 2) * 32 + l] = d[2];
+}
+
+__device__ inline FilterView filter_view(const DevProblem& P) {
+  FilterView V;
+  V.ext = P.ext; V.cam_rec = P.cam_rec; V.intr = P.intr; V.pt = P.pt; V.xy = P.xy;
+  V.slot_cam = P.slot_cam; V.cam_group = P.cam_group; V.group_model = P.group_model;
+  return V;
+}
+
+// TrackEstimator::EstimateTrack for every non-constant packed point (one thread per point; thousands of independent
+// 4-parameter problems).  cost2[k] = {initial, final} cost of the per-track BA (-1 when it did not run).
+__global__ void k_estimate_tracks(DevProblem P, const long long* __restrict__ pt_slot, const int* __restrict__ pt_len,
+                                  const double* __restrict__ ray, TrackEstimatorOptions o, uint8_t* __restrict__ status,
+                                  double* __restrict__ cost2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n_pt) return;
+  if (P.pt_const[k]) { status[k] = kTrackSkipped; cost2[2 * k] = cost2[2 * k + 1] = -1.0; return; }
+  const FilterView V = filter_view(P);
+  double X[4] = {P.pt[(size_t)k * 4], P.pt[(size_t)k * 4 + 1], P.pt[(size_t)k * 4 + 2], P.pt[(size_t)k * 4 + 3]};
+  PointLmResult lm;
+  status[k] = estimate_track(V, ray, pt_slot[k], pt_len[k], X, o, &lm);
+  for (int j = 0; j < 4; ++j) P.pt[(size_t)k * 4 + j] = X[j];
+  cost2[2 * k] = lm.initial_cost; cost2[2 * k + 1] = lm.final_cost;
+}
+
+// BundleAdjustTrack (bundle_adjustment.cc:96-107) for every non-constant packed point: LM on the point, cameras constant.
+// status: Ceres termination type (0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE), 255 = constant point (not adjusted).
+__global__ void k_adjust_tracks(DevProblem P, const long long* __restrict__ pt_slot, const int* __restrict__ pt_len, PointLmOptions o,
+                                uint8_t* __restrict__ status, double* __restrict__ cost2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n_pt) return;
+  if (P.pt_const[k]) { status[k] = kTrackSkipped; cost2[2 * k] = cost2[2 * k + 1] = -1.0; return; }
+  const FilterView V = filter_view(P);
+  double X[4] = {P.pt[(size_t)k * 4], P.pt[(size_t)k * 4 + 1], P.pt[(size_t)k * 4 + 2], P.pt[(size_t)k * 4 + 3]};
+  const PointLmResult lm = point_lm(V, pt_slot[k], pt_len[k], X, o);
+  for (int j = 0; j < 4; ++j) P.pt[(size_t)k * 4 + j] = X[j];
+  status[k] = (uint8_t)lm.termination;
+  cost2[2 * k] = lm.initial_cost; cost2[2 * k + 1] = lm.final_cost;
 }
 
 // --------------------------------------------------------- per-point blocks

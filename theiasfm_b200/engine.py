@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks",
 ]
 
 
@@ -58,6 +58,8 @@ def lib():
         L.tba_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
         L.tba_solve_multi.argtypes = [C.POINTER(_abi.tba_options), C.POINTER(_abi.tba_problem), C.POINTER(_abi.tba_summary), C.c_int]
         L.tba_debug_pack.restype = C.c_int
+        L.tba_adjust_tracks.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
+        L.tba_estimate_tracks.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
         L.tba_filter_tracks.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_uint8), dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -233,6 +235,23 @@ class Engine:
         self._check(lib().tba_filter_tracks(self._h, max_inlier_reprojection_error, min_triangulation_angle_degrees,
                                             status.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(mean), C.byref(nb), C.byref(ni)))
         return status[:n], mean[:n], nb.value, ni.value
+
+    def adjust_tracks(self, options):
+        """tba_adjust_tracks (batched BundleAdjustTrack) on the device-resident problem; call download() for the points.
+        Returns (status [n_pt] uint8, initial_cost, final_cost, n_failed)."""
+        n = max(self._problem.n_pt, 1)
+        status = np.zeros(n, np.uint8); ic = np.zeros(n); fc = np.zeros(n); nf = C.c_int32()
+        self._check(lib().tba_adjust_tracks(self._h, C.byref(options), status.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(ic), _dp(fc), C.byref(nf)))
+        n = self._problem.n_pt
+        return status[:n], ic[:n], fc[:n], nf.value
+
+    def estimate_tracks(self, options, max_reprojection_error_pixels=5.0, min_triangulation_angle_degrees=3.0, bundle_adjustment=True):
+        """tba_estimate_tracks (batched TrackEstimator::EstimateTrack); call download() for the points. Returns (status, counts[5])."""
+        status = np.zeros(max(self._problem.n_pt, 1), np.uint8); counts = np.zeros(5, np.int32)
+        self._check(lib().tba_estimate_tracks(self._h, C.byref(options), max_reprojection_error_pixels, min_triangulation_angle_degrees,
+                                              int(bundle_adjustment), status.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                              counts.ctypes.data_as(C.POINTER(C.c_int32))))
+        return status[:self._problem.n_pt], counts
 
     def reset_parameters(self, problem):
         st = problem.as_struct()
