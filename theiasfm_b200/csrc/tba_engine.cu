@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -120,6 +121,10 @@ struct tba_context {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_spans[2];  // 0: matvec, 1: linearize ; indices into ev_pool
+  // set by tba_solve_multi (which sees the whole problem) before tba_upload: global per-camera observation counts and the
+  // global number of free points, so that the upload needs no collective
+  const double* preset_cnt_cam = nullptr;
+  int64_t preset_free_pt = -1;
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
   bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
@@ -603,7 +608,11 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
   c->n_free_pt = H.n_free_pt;
   c->n_free_pt_global = c->n_free_pt;
-  if (c->world > 1) {  // counts are global properties
+  if (c->world > 1 && c->preset_cnt_cam != nullptr) {  // single-process multi-GPU: the caller counted over the whole problem
+    std::fill(cnt_g.begin(), cnt_g.end(), 0.0);
+    for (int i = 0; i < nc; ++i) { cnt_c[i] = c->preset_cnt_cam[i]; cnt_g[p->cam_group[i]] += cnt_c[i]; }
+    c->n_free_pt_global = c->preset_free_pt;
+  } else if (c->world > 1) {  // counts are global properties
     std::vector<double> tmp(cnt_c);
     tmp.insert(tmp.end(), cnt_g.begin(), cnt_g.end());
     tmp.push_back((double)c->n_free_pt);
@@ -1094,8 +1103,17 @@ int tba_solve_multi(const tba_options* options, tba_problem* problem, tba_summar
   const int np = problem->n_pt;
   for (int64_t i = 0; i < problem->n_obs; ++i)
     if (problem->obs_pt[i] < 0 || problem->obs_pt[i] >= np) return TBA_ERR_INVALID_ARGUMENT;
+  for (int64_t i = 0; i < problem->n_obs; ++i)
+    if (problem->obs_cam[i] < 0 || problem->obs_cam[i] >= problem->n_cam) return TBA_ERR_INVALID_ARGUMENT;
   std::vector<int32_t> cnt((size_t)np, 0);
-  for (int64_t i = 0; i < problem->n_obs; ++i) cnt[problem->obs_pt[i]]++;
+  std::vector<double> cnt_cam((size_t)std::max(problem->n_cam, 1), 0.0);
+  for (int64_t i = 0; i < problem->n_obs; ++i) { cnt[problem->obs_pt[i]]++; cnt_cam[problem->obs_cam[i]] += 1.0; }
+  int64_t n_free_pt = 0;  // free points that have observations (the only ones in the program)
+  for (int q = 0; q < np; ++q) n_free_pt += (cnt[q] > 0 && !problem->pt_const[q]) ? 1 : 0;
+  std::mutex bar_mu;
+  std::condition_variable bar_cv;
+  int bar_count = 0;
+  std::atomic<bool> failed(false);
   struct Shard { int32_t b = 0, e = 0; std::vector<double> ext, intr, pt, xy; std::vector<int32_t> cam, ptl; tba_summary s; int rc = 0; };
   std::vector<Shard> sh((size_t)n_devices);
   tba_iteration* itbuf = summary->iterations;
@@ -1119,7 +1137,26 @@ int tba_solve_multi(const tba_options* options, tba_problem* problem, tba_summar
       p.n_obs = (int64_t)S.cam.size(); p.obs_cam = S.cam.data(); p.obs_pt = S.ptl.data(); p.obs_xy = S.xy.data();
       memset(&S.s, 0, sizeof S.s);
       if (r == 0) { S.s.iterations = itbuf; S.s.iterations_capacity = itcap; }
-      S.rc = tba_solve(g_multi_ctx[r], options, &p, &S.s);
+      // tba_solve split in phases with a host barrier in between: every allocation (cudaMalloc / cudaMallocHost /
+      // cudaFree of a grown buffer) of every rank happens while no NCCL kernel of this process is in flight, and a rank
+      // whose upload failed keeps the others out of the collectives of tba_minimize
+      tba_context* cx = g_multi_ctx[r];
+      cx->preset_cnt_cam = cnt_cam.data(); cx->preset_free_pt = n_free_pt;
+      S.rc = tba_upload(cx, options, &p);
+      cx->preset_cnt_cam = nullptr; cx->preset_free_pt = -1;
+      if (S.rc != TBA_OK) { failed.store(true); S.s.termination_type = TBA_FAILURE; snprintf(S.s.message, sizeof S.s.message, "%s", tba_last_error(cx)); }
+      {
+        std::unique_lock<std::mutex> bl(bar_mu);
+        if (++bar_count == n_devices) bar_cv.notify_all();
+        else bar_cv.wait(bl, [&] { return bar_count == n_devices; });
+      }
+      if (failed.load()) { if (S.rc == TBA_OK) S.rc = TBA_ERR_INVALID_ARGUMENT; return; }
+      S.rc = tba_minimize(cx, &S.s);
+      if (S.rc != TBA_OK) return;
+      const double t0 = now_s();
+      S.rc = tba_download(cx, &p);
+      S.s.solve_time_in_seconds += now_s() - t0;
+      S.s.d2h_bytes = cx->d2h_bytes;
     });
   for (auto& t : th) t.join();
   for (int r = 0; r < n_devices; ++r)
