@@ -241,6 +241,54 @@ BundleAdjustmentSummary BundleAdjusterB200::Optimize() {
   return summary;
 }
 
+BundleAdjustmentSummary BundleAdjusterB200::OptimizeTracks() {
+  BundleAdjustmentSummary summary;
+  B200_CHECK(optimized_views_.empty(), "OptimizeTracks() is for problems built with AddTrack only");
+  Flat flat;
+  tba_options opts;
+  Flatten(&flat, &opts);
+  opts.use_inner_iterations = 0;                 // bundle_adjustment.cc:101
+  opts.linear_solver_type = TBA_DENSE_QR;        // bundle_adjustment.cc:100 (any exact type: a 4x4 solve per track)
+  tba_problem problem = flat.AsProblem();
+  const double internal_setup_time = NowSeconds() - start_time_;
+  std::lock_guard<std::mutex> lock(b200::Mutex());
+  tba_context* ctx = AcquireContext();
+  std::memset(&last_summary_, 0, sizeof last_summary_);
+  if (ctx == nullptr) {
+    std::fprintf(stderr, "theia_ba_b200: no usable CUDA device; bundle adjustment not run (there is no CPU fallback)\n");
+    std::snprintf(last_summary_.message, sizeof last_summary_.message, "no usable CUDA device");
+    return summary;
+  }
+  const double t0 = NowSeconds();
+  resident_ = false;
+  ++b200::Generation();
+  const size_t n = flat.track_of_pt.size();
+  std::vector<uint8_t> status(n + 1);
+  std::vector<double> ic(n + 1), fc(n + 1);
+  int32_t failed = 0;
+  int rc = tba_upload(ctx, &opts, &problem);
+  const double t1 = NowSeconds();
+  if (rc == TBA_OK) rc = tba_adjust_tracks(ctx, &opts, status.data(), ic.data(), fc.data(), &failed);
+  if (rc == TBA_OK) rc = tba_download(ctx, &problem);
+  if (rc != TBA_OK) {
+    std::snprintf(last_summary_.message, sizeof last_summary_.message, "%s", tba_last_error(ctx));
+    std::fprintf(stderr, "theia_ba_b200: %s\n", last_summary_.message);
+    return summary;
+  }
+  for (size_t q = 0; q < n; ++q) {
+    if (status[q] == TBA_TRACK_SKIPPED) continue;
+    std::memcpy(reconstruction_->MutableTrack(flat.track_of_pt[q])->MutablePoint()->data(), &flat.pt[q * 4], 4 * sizeof(double));
+    if (ic[q] >= 0.0) summary.initial_cost += ic[q];
+    if (fc[q] >= 0.0) summary.final_cost += fc[q];
+  }
+  summary.setup_time_in_seconds = internal_setup_time + (t1 - t0);
+  summary.solve_time_in_seconds = NowSeconds() - t1;
+  summary.success = failed == 0;
+  last_summary_.success = summary.success; last_summary_.initial_cost = summary.initial_cost; last_summary_.final_cost = summary.final_cost;
+  last_summary_.termination_type = n == 1 ? static_cast<int32_t>(status[0]) : static_cast<int32_t>(failed ? TBA_FAILURE : TBA_CONVERGENCE);
+  return summary;
+}
+
 int BundleAdjusterB200::SetOutlierTracksToUnestimated(const double max_inlier_reprojection_error,
                                                       const double min_triangulation_angle_degrees) {
   std::lock_guard<std::mutex> lock(b200::Mutex());
@@ -272,6 +320,26 @@ BundleAdjustmentSummary BundleAdjustPartialReconstructionB200(const BundleAdjust
   for (const ViewId view_id : view_ids) bundle_adjuster.AddView(view_id);
   for (const TrackId track_id : track_ids) bundle_adjuster.AddTrack(track_id);
   return bundle_adjuster.Optimize();
+}
+
+// bundle_adjustment.cc:82-93
+BundleAdjustmentSummary BundleAdjustViewB200(const BundleAdjustmentOptions& options, const ViewId view_id, Reconstruction* reconstruction) {
+  BundleAdjustmentOptions ba_options = options;
+  ba_options.linear_solver_type = ceres::DENSE_QR;
+  ba_options.use_inner_iterations = false;
+  BundleAdjusterB200 bundle_adjuster(ba_options, reconstruction);
+  bundle_adjuster.AddView(view_id);
+  return bundle_adjuster.Optimize();
+}
+
+// bundle_adjustment.cc:95-107
+BundleAdjustmentSummary BundleAdjustTrackB200(const BundleAdjustmentOptions& options, const TrackId track_id, Reconstruction* reconstruction) {
+  BundleAdjustmentOptions ba_options = options;
+  ba_options.linear_solver_type = ceres::DENSE_QR;
+  ba_options.use_inner_iterations = false;
+  BundleAdjusterB200 bundle_adjuster(ba_options, reconstruction);
+  bundle_adjuster.AddTrack(track_id);
+  return bundle_adjuster.OptimizeTracks();
 }
 
 // bundle_adjustment.cc:66-80

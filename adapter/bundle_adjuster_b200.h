@@ -68,6 +68,11 @@ class BundleAdjusterB200 {
   void AddTrack(const TrackId track_id);
   BundleAdjustmentSummary Optimize();
 
+  // For problems built with AddTrack only (every camera constant, bundle_adjuster.cc:156-175): each track is its own
+  // 4-parameter problem; they are solved independently, one GPU thread per track (tba_adjust_tracks), which for one track
+  // is exactly BundleAdjustTrack.  success = no track failed; costs are summed over the tracks.
+  BundleAdjustmentSummary OptimizeTracks();
+
   // The flattened problem Optimize() hands to tba_solve (exposed for tests / tools).
   struct Flat {
     std::vector<double> ext, intr, pt, obs_xy;
@@ -106,6 +111,12 @@ class BundleAdjusterB200 {
   bool resident_ = false;
   uint64_t generation_ = 0;               // b200::Generation() when that problem was uploaded
 };
+
+// Drop-ins for bundle_adjustment.h:145-155 (bundle_adjustment.cc:82-107).  The reference forces DENSE_QR and no inner
+// iterations; the engine computes the same exact LM step (see tba_options::linear_solver_type).  BundleAdjustTrackB200
+// is provided for API completeness: one call = one tiny GPU launch sequence; use TrackEstimatorB200 for batches.
+BundleAdjustmentSummary BundleAdjustViewB200(const BundleAdjustmentOptions& options, const ViewId view_id, Reconstruction* reconstruction);
+BundleAdjustmentSummary BundleAdjustTrackB200(const BundleAdjustmentOptions& options, const TrackId track_id, Reconstruction* reconstruction);
 
 // Shared by the adapters of this directory: the process-wide engine context (guarded by Mutex()), a counter that
 // identifies which flattened problem currently lives on the device, and the options copy.

@@ -77,7 +77,7 @@ enum { TBA_OK = 0, TBA_ERR_INVALID_ARGUMENT = -1, TBA_ERR_UNSUPPORTED = -2,
 typedef struct tba_options {
   int32_t loss_function_type;          /* TRIVIAL */
   double  robust_loss_width;           /* 2.0 */
-  int32_t linear_solver_type;          /* SPARSE_SCHUR; engine: ITERATIVE_SCHUR, and DENSE/SPARSE_SCHUR solved by PCG to the fp64 floor */
+  int32_t linear_solver_type;          /* SPARSE_SCHUR; engine: ITERATIVE_SCHUR as such; every factorising type (0..4) = the same exact LM step, solved by PCG to the fp64 floor; CGNR refused */
   int32_t preconditioner_type;         /* SCHUR_JACOBI */
   int32_t visibility_clustering_type;  /* CANONICAL_VIEWS = 0 */
   int32_t verbose;                     /* 0 */

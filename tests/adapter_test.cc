@@ -361,11 +361,87 @@ static int TestTracks(const char* oracle_path) {
   return 0;
 }
 
+// N3: BundleAdjustViewB200 / BundleAdjustTrackB200 (bundle_adjustment.cc:82-107) against the oracle on the same flattening.
+static int TestMicro(const char* oracle_path, bool gpu) {
+  Scene sc;
+  BuildScene(&sc, 12, 400, 5, 5, 23);
+  if (gpu) EXPECT(BundleAdjustReconstructionB200(IterativeOptions(), &sc.rec).success);
+  void* h = dlopen(oracle_path, RTLD_NOW);
+  EXPECT(h != nullptr);
+  oracle_solve_fn solve = (oracle_solve_fn)dlsym(h, "oracle_solve");
+  EXPECT(solve != nullptr);
+  BundleAdjustmentOptions o;  // Theia defaults: the free functions override solver type and inner iterations themselves
+  o.intrinsics_to_optimize = OptimizeIntrinsicsType::NONE;
+  // ---- one view: pose disturbed, all its tracks constant
+  {
+    const ViewId v = sc.views[4];
+    double* e = sc.rec.MutableView(v)->MutableCamera()->mutable_extrinsics();
+    e[0] += 0.08; e[1] -= 0.05; e[3] += 0.01; e[5] -= 0.008;
+    Scene copy = sc;
+    BundleAdjustmentOptions oo = o; oo.linear_solver_type = ceres::DENSE_QR; oo.use_inner_iterations = false;
+    BundleAdjusterB200 ba(oo, &copy.rec);
+    ba.AddView(v);
+    BundleAdjusterB200::Flat f; tba_options to;
+    ba.Flatten(&f, &to);
+    EXPECT(f.view_of_cam.size() == 1 && f.ext_const[0] == 0);
+    for (uint8_t c : f.pt_const) EXPECT(c == 1);
+    tba_problem p = f.AsProblem();
+    tba_summary os; std::memset(&os, 0, sizeof os);
+    EXPECT(solve(&to, &p, &os) == 0 && os.success);
+    EXPECT(os.final_cost < 0.5 * os.initial_cost);
+    const double before = sc.rec.MutableTrack(sc.tracks[0])->Point().v[0];
+    if (gpu) {
+    BundleAdjustmentSummary s = BundleAdjustViewB200(o, v, &sc.rec);
+    EXPECT(s.success);
+    EXPECT(std::fabs(s.initial_cost - os.initial_cost) <= 1e-10 * os.initial_cost);
+    EXPECT(std::fabs(s.final_cost - os.final_cost) <= 1e-6 * os.final_cost);
+    EXPECT(s.final_cost < 0.5 * s.initial_cost);
+    const double* got = sc.rec.MutableView(v)->MutableCamera()->extrinsics();
+    for (int j = 0; j < 6; ++j) EXPECT(std::fabs(got[j] - f.ext[j]) <= 1e-6 * (1.0 + std::fabs(f.ext[j])));
+    EXPECT(sc.rec.MutableTrack(sc.tracks[0])->Point().v[0] == before);  // tracks constant
+    }
+  }
+  // ---- one track: point disturbed, all its views constant
+  {
+    const TrackId t = sc.tracks[17];
+    Track* tr = sc.rec.MutableTrack(t);
+    (*tr->MutablePoint())[0] += 0.2; (*tr->MutablePoint())[2] -= 0.3;
+    Scene copy = sc;
+    BundleAdjustmentOptions oo = o; oo.linear_solver_type = ceres::DENSE_QR; oo.use_inner_iterations = false;
+    BundleAdjusterB200 ba(oo, &copy.rec);
+    ba.AddTrack(t);
+    BundleAdjusterB200::Flat f; tba_options to;
+    ba.Flatten(&f, &to);
+    EXPECT(f.track_of_pt.size() == 1 && f.pt_const[0] == 0);
+    for (uint8_t c : f.ext_const) EXPECT(c == TBA_EXT_ALL_CONST);
+    tba_problem p = f.AsProblem();
+    tba_summary os; std::memset(&os, 0, sizeof os);
+    EXPECT(solve(&to, &p, &os) == 0 && os.success);
+    const ViewId v0 = *tr->ViewIds().begin();
+    double ext_before[6];
+    std::memcpy(ext_before, sc.rec.MutableView(v0)->MutableCamera()->extrinsics(), 48);
+    EXPECT(os.final_cost < os.initial_cost);
+    if (gpu) {
+    BundleAdjustmentSummary s = BundleAdjustTrackB200(o, t, &sc.rec);
+    EXPECT(s.success);
+    EXPECT(std::fabs(s.initial_cost - os.initial_cost) <= 1e-10 * os.initial_cost);
+    EXPECT(std::fabs(s.final_cost - os.final_cost) <= 1e-6 * (1.0 + os.final_cost));
+    const double* a = tr->Point().data();
+    for (int j = 0; j < 3; ++j) EXPECT(std::fabs(a[j] / a[3] - f.pt[j] / f.pt[3]) <= 1e-6 * (1.0 + std::fabs(f.pt[j] / f.pt[3])));
+    EXPECT(std::memcmp(ext_before, sc.rec.MutableView(v0)->MutableCamera()->extrinsics(), 48) == 0);
+    }
+  }
+  std::printf(gpu ? "micro ok\n" : "micro-oracle ok\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "flatten") return TestFlatten();
   if (argc >= 3 && std::string(argv[1]) == "solve") return TestSolve(argv[2]);
   if (argc >= 2 && std::string(argv[1]) == "tracks-nogpu") return TestTracksNoGpu();
   if (argc >= 3 && std::string(argv[1]) == "tracks") return TestTracks(argv[2]);
-  std::fprintf(stderr, "usage: adapter_test flatten | tracks-nogpu | solve <libba_oracle.so> | tracks <libba_oracle.so>\n");
+  if (argc >= 3 && std::string(argv[1]) == "micro") return TestMicro(argv[2], true);
+  if (argc >= 3 && std::string(argv[1]) == "micro-oracle") return TestMicro(argv[2], false);  // CPU: flattening + oracle half only
+  std::fprintf(stderr, "usage: adapter_test flatten | tracks-nogpu | solve <libba_oracle.so> | tracks <libba_oracle.so> | micro <libba_oracle.so>\n");
   return 2;
 }

@@ -27,3 +27,11 @@ def test_track_estimator_host_logic_and_loud_refusal_without_gpu(adapter_test_bi
     out = subprocess.run([adapter_test_bin, "tracks-nogpu"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "tracks-nogpu ok" in out.stdout
+
+
+def test_view_only_and_track_only_problems_flatten_and_solve_in_the_oracle(adapter_test_bin):
+    """The CPU half of the BundleAdjustViewB200 / BundleAdjustTrackB200 test (bundle_adjustment.cc:82-107): AddView-only and
+    AddTrack-only flattenings have the reference's constness pattern and the oracle solves them with the exact solver type."""
+    out = subprocess.run([adapter_test_bin, "micro-oracle", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "micro-oracle ok" in out.stdout

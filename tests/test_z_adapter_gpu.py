@@ -29,3 +29,11 @@ def test_track_estimator_end_to_end_against_oracle(adapter_test_bin):
     out = subprocess.run([adapter_test_bin, "tracks", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "tracks ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_bundle_adjust_view_and_track_against_oracle(adapter_test_bin):
+    """BundleAdjustViewB200 / BundleAdjustTrackB200 (bundle_adjustment.cc:82-107) against the oracle on the same flattening."""
+    out = subprocess.run([adapter_test_bin, "micro", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "micro ok" in out.stdout

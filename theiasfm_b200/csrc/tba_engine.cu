@@ -460,8 +460,8 @@ void push_iter(tba_summary* s, const tba_iteration& it) {
 
 int check_options(tba_context* c, const tba_options* o) {
   if (o->use_inner_iterations) { set_err(c, "use_inner_iterations=true is not implemented by the GPU engine (set it to false, as Theia's incremental/hybrid estimators do)"); return TBA_ERR_UNSUPPORTED; }
-  if (o->linear_solver_type != TBA_ITERATIVE_SCHUR && o->linear_solver_type != TBA_DENSE_SCHUR && o->linear_solver_type != TBA_SPARSE_SCHUR) {
-    set_err(c, "linear_solver_type %d unsupported: the GPU engine implements ITERATIVE_SCHUR, and DENSE_SCHUR / SPARSE_SCHUR as the same Schur system solved to the fp64 floor", o->linear_solver_type);
+  if (o->linear_solver_type < TBA_DENSE_NORMAL_CHOLESKY || o->linear_solver_type > TBA_ITERATIVE_SCHUR) {
+    set_err(c, "linear_solver_type %d unsupported: the GPU engine implements ITERATIVE_SCHUR, and the exact solver types (DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR) as the same LM step solved to the fp64 floor; CGNR is not implemented", o->linear_solver_type);
     return TBA_ERR_UNSUPPORTED;
   }
   if (o->linear_solver_type == TBA_ITERATIVE_SCHUR && o->preconditioner_type != TBA_PRECOND_SCHUR_JACOBI && o->preconditioner_type != TBA_PRECOND_IDENTITY) { set_err(c, "preconditioner_type %d unsupported (SCHUR_JACOBI or IDENTITY)", o->preconditioner_type); return TBA_ERR_UNSUPPORTED; }
@@ -578,7 +578,9 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   if (rc) return rc;
   CUDA_OK(c, cudaSetDevice(c->device));
   c->opt = *options;
-  if (options->linear_solver_type == TBA_DENSE_SCHUR || options->linear_solver_type == TBA_SPARSE_SCHUR) {
+  if (options->linear_solver_type != TBA_ITERATIVE_SCHUR) {
+    // Every factorising solver type (DENSE_QR / *_NORMAL_CHOLESKY on the full normal equations, *_SCHUR on the reduced
+    // system) computes the SAME Levenberg-Marquardt step exactly; Schur elimination is an exact algebraic rewrite of it.
     // The exact Schur solver types (Theia's default, and what SetBundleAdjustmentOptions picks below 1000 views:
     // reconstruction_estimator_utils.cc:110-133) solve the SAME reduced system a Cholesky factorisation of S solves;
     // here it is solved by the preconditioned CG run until the quadratic model stops changing at fp64 resolution.
