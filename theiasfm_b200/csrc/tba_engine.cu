@@ -90,7 +90,8 @@ struct tba_context {
   DevProblem P;
   int n_cam = 0, n_group = 0, n_pt = 0, n_tiles = 0;
   int64_t n_obs = 0, n_slots = 0;
-  std::vector<int64_t> slot_orig;  // slot -> caller observation index (-1 padding)
+  std::vector<int64_t> slot_orig;  // slot -> caller observation index (-1 padding); built on demand by the debug read-back
+  HostPack pack;                   // host packing scratch + result of the last upload (kept: capacity and faulted-in pages are reused)
   int64_t launches = 0;
   double h2d_bytes = 0, d2h_bytes = 0;
   double setup_seconds = 0;
@@ -600,7 +601,8 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   for (int i = 0; i < nc; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= ng) { set_err(c, "cam_group out of range"); return TBA_ERR_INVALID_ARGUMENT; }
   // ---- host packing (tba_pack.h: phases A-E, multi-threaded), into pinned staging memory
   const int T = std::max(1, std::min<int>(32, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
-  HostPack H;
+  HostPack& H = c->pack;
+  c->slot_orig.clear();
   pack_count_and_sort(p, T, &H);  // A, B, C
   if (H.bad >= 0) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)H.bad, p->obs_cam[H.bad], p->obs_pt[H.bad]); return TBA_ERR_INVALID_ARGUMENT; }
   if (H.maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", H.maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
@@ -666,11 +668,10 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   int16_t* h_slot_run = (int16_t*)carve((size_t)n_slots * 2);
   uint8_t* h_slot_flags = carve((size_t)n_slots);
   uint8_t* h_pt_const = carve((size_t)npk);
-  c->slot_orig.assign((size_t)n_slots, (int64_t)-1);
   {
     PackDest d;
     d.xy = h_xy; d.pt = h_pt; d.slot_cam = h_slot_cam; d.slot_pt = h_slot_pt; d.slot_run = h_slot_run; d.slot_flags = h_slot_flags;
-    d.pt_const = h_pt_const; d.slot_orig = c->slot_orig.data();
+    d.pt_const = h_pt_const; d.slot_orig = nullptr;  // not part of the upload (see TBA_VEC_RESIDUALS in tba_debug_read)
     pack_fill(p, H, T, d);
   }
   c->n_long_points = n_long;
@@ -756,12 +757,22 @@ int tba_download(tba_context* c, tba_problem* p) {
   if (!c || !p || !c->uploaded) return TBA_ERR_INVALID_ARGUMENT;
   CUDA_OK(c, cudaSetDevice(c->device));
   if (p->n_cam != c->n_cam || p->n_group != c->n_group || p->n_pt != c->n_pt_caller) { set_err(c, "download: problem shape differs from the uploaded one"); return TBA_ERR_INVALID_ARGUMENT; }
-  std::vector<double> ptk((size_t)c->n_pt * 4);
+  // packed points come back through the pinned staging buffer of the upload (idle by now), then scatter to caller order
+  std::vector<double> ptk_fallback;
+  double* ptk = reinterpret_cast<double*>(c->stage);
+  if (c->stage == nullptr || c->stage_cap < (size_t)c->n_pt * 32) { ptk_fallback.resize((size_t)c->n_pt * 4); ptk = ptk_fallback.data(); }
   CUDA_OK(c, cudaMemcpyAsync(p->ext, c->P.ext, (size_t)c->n_cam * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaMemcpyAsync(p->intr, c->P.intr, (size_t)c->n_group * 10 * 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(c, cudaMemcpyAsync(ptk.data(), c->P.pt, (size_t)c->n_pt * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(ptk, c->P.pt, (size_t)c->n_pt * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < c->n_pt; ++k) memcpy(p->pt + (size_t)c->pk2caller[k] * 4, &ptk[(size_t)k * 4], 32);
+  {
+    const int T = std::max(1, std::min<int>(16, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
+    const int* pk2caller = c->pk2caller.data();
+    double* dst = p->pt;
+    parallel_for(c->n_pt, T, [=](int64_t b0, int64_t e0, int) {
+      for (int64_t k = b0; k < e0; ++k) memcpy(dst + (size_t)pk2caller[k] * 4, ptk + (size_t)k * 4, 32);
+    });
+  }
   c->d2h_bytes += (double)c->n_cam * 48 + (double)c->n_group * 80 + (double)c->n_pt * 32;
   return TBA_OK;
 }
@@ -1331,6 +1342,7 @@ int tba_debug_read(tba_context* c, int which, double* out, int64_t n) {
     case TBA_VEC_RESIDUALS: {
       if (n != c->n_obs * 2) return TBA_ERR_INVALID_ARGUMENT;
       if ((rc = fetch(P.res, c->n_slots * 2, tmp))) return rc;
+      if ((int64_t)c->slot_orig.size() != c->n_slots) { c->slot_orig.resize((size_t)c->n_slots); pack_slot_orig(c->pack, 8, c->slot_orig.data()); }
       for (int64_t s = 0; s < c->n_slots; ++s) {
         const int64_t oi = c->slot_orig[s];
         if (oi < 0) continue;

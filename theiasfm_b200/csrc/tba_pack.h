@@ -36,9 +36,11 @@ void parallel_for(int64_t n, int nthreads, F f) {
   for (auto& x : th) x.join();
 }
 
-struct HostPack {
+struct HostPack {  // lives in the engine context: the vectors keep their capacity (and their faulted-in pages) across uploads
   // phases A-C
   std::vector<int> cnt_pt, cnt_cam;
+  std::vector<int> cam_hist;       // per-thread camera histograms of phase A
+  std::vector<int64_t> cursor;     // per-point write cursors of phase C
   std::vector<int64_t> off, order;
   std::vector<uint8_t> pt_nruns;
   int maxlen = 0;
@@ -66,53 +68,92 @@ struct PackDest {
   int16_t* slot_run;
   uint8_t* slot_flags;
   uint8_t* pt_const;  // [packed point]
-  int64_t* slot_orig; // pre-filled with -1
+  int64_t* slot_orig; // optional (nullptr: not wanted); pre-filled with -1
 };
 
 // A: validate + per-point / per-camera counts; B: offsets; C: observations grouped by point and sorted inside a point.
+// Written for both input orders that occur: grouped by point (synthetic scenes, BAL-style files) and grouped by view (the
+// adapter's flattening, bundle_adjuster.cc:125-134): per-thread camera histograms instead of contended atomics, one
+// atomic per RUN of equal point indices instead of one per observation, and the per-point sort works on locally
+// gathered (group, camera) keys and is skipped when the run is already in order.
 inline void pack_count_and_sort(const tba_problem* p, int T, HostPack* H) {
   const int nc = p->n_cam, np = p->n_pt;
   const int64_t no = p->n_obs;
+  T = std::max(1, T);
   H->cnt_pt.assign((size_t)np, 0);
   H->cnt_cam.assign((size_t)nc, 0);
+  const bool use_hist = (int64_t)nc * T <= ((int64_t)1 << 24);
+  if (use_hist) H->cam_hist.assign((size_t)nc * T, 0);
   std::atomic<int64_t> bad(-1);
   int* cnt_pt = H->cnt_pt.data();
   int* cnt_cam = H->cnt_cam.data();
-  parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
+  parallel_for(no, T, [&](int64_t b0, int64_t e0, int t) {
+    int* hist = use_hist ? H->cam_hist.data() + (size_t)t * nc : nullptr;
+    int cur = -1, run = 0;
     for (int64_t i = b0; i < e0; ++i) {
       const int q = p->obs_pt[i], cam = p->obs_cam[i];
       if (q < 0 || q >= np || cam < 0 || cam >= nc) { bad.store(i); return; }
-      __atomic_fetch_add(&cnt_pt[q], 1, __ATOMIC_RELAXED);
-      __atomic_fetch_add(&cnt_cam[cam], 1, __ATOMIC_RELAXED);
+      if (hist) ++hist[cam]; else __atomic_fetch_add(&cnt_cam[cam], 1, __ATOMIC_RELAXED);
+      if (q == cur) { ++run; continue; }
+      if (run) __atomic_fetch_add(&cnt_pt[cur], run, __ATOMIC_RELAXED);
+      cur = q; run = 1;
     }
+    if (run) __atomic_fetch_add(&cnt_pt[cur], run, __ATOMIC_RELAXED);
   });
   H->bad = bad.load();
   if (H->bad >= 0) return;
+  if (use_hist)
+    parallel_for(nc, T, [&](int64_t b0, int64_t e0, int) {
+      for (int t = 0; t < T; ++t) {
+        const int* hist = H->cam_hist.data() + (size_t)t * nc;
+        for (int64_t i = b0; i < e0; ++i) cnt_cam[i] += hist[i];
+      }
+    });
   H->off.assign((size_t)np + 1, 0);
   H->maxlen = 0;
   for (int q = 0; q < np; ++q) { H->maxlen = std::max(H->maxlen, cnt_pt[q]); H->off[(size_t)q + 1] = H->off[q] + cnt_pt[q]; }
   if (H->maxlen > kPackTile) return;
-  H->order.assign((size_t)no, 0);
+  H->order.resize((size_t)no);
+  H->cursor.assign(H->off.begin(), H->off.end() - 1);
   {
-    std::vector<int64_t> cur(H->off.begin(), H->off.end() - 1);
+    int64_t* cur = H->cursor.data();
     int64_t* order = H->order.data();
     parallel_for(no, T, [&](int64_t b0, int64_t e0, int) {
-      for (int64_t i = b0; i < e0; ++i) order[(size_t)__atomic_fetch_add(&cur[p->obs_pt[i]], (int64_t)1, __ATOMIC_RELAXED)] = i;
+      int64_t i = b0;
+      while (i < e0) {
+        const int q = p->obs_pt[i];
+        int64_t j = i + 1;
+        while (j < e0 && p->obs_pt[j] == q) ++j;
+        int64_t dst = __atomic_fetch_add(&cur[q], j - i, __ATOMIC_RELAXED);
+        for (; i < j; ++i) order[(size_t)dst++] = i;
+      }
     });
   }
   H->pt_nruns.assign((size_t)np, 0);
   parallel_for(np, T, [&](int64_t b0, int64_t e0, int) {
+    uint64_t key[kPackTile];
     for (int64_t q = b0; q < e0; ++q) {
-      auto bb = H->order.begin() + H->off[q], ee = H->order.begin() + H->off[(size_t)q + 1];
-      if (ee - bb > 1)
-        std::sort(bb, ee, [&](int64_t a, int64_t d) {
-          const int ga = p->cam_group[p->obs_cam[a]], gb = p->cam_group[p->obs_cam[d]];
-          if (ga != gb) return ga < gb;
-          if (p->obs_cam[a] != p->obs_cam[d]) return p->obs_cam[a] < p->obs_cam[d];
-          return a < d;
-        });
-      int runs = 0, last = -1;
-      for (auto it2 = bb; it2 != ee; ++it2) { const int g = p->cam_group[p->obs_cam[*it2]]; if (g != last) { ++runs; last = g; } }
+      int64_t* o = H->order.data() + H->off[q];
+      const int n = (int)(H->off[(size_t)q + 1] - H->off[q]);
+      if (n == 0) continue;
+      // key = (intrinsics group, camera); ties (a camera observing the point twice) fall back to the observation index
+      bool sorted = true;
+      for (int j = 0; j < n; ++j) {
+        const int cam = p->obs_cam[o[j]];
+        key[j] = ((uint64_t)(uint32_t)p->cam_group[cam] << 32) | (uint32_t)cam;
+        if (j > 0 && (key[j] < key[j - 1] || (key[j] == key[j - 1] && o[j] < o[j - 1]))) sorted = false;
+      }
+      if (!sorted) {  // insertion sort: n <= 256, almost always <= 32
+        for (int j = 1; j < n; ++j) {
+          const uint64_t kj = key[j];
+          const int64_t oj = o[j];
+          int m = j - 1;
+          while (m >= 0 && (key[m] > kj || (key[m] == kj && o[m] > oj))) { key[m + 1] = key[m]; o[m + 1] = o[m]; --m; }
+          key[m + 1] = kj; o[m + 1] = oj;
+        }
+      }
+      int runs = 1;
+      for (int j = 1; j < n; ++j) runs += (key[j] >> 32) != (key[j - 1] >> 32);
       H->pt_nruns[q] = (uint8_t)std::min(runs, 255);
     }
   });
@@ -128,7 +169,13 @@ inline void pack_points(const tba_problem* p, HostPack* H, bool sort_by_anchor =
   H->pk2caller.reserve((size_t)np);
   H->n_long = 0;
   H->n_free_pt = 0;
-  for (int q = 0; q < np; ++q) if (H->cnt_pt[q] > 0 && H->cnt_pt[q] <= 32) H->pk2caller.push_back(q);
+  std::vector<int> long_pts;
+  for (int q = 0; q < np; ++q) {
+    const int n = H->cnt_pt[q];
+    if (n == 0) continue;
+    if (n <= 32) H->pk2caller.push_back(q); else long_pts.push_back(q);
+    H->n_free_pt += p->pt_const[q] ? 0 : 1;
+  }
   if (sort_by_anchor) {
     std::vector<int> anchor((size_t)np, 0);
     for (int q : H->pk2caller) {
@@ -138,8 +185,8 @@ inline void pack_points(const tba_problem* p, HostPack* H, bool sort_by_anchor =
     }
     std::stable_sort(H->pk2caller.begin(), H->pk2caller.end(), [&](int a, int b) { return anchor[a] < anchor[b]; });
   }
-  for (int q = 0; q < np; ++q) if (H->cnt_pt[q] > 32) { H->pk2caller.push_back(q); ++H->n_long; }
-  for (int q : H->pk2caller) H->n_free_pt += p->pt_const[q] ? 0 : 1;
+  H->n_long = (int)long_pts.size();
+  H->pk2caller.insert(H->pk2caller.end(), long_pts.begin(), long_pts.end());
 }
 
 // Free-coordinate masks (cnt_c / cnt_g are the GLOBAL observation counts per camera / group) and phase D: tiles.
@@ -196,38 +243,53 @@ inline void pack_masks_and_tiles(const tba_problem* p, const std::vector<double>
   H->n_slots = (int64_t)H->n_tiles * kPackTile;
 }
 
-// E: fill the slot arrays, parallel over packed points.
-inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const PackDest& d) {
-  const int nc = p->n_cam;
+// slot -> caller observation index (-1 for padding), derived from the grouped order: what the debug read-back of
+// per-observation quantities and the CPU tests need; not part of the upload.
+inline void pack_slot_orig(const HostPack& H, int T, int64_t* slot_orig) {
+  parallel_for(H.n_slots, T, [&](int64_t b0, int64_t e0, int) { for (int64_t s = b0; s < e0; ++s) slot_orig[s] = -1; });
   const int npk = (int)H.pk2caller.size();
-  parallel_for(H.n_slots, T, [&](int64_t b0, int64_t e0, int) {
-    memset(d.slot_cam + b0, 0xFF, (size_t)(e0 - b0) * 4);
-    memset(d.slot_pt + b0, 0, (size_t)(e0 - b0) * 4);
-    memset(d.slot_run + b0, 0xFF, (size_t)(e0 - b0) * 2);
-    memset(d.slot_flags + b0, 0, (size_t)(e0 - b0));
-  });
-  parallel_for((int64_t)H.n_tiles * 2, T, [&](int64_t b0, int64_t e0, int) { memset(d.xy + b0 * kPackTile, 0, (size_t)(e0 - b0) * kPackTile * 8); });
   parallel_for(npk, T, [&](int64_t b0, int64_t e0, int) {
     for (int64_t k = b0; k < e0; ++k) {
       const int q = H.pk2caller[k];
-      d.pt_const[k] = p->pt_const[q] ? 1 : 0;
-      memcpy(d.pt + (size_t)k * 4, p->pt + (size_t)q * 4, 32);
       int64_t s0 = H.pt_slot[k];
-      int run = H.pt_runbase[k] - 1, last_grp = -1;
-      for (int64_t kk = H.off[q]; kk < H.off[(size_t)q + 1]; ++kk, ++s0) {
-        const int64_t oi = H.order[kk];
-        const int cam = p->obs_cam[oi], g = p->cam_group[cam];
-        if (g != last_grp) { ++run; last_grp = g; }
-        d.slot_cam[s0] = cam; d.slot_pt[s0] = (int)k; d.slot_run[s0] = (int16_t)run;
-        const bool any_free = H.blk_free[cam] != 0.0 || H.blk_free[(size_t)nc + g] != 0.0 || !d.pt_const[k];
-        d.slot_flags[s0] = any_free ? 0 : 1;
-        d.slot_orig[(size_t)s0] = oi;
-        const int64_t wq = s0 / 32, l = s0 % 32;  // [tile][warp][2][32]
-        d.xy[(size_t)(wq * 2 + 0) * 32 + l] = p->obs_xy[2 * oi];
-        d.xy[(size_t)(wq * 2 + 1) * 32 + l] = p->obs_xy[2 * oi + 1];
+      for (int64_t kk = H.off[q]; kk < H.off[(size_t)q + 1]; ++kk, ++s0) slot_orig[s0] = H.order[kk];
+    }
+  });
+}
+
+// E: fill the slot arrays, parallel over tiles (each tile is cleared and filled while it is in cache).
+inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const PackDest& d) {
+  const int nc = p->n_cam;
+  parallel_for(H.n_tiles, T, [&](int64_t t0, int64_t t1, int) {
+    for (int64_t t = t0; t < t1; ++t) {
+      const int64_t sb = t * kPackTile;
+      memset(d.slot_cam + sb, 0xFF, (size_t)kPackTile * 4);
+      memset(d.slot_pt + sb, 0, (size_t)kPackTile * 4);
+      memset(d.slot_run + sb, 0xFF, (size_t)kPackTile * 2);
+      memset(d.slot_flags + sb, 0, (size_t)kPackTile);
+      memset(d.xy + sb * 2, 0, (size_t)kPackTile * 16);
+      for (int k = H.tile_pt_begin[t]; k < H.tile_pt_begin[t + 1]; ++k) {
+        const int q = H.pk2caller[k];
+        const bool ptc = p->pt_const[q] != 0;
+        d.pt_const[k] = ptc ? 1 : 0;
+        memcpy(d.pt + (size_t)k * 4, p->pt + (size_t)q * 4, 32);
+        int64_t s0 = H.pt_slot[k];
+        int run = H.pt_runbase[k] - 1, last_grp = -1;
+        for (int64_t kk = H.off[q]; kk < H.off[(size_t)q + 1]; ++kk, ++s0) {
+          const int64_t oi = H.order[kk];
+          const int cam = p->obs_cam[oi], g = p->cam_group[cam];
+          if (g != last_grp) { ++run; last_grp = g; }
+          d.slot_cam[s0] = cam; d.slot_pt[s0] = k; d.slot_run[s0] = (int16_t)run;
+          const bool any_free = H.blk_free[cam] != 0.0 || H.blk_free[(size_t)nc + g] != 0.0 || !ptc;
+          d.slot_flags[s0] = any_free ? 0 : 1;
+          const int64_t wq = s0 / 32, l = s0 % 32;  // [tile][warp][2][32]
+          d.xy[(size_t)(wq * 2 + 0) * 32 + l] = p->obs_xy[2 * oi];
+          d.xy[(size_t)(wq * 2 + 1) * 32 + l] = p->obs_xy[2 * oi + 1];
+        }
       }
     }
   });
+  if (d.slot_orig) pack_slot_orig(H, T, d.slot_orig);
 }
 
 }  // namespace tba
