@@ -35,7 +35,15 @@ extern "C" {
 #define TBA_PT_SIZE 4         /* homogeneous point, track.h:87 */
 
 /* CameraIntrinsicsModelType, camera_intrinsics_model_type.h:46-53 */
-enum { TBA_MODEL_PINHOLE = 0, TBA_MODEL_PINHOLE_RADIAL_TANGENTIAL = 1 };
+enum { TBA_MODEL_PINHOLE = 0, TBA_MODEL_PINHOLE_RADIAL_TANGENTIAL = 1, TBA_MODEL_FISHEYE = 2, TBA_MODEL_FOV = 3,
+       TBA_MODEL_DIVISION_UNDISTORTION = 4 };
+/* Number of intrinsic parameters of each model (NumParameters(): pinhole_camera_model.h:86-94 = 7,
+ * pinhole_radial_tangential_camera_model.h:91-102 = 10, fisheye_camera_model.h:67-77 = 9, fov_camera_model.h:69-75 = 5,
+ * division_undistortion_camera_model.h:76-82 = 5).  intr rows are always TBA_INTR_STRIDE wide; entries past the count
+ * are ignored and returned unchanged. */
+static inline int tba_model_num_parameters(int model) {
+  return model == 0 ? 7 : model == 1 ? 10 : model == 2 ? 9 : (model == 3 || model == 4) ? 5 : -1;
+}
 
 /* LossFunctionType, create_loss_function.h:51-58 */
 enum { TBA_LOSS_TRIVIAL = 0, TBA_LOSS_HUBER = 1, TBA_LOSS_SOFTLONE = 2,

@@ -8,9 +8,10 @@ from theiasfm_b200 import _abi
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reprojection_golden.npz")
 
 
-def golden_problem():
-    """All golden cases as ONE problem: case i = camera i, group i, point i, observation i."""
-    g = np.load(GOLDEN)
+def golden_problem(ext=False):
+    """All golden cases as ONE problem: case i = camera i, group i, point i, observation i.  ext=True: the FISHEYE / FOV /
+    DIVISION_UNDISTORTION vectors (reprojection_golden_ext.npz)."""
+    g = np.load(GOLDEN.replace("reprojection_golden.npz", "reprojection_golden_ext.npz") if ext else GOLDEN)
     n = len(g["model"])
     prob = _abi.Problem(g["ext"], np.zeros(n, np.uint8), np.arange(n, dtype=np.int32), g["model"], g["intr"],
                         np.zeros(n, np.uint32), g["pt"], np.zeros(n, np.uint8), np.arange(n, dtype=np.int32),

@@ -2,6 +2,7 @@
 import numpy as np
 
 from helpers import golden_problem
+from theiasfm_b200 import _abi
 
 
 def test_oracle_residual_and_jacobian_match_golden(oracle):
@@ -14,6 +15,30 @@ def test_oracle_residual_and_jacobian_match_golden(oracle):
         assert np.abs(r[i] - g["r"][i]).max() <= 1e-12 * scale_r, (i, str(g["tag"][i]))
         scale_j = np.abs(g["J"][i]).max()
         assert np.abs(J[i] - g["J"][i]).max() <= 1e-12 * scale_j, (i, str(g["tag"][i]))
+
+
+def test_oracle_matches_golden_for_fisheye_fov_division(oracle):
+    """The three other camera models, every branch of their DistortPoint, against torch jacfwd."""
+    prob, g = golden_problem(ext=True)
+    r, J, ok = oracle.residual_jacobian(prob)
+    assert ok.all() and set(g["model"].tolist()) == {2, 3, 4}
+    from theiasfm_b200.synthetic import rotation_from_angle_axis
+    for i in range(prob.n_obs):
+        scale_r = max(1.0, np.abs(g["r"][i]).max())
+        assert np.abs(r[i] - g["r"][i]).max() <= 1e-12 * scale_r, (i, str(g["tag"][i]))
+        tol = np.full(20, 1e-12)
+        if g["model"][i] == _abi.MODEL_DIVISION_UNDISTORTION and g["intr"][i][4] != 0.0:
+            # (1 - sqrt(1 - x)) / (x / 2), x = 4 k r_u^2, cancels: two correct evaluations differ by eps / x, and by eps / x^2
+            # in the derivative with respect to k (measured: err * x ~ 1e-15, err_k * x^2 ~ 2e-15)
+            e, X, k = g["ext"][i], g["pt"][i], g["intr"][i]
+            q = rotation_from_angle_axis(e[3:6])[0] @ (X[:3] - X[3] * e[:3])
+            x = abs(4.0 * k[4] * ((k[0] * q[0] / q[2]) ** 2 + (k[0] * k[1] * q[1] / q[2]) ** 2))
+            tol = np.maximum(tol, 2e-14 / x)
+            tol[6 + 4] = max(1e-12, 2e-14 / x ** 2)
+        scale_j = np.abs(g["J"][i]).max()
+        assert (np.abs(J[i] - g["J"][i]).max(axis=0) <= tol * scale_j).all(), (i, str(g["tag"][i]))
+    tags = set(str(t) for t in g["tag"])
+    assert {"fisheye_r_sq_below_1e-8", "fov_small_omega", "fov_small_radius", "division_k_zero", "division_negative_sqrt_argument"} <= tags
 
 
 def test_golden_covers_both_rotation_branches():

@@ -13,7 +13,10 @@ PT_SIZE = 4
 
 MODEL_PINHOLE = 0
 MODEL_PINHOLE_RADIAL_TANGENTIAL = 1
-MODEL_NUM_PARAMS = {MODEL_PINHOLE: 7, MODEL_PINHOLE_RADIAL_TANGENTIAL: 10}
+MODEL_FISHEYE = 2
+MODEL_FOV = 3
+MODEL_DIVISION_UNDISTORTION = 4
+MODEL_NUM_PARAMS = {MODEL_PINHOLE: 7, MODEL_PINHOLE_RADIAL_TANGENTIAL: 10, MODEL_FISHEYE: 9, MODEL_FOV: 5, MODEL_DIVISION_UNDISTORTION: 5}
 
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_SOFTLONE, LOSS_CAUCHY, LOSS_ARCTAN, LOSS_TUKEY = range(6)
 
@@ -227,6 +230,16 @@ def constant_intrinsics_mask(model, intrinsics_to_optimize):
     m = 0
     if intrinsics_to_optimize == INTR_ALL:
         return 0
+    if model in (MODEL_FOV, MODEL_DIVISION_UNDISTORTION):   # f, aspect, cx, cy, one distortion term (fov_camera_model.cc, division_...cc)
+        if not intrinsics_to_optimize & INTR_FOCAL_LENGTH:
+            m |= 1 << 0
+        if not intrinsics_to_optimize & INTR_ASPECT_RATIO:
+            m |= 1 << 1
+        if not intrinsics_to_optimize & INTR_PRINCIPAL_POINTS:
+            m |= (1 << 2) | (1 << 3)
+        if not intrinsics_to_optimize & INTR_RADIAL_DISTORTION:
+            m |= 1 << 4
+        return m
     if not intrinsics_to_optimize & INTR_FOCAL_LENGTH:
         m |= 1 << 0
     if not intrinsics_to_optimize & INTR_ASPECT_RATIO:
@@ -238,6 +251,9 @@ def constant_intrinsics_mask(model, intrinsics_to_optimize):
     if model == MODEL_PINHOLE:
         if not intrinsics_to_optimize & INTR_RADIAL_DISTORTION:
             m |= (1 << 5) | (1 << 6)
+    elif model == MODEL_FISHEYE:                              # four radial terms, no tangential (fisheye_camera_model.cc)
+        if not intrinsics_to_optimize & INTR_RADIAL_DISTORTION:
+            m |= (1 << 5) | (1 << 6) | (1 << 7) | (1 << 8)
     else:
         if not intrinsics_to_optimize & INTR_RADIAL_DISTORTION:
             m |= (1 << 5) | (1 << 6) | (1 << 7)
