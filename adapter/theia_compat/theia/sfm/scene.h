@@ -45,7 +45,16 @@ class CameraIntrinsicsModel {
   explicit CameraIntrinsicsModel(CameraIntrinsicsModelType t) : type_(t), parameters_(NumParametersOf(t), 0.0) {
     parameters_[0] = 1.0; parameters_[1] = 1.0;  // focal length 1, aspect ratio 1 (pinhole_camera_model.cc:56-64)
   }
-  static int NumParametersOf(CameraIntrinsicsModelType t) { return t == CameraIntrinsicsModelType::PINHOLE ? 7 : t == CameraIntrinsicsModelType::PINHOLE_RADIAL_TANGENTIAL ? 10 : 0; }
+  static int NumParametersOf(CameraIntrinsicsModelType t) {  // NumParameters() of the five models
+    switch (t) {
+      case CameraIntrinsicsModelType::PINHOLE: return 7;
+      case CameraIntrinsicsModelType::PINHOLE_RADIAL_TANGENTIAL: return 10;
+      case CameraIntrinsicsModelType::FISHEYE: return 9;
+      case CameraIntrinsicsModelType::FOV: return 5;
+      case CameraIntrinsicsModelType::DIVISION_UNDISTORTION: return 5;
+      default: return 0;
+    }
+  }
   int NumParameters() const { return static_cast<int>(parameters_.size()); }
   CameraIntrinsicsModelType Type() const { return type_; }
   const double* parameters() const { return parameters_.data(); }
@@ -55,6 +64,22 @@ class CameraIntrinsicsModel {
     std::vector<int> c;
     if (m == OptimizeIntrinsicsType::ALL) return c;
     auto off = [&](OptimizeIntrinsicsType f) { return (m & f) == OptimizeIntrinsicsType::NONE; };
+    if (type_ == CameraIntrinsicsModelType::FOV || type_ == CameraIntrinsicsModelType::DIVISION_UNDISTORTION) {
+      // f, aspect, cx, cy, one distortion term (fov_camera_model.cc / division_undistortion_camera_model.cc)
+      if (off(OptimizeIntrinsicsType::FOCAL_LENGTH)) c.push_back(0);
+      if (off(OptimizeIntrinsicsType::ASPECT_RATIO)) c.push_back(1);
+      if (off(OptimizeIntrinsicsType::PRINCIPAL_POINTS)) { c.push_back(2); c.push_back(3); }
+      if (off(OptimizeIntrinsicsType::RADIAL_DISTORTION)) c.push_back(4);
+      return c;
+    }
+    if (type_ == CameraIntrinsicsModelType::FISHEYE) {  // fisheye_camera_model.cc: pinhole layout, four radial terms
+      if (off(OptimizeIntrinsicsType::FOCAL_LENGTH)) c.push_back(0);
+      if (off(OptimizeIntrinsicsType::ASPECT_RATIO)) c.push_back(1);
+      if (off(OptimizeIntrinsicsType::SKEW)) c.push_back(2);
+      if (off(OptimizeIntrinsicsType::PRINCIPAL_POINTS)) { c.push_back(3); c.push_back(4); }
+      if (off(OptimizeIntrinsicsType::RADIAL_DISTORTION)) { c.push_back(5); c.push_back(6); c.push_back(7); c.push_back(8); }
+      return c;
+    }
     if (off(OptimizeIntrinsicsType::FOCAL_LENGTH)) c.push_back(0);
     if (off(OptimizeIntrinsicsType::ASPECT_RATIO)) c.push_back(1);
     if (off(OptimizeIntrinsicsType::SKEW)) c.push_back(2);

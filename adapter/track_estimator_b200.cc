@@ -62,7 +62,7 @@ TrackEstimatorB200::Summary TrackEstimatorB200::EstimateTracks(const std::unorde
         if (git == idx_of_group.end()) {
           git = idx_of_group.emplace(gid, static_cast<int32_t>(group_model.size())).first;
           const int model = static_cast<int>(camera->GetCameraIntrinsicsModelType());
-          if (model != TBA_MODEL_PINHOLE && model != TBA_MODEL_PINHOLE_RADIAL_TANGENTIAL) supported = false;
+          if (TBA_MODEL_NUM_PARAMETERS(model) < 0) supported = false;
           group_model.push_back(model);
           const int K = camera->MutableCameraIntrinsics()->NumParameters();
           for (int j = 0; j < TBA_INTR_STRIDE; ++j) intr.push_back(j < K ? camera->intrinsics()[j] : 0.0);
@@ -80,7 +80,7 @@ TrackEstimatorB200::Summary TrackEstimatorB200::EstimateTracks(const std::unorde
     }
   }
   if (!supported) {
-    std::fprintf(stderr, "theia_ba_b200: track estimation supports PINHOLE and PINHOLE_RADIAL_TANGENTIAL cameras only; nothing estimated\n");
+    std::fprintf(stderr, "theia_ba_b200: unknown camera intrinsics model type; nothing estimated\n");
     engine_ok_ = false;
     return summary;
   }

@@ -41,9 +41,8 @@ enum { TBA_MODEL_PINHOLE = 0, TBA_MODEL_PINHOLE_RADIAL_TANGENTIAL = 1, TBA_MODEL
  * pinhole_radial_tangential_camera_model.h:91-102 = 10, fisheye_camera_model.h:67-77 = 9, fov_camera_model.h:69-75 = 5,
  * division_undistortion_camera_model.h:76-82 = 5).  intr rows are always TBA_INTR_STRIDE wide; entries past the count
  * are ignored and returned unchanged. */
-static inline int tba_model_num_parameters(int model) {
-  return model == 0 ? 7 : model == 1 ? 10 : model == 2 ? 9 : (model == 3 || model == 4) ? 5 : -1;
-}
+#define TBA_MODEL_NUM_PARAMETERS(model) \
+  ((model) == 0 ? 7 : (model) == 1 ? 10 : (model) == 2 ? 9 : ((model) == 3 || (model) == 4) ? 5 : -1)
 
 /* LossFunctionType, create_loss_function.h:51-58 */
 enum { TBA_LOSS_TRIVIAL = 0, TBA_LOSS_HUBER = 1, TBA_LOSS_SOFTLONE = 2,

@@ -18,8 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def H():
     so = os.path.join(HERE, "_host_models.so")
     src = os.path.join(HERE, "host_models.cc")
-    hdr = os.path.join(HERE, "..", "theiasfm_b200", "csrc", "tba_camera_models.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+    hdrs = [os.path.join(HERE, "..", "theiasfm_b200", "csrc", h) for h in ("tba_camera_models.cuh", "tba_camera_models_ext.cuh")]
+    if not os.path.exists(so) or max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]) > os.path.getmtime(so):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", src, "-o", so])
     L = C.CDLL(so)
@@ -27,6 +27,7 @@ def H():
     L.host_linearize.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp, dp]
     L.host_reproject.argtypes = [C.c_int, dp, dp, dp, dp, dp]
     L.host_loss.argtypes = [C.c_int, C.c_double, C.c_double, dp]
+    L.host_pixel_to_camera_ext.argtypes = [C.c_int, dp, dp, dp]
     return L
 
 
@@ -48,6 +49,38 @@ def test_analytic_jacobian_matches_golden(H):
         tol = 1e-7 if tag == "w_small_rodrigues" else 1e-12
         assert np.abs(J - g["J"][i]).max() <= tol * np.abs(g["J"][i]).max(), (i, tag)
         assert abs(rho0.value - (g["r"][i] ** 2).sum()) <= 1e-12 * max(1.0, (g["r"][i] ** 2).sum())
+
+
+def test_dual_number_jacobian_of_the_other_models_matches_golden(H, oracle):
+    """FISHEYE / FOV / DIVISION_UNDISTORTION (tba_camera_models_ext.cuh: templated projection + forward-mode duals) against
+    the torch jacfwd vectors, every DistortPoint branch, and with a robust loss against the oracle's corrector."""
+    from theiasfm_b200 import _abi
+    from theiasfm_b200.synthetic import rotation_from_angle_axis
+    prob, g = golden_problem(ext=True)
+    for i in range(prob.n_obs):
+        r = np.zeros(2); rho0 = C.c_double(); J = np.zeros((2, 20))
+        ext, intr, pt, xy = (np.ascontiguousarray(g[k][i], np.float64) for k in ("ext", "intr", "pt", "xy"))
+        assert H.host_linearize(int(g["model"][i]), _dp(ext), _dp(intr), _dp(pt), _dp(xy), 0, 2.0, _dp(r), C.byref(rho0), _dp(J)) == 1
+        tag = str(g["tag"][i])
+        assert np.abs(r - g["r"][i]).max() <= 1e-12 * max(1.0, np.abs(g["r"][i]).max()), (i, tag)
+        tol = np.full(20, 1e-12)
+        if g["model"][i] == _abi.MODEL_DIVISION_UNDISTORTION and intr[4] != 0.0:   # cancellation, see tests/test_oracle_golden.py
+            q = rotation_from_angle_axis(ext[3:6])[0] @ (pt[:3] - pt[3] * ext[:3])
+            x = abs(4.0 * intr[4] * ((intr[0] * q[0] / q[2]) ** 2 + (intr[0] * intr[1] * q[1] / q[2]) ** 2))
+            tol = np.maximum(tol, 2e-14 / x); tol[10] = max(1e-12, 2e-14 / x ** 2)
+        assert (np.abs(J - g["J"][i]).max(axis=0) <= tol * np.abs(g["J"][i]).max()).all(), (i, tag)
+        rr = np.zeros(2)
+        assert H.host_reproject(int(g["model"][i]), _dp(ext), _dp(intr), _dp(pt), _dp(xy), _dp(rr)) == 1
+        assert np.abs(rr - g["r"][i]).max() <= 1e-12 * max(1.0, np.abs(g["r"][i]).max())
+    # viewing rays: PixelToCameraCoordinates against the oracle's restatement on a pixel grid
+    for model, intr in ((2, [1200.0, 1.02, 0.3, 600, 400, 0.01, 0.001, 0.001, 0.001, 0]), (3, [1200.0, 0.98, 600, 400, 0.1, 0, 0, 0, 0, 0]),
+                        (3, [1200.0, 1.0, 600, 400, 1e-4, 0, 0, 0, 0, 0]), (4, [1200.0, 1.01, 600, 400, -1e-6, 0, 0, 0, 0, 0])):
+        k = np.array(intr, np.float64)
+        for x in np.arange(0.0, 1200.0, 97.0):
+            for y in np.arange(0.0, 800.0, 89.0):
+                out = np.zeros(3); pix = np.array([x, y])
+                H.host_pixel_to_camera_ext(model, _dp(k), _dp(pix), _dp(out))
+                assert np.abs(out - oracle.pixel_to_camera(model, k, pix)).max() <= 1e-14
 
 
 def test_small_angle_branch_is_the_exact_derivative_of_that_branch(H):

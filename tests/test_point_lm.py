@@ -57,9 +57,10 @@ def oracle_per_track(oracle, p, tracks, loss=0, width=2.0, max_iters=100):
     return res
 
 
-@pytest.mark.parametrize("loss", [_abi.LOSS_TRIVIAL, _abi.LOSS_HUBER])
-def test_point_lm_matches_per_track_oracle(H, oracle, loss):
-    p = synthetic.make_scene(n_cam=30, n_pt=300, obs_per_pt=6, seed=19)   # points perturbed, cameras perturbed (held constant)
+@pytest.mark.parametrize("loss,model", [(_abi.LOSS_TRIVIAL, 0), (_abi.LOSS_HUBER, 0), (_abi.LOSS_HUBER, _abi.MODEL_FISHEYE),
+                                        (_abi.LOSS_TRIVIAL, _abi.MODEL_FOV), (_abi.LOSS_CAUCHY, _abi.MODEL_DIVISION_UNDISTORTION)])
+def test_point_lm_matches_per_track_oracle(H, oracle, loss, model):
+    p = synthetic.make_scene(n_cam=30, n_pt=300, obs_per_pt=6, seed=19, model=model)   # points perturbed, cameras perturbed (held constant)
     if loss:
         p.obs_xy[::23] += 35.0
     p.pt[5, :3] = p.ext[p.obs_cam[p.obs_pt == 5][0], :3]; p.pt[5, 3] = 1.0  # on a camera centre: evaluation fails

@@ -56,7 +56,8 @@ def scene(seed, model, n_cam=24, n_pt=400):
     return p, truth
 
 
-@pytest.mark.parametrize("model", [_abi.MODEL_PINHOLE, _abi.MODEL_PINHOLE_RADIAL_TANGENTIAL])
+@pytest.mark.parametrize("model", [_abi.MODEL_PINHOLE, _abi.MODEL_PINHOLE_RADIAL_TANGENTIAL, _abi.MODEL_FISHEYE, _abi.MODEL_FOV,
+                                   _abi.MODEL_DIVISION_UNDISTORTION])
 @pytest.mark.parametrize("ba", [True, False])
 def test_estimate_tracks_matches_oracle(H, oracle, model, ba):
     p, truth = scene(31, model)

@@ -23,6 +23,8 @@
 #include <cstdint>
 #include <cfloat>
 
+#include "tba_camera_models_ext.cuh"  // FISHEYE / FOV / DIVISION_UNDISTORTION (only in EXT = true instantiations)
+
 // '#pragma unroll' only where the device compiler sees it (the host pass of __host__ __device__ code warns otherwise)
 #ifdef __CUDA_ARCH__
 #define TBA_UNROLL _Pragma("unroll")
@@ -279,6 +281,126 @@ __host__ __device__ inline bool linearize_obs(int model, const double* __restric
     }
   }
   return true;
+}
+
+// ------------------------------------------------------------------ the three other camera models (EXT instantiations)
+__host__ __device__ inline void project_pixel_ext(int model, const double* __restrict__ C, const double* __restrict__ R,
+                                                  const double* __restrict__ k, const double X0, const double X1, const double X2, const double h,
+                                                  double& px, double& py, double& qz, double& a_sq) {
+  const double a0 = X0 - h * C[0], a1 = X1 - h * C[1], a2 = X2 - h * C[2];
+  a_sq = a0 * a0 + a1 * a1 + a2 * a2;
+  double q[3], pix[2];
+  q[0] = R[0] * a0 + R[1] * a1 + R[2] * a2;
+  q[1] = R[3] * a0 + R[4] * a1 + R[5] * a2;
+  q[2] = R[6] * a0 + R[7] * a1 + R[8] * a2;
+  qz = q[2];
+  camera_to_pixel_ext<double>(model, k, q, pix);
+  px = pix[0]; py = pix[1];
+}
+
+// linearize_obs for FISHEYE / FOV / DIVISION_UNDISTORTION: d pixel / d (q, k) by forward-mode duals, then the same
+// robustification and the same chain J_a = J_q R, J_h = -J_a C, J_w = -(J_q x b) L as above.
+template <uint32_t IMASK>
+__host__ __device__ inline bool linearize_obs_ext(int model, const double* __restrict__ C, const double* __restrict__ rec,
+                                                  const double* __restrict__ k, const double X0, const double X1, const double X2,
+                                                  const double h, const double x, const double y, int loss_type, double loss_width,
+                                                  double r[2], double& rho0, double Ja[6], double Jw[6], double Jh[2], double* Ji) {
+  constexpr int NI = popcount10(IMASK);
+  const double* R = rec;
+  const double* L = rec + 9;
+  const bool small = rec[18] != 0.0;
+  const double a0 = X0 - h * C[0], a1 = X1 - h * C[1], a2 = X2 - h * C[2];
+  if (a0 * a0 + a1 * a1 + a2 * a2 < 1e-8) return false;
+  const double q0 = R[0] * a0 + R[1] * a1 + R[2] * a2;
+  const double q1 = R[3] * a0 + R[4] * a1 + R[5] * a2;
+  const double q2 = R[6] * a0 + R[7] * a1 + R[8] * a2;
+  typedef Dual<13> D;  // partials: 0..2 = q, 3..12 = intrinsics
+  D qd[3], kd[10], pix[2];
+  const double qv[3] = {q0, q1, q2};
+  for (int i = 0; i < 3; ++i) { qd[i].v = qv[i]; for (int j = 0; j < 13; ++j) qd[i].d[j] = 0.0; qd[i].d[i] = 1.0; }
+  const int K = model_num_parameters(model);
+  for (int i = 0; i < 10; ++i) { kd[i].v = i < K ? k[i] : 0.0; for (int j = 0; j < 13; ++j) kd[i].d[j] = 0.0; if (i < K) kd[i].d[3 + i] = 1.0; }
+  camera_to_pixel_ext<D>(model, kd, qd, pix);
+  const double rr0 = pix[0].v - x, rr1 = pix[1].v - y;
+  const double s = rr0 * rr0 + rr1 * rr1;
+  double rho[3];
+  loss_evaluate(loss_type, loss_width, s, rho);
+  rho0 = rho[0];
+  const double sq = sqrt(rho[1]);
+  double P00 = sq, P01 = 0.0, P10 = 0.0, P11 = sq, rscale = sq;
+  if (!(s == 0.0 || rho[2] <= 0.0)) {
+    const double Dd = 1.0 + 2.0 * s * rho[2] / rho[1];
+    const double alpha = 1.0 - sqrt(Dd);
+    rscale = sq / (1.0 - alpha);
+    const double an = alpha / s;
+    P00 = sq * (1.0 - an * rr0 * rr0); P01 = -sq * an * rr0 * rr1; P10 = P01; P11 = sq * (1.0 - an * rr1 * rr1);
+  }
+  r[0] = rr0 * rscale; r[1] = rr1 * rscale;
+  const double Jq00 = P00 * pix[0].d[0] + P01 * pix[1].d[0], Jq01 = P00 * pix[0].d[1] + P01 * pix[1].d[1], Jq02 = P00 * pix[0].d[2] + P01 * pix[1].d[2];
+  const double Jq10 = P10 * pix[0].d[0] + P11 * pix[1].d[0], Jq11 = P10 * pix[0].d[1] + P11 * pix[1].d[1], Jq12 = P10 * pix[0].d[2] + P11 * pix[1].d[2];
+  Ja[0] = Jq00 * R[0] + Jq01 * R[3] + Jq02 * R[6];
+  Ja[1] = Jq00 * R[1] + Jq01 * R[4] + Jq02 * R[7];
+  Ja[2] = Jq00 * R[2] + Jq01 * R[5] + Jq02 * R[8];
+  Ja[3] = Jq10 * R[0] + Jq11 * R[3] + Jq12 * R[6];
+  Ja[4] = Jq10 * R[1] + Jq11 * R[4] + Jq12 * R[7];
+  Ja[5] = Jq10 * R[2] + Jq11 * R[5] + Jq12 * R[8];
+  Jh[0] = -(Ja[0] * C[0] + Ja[1] * C[1] + Ja[2] * C[2]);
+  Jh[1] = -(Ja[3] * C[0] + Ja[4] * C[1] + Ja[5] * C[2]);
+  const double b0 = small ? a0 : q0, b1 = small ? a1 : q1, b2 = small ? a2 : q2;
+  const double c00 = Jq01 * b2 - Jq02 * b1, c01 = Jq02 * b0 - Jq00 * b2, c02 = Jq00 * b1 - Jq01 * b0;
+  const double c10 = Jq11 * b2 - Jq12 * b1, c11 = Jq12 * b0 - Jq10 * b2, c12 = Jq10 * b1 - Jq11 * b0;
+  Jw[0] = -(c00 * L[0] + c01 * L[3] + c02 * L[6]);
+  Jw[1] = -(c00 * L[1] + c01 * L[4] + c02 * L[7]);
+  Jw[2] = -(c00 * L[2] + c01 * L[5] + c02 * L[8]);
+  Jw[3] = -(c10 * L[0] + c11 * L[3] + c12 * L[6]);
+  Jw[4] = -(c10 * L[1] + c11 * L[4] + c12 * L[7]);
+  Jw[5] = -(c10 * L[2] + c11 * L[5] + c12 * L[8]);
+  if (NI > 0) {
+    TBA_UNROLL
+    for (int j = 0; j < NI; ++j) {
+      constexpr uint32_t M = IMASK;
+      const int idx = nth_bit(M, j);
+      Ji[j] = P00 * pix[0].d[3 + idx] + P01 * pix[1].d[3 + idx];
+      Ji[NI + j] = P10 * pix[0].d[3 + idx] + P11 * pix[1].d[3 + idx];
+    }
+  }
+  return true;
+}
+
+// Model dispatch: EXT = false is the PINHOLE / PINHOLE_RADIAL_TANGENTIAL code above and nothing else.
+template <bool EXT>
+__host__ __device__ inline void project_pixel_any(int model, const double* __restrict__ C, const double* __restrict__ R,
+                                                  const double* __restrict__ k, const double X0, const double X1, const double X2, const double h,
+                                                  double& px, double& py, double& qz, double& a_sq) {
+  if (EXT) {
+    if (model >= kModelFisheye) { project_pixel_ext(model, C, R, k, X0, X1, X2, h, px, py, qz, a_sq); return; }
+  }
+  project_pixel(model, C, R, k, X0, X1, X2, h, px, py, qz, a_sq);
+}
+template <bool EXT>
+__host__ __device__ inline bool reproject_any(int model, const double* __restrict__ C, const double* __restrict__ R,
+                                              const double* __restrict__ k, const double X0, const double X1, const double X2,
+                                              const double h, const double x, const double y, double& r0, double& r1) {
+  if (EXT) {
+    if (model >= kModelFisheye) {
+      double px, py, qz, a_sq;
+      project_pixel_ext(model, C, R, k, X0, X1, X2, h, px, py, qz, a_sq);
+      if (a_sq < 1e-8) return false;
+      r0 = px - x; r1 = py - y;
+      return true;
+    }
+  }
+  return reproject(model, C, R, k, X0, X1, X2, h, x, y, r0, r1);
+}
+template <uint32_t IMASK, bool EXT>
+__host__ __device__ inline bool linearize_obs_any(int model, const double* __restrict__ C, const double* __restrict__ rec,
+                                                  const double* __restrict__ k, const double X0, const double X1, const double X2,
+                                                  const double h, const double x, const double y, int loss_type, double loss_width,
+                                                  double r[2], double& rho0, double Ja[6], double Jw[6], double Jh[2], double* Ji) {
+  if (EXT) {
+    if (model >= kModelFisheye) return linearize_obs_ext<IMASK>(model, C, rec, k, X0, X1, X2, h, x, y, loss_type, loss_width, r, rho0, Ja, Jw, Jh, Ji);
+  }
+  return linearize_obs<IMASK>(model, C, rec, k, X0, X1, X2, h, x, y, loss_type, loss_width, r, rho0, Ja, Jw, Jh, Ji);
 }
 
 }  // namespace tba

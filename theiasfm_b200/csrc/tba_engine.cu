@@ -126,6 +126,7 @@ struct tba_context {
   // global number of free points, so that the upload needs no collective
   const double* preset_cnt_cam = nullptr;
   int64_t preset_free_pt = -1;
+  bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
   bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
@@ -240,9 +241,14 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
+    if (c->has_ext_models) {  // FISHEYE / FOV / DIVISION_UNDISTORTION present: the dual-number instantiation, all 10 columns
+      auto kfn = k_linearize<0x3FFu, true>;
+      LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p);
+    } else {
 #define F(M) LAUNCH(c, k_linearize<M>, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p)
-    DISPATCH_IMASK(c->imask, F)
+      DISPATCH_IMASK(c->imask, F)
 #undef F
+    }
     prof_end(c, 1, pb);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, lin_g(c) + P.ne, lin_cn(c) + P.ne, lin_scal(c));
   }
@@ -416,7 +422,8 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
   DevProblem& P = c->P;
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
   if (P.n_tiles > 0) {
-    LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p);
+    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   int rc = allreduce_sum(c, c->scal2.p, 8);
@@ -593,11 +600,14 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   const int nc = p->n_cam, ng = p->n_group, np = p->n_pt;
   const int64_t no = p->n_obs;
   if (nc < 0 || ng < 0 || np < 0 || no < 0) { set_err(c, "negative sizes"); return TBA_ERR_INVALID_ARGUMENT; }
-  for (int g = 0; g < ng; ++g)
-    if (p->group_model[g] != TBA_MODEL_PINHOLE && p->group_model[g] != TBA_MODEL_PINHOLE_RADIAL_TANGENTIAL) {
-      set_err(c, "camera intrinsics model %d of group %d is not supported by the GPU engine (PINHOLE, PINHOLE_RADIAL_TANGENTIAL)", p->group_model[g], g);
+  c->has_ext_models = false;
+  for (int g = 0; g < ng; ++g) {
+    if (TBA_MODEL_NUM_PARAMETERS(p->group_model[g]) < 0) {
+      set_err(c, "camera intrinsics model %d of group %d is not a CameraIntrinsicsModelType (0..4)", p->group_model[g], g);
       return TBA_ERR_UNSUPPORTED;
     }
+    if (p->group_model[g] >= TBA_MODEL_FISHEYE) c->has_ext_models = true;
+  }
   for (int i = 0; i < nc; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= ng) { set_err(c, "cam_group out of range"); return TBA_ERR_INVALID_ARGUMENT; }
   // ---- host packing (tba_pack.h: phases A-E, multi-threaded), into pinned staging memory
   const int T = std::max(1, std::min<int>(32, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
@@ -645,6 +655,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   c->n_free_cs = H.n_free_cs;
   c->imask = 0x3FFu;
   for (uint32_t m : kMasks) if ((H.union_free & ~m) == 0) { c->imask = m; break; }
+  if (c->has_ext_models) c->imask = 0x3FFu;  // one instantiation for the other models: every intrinsics column stored
   c->NI = popcount10(c->imask);
   c->NJ = 14 + 2 * c->NI;
   const int npk = (int)H.pk2caller.size();
@@ -1290,7 +1301,8 @@ int tba_debug_evaluate_step(tba_context* c, double* candidate_cost) {
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
   if (P.n_tiles > 0) {
-    LAUNCH(c, k_cost, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p);
+    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   int rc = allreduce_sum(c, c->scal2.p, 3);

@@ -38,7 +38,7 @@ __host__ __device__ inline uint8_t filter_track(const FilterView& V, int k, long
     const int l = (int)(s & 31);
     const double x = V.xy[(size_t)(wq * 2 + 0) * 32 + l], y = V.xy[(size_t)(wq * 2 + 1) * 32 + l];
     double px, py, qz, a_sq;
-    project_pixel(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X0, X1, X2, h,
+    project_pixel_any<true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X0, X1, X2, h,
                   px, py, qz, a_sq);
     if (qz / h < 0.0) behind = true;
     sum += (px - x) * (px - x) + (py - y) * (py - y);

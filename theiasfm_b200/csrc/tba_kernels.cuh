@@ -126,7 +126,7 @@ __device__ __forceinline__ size_t wslice(int tile, int warp, int rows) { return 
 // gradient / squared column norms (fp64 RED to global) and cost / failure counters (replicas).
 // Normal tiles: a point never straddles a warp -> per-point sums by warp-shuffle segmented reduction only, no
 // block barrier.  Long tiles (tracks > 32 observations): combined across warps in shared memory.
-template <uint32_t IMASK>
+template <uint32_t IMASK, bool EXT = false>
 __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
                                                     double* __restrict__ rep) {
   constexpr int NI = popcount10(IMASK);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
     const double* xyw = P.xy + wslice(tile, warp, 2) + lane;
     const double x = xyw[0], y = xyw[32];
     double rho0 = 0.0;
-    const bool ok = linearize_obs<IMASK>(P.group_model[grp], P.ext + (size_t)cam * 6, P.cam_rec + (size_t)cam * kCamRec,
+    const bool ok = linearize_obs_any<IMASK, EXT>(P.group_model[grp], P.ext + (size_t)cam * 6, P.cam_rec + (size_t)cam * kCamRec,
                                          P.intr + (size_t)grp * 10, X.x, X.y, X.z, X.w, x, y, P.loss_type, P.loss_width,
                                          r, rho0, Ja, Jw, Jh, Ji);
     const bool is_fixed = (P.slot_flags[slot] & 1) != 0;
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
 }
 
 // ------------------------------------------------------- K3 cost at candidate
+template <bool EXT = false>
 __global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __restrict__ ext, const double* __restrict__ rec,
                                                const double* __restrict__ intr, const double* __restrict__ pt,
                                                double* __restrict__ rep) {
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __res
     const double4 X = *reinterpret_cast<const double4*>(pt + (size_t)p * 4);
     const double* xyw = P.xy + wslice(tile, warp, 2) + lane;
     double r0, r1;
-    if (!reproject(P.group_model[grp], ext + (size_t)cam * 6, rec + (size_t)cam * kCamRec, intr + (size_t)grp * 10, X.x, X.y,
+    if (!reproject_any<EXT>(P.group_model[grp], ext + (size_t)cam * 6, rec + (size_t)cam * kCamRec, intr + (size_t)grp * 10, X.x, X.y,
                    X.z, X.w, xyw[0], xyw[32], r0, r1)) {
       failed = 1.0;
     } else {

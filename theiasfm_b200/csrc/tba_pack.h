@@ -206,7 +206,7 @@ inline void pack_masks_and_tiles(const tba_problem* p, const std::vector<double>
   }
   for (int g = 0; g < ng; ++g) {
     if (cnt_g[g] == 0.0) continue;
-    const int K = p->group_model[g] == TBA_MODEL_PINHOLE ? 7 : 10;
+    const int K = TBA_MODEL_NUM_PARAMETERS(p->group_model[g]);
     for (int j = 0; j < K; ++j)
       if (!((p->group_const_mask[g] >> j) & 1u)) { H->mask[(size_t)ne + g * 10 + j] = 1.0; H->blk_free[(size_t)nc + g] = 1.0; H->union_free |= 1u << j; H->n_free_cs++; }
   }

@@ -77,7 +77,7 @@ __host__ __device__ inline bool point_linearize(const FilterView& V, long long s
     const double x = V.xy[(size_t)(wq * 2 + 0) * 32 + l], y = V.xy[(size_t)(wq * 2 + 1) * 32 + l];
     if (need_derivatives) {
       double r[2], rho0, Ja[6], Jw[6], Jh[2];
-      if (!linearize_obs<0u>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0],
+      if (!linearize_obs_any<0u, true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0],
                              X[1], X[2], X[3], x, y, loss_type, loss_width, r, rho0, Ja, Jw, Jh, nullptr))
         return false;
       c += 0.5 * rho0;
@@ -89,7 +89,7 @@ __host__ __device__ inline bool point_linearize(const FilterView& V, long long s
       }
     } else {
       double r0, r1;
-      if (!reproject(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1],
+      if (!reproject_any<true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1],
                      X[2], X[3], x, y, r0, r1))
         return false;
       double rho[3];

@@ -45,10 +45,13 @@ __host__ __device__ inline void undistort_point(int model, const double* __restr
 
 // Unit world-frame ray of pixel (x, y): normalise(R^T [undistort(K^-1 pixel), 1]).
 __host__ __device__ inline void observation_ray(int model, const double* __restrict__ R, const double* __restrict__ k, double x, double y, double d[3]) {
-  const double yd = (y - k[4]) / (k[0] * k[1]);
-  const double xd = (x - k[3] - yd * k[2]) / k[0];
   double xu, yu;
-  undistort_point(model, k, xd, yd, xu, yu);
+  if (model >= kModelFisheye) pixel_to_camera_ext(model, k, x, y, xu, yu);
+  else {
+    const double yd = (y - k[4]) / (k[0] * k[1]);
+    const double xd = (x - k[3] - yd * k[2]) / k[0];
+    undistort_point(model, k, xd, yd, xu, yu);
+  }
   const double d0 = R[0] * xu + R[3] * yu + R[6];
   const double d1 = R[1] * xu + R[4] * yu + R[7];
   const double d2 = R[2] * xu + R[5] * yu + R[8];
@@ -110,7 +113,7 @@ __host__ __device__ inline uint8_t estimate_track(const FilterView& V, const dou
     const int l = (int)(s & 31);
     const double x = V.xy[(size_t)(wq * 2 + 0) * 32 + l], y = V.xy[(size_t)(wq * 2 + 1) * 32 + l];
     double px, py, qz, a_sq;
-    project_pixel(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1], X[2], X[3],
+    project_pixel_any<true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1], X[2], X[3],
                   px, py, qz, a_sq);
     if (qz / X[3] < 0.0) return kTrackBadReprojection;
     sum += (x - px) * (x - px) + (y - py) * (y - py);

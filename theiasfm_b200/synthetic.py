@@ -64,6 +64,8 @@ def project(model, ext, intr, pt, R=None):
     if R is None:
         R = rotation_from_angle_axis(ext[:, 3:6])
     q = np.stack([(R[:, i, :] * a).sum(axis=1) for i in range(3)], axis=1)
+    if model >= _abi.MODEL_FISHEYE:
+        return _project_other_models(model, intr, q), q[:, 2] / pt[:, 3]
     u, v = q[:, 0] / q[:, 2], q[:, 1] / q[:, 2]
     r2 = u * u + v * v
     if model == _abi.MODEL_PINHOLE:
@@ -77,6 +79,35 @@ def project(model, ext, intr, pt, R=None):
     px = intr[:, 0] * ud + intr[:, 2] * vd + intr[:, 3]
     py = intr[:, 0] * intr[:, 1] * vd + intr[:, 4]
     return np.stack([px, py], axis=1), q[:, 2] / pt[:, 3]
+
+
+def _project_other_models(model, k, q):
+    """CameraToPixelCoordinates of FISHEYE / FOV / DIVISION_UNDISTORTION (fisheye_camera_model.h:160-270,
+    fov_camera_model.h:157-258, division_undistortion_camera_model.h:171-286), vectorised; scene synthesis only."""
+    with np.errstate(all="ignore"):
+        if model == _abi.MODEL_FISHEYE:
+            r = np.sqrt(q[:, 0] ** 2 + q[:, 1] ** 2)
+            theta = np.arctan2(r, np.abs(q[:, 2]))
+            t2 = theta * theta
+            theta_d = theta * (1.0 + k[:, 5] * t2 + k[:, 6] * t2 * t2 + k[:, 7] * t2 ** 3 + k[:, 8] * t2 ** 4)
+            s = np.where(r * r < 1e-8, 1.0, theta_d / np.where(r > 0, r, 1.0)) * np.where((q[:, 2] < 0) & (r * r >= 1e-8), -1.0, 1.0)
+            ud, vd = s * q[:, 0], s * q[:, 1]
+            return np.stack([k[:, 0] * ud + k[:, 2] * vd + k[:, 3], k[:, 0] * k[:, 1] * vd + k[:, 4]], axis=1)
+        u, v = q[:, 0] / q[:, 2], q[:, 1] / q[:, 2]
+        if model == _abi.MODEL_FOV:
+            w, r2 = k[:, 4], u * u + v * v
+            ru = np.sqrt(r2)
+            th = np.tan(w / 2.0)
+            r_d = np.where(w < 1e-3, (w * w * r2) / 3.0 - w * w / 12.0 + 1.0,
+                           np.where(r2 < 1e-3, (-2.0 * th * (4.0 * r2 * th * th - 3.0)) / (3.0 * np.where(w != 0, w, 1.0)),
+                                    np.arctan(2.0 * ru * th) / np.where(ru * w != 0, ru * w, 1.0)))
+            return np.stack([k[:, 0] * (r_d * u) + k[:, 2], k[:, 0] * k[:, 1] * (r_d * v) + k[:, 3]], axis=1)
+        up0, up1 = k[:, 0] * u, k[:, 0] * k[:, 1] * v
+        r2 = up0 * up0 + up1 * up1
+        denom, inner = 2.0 * k[:, 4] * r2, 1.0 - 4.0 * k[:, 4] * r2
+        ident = (np.abs(denom) < np.finfo(float).eps) | (inner < 0.0)
+        scale = np.where(ident, 1.0, (1.0 - np.sqrt(np.where(inner > 0, inner, 0.0))) / np.where(ident, 1.0, denom))
+        return np.stack([up0 * scale + k[:, 2], up1 * scale + k[:, 3]], axis=1)
 
 
 def make_scene(n_cam, n_pt, obs_per_pt=10, model=_abi.MODEL_PINHOLE, shared_intrinsics=True, seed=0,
@@ -106,6 +137,14 @@ def make_scene(n_cam, n_pt, obs_per_pt=10, model=_abi.MODEL_PINHOLE, shared_intr
     intr_gt[:, 5], intr_gt[:, 6] = -0.05, 0.01
     if model == _abi.MODEL_PINHOLE_RADIAL_TANGENTIAL:
         intr_gt[:, 7], intr_gt[:, 8], intr_gt[:, 9] = 0.001, 1e-3, -5e-4
+    elif model == _abi.MODEL_FISHEYE:          # f, aspect, skew, cx, cy, k1..k4
+        intr_gt[:, 5:9] = [-0.02, 0.004, -0.001, 0.0002]
+    elif model == _abi.MODEL_FOV:              # f, aspect, cx, cy, omega
+        intr_gt[:, :] = 0.0
+        intr_gt[:, 0], intr_gt[:, 1], intr_gt[:, 2], intr_gt[:, 3], intr_gt[:, 4] = 800.0, 1.0, 500.0, 500.0, 0.35
+    elif model == _abi.MODEL_DIVISION_UNDISTORTION:   # f, aspect, cx, cy, k (pixel units)
+        intr_gt[:, :] = 0.0
+        intr_gt[:, 0], intr_gt[:, 1], intr_gt[:, 2], intr_gt[:, 3], intr_gt[:, 4] = 800.0, 1.0, 500.0, 500.0, -2e-7
     # --- ground-truth points: uniform in a ball of radius 0.4 R0
     d = rng.normal(size=(n_pt, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
@@ -139,9 +178,11 @@ def make_scene(n_cam, n_pt, obs_per_pt=10, model=_abi.MODEL_PINHOLE, shared_intr
     pt0[:, :3] += perturb * 0.005 * R0 * rng.normal(size=(n_pt, 3))
     intr0 = intr_gt.copy()
     intr0[:, 0] *= 1.0 + perturb * 0.01 * rng.normal(size=n_group)
-    if perturb:
+    if perturb and model <= _abi.MODEL_FISHEYE:
         intr0[:, 5] = 0.0
         intr0[:, 6] = 0.0
+    elif perturb:   # FOV / DIVISION_UNDISTORTION: the single distortion term starts 20 % off
+        intr0[:, 4] *= 0.8
     group_model = np.full(n_group, model, dtype=np.int32)
     mask = np.full(n_group, _abi.constant_intrinsics_mask(model, intrinsics_to_optimize), dtype=np.uint32)
     prob = _abi.Problem(ext0, np.zeros(n_cam, np.uint8), cam_group, group_model, intr0, mask, pt0,
