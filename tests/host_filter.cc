@@ -24,5 +24,5 @@ extern "C" void host_filter(int n_cam, const double* ext, const double* intr, co
   V.ext = ext; V.cam_rec = rec.data(); V.intr = intr; V.pt = pt_packed; V.xy = xy; V.slot_cam = slot_cam; V.cam_group = cam_group;
   V.group_model = group_model;
   const double cos_min = std::cos(min_angle_deg * 3.14159265358979323846 / 180.0);
-  for (int k = 0; k < n_pk; ++k) status[k] = tba::filter_track(V, k, pt_slot[k], pt_len[k], max_err * max_err, cos_min, &mean[k]);
+  for (int k = 0; k < n_pk; ++k) status[k] = tba::filter_track<true>(V, k, pt_slot[k], pt_len[k], max_err * max_err, cos_min, &mean[k]);
 }

@@ -33,7 +33,7 @@ extern "C" void host_adjust_tracks(int n_cam, const double* ext, const double* i
   o.initial_radius = 1e4; o.max_radius = 1e12; o.min_radius = 1e-32; o.min_relative_decrease = 1e-3; o.min_diag = 1e-6; o.max_diag = 1e32;
   o.jacobi_scaling = 1; o.max_consecutive_invalid = 5;
   for (int k = 0; k < n_pk; ++k) {
-    const tba::PointLmResult r = tba::point_lm(V, pt_slot[k], pt_len[k], pt_packed + (size_t)k * 4, o);
+    const tba::PointLmResult r = tba::point_lm<true>(V, pt_slot[k], pt_len[k], pt_packed + (size_t)k * 4, o);
     initial_cost[k] = r.initial_cost; final_cost[k] = r.final_cost; termination[k] = r.termination; iterations[k] = r.iterations;
   }
 }
@@ -73,6 +73,6 @@ extern "C" void host_estimate_tracks(int n_cam, const double* ext, const double*
   o.bundle_adjustment = bundle_adjustment; o.lm = default_lm(loss_type, loss_width, max_iters);
   for (int k = 0; k < n_pk; ++k) {
     tba::PointLmResult lm;
-    status[k] = tba::estimate_track(V, ray.data(), pt_slot[k], pt_len[k], pt_packed + (size_t)k * 4, o, &lm);
+    status[k] = tba::estimate_track<true>(V, ray.data(), pt_slot[k], pt_len[k], pt_packed + (size_t)k * 4, o, &lm);
   }
 }

@@ -991,7 +991,10 @@ int tba_filter_tracks(tba_context* c, double max_inlier_reprojection_error, doub
   CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
   // the per-camera rotation records must describe the CURRENT extrinsics
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
-  if (P.n_pt > 0) LAUNCH(c, k_filter_tracks, (P.n_pt + 127) / 128, 128, 0, P, c->pt_slot.p, c->pt_len.p, max_sq, cos_min, d_status.p, c->pt_stat.p);
+  if (P.n_pt > 0) {
+    auto kfn = c->has_ext_models ? k_filter_tracks<true> : k_filter_tracks<false>;
+    LAUNCH(c, kfn, (P.n_pt + 127) / 128, 128, 0, P, c->pt_slot.p, c->pt_len.p, max_sq, cos_min, d_status.p, c->pt_stat.p);
+  }
   std::vector<uint8_t> hs((size_t)P.n_pt);
   std::vector<double> hm((size_t)P.n_pt);
   CUDA_OK(c, cudaMemcpyAsync(hs.data(), d_status.p, (size_t)P.n_pt, cudaMemcpyDeviceToHost, c->stream));
@@ -1056,7 +1059,10 @@ int tba_adjust_tracks(tba_context* c, const tba_options* options, uint8_t* statu
   CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
   CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
-  if (P.n_pt > 0) LAUNCH(c, k_adjust_tracks, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, point_lm_options(*options), d_status.p, d_cost2.p);
+  if (P.n_pt > 0) {
+    auto kfn = c->has_ext_models ? k_adjust_tracks<true> : k_adjust_tracks<false>;
+    LAUNCH(c, kfn, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, point_lm_options(*options), d_status.p, d_cost2.p);
+  }
   const int rc = gather_track_outputs(c, d_status.p, d_cost2.p, kTrackSkipped, status, initial_cost, final_cost);
   if (rc) return rc;
   int nf = 0;
@@ -1083,7 +1089,10 @@ int tba_estimate_tracks(tba_context* c, const tba_options* ba_options, double ma
   // the rays live in the Jacobian store (NJ >= 14 doubles per slot; re-linearised by the next tba_minimize anyway)
   double* ray = P.J;
   if (c->n_slots > 0) LAUNCH(c, k_track_rays, (unsigned)((c->n_slots + 255) / 256), 256, 0, P, (long long)c->n_slots, ray);
-  if (P.n_pt > 0) LAUNCH(c, k_estimate_tracks, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, ray, o, d_status.p, d_cost2.p);
+  if (P.n_pt > 0) {
+    auto kfn = c->has_ext_models ? k_estimate_tracks<true> : k_estimate_tracks<false>;
+    LAUNCH(c, kfn, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, ray, o, d_status.p, d_cost2.p);
+  }
   // caller points without any observation: "view_ids.size() < 2" -> bad angle bucket
   const int rc = gather_track_outputs(c, d_status.p, d_cost2.p, kTrackBadAngle, status, nullptr, nullptr);
   if (rc) return rc;

@@ -21,10 +21,12 @@ struct FilterView {
   const int* group_model;  // [n_group]
 };
 
+// EXT: the problem may contain FISHEYE / FOV / DIVISION_UNDISTORTION groups (tba_camera_models_ext.cuh).
 // Status of packed point k whose observations occupy slots [s0, s0 + len): 0 keep, 1 bad reprojection (a view sees the
 // point at negative depth, or the mean squared reprojection error exceeds max_sq_err), 2 insufficient viewing angle
 // (no pair of unit rays X/h - C with dot < cos_min_angle).  The reference "breaks" at the first negative depth, which
 // only affects counters that are discarded for such a track: the result does not depend on its hash-map view order.
+template <bool EXT>
 __host__ __device__ inline uint8_t filter_track(const FilterView& V, int k, long long s0, int len, double max_sq_err, double cos_min_angle,
                                                 double* mean_sq_err) {
   const double X0 = V.pt[(size_t)k * 4], X1 = V.pt[(size_t)k * 4 + 1], X2 = V.pt[(size_t)k * 4 + 2], h = V.pt[(size_t)k * 4 + 3];
@@ -38,7 +40,7 @@ __host__ __device__ inline uint8_t filter_track(const FilterView& V, int k, long
     const int l = (int)(s & 31);
     const double x = V.xy[(size_t)(wq * 2 + 0) * 32 + l], y = V.xy[(size_t)(wq * 2 + 1) * 32 + l];
     double px, py, qz, a_sq;
-    project_pixel_any<true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X0, X1, X2, h,
+    project_pixel_any<EXT>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X0, X1, X2, h,
                   px, py, qz, a_sq);
     if (qz / h < 0.0) behind = true;
     sum += (px - x) * (px - x) + (py - y) * (py - y);

@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __res
 // "breaks" at the first negative depth, which only affects counters that are discarded for such a track, so the
 // result does not depend on its (hash-map) view order.  One thread per point; mean_sq_err (optional) receives the
 // mean squared reprojection error (ComputeStatisticsForTrack, select_good_tracks_for_bundle_adjustment.cc:79-108).
+template <bool EXT>
 __global__ void k_filter_tracks(DevProblem P, const long long* __restrict__ pt_slot, const int* __restrict__ pt_len, double max_sq_err,
                                 double cos_min_angle, uint8_t* __restrict__ status, double* __restrict__ mean_sq_err) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,7 +317,7 @@ __global__ void k_filter_tracks(DevProblem P, const long long* __restrict__ pt_s
   V.ext = P.ext; V.cam_rec = P.cam_rec; V.intr = P.intr; V.pt = P.pt; V.xy = P.xy;
   V.slot_cam = P.slot_cam; V.cam_group = P.cam_group; V.group_model = P.group_model;
   double mean;
-  status[k] = filter_track(V, k, pt_slot[k], pt_len[k], max_sq_err, cos_min_angle, &mean);
+  status[k] = filter_track<EXT>(V, k, pt_slot[k], pt_len[k], max_sq_err, cos_min_angle, &mean);
   if (mean_sq_err) mean_sq_err[k] = mean;
 }
 
@@ -347,6 +348,7 @@ __device__ inline FilterView filter_view(const DevProblem& P) {
 
 // TrackEstimator::EstimateTrack for every non-constant packed point (one thread per point; thousands of independent
 // 4-parameter problems).  cost2[k] = {initial, final} cost of the per-track BA (-1 when it did not run).
+template <bool EXT>
 __global__ void k_estimate_tracks(DevProblem P, const long long* __restrict__ pt_slot, const int* __restrict__ pt_len,
                                   const double* __restrict__ ray, TrackEstimatorOptions o, uint8_t* __restrict__ status,
                                   double* __restrict__ cost2) {
@@ -356,13 +358,14 @@ __global__ void k_estimate_tracks(DevProblem P, const long long* __restrict__ pt
   const FilterView V = filter_view(P);
   double X[4] = {P.pt[(size_t)k * 4], P.pt[(size_t)k * 4 + 1], P.pt[(size_t)k * 4 + 2], P.pt[(size_t)k * 4 + 3]};
   PointLmResult lm;
-  status[k] = estimate_track(V, ray, pt_slot[k], pt_len[k], X, o, &lm);
+  status[k] = estimate_track<EXT>(V, ray, pt_slot[k], pt_len[k], X, o, &lm);
   for (int j = 0; j < 4; ++j) P.pt[(size_t)k * 4 + j] = X[j];
   cost2[2 * k] = lm.initial_cost; cost2[2 * k + 1] = lm.final_cost;
 }
 
 // BundleAdjustTrack (bundle_adjustment.cc:96-107) for every non-constant packed point: LM on the point, cameras constant.
 // status: Ceres termination type (0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE), 255 = constant point (not adjusted).
+template <bool EXT>
 __global__ void k_adjust_tracks(DevProblem P, const long long* __restrict__ pt_slot, const int* __restrict__ pt_len, PointLmOptions o,
                                 uint8_t* __restrict__ status, double* __restrict__ cost2) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,7 +373,7 @@ __global__ void k_adjust_tracks(DevProblem P, const long long* __restrict__ pt_s
   if (P.pt_const[k]) { status[k] = kTrackSkipped; cost2[2 * k] = cost2[2 * k + 1] = -1.0; return; }
   const FilterView V = filter_view(P);
   double X[4] = {P.pt[(size_t)k * 4], P.pt[(size_t)k * 4 + 1], P.pt[(size_t)k * 4 + 2], P.pt[(size_t)k * 4 + 3]};
-  const PointLmResult lm = point_lm(V, pt_slot[k], pt_len[k], X, o);
+  const PointLmResult lm = point_lm<EXT>(V, pt_slot[k], pt_len[k], X, o);
   for (int j = 0; j < 4; ++j) P.pt[(size_t)k * 4 + j] = X[j];
   status[k] = (uint8_t)lm.termination;
   cost2[2 * k] = lm.initial_cost; cost2[2 * k + 1] = lm.final_cost;

@@ -61,6 +61,7 @@ __host__ __device__ inline bool spd4_solve(const double* A, const double* b, dou
 
 // cost, and optionally gradient g = J_p^T r (4) and H = J_p^T J_p (10, upper), of the point X over its observation slots.
 // Returns false when the residual functor fails (||X - hC||^2 < 1e-8, reprojection_error.h:75-77).
+template <bool EXT>
 __host__ __device__ inline bool point_linearize(const FilterView& V, long long s0, int len, const double* X, int loss_type, double loss_width,
                                                 bool need_derivatives, double* cost, double* g, double* H) {
   double c = 0.0;
@@ -77,7 +78,7 @@ __host__ __device__ inline bool point_linearize(const FilterView& V, long long s
     const double x = V.xy[(size_t)(wq * 2 + 0) * 32 + l], y = V.xy[(size_t)(wq * 2 + 1) * 32 + l];
     if (need_derivatives) {
       double r[2], rho0, Ja[6], Jw[6], Jh[2];
-      if (!linearize_obs_any<0u, true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0],
+      if (!linearize_obs_any<0u, EXT>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0],
                              X[1], X[2], X[3], x, y, loss_type, loss_width, r, rho0, Ja, Jw, Jh, nullptr))
         return false;
       c += 0.5 * rho0;
@@ -89,7 +90,7 @@ __host__ __device__ inline bool point_linearize(const FilterView& V, long long s
       }
     } else {
       double r0, r1;
-      if (!reproject_any<true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1],
+      if (!reproject_any<EXT>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1],
                      X[2], X[3], x, y, r0, r1))
         return false;
       double rho[3];
@@ -102,11 +103,12 @@ __host__ __device__ inline bool point_linearize(const FilterView& V, long long s
 }
 
 // Minimise over the point X (in/out).  Mirrors TrustRegionMinimizer::Minimize for a single 4-vector block.
+template <bool EXT>
 __host__ __device__ inline PointLmResult point_lm(const FilterView& V, long long s0, int len, double* X, const PointLmOptions& o) {
   PointLmResult res;
   res.initial_cost = res.final_cost = -1.0; res.iterations = 0; res.termination = 2;
   double cost, g[4], H[10];
-  if (!point_linearize(V, s0, len, X, o.loss_type, o.loss_width, true, &cost, g, H)) return res;  // "Residual and Jacobian evaluation failed."
+  if (!point_linearize<EXT>(V, s0, len, X, o.loss_type, o.loss_width, true, &cost, g, H)) return res;  // "Residual and Jacobian evaluation failed."
   res.initial_cost = res.final_cost = cost;
   const int dg[4] = {0, 4, 7, 9};
   double sc[4];
@@ -158,7 +160,7 @@ __host__ __device__ inline PointLmResult point_lm(const FilterView& V, long long
     double Xc[4], dn = 0.0;
     for (int a = 0; a < 4; ++a) { const double d = step[a] * sc[a]; Xc[a] = X[a] + d; dn += d * d; }
     double cand;
-    if (!point_linearize(V, s0, len, Xc, o.loss_type, o.loss_width, false, &cand, nullptr, nullptr)) cand = 1.7976931348623157e308;
+    if (!point_linearize<EXT>(V, s0, len, Xc, o.loss_type, o.loss_width, false, &cand, nullptr, nullptr)) cand = 1.7976931348623157e308;
     if (sqrt(dn) <= o.parameter_tolerance * (xnorm + o.parameter_tolerance)) { res.termination = 0; break; }
     const double cost_change = cost - cand;
     if (fabs(cost_change) <= o.function_tolerance * cost) { res.termination = 0; break; }
@@ -166,7 +168,7 @@ __host__ __device__ inline PointLmResult point_lm(const FilterView& V, long long
     if (rho > o.min_relative_decrease) {  // HandleSuccessfulStep
       for (int a = 0; a < 4; ++a) X[a] = Xc[a];
       xnorm = sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2] + X[3] * X[3]);
-      if (!point_linearize(V, s0, len, X, o.loss_type, o.loss_width, true, &cost, g, H)) { res.termination = 2; break; }
+      if (!point_linearize<EXT>(V, s0, len, X, o.loss_type, o.loss_width, true, &cost, g, H)) { res.termination = 2; break; }
       res.final_cost = cost;
       const double t = 2.0 * rho - 1.0;
       radius = radius / fmax(1.0 / 3.0, 1.0 - t * t * t);

@@ -67,6 +67,7 @@ __host__ __device__ inline void load_ray(const double* __restrict__ ray, long lo
 
 // Estimates packed point X (in/out, written at the same stages the reference overwrites Track::MutablePoint) from the
 // observations in slots [s0, s0 + len) whose unit rays are in `ray`.
+template <bool EXT>
 __host__ __device__ inline uint8_t estimate_track(const FilterView& V, const double* __restrict__ ray, long long s0, int len, double* X,
                                                   const TrackEstimatorOptions& o, PointLmResult* lm) {
   lm->initial_cost = lm->final_cost = -1.0; lm->iterations = 0; lm->termination = 2;
@@ -100,7 +101,7 @@ __host__ __device__ inline uint8_t estimate_track(const FilterView& V, const dou
   if (!spd4_solve(A, b, Y)) return kTrackTriangulationFailed;
   X[0] = Y[0]; X[1] = Y[1]; X[2] = Y[2]; X[3] = Y[3];
   if (o.bundle_adjustment) {
-    *lm = point_lm(V, s0, len, X, o.lm);
+    *lm = point_lm<EXT>(V, s0, len, X, o.lm);
     if (lm->termination == 2) return kTrackBaFailed;
   }
   // AcceptableReprojectionError: any view behind -> false; mean squared error must be < max^2
@@ -113,7 +114,7 @@ __host__ __device__ inline uint8_t estimate_track(const FilterView& V, const dou
     const int l = (int)(s & 31);
     const double x = V.xy[(size_t)(wq * 2 + 0) * 32 + l], y = V.xy[(size_t)(wq * 2 + 1) * 32 + l];
     double px, py, qz, a_sq;
-    project_pixel_any<true>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1], X[2], X[3],
+    project_pixel_any<EXT>(V.group_model[grp], V.ext + (size_t)cam * 6, V.cam_rec + (size_t)cam * kCamRec, V.intr + (size_t)grp * 10, X[0], X[1], X[2], X[3],
                   px, py, qz, a_sq);
     if (qz / X[3] < 0.0) return kTrackBadReprojection;
     sum += (x - px) * (x - px) + (y - py) * (y - py);
