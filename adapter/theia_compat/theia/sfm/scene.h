@@ -40,6 +40,9 @@ enum class CameraIntrinsicsModelType { INVALID = -1, PINHOLE = 0, PINHOLE_RADIAL
 struct Vector4d { double v[4] = {0, 0, 0, 1}; double* data() { return v; } const double* data() const { return v; } double& operator[](int i) { return v[i]; } };
 struct Feature { double v[2] = {0, 0}; Feature() {} Feature(double x, double y) { v[0] = x; v[1] = y; } double x() const { return v[0]; } double y() const { return v[1]; } };
 
+// matching/feature_correspondence.h:50-63
+struct FeatureCorrespondence { Feature feature1, feature2; FeatureCorrespondence() {} FeatureCorrespondence(const Feature& a, const Feature& b) : feature1(a), feature2(b) {} };
+
 class CameraIntrinsicsModel {
  public:
   explicit CameraIntrinsicsModel(CameraIntrinsicsModelType t) : type_(t), parameters_(NumParametersOf(t), 0.0) {

@@ -14,6 +14,7 @@
 
 #include "bundle_adjuster_b200.h"
 #include "track_estimator_b200.h"
+#include "bundle_adjust_two_views_b200.h"
 
 using namespace theia;
 
@@ -435,12 +436,72 @@ static int TestMicro(const char* oracle_path, bool gpu) {
   return 0;
 }
 
+// BundleAdjustTwoViewsB200 (bundle_adjust_two_views.cc:112-191): flattening rules on the CPU, solve vs oracle on the GPU.
+static int TestTwoViews(const char* oracle_path, bool gpu) {
+  std::mt19937 rng(77);
+  std::normal_distribution<double> N(0.0, 1.0);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  Camera cam1, cam2;
+  const double kgt[7] = {800.0, 1.0, 0.0, 500.0, 500.0, 0.0, 0.0};
+  for (int j = 0; j < 7; ++j) { cam1.mutable_intrinsics()[j] = kgt[j]; cam2.mutable_intrinsics()[j] = kgt[j]; }
+  const double e2gt[6] = {1.0, 0.1, -0.05, 0.02, -0.15, 0.01};
+  const double e1[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<FeatureCorrespondence> corr;
+  std::vector<TwoViewPoint> pts;
+  for (int i = 0; i < 180; ++i) {
+    const double X[4] = {2.0 * U(rng), 2.0 * U(rng), 7.0 + 2.0 * U(rng), 1.0};
+    double p1[2], p2[2];
+    Project(e1, kgt, X, p1); Project(e2gt, kgt, X, p2);
+    corr.emplace_back(Feature(p1[0] + 0.3 * N(rng), p1[1] + 0.3 * N(rng)), Feature(p2[0] + 0.3 * N(rng), p2[1] + 0.3 * N(rng)));
+    TwoViewPoint P; for (int j = 0; j < 3; ++j) P[j] = X[j] + 0.05 * N(rng); P[3] = 1.0;
+    pts.push_back(P);
+  }
+  for (int j = 0; j < 6; ++j) cam2.mutable_extrinsics()[j] = e2gt[j] + (j < 3 ? 0.03 : 0.005) * N(rng);
+  cam2.mutable_intrinsics()[0] = 780.0;  // wrong focal length: recovered only when camera 2's intrinsics are not constant
+  void* h = dlopen(oracle_path, RTLD_NOW);
+  EXPECT(h != nullptr);
+  oracle_solve_fn solve = (oracle_solve_fn)dlsym(h, "oracle_solve");
+  EXPECT(solve != nullptr);
+  for (int variant = 0; variant < 2; ++variant) {
+    TwoViewBundleAdjustmentOptions o;
+    o.constant_camera2_intrinsics = variant == 0;
+    Camera c1 = cam1, c2 = cam2;
+    c1.MutableCameraIntrinsics().reset(new CameraIntrinsicsModel(*cam1.CameraIntrinsics()));  // private copies per variant
+    c2.MutableCameraIntrinsics().reset(new CameraIntrinsicsModel(*cam2.CameraIntrinsics()));
+    std::vector<TwoViewPoint> p = pts;
+    BundleAdjusterB200::Flat f; tba_options to;
+    FlattenTwoViewProblem(o, corr, &c1, &c2, &p, &f, &to);
+    EXPECT(f.ext_const[0] == TBA_EXT_ALL_CONST && f.ext_const[1] == 0 && f.cam_group[0] == 0 && f.cam_group[1] == 1);
+    EXPECT(f.group_const_mask[0] == 0x7Fu && f.group_const_mask[1] == (variant == 0 ? 0x7Fu : 0x7Eu));
+    EXPECT(to.linear_solver_type == TBA_DENSE_SCHUR && to.max_num_iterations == 200 && to.use_inner_iterations == 0 && to.max_trust_region_radius == 1e16);
+    EXPECT(f.obs_cam.size() == 360 && f.obs_cam[0] == 0 && f.obs_cam[1] == 1 && f.obs_pt[1] == 0 && f.obs_pt[2] == 1);
+    tba_problem prob = f.AsProblem();
+    tba_summary os; std::memset(&os, 0, sizeof os);
+    EXPECT(solve(&to, &prob, &os) == 0 && os.success && os.final_cost < 0.2 * os.initial_cost);
+    if (variant == 1) EXPECT(std::fabs(f.intr[TBA_INTR_STRIDE] - 800.0) < 8.0);  // focal length of camera 2 recovered
+    else EXPECT(f.intr[TBA_INTR_STRIDE] == 780.0);
+    if (!gpu) continue;
+    BundleAdjustmentSummary s = BundleAdjustTwoViewsB200(o, corr, &c1, &c2, &p);
+    EXPECT(s.success);
+    EXPECT(std::fabs(s.initial_cost - os.initial_cost) <= 1e-10 * os.initial_cost);
+    EXPECT(std::fabs(s.final_cost - os.final_cost) <= 1e-5 * os.final_cost);
+    for (int j = 0; j < 6; ++j) EXPECT(std::fabs(c2.extrinsics()[j] - f.ext[6 + j]) <= 1e-4 * (1.0 + std::fabs(f.ext[6 + j])));
+    EXPECT(std::fabs(c2.intrinsics()[0] - f.intr[TBA_INTR_STRIDE]) <= 1e-4 * 800.0);
+    for (int j = 0; j < 6; ++j) EXPECT(c1.extrinsics()[j] == 0.0);
+    EXPECT(c1.intrinsics()[0] == 800.0);
+  }
+  std::printf(gpu ? "twoview ok\n" : "twoview-oracle ok\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "flatten") return TestFlatten();
   if (argc >= 3 && std::string(argv[1]) == "solve") return TestSolve(argv[2]);
   if (argc >= 2 && std::string(argv[1]) == "tracks-nogpu") return TestTracksNoGpu();
   if (argc >= 3 && std::string(argv[1]) == "tracks") return TestTracks(argv[2]);
   if (argc >= 3 && std::string(argv[1]) == "micro") return TestMicro(argv[2], true);
+  if (argc >= 3 && std::string(argv[1]) == "twoview") return TestTwoViews(argv[2], true);
+  if (argc >= 3 && std::string(argv[1]) == "twoview-oracle") return TestTwoViews(argv[2], false);
   if (argc >= 3 && std::string(argv[1]) == "micro-oracle") return TestMicro(argv[2], false);  // CPU: flattening + oracle half only
   std::fprintf(stderr, "usage: adapter_test flatten | tracks-nogpu | solve <libba_oracle.so> | tracks <libba_oracle.so> | micro <libba_oracle.so>\n");
   return 2;

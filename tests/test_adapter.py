@@ -35,3 +35,11 @@ def test_view_only_and_track_only_problems_flatten_and_solve_in_the_oracle(adapt
     out = subprocess.run([adapter_test_bin, "micro-oracle", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "micro-oracle ok" in out.stdout
+
+
+def test_two_view_flattening_and_oracle_solve(adapter_test_bin):
+    """BundleAdjustTwoViewsB200 (bundle_adjust_two_views.cc:112-191): camera 1 fixed, focal-only intrinsics subsets, DENSE_SCHUR,
+    200 iterations, Ceres-default tolerances -- the CPU half (flattening + oracle); the GPU half is tests/test_z_adapter_gpu.py."""
+    out = subprocess.run([adapter_test_bin, "twoview-oracle", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "twoview-oracle ok" in out.stdout

@@ -37,3 +37,10 @@ def test_bundle_adjust_view_and_track_against_oracle(adapter_test_bin):
     out = subprocess.run([adapter_test_bin, "micro", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "micro ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_bundle_adjust_two_views_against_oracle(adapter_test_bin):
+    out = subprocess.run([adapter_test_bin, "twoview", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "twoview ok" in out.stdout
