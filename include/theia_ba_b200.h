@@ -257,6 +257,34 @@ int tba_estimate_tracks(tba_context* ctx, const tba_options* ba_options, double 
 enum { TBA_TRACK_ESTIMATED = 0, TBA_TRACK_BAD_ANGLE = 1, TBA_TRACK_TRIANGULATION_FAILED = 2, TBA_TRACK_BA_FAILED = 3,
        TBA_TRACK_BAD_REPROJECTION = 4, TBA_TRACK_SKIPPED = 255 };
 
+/*
+ * N3: BundleAdjustTwoViews (src/theia/sfm/bundle_adjustment/bundle_adjust_two_views.cc:112-191) for MANY image pairs in one
+ * call -- what TwoViewMatchGeometricVerification issues once per pair (two_view_match_geometric_verification.cc:268-296).
+ * Per pair: camera 1 fixed, camera 2's extrinsics free, each camera's intrinsics constant or focal-length-only, every point
+ * free, no robust loss, exact (DENSE_SCHUR) step, 200 iterations, Ceres' default tolerances -- all fixed by the reference
+ * (.cc:54-69), so there is no options argument.  Pair p owns correspondences [pair_off[p], pair_off[p+1]).  The two cameras of
+ * a pair have their own intrinsics rows.  Independent of any uploaded problem; ctx supplies device and stream.
+ * termination[p]: TBA_CONVERGENCE / NO_CONVERGENCE / FAILURE (BundleAdjustmentSummary::success = termination != FAILURE,
+ * .cc:185); initial_cost / final_cost / iterations: optional, [n_pairs].
+ */
+typedef struct tba_two_view_batch {
+  int32_t n_pairs;
+  const int64_t* pair_off;               /* [n_pairs + 1] */
+  const double* ext1;                    /* [n_pairs * 6] camera 1 extrinsics (held constant) */
+  double* ext2;                          /* [n_pairs * 6] in/out */
+  double* intr1;                         /* [n_pairs * TBA_INTR_STRIDE] in/out (only the focal length can change) */
+  double* intr2;                         /* [n_pairs * TBA_INTR_STRIDE] in/out */
+  const int32_t* model1;                 /* [n_pairs] TBA_MODEL_* */
+  const int32_t* model2;
+  const uint8_t* constant_intrinsics1;   /* [n_pairs] TwoViewBundleAdjustmentOptions::constant_camera1_intrinsics */
+  const uint8_t* constant_intrinsics2;
+  const double* xy1;                     /* [n_corr * 2] FeatureCorrespondence::feature1 */
+  const double* xy2;                     /* [n_corr * 2] feature2 */
+  double* points;                        /* [n_corr * 4] in/out triangulated points */
+} tba_two_view_batch;
+int tba_two_view_ba_batch(tba_context* ctx, tba_two_view_batch* batch, uint8_t* termination, double* initial_cost, double* final_cost,
+                          int32_t* iterations);
+
 /* Re-load ext / intr / pt of an uploaded problem (same shape) without re-packing. */
 int tba_reset_parameters(tba_context* ctx, const tba_problem* problem);
 

@@ -148,6 +148,20 @@ def estimate_tracks(problem, options=None, max_reprojection_error_pixels=5.0, mi
     return status[:problem.n_pt], counts
 
 
+def two_view_ba_batch(batch):
+    """oracle_two_view_ba_batch: every pair solved by oracle_solve; updates the batch in place.
+    Returns (termination [n_pairs] uint8, initial_cost, final_cost, iterations)."""
+    n = max(batch.n_pairs, 1)
+    term = np.zeros(n, np.uint8); ic = np.zeros(n); fc = np.zeros(n); it = np.zeros(n, np.int32)
+    st = batch.as_struct()
+    L = lib()
+    L.oracle_two_view_ba_batch.argtypes = [C.POINTER(_abi.tba_two_view_batch), C.POINTER(C.c_uint8), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    L.oracle_two_view_ba_batch(C.byref(st), term.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(ic), _dp(fc), it.ctypes.data_as(C.POINTER(C.c_int32)))
+    n = batch.n_pairs
+    return term[:n], ic[:n], fc[:n], it[:n]
+
+
 def loss(kind, width, s):
     rho = np.zeros(3)
     lib().oracle_loss(kind, width, s, _dp(rho))

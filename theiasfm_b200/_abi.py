@@ -119,6 +119,60 @@ class tba_iteration(C.Structure):
     ]
 
 
+class tba_two_view_batch(C.Structure):
+    """include/theia_ba_b200.h: tba_two_view_batch (batched BundleAdjustTwoViews)."""
+    _fields_ = [
+        ("n_pairs", C.c_int32),
+        ("pair_off", C.POINTER(C.c_int64)),
+        ("ext1", C.POINTER(C.c_double)),
+        ("ext2", C.POINTER(C.c_double)),
+        ("intr1", C.POINTER(C.c_double)),
+        ("intr2", C.POINTER(C.c_double)),
+        ("model1", C.POINTER(C.c_int32)),
+        ("model2", C.POINTER(C.c_int32)),
+        ("constant_intrinsics1", C.POINTER(C.c_uint8)),
+        ("constant_intrinsics2", C.POINTER(C.c_uint8)),
+        ("xy1", C.POINTER(C.c_double)),
+        ("xy2", C.POINTER(C.c_double)),
+        ("points", C.POINTER(C.c_double)),
+    ]
+
+
+class TwoViewBatch:
+    """Host arrays of a batch of two-view BA problems (pair p owns correspondences pair_off[p]:pair_off[p+1])."""
+
+    def __init__(self, pair_off, ext1, ext2, intr1, intr2, model1, model2, const1, const2, xy1, xy2, points):
+        self.pair_off = np.ascontiguousarray(pair_off, np.int64)
+        self.ext1 = np.ascontiguousarray(ext1, np.float64).reshape(-1, 6)
+        self.ext2 = np.ascontiguousarray(ext2, np.float64).reshape(-1, 6).copy()
+        self.intr1 = np.ascontiguousarray(intr1, np.float64).reshape(-1, INTR_STRIDE).copy()
+        self.intr2 = np.ascontiguousarray(intr2, np.float64).reshape(-1, INTR_STRIDE).copy()
+        self.model1 = np.ascontiguousarray(model1, np.int32)
+        self.model2 = np.ascontiguousarray(model2, np.int32)
+        self.const1 = np.ascontiguousarray(const1, np.uint8)
+        self.const2 = np.ascontiguousarray(const2, np.uint8)
+        self.xy1 = np.ascontiguousarray(xy1, np.float64).reshape(-1, 2)
+        self.xy2 = np.ascontiguousarray(xy2, np.float64).reshape(-1, 2)
+        self.points = np.ascontiguousarray(points, np.float64).reshape(-1, 4).copy()
+        self.n_pairs = len(self.pair_off) - 1
+
+    def copy(self):
+        return TwoViewBatch(self.pair_off, self.ext1, self.ext2, self.intr1, self.intr2, self.model1, self.model2, self.const1,
+                            self.const2, self.xy1, self.xy2, self.points)
+
+    def as_struct(self):
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        s = tba_two_view_batch()
+        s.n_pairs = self.n_pairs
+        s.pair_off = self.pair_off.ctypes.data_as(C.POINTER(C.c_int64))
+        s.ext1, s.ext2, s.intr1, s.intr2 = dp(self.ext1), dp(self.ext2), dp(self.intr1), dp(self.intr2)
+        s.model1 = self.model1.ctypes.data_as(C.POINTER(C.c_int32)); s.model2 = self.model2.ctypes.data_as(C.POINTER(C.c_int32))
+        s.constant_intrinsics1 = self.const1.ctypes.data_as(C.POINTER(C.c_uint8))
+        s.constant_intrinsics2 = self.const2.ctypes.data_as(C.POINTER(C.c_uint8))
+        s.xy1, s.xy2, s.points = dp(self.xy1), dp(self.xy2), dp(self.points)
+        return s
+
+
 class tba_summary(C.Structure):
     _fields_ = [
         ("success", C.c_int32),

@@ -1104,6 +1104,69 @@ int tba_estimate_tracks(tba_context* c, const tba_options* ba_options, double ma
   return TBA_OK;
 }
 
+// --------------------------------------------------------------------------- N3: batched two-view BA
+int tba_two_view_ba_batch(tba_context* c, tba_two_view_batch* b, uint8_t* termination, double* initial_cost, double* final_cost,
+                          int32_t* iterations) {
+  if (!c || !b || !termination || b->n_pairs < 0 || (b->n_pairs > 0 && !b->pair_off)) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const int np = b->n_pairs;
+  if (np == 0) return TBA_OK;
+  const int64_t nc = b->pair_off[np];
+  bool ext_models = false;
+  for (int p = 0; p < np; ++p) {
+    if (b->pair_off[p + 1] < b->pair_off[p] || b->pair_off[p] < 0) { set_err(c, "pair_off is not non-decreasing"); return TBA_ERR_INVALID_ARGUMENT; }
+    if (TBA_MODEL_NUM_PARAMETERS(b->model1[p]) < 0 || TBA_MODEL_NUM_PARAMETERS(b->model2[p]) < 0) { set_err(c, "unknown camera model in pair %d", p); return TBA_ERR_UNSUPPORTED; }
+    ext_models |= b->model1[p] >= TBA_MODEL_FISHEYE || b->model2[p] >= TBA_MODEL_FISHEYE;
+  }
+  DevBuf<long long> d_off;
+  DevBuf<double> d_ext1, d_ext2, d_k1, d_k2, d_xy1, d_xy2, d_pt, d_sp, d_ptc, d_cost2;
+  DevBuf<int> d_m1, d_m2, d_it;
+  DevBuf<uint8_t> d_c1, d_c2, d_term;
+  CUDA_OK(c, d_off.alloc((size_t)np + 1)); CUDA_OK(c, d_ext1.alloc((size_t)np * 6)); CUDA_OK(c, d_ext2.alloc((size_t)np * 6));
+  CUDA_OK(c, d_k1.alloc((size_t)np * 10)); CUDA_OK(c, d_k2.alloc((size_t)np * 10)); CUDA_OK(c, d_m1.alloc((size_t)np)); CUDA_OK(c, d_m2.alloc((size_t)np));
+  CUDA_OK(c, d_c1.alloc((size_t)np)); CUDA_OK(c, d_c2.alloc((size_t)np)); CUDA_OK(c, d_term.alloc((size_t)np)); CUDA_OK(c, d_cost2.alloc((size_t)np * 2));
+  CUDA_OK(c, d_it.alloc((size_t)np));
+  CUDA_OK(c, d_xy1.alloc((size_t)nc * 2)); CUDA_OK(c, d_xy2.alloc((size_t)nc * 2)); CUDA_OK(c, d_pt.alloc((size_t)nc * 4));
+  CUDA_OK(c, d_sp.alloc((size_t)nc * 4)); CUDA_OK(c, d_ptc.alloc((size_t)nc * 4));
+  std::vector<long long> h_off((size_t)np + 1);
+  for (int p = 0; p <= np; ++p) h_off[p] = (long long)b->pair_off[p];
+#define UP(dst, src, n) do { CUDA_OK(c, cudaMemcpyAsync((dst).p, (src), (size_t)(n) * sizeof(*(dst).p), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (double)((size_t)(n) * sizeof(*(dst).p)); } while (0)
+  UP(d_off, h_off.data(), np + 1); UP(d_ext1, b->ext1, np * 6); UP(d_ext2, b->ext2, np * 6); UP(d_k1, b->intr1, np * 10); UP(d_k2, b->intr2, np * 10);
+  UP(d_m1, b->model1, np); UP(d_m2, b->model2, np); UP(d_c1, b->constant_intrinsics1, np); UP(d_c2, b->constant_intrinsics2, np);
+  UP(d_xy1, b->xy1, nc * 2); UP(d_xy2, b->xy2, nc * 2); UP(d_pt, b->points, nc * 4);
+#undef UP
+  TwoViewBatchDev B;
+  B.n_pairs = np; B.off = d_off.p; B.ext1 = d_ext1.p; B.ext2 = d_ext2.p; B.k1 = d_k1.p; B.k2 = d_k2.p; B.model1 = d_m1.p; B.model2 = d_m2.p;
+  B.const1 = d_c1.p; B.const2 = d_c2.p; B.xy1 = d_xy1.p; B.xy2 = d_xy2.p; B.pt = d_pt.p; B.sp = d_sp.p; B.pt_c = d_ptc.p;
+  // SetSolverOptions of bundle_adjust_two_views.cc:54-69: everything but the solver type / iteration cap is Ceres' default
+  PointLmOptions o;
+  o.loss_type = TBA_LOSS_TRIVIAL; o.loss_width = 1.0; o.max_num_iterations = 200;
+  o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8;
+  o.initial_radius = 1e4; o.max_radius = 1e16; o.min_radius = 1e-32; o.min_relative_decrease = 1e-3; o.min_diag = 1e-6; o.max_diag = 1e32;
+  o.jacobi_scaling = 1; o.max_consecutive_invalid = 5;
+  {
+    auto kfn = ext_models ? k_two_view_ba<true> : k_two_view_ba<false>;
+    LAUNCH(c, kfn, (np + 31) / 32, 32, 0, B, o, d_term.p, d_cost2.p, d_it.p);
+  }
+  std::vector<double> hc((size_t)np * 2);
+  std::vector<int> hit((size_t)np);
+  CUDA_OK(c, cudaMemcpyAsync(termination, d_term.p, (size_t)np, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(hc.data(), d_cost2.p, (size_t)np * 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(hit.data(), d_it.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(b->ext2, d_ext2.p, (size_t)np * 48, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(b->intr1, d_k1.p, (size_t)np * 80, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(b->intr2, d_k2.p, (size_t)np * 80, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(b->points, d_pt.p, (size_t)nc * 32, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += (double)np * (1 + 16 + 4 + 48 + 160) + (double)nc * 32;
+  for (int p = 0; p < np; ++p) {
+    if (initial_cost) initial_cost[p] = hc[(size_t)2 * p];
+    if (final_cost) final_cost[p] = hc[(size_t)2 * p + 1];
+    if (iterations) iterations[p] = hit[p];
+  }
+  return TBA_OK;
+}
+
 // --------------------------------------------------------------------------- single-process multi-GPU
 // The drop-in is called from ONE host thread (Theia's estimators); this entry point shards points + observations over
 // n_devices GPUs of the box, runs one rank per device on its own host thread (each with its own context, stream and

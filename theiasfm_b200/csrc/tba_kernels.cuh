@@ -12,6 +12,7 @@
 #include "tba_camera_models.cuh"
 #include "tba_filter.cuh"
 #include "tba_track_estimator.cuh"
+#include "tba_two_view.cuh"
 
 namespace tba {
 
@@ -377,6 +378,36 @@ __global__ void k_adjust_tracks(DevProblem P, const long long* __restrict__ pt_s
   for (int j = 0; j < 4; ++j) P.pt[(size_t)k * 4 + j] = X[j];
   status[k] = (uint8_t)lm.termination;
   cost2[2 * k] = lm.initial_cost; cost2[2 * k + 1] = lm.final_cost;
+}
+
+// --------------------------------------------------------- N3: batched two-view bundle adjustment
+// BundleAdjustTwoViews for many image pairs at once: one thread runs the whole Levenberg-Marquardt of one pair
+// (tba_two_view.cuh).  Pairs are independent and of similar size (a few hundred correspondences), so thread-level
+// parallelism over pairs fills the machine when geometric verification hands over its thousands of pairs.
+struct TwoViewBatchDev {
+  int n_pairs;
+  const long long* off;       // [n_pairs + 1] into the correspondence arrays
+  const double* ext1; double* ext2; double* k1; double* k2;
+  const int* model1; const int* model2;
+  const uint8_t* const1; const uint8_t* const2;  // constant_cameraN_intrinsics
+  const double* xy1; const double* xy2;
+  double* pt; double* sp; double* pt_c;
+};
+template <bool EXT>
+__global__ void k_two_view_ba(TwoViewBatchDev B, PointLmOptions o, uint8_t* __restrict__ termination, double* __restrict__ cost2,
+                              int* __restrict__ iterations) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B.n_pairs) return;
+  TwoViewPair P;
+  const long long b = B.off[p];
+  P.ext1 = B.ext1 + (size_t)p * 6; P.ext2 = B.ext2 + (size_t)p * 6; P.k1 = B.k1 + (size_t)p * 10; P.k2 = B.k2 + (size_t)p * 10;
+  P.model1 = B.model1[p]; P.model2 = B.model2[p]; P.free_f1 = B.const1[p] ? 0 : 1; P.free_f2 = B.const2[p] ? 0 : 1;
+  P.n = (int)(B.off[p + 1] - b);
+  P.pt = B.pt + (size_t)b * 4; P.xy1 = B.xy1 + (size_t)b * 2; P.xy2 = B.xy2 + (size_t)b * 2; P.sp = B.sp + (size_t)b * 4; P.pt_c = B.pt_c + (size_t)b * 4;
+  const PointLmResult r = two_view_lm<EXT>(P, o);
+  termination[p] = (uint8_t)r.termination;
+  cost2[2 * p] = r.initial_cost; cost2[2 * p + 1] = r.final_cost;
+  iterations[p] = r.iterations;
 }
 
 // --------------------------------------------------------- per-point blocks

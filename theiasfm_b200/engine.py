@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch",
 ]
 
 
@@ -60,6 +60,7 @@ def lib():
         L.tba_debug_pack.restype = C.c_int
         L.tba_adjust_tracks.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
         L.tba_estimate_tracks.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+        L.tba_two_view_ba_batch.argtypes = [C.c_void_p, C.POINTER(_abi.tba_two_view_batch), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
         L.tba_filter_tracks.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_uint8), dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -252,6 +253,17 @@ class Engine:
                                               int(bundle_adjustment), status.ctypes.data_as(C.POINTER(C.c_uint8)),
                                               counts.ctypes.data_as(C.POINTER(C.c_int32))))
         return status[:self._problem.n_pt], counts
+
+    def two_view_ba_batch(self, batch):
+        """tba_two_view_ba_batch (batched BundleAdjustTwoViews): updates batch.ext2 / intr1 / intr2 / points in place.
+        Returns (termination [n_pairs] uint8, initial_cost, final_cost, iterations)."""
+        n = max(batch.n_pairs, 1)
+        term = np.zeros(n, np.uint8); ic = np.zeros(n); fc = np.zeros(n); it = np.zeros(n, np.int32)
+        st = batch.as_struct()
+        self._check(lib().tba_two_view_ba_batch(self._h, C.byref(st), term.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(ic), _dp(fc),
+                                                it.ctypes.data_as(C.POINTER(C.c_int32))))
+        n = batch.n_pairs
+        return term[:n], ic[:n], fc[:n], it[:n]
 
     def reset_parameters(self, problem):
         st = problem.as_struct()

@@ -196,3 +196,43 @@ def make_config(name, **overrides):
     kw = dict(CONFIGS[name])
     kw.update(overrides)
     return make_scene(**kw)
+
+
+def make_two_view_batch(n_pairs, min_corr=60, max_corr=400, seed=0, models=(_abi.MODEL_PINHOLE,), noise_px=0.5, free_focal_fraction=0.5):
+    """Seeded batch of two-view BA problems (BundleAdjustTwoViews inputs): camera 1 at a fixed pose, camera 2 displaced by a
+    baseline and a small rotation, points in front of both, noisy correspondences, noisy triangulated points, camera 2 pose
+    and (when its intrinsics are free) its focal length perturbed."""
+    rng = np.random.default_rng(seed)
+    n = rng.integers(min_corr, max_corr + 1, n_pairs)
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    model = np.asarray(models)[rng.integers(0, len(models), n_pairs)].astype(np.int32)
+    ext1 = np.concatenate([0.1 * rng.normal(size=(n_pairs, 3)), 0.05 * rng.normal(size=(n_pairs, 3))], axis=1)
+    ext2_gt = ext1.copy()
+    ext2_gt[:, :3] += np.stack([rng.uniform(0.6, 1.4, n_pairs) * rng.choice([-1, 1], n_pairs), 0.15 * rng.normal(size=n_pairs), 0.1 * rng.normal(size=n_pairs)], 1)
+    ext2_gt[:, 3:] += 0.08 * rng.normal(size=(n_pairs, 3))
+    intr_gt = np.zeros((n_pairs, _abi.INTR_STRIDE))
+    for p in range(n_pairs):
+        m = model[p]
+        if m <= _abi.MODEL_FISHEYE:
+            intr_gt[p, :5] = [rng.uniform(600, 1000), 1.0, 0.0, 500.0, 500.0]
+            intr_gt[p, 5:7] = [-0.03, 0.005]
+        else:
+            intr_gt[p, :4] = [rng.uniform(600, 1000), 1.0, 500.0, 500.0]
+            intr_gt[p, 4] = 0.3 if m == _abi.MODEL_FOV else -1.5e-7
+    const1 = np.ones(n_pairs, np.uint8)
+    const2 = (rng.uniform(size=n_pairs) >= free_focal_fraction).astype(np.uint8)
+    const1[rng.uniform(size=n_pairs) < 0.2 * free_focal_fraction] = 0
+    total = int(off[-1])
+    X = np.concatenate([rng.uniform(-2, 2, (total, 2)), rng.uniform(5, 9, (total, 1)), np.ones((total, 1))], axis=1)
+    pair_of = np.repeat(np.arange(n_pairs), n)
+    xy1 = np.zeros((total, 2)); xy2 = np.zeros((total, 2))
+    for m in np.unique(model):
+        sel = model[pair_of] == m
+        xy1[sel] = project(int(m), ext1[pair_of[sel]], intr_gt[pair_of[sel]], X[sel])[0]
+        xy2[sel] = project(int(m), ext2_gt[pair_of[sel]], intr_gt[pair_of[sel]], X[sel])[0]
+    xy1 += noise_px * rng.normal(size=xy1.shape); xy2 += noise_px * rng.normal(size=xy2.shape)
+    ext2 = ext2_gt + np.concatenate([0.03 * rng.normal(size=(n_pairs, 3)), 0.005 * rng.normal(size=(n_pairs, 3))], axis=1)
+    intr1, intr2 = intr_gt.copy(), intr_gt.copy()
+    intr2[const2 == 0, 0] *= 1.0 + 0.03 * rng.normal(size=int((const2 == 0).sum()))
+    pts = X.copy(); pts[:, :3] += 0.05 * rng.normal(size=(total, 3))
+    return _abi.TwoViewBatch(off, ext1, ext2, intr1, intr2, model, model, const1, const2, xy1, xy2, pts)
