@@ -260,7 +260,12 @@ def main():
                 "linearize": {"avg_launch_ms": lin_ms, "algorithmic_bytes_per_launch": lin_bytes,
                               "achieved": lin_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0,
                               "frac": (lin_bytes / (lin_ms * 1e-3) / 1e9 / peak) if lin_ms > 0 else 0.0,
-                              "share_of_step": prof["linearize_ms"] * 1e-3 / dev_s if dev_s > 0 else None}}
+                              "share_of_step": prof["linearize_ms"] * 1e-3 / dev_s if dev_s > 0 else None,
+                              # the linearisation is the fp64-heavy kernel (about 650 flop / observation: residual +
+                              # analytic Jacobian 450, block outer products 200): report it against the measured DFMA peak too
+                              "fp64_tflops_estimate": (650.0 * prof["observations"] / (lin_ms * 1e-3) * 1e-12) if lin_ms > 0 else None,
+                              "frac_of_measured_fp64": (650.0 * prof["observations"] / (lin_ms * 1e-3) * 1e-12 / micro["fp64_fma_tflops"])
+                              if (lin_ms > 0 and micro and micro.get("fp64_fma_tflops")) else None}}
     # ---- e2e: the drop-in call with host buffers (pack + H2D + solve + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -283,6 +288,8 @@ def main():
                 "ms_per_step": 1e3 * t_max / iters, "steps_run": iters, "note": note, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "microbench": micro, "cpu_baseline": cb, "lm_iters_per_s": iters / t_max,
+                # observation passes = linearisations + PCG matvecs + step evaluations, all ranks' shards together
+                "obs_passes_per_s": n_obs_total * (prof["linearize_launches"] + prof["matvec_launches"] + iters) / t_max,
                 "pcg_iterations": s.num_linear_solver_iterations, "initial_cost": s.initial_cost, "final_cost": s.final_cost,
                 "wall_seconds_timed_region": wall, "n_obs": n_obs_total}
         print(json.dumps(line))
