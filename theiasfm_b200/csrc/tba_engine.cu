@@ -1280,7 +1280,11 @@ int tba_debug_pack(const tba_problem* p, int64_t cap_slots, int64_t* sizes_out, 
                    int32_t* tile_nruns, uint8_t* tile_flags, double* mask) {
   if (!p || !sizes_out) return TBA_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < p->n_cam; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= p->n_group) return TBA_ERR_INVALID_ARGUMENT;
-  HostPack H;
+  // one HostPack reused by every call, like the engine context's (tba_context::pack): the CPU tests, which call this with
+  // problems of different shapes back to back, thereby also cover the reuse of its buffers
+  static std::mutex mu;
+  static HostPack H;
+  std::lock_guard<std::mutex> lk(mu);
   pack_count_and_sort(p, 4, &H);
   if (H.bad >= 0) return TBA_ERR_INVALID_ARGUMENT;
   if (H.maxlen > TILE) return TBA_ERR_UNSUPPORTED;
