@@ -94,7 +94,7 @@ typedef struct tba_options {
   int32_t num_threads;                 /* 1 (host threads; unused on GPU) */
   int32_t max_num_iterations;          /* 100 */
   double  max_solver_time_in_seconds;  /* 3600 */
-  int32_t use_inner_iterations;        /* 1 in Theia; see DESIGN.md */
+  int32_t use_inner_iterations;        /* 1 in Theia: coordinate descent over extrinsics / intrinsics / points after every LM step */
   double  function_tolerance;          /* 1e-6 */
   double  gradient_tolerance;          /* 1e-10 */
   double  parameter_tolerance;         /* 1e-8 */

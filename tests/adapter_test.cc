@@ -161,11 +161,14 @@ typedef int (*oracle_solve_fn)(const tba_options*, tba_problem*, tba_summary*);
 static int TestSolve(const char* oracle_path) {
   Scene sc;
   BuildScene(&sc, 12, 400, 5, 5, 21);
-  // default Theia options (SPARSE_SCHUR + inner iterations) are refused loudly, parameters untouched
+  const Scene sc0 = sc;  // the untouched start, for the second solve with Theia's default options
+  // an option set the engine does not implement (CGNR) is refused loudly, parameters untouched
   {
     Scene copy = sc;
     const double before = copy.rec.MutableTrack(copy.tracks[3])->Point().v[0];
-    BundleAdjustmentSummary s = BundleAdjustReconstructionB200(BundleAdjustmentOptions(), &copy.rec);
+    BundleAdjustmentOptions unsupported;
+    unsupported.linear_solver_type = ceres::CGNR;
+    BundleAdjustmentSummary s = BundleAdjustReconstructionB200(unsupported, &copy.rec);
     EXPECT(!s.success);
     EXPECT(copy.rec.MutableTrack(copy.tracks[3])->Point().v[0] == before);
   }
@@ -192,6 +195,15 @@ static int TestSolve(const char* oracle_path) {
   EXPECT(std::fabs(s.initial_cost - oracle_initial) <= 1e-10 * oracle_initial);
   EXPECT(std::fabs(s.final_cost - oracle_final) <= 1e-6 * oracle_final);
   EXPECT(s.final_cost < 0.05 * s.initial_cost);
+  // Theia's DEFAULT options (SPARSE_SCHUR + inner iterations, bundle_adjustment.h:78-122) run as they are
+  {
+    Scene copy0 = sc0;
+    BundleAdjustmentOptions defaults;
+    defaults.max_num_iterations = 15;
+    BundleAdjustmentSummary sd = BundleAdjustReconstructionB200(defaults, &copy0.rec);
+    EXPECT(sd.success && sd.final_cost < 0.05 * sd.initial_cost);
+    EXPECT(std::fabs(sd.final_cost - oracle_final) <= 2e-2 * oracle_final);  // same minimum, different path
+  }
   // the in-place update happened: reprojection with the refined parameters reproduces final_cost
   double cost = 0;
   for (TrackId t : sc.rec.TrackIds()) {

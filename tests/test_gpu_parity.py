@@ -232,7 +232,7 @@ def test_edge_cases(eng, oracle):
     s = eng.solve(f, _opts(engine))
     assert s.rc == 0 and not s.success and s.termination_type == _abi.FAILURE
     # unsupported options fail loudly instead of silently doing something else
-    s = eng.solve(_scene("pinhole_shared"), engine.default_options())
+    s = eng.solve(_scene("pinhole_shared"), engine.default_options(linear_solver_type=6))  # CGNR
     assert s.rc == _abi.ERR_UNSUPPORTED and not s.success
     # a track longer than the engine limit is refused
     big = synthetic.make_scene(n_cam=600, n_pt=3, obs_per_pt=290, seed=1)

@@ -156,8 +156,10 @@ def test_robust_loss_and_constant_blocks_solve(oracle):
 
 def test_unsupported_options_fail_loudly(oracle):
     p = _tiny()
-    s = oracle.solve(p, oracle.default_options())  # Theia defaults: SPARSE_SCHUR + inner iterations
+    s = oracle.solve(p, oracle.default_options(linear_solver_type=6))  # CGNR: the one solver type that is not restated
     assert s.rc == _abi.ERR_UNSUPPORTED and not s.success
+    s = oracle.solve(_tiny(), oracle.default_options(max_num_iterations=5))  # Theia defaults (SPARSE_SCHUR + inner iterations) run
+    assert s.rc == 0 and s.success
 
 
 @pytest.mark.parametrize("loss", [_abi.LOSS_HUBER, _abi.LOSS_SOFTLONE, _abi.LOSS_CAUCHY, _abi.LOSS_ARCTAN, _abi.LOSS_TUKEY])

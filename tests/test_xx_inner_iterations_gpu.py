@@ -1,0 +1,52 @@
+"""N4 on the GPU: use_inner_iterations = true (Theia's default, bundle_adjustment.h:114) through the C-ABI -- the lockstep
+per-block LM driver with k_block_pass for cameras and intrinsics groups, k_adjust_tracks on the candidate for the points --
+against the oracle, whose inner iterations build and solve every block's mini-program explicitly.  The driver and the
+per-observation bodies are checked on the host by tests/test_inner_iterations.py.  Never executed on hardware in round 1."""
+import numpy as np
+import pytest
+
+from helpers import rel_err
+from theiasfm_b200 import _abi, engine, synthetic
+
+pytestmark = pytest.mark.gpu
+
+SCENES = {
+    "pinhole_shared": dict(n_cam=12, n_pt=300, obs_per_pt=5, seed=61),
+    "radtan_per_camera": dict(n_cam=10, n_pt=400, obs_per_pt=6, seed=62, model=_abi.MODEL_PINHOLE_RADIAL_TANGENTIAL, shared_intrinsics=False,
+                              intrinsics_to_optimize=_abi.INTR_ALL),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("solver", [_abi.SPARSE_SCHUR, _abi.ITERATIVE_SCHUR])
+def test_theia_default_options_match_the_oracle(oracle, name, solver):
+    p = synthetic.make_scene(**SCENES[name])
+    p.ext_const[1] = _abi.EXT_ALL_CONST; p.ext_const[2] = _abi.EXT_POSITION_CONST; p.pt_const[[4, 9]] = 1
+    kw = dict(use_inner_iterations=1, linear_solver_type=solver, max_num_iterations=12)
+    po, pg = p.copy(), p.copy()
+    so = oracle.solve(po, oracle.default_options(**kw))
+    eng = engine.Engine()
+    sg = eng.solve(pg, engine.default_options(**kw))
+    eng.close()
+    assert sg.rc == 0 and sg.success and so.success
+    assert abs(sg.initial_cost - so.initial_cost) <= 1e-11 * so.initial_cost
+    assert abs(sg.num_iterations - so.num_iterations) <= 1
+    n = min(len(sg.costs), len(so.costs))
+    # the coordinate descent re-solves every block to a 1e-6 function tolerance: costs agree to that level, not to rounding
+    assert np.all(np.abs(sg.costs[:n] - so.costs[:n]) <= 1e-5 * so.costs[:n])
+    assert abs(sg.final_cost - so.final_cost) <= 1e-5 * so.final_cost
+    assert sg.final_cost < 0.05 * sg.initial_cost and sg.costs[1] < 0.2 * sg.costs[0]
+    assert rel_err(pg.ext, po.ext) < 1e-4 and rel_err(pg.intr, po.intr) < 1e-4
+    assert np.array_equal(pg.ext[1], p.ext[1]) and np.array_equal(pg.ext[2, :3], p.ext[2, :3]) and np.array_equal(pg.pt[[4, 9]], p.pt[[4, 9]])
+
+
+def test_inner_iterations_lower_the_cost_of_every_iteration():
+    p = synthetic.make_scene(n_cam=30, n_pt=3000, obs_per_pt=7, seed=63)
+    a, b = p.copy(), p.copy()
+    eng = engine.Engine()
+    sa = eng.solve(a, engine.default_options(max_num_iterations=10))                                  # Theia defaults
+    sb = eng.solve(b, engine.default_options(max_num_iterations=10, use_inner_iterations=0, linear_solver_type=_abi.ITERATIVE_SCHUR))
+    eng.close()
+    assert sa.rc == 0 and sb.rc == 0 and sa.success and sb.success
+    assert sa.costs[1] < sb.costs[1]
+    assert abs(sa.final_cost - sb.final_cost) <= 5e-3 * sb.final_cost

@@ -25,6 +25,7 @@
 #include "../../include/theia_ba_b200.h"
 #include "tba_kernels.cuh"
 #include "tba_pack.h"
+#include "tba_block_lm.h"
 
 namespace tba {
 
@@ -126,6 +127,14 @@ struct tba_context {
   // global number of free points, so that the upload needs no collective
   const double* preset_cnt_cam = nullptr;
   int64_t preset_free_pt = -1;
+  // N4 inner iterations: host copies of the constness description and their device mirrors (allocated only when requested)
+  std::vector<uint8_t> h_ext_const;
+  std::vector<uint32_t> h_group_mask;
+  std::vector<int> h_group_model;
+  DevBuf<uint8_t> d_ext_const, d_blk_active;
+  DevBuf<uint32_t> d_group_mask;
+  DevBuf<double> d_blk_vals, d_blk_rec, d_blk_acc;
+  int64_t inner_passes = 0;
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
   bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
@@ -459,6 +468,141 @@ void accept_candidate(tba_context* c) {
   std::swap(P.cam_rec, P.cam_rec_c);
 }
 
+// ---- N4: inner iterations -------------------------------------------------------------------------------
+// The candidate buffers seen as "the problem": kernels that read P.ext / P.intr / P.pt / P.cam_rec then work on the candidate.
+DevProblem candidate_view(const DevProblem& P) {
+  DevProblem Q = P;
+  Q.ext = P.ext_c; Q.intr = P.intr_c; Q.pt = P.pt_c; Q.cam_rec = P.cam_rec_c;
+  return Q;
+}
+
+// One independent set (all cameras, or all intrinsics groups) of the coordinate descent: per-block LM state on the host in
+// lockstep (tba_block_lm.h), observation passes on the device (k_block_pass).  Works on the candidate buffers in place.
+template <int KIND>
+int run_block_stage(tba_context* c) {
+  DevProblem& P = c->P;
+  constexpr int ND = block_dim(KIND), NA = block_acc(KIND);
+  const int nb = KIND == kBlockCamera ? P.n_cam : P.n_group;
+  if (nb == 0) return TBA_OK;  // (a rank without observations still takes part in the all-reduces below)
+  const BlockLmOptions lo;
+  const std::vector<double>& mask = c->pack.mask;  // 1 = free coordinate of a block that takes part in the problem
+  std::vector<double> vals((size_t)nb * ND);
+  double* dev_vals = KIND == kBlockCamera ? P.ext_c : P.intr_c;
+  CUDA_OK(c, cudaMemcpyAsync(vals.data(), dev_vals, vals.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  std::vector<BlockLm> B((size_t)nb);
+  std::vector<int> dims((size_t)nb, ND);
+  int n_live = 0;
+  for (int b = 0; b < nb; ++b) {
+    bool fr[kBlkMaxN];
+    const int N = KIND == kBlockCamera ? 6 : TBA_MODEL_NUM_PARAMETERS(c->h_group_model[b]);
+    dims[b] = N;
+    for (int j = 0; j < N; ++j) fr[j] = mask[(KIND == kBlockCamera ? (size_t)b * 6 : (size_t)P.ne + (size_t)b * 10) + j] != 0.0;
+    block_lm_init(B[b], N, fr, &vals[(size_t)b * ND], lo);
+    n_live += B[b].phase != kBlkDone;
+  }
+  if (n_live == 0) return TBA_OK;
+  const int n_rep = (KIND == kBlockGroup && nb == 1) ? 256 : 1;
+  CUDA_OK(c, c->d_blk_vals.alloc((size_t)nb * ND));
+  CUDA_OK(c, c->d_blk_active.alloc((size_t)nb));
+  CUDA_OK(c, c->d_blk_acc.alloc((size_t)n_rep * nb * NA));
+  if (KIND == kBlockCamera) CUDA_OK(c, c->d_blk_rec.alloc((size_t)nb * kCamRec));
+  std::vector<double> acc((size_t)n_rep * nb * NA);
+  BlockPassArgs A;
+  A.ext = KIND == kBlockCamera ? c->d_blk_vals.p : P.ext_c;
+  A.rec = KIND == kBlockCamera ? c->d_blk_rec.p : P.cam_rec_c;
+  A.intr = KIND == kBlockCamera ? P.intr_c : c->d_blk_vals.p;
+  A.pt = P.pt_c;
+  A.active = c->d_blk_active.p; A.ext_const = c->d_ext_const.p; A.group_const = c->d_group_mask.p;
+  A.acc = c->d_blk_acc.p; A.n_rep = n_rep;
+  auto exec = [&](int pass, const std::vector<uint8_t>& active, const std::vector<double>& pv, std::vector<double>& sum) -> int {
+    CUDA_OK(c, cudaMemcpyAsync(c->d_blk_vals.p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_blk_active.p, active.data(), (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(c->d_blk_acc.p, 0, acc.size() * 8, c->stream));
+    if (KIND == kBlockCamera) LAUNCH(c, k_cam_prep, (nb + 127) / 128, 128, 0, nb, c->d_blk_vals.p, c->d_blk_rec.p);
+    if (P.n_tiles > 0 && pass == 0) {
+      auto kfn = c->has_ext_models ? k_block_pass<KIND, true, false> : k_block_pass<KIND, false, false>;
+      LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, A);
+    } else if (P.n_tiles > 0) {
+      auto kfn = c->has_ext_models ? k_block_pass<KIND, true, true> : k_block_pass<KIND, false, true>;
+      LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, A);
+    }
+    const int rc = allreduce_sum(c, c->d_blk_acc.p, acc.size());
+    if (rc) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(acc.data(), c->d_blk_acc.p, acc.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += (double)pv.size() * 8 + nb; c->d2h_bytes += (double)acc.size() * 8;
+    c->inner_passes++;
+    std::fill(sum.begin(), sum.end(), 0.0);
+    for (int r = 0; r < n_rep; ++r) for (size_t i = 0; i < sum.size(); ++i) sum[i] += acc[(size_t)r * sum.size() + i];  // fixed order
+    return TBA_OK;
+  };
+  {
+    const int rc = block_lm_run_lockstep(B, dims, ND, NA, lo, exec);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < nb; ++b) for (int j = 0; j < dims[b]; ++j) vals[(size_t)b * ND + j] = B[b].x[j];
+  CUDA_OK(c, cudaMemcpyAsync(dev_vals, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return TBA_OK;
+}
+
+// CoordinateDescentMinimizer::Minimize on the candidate: extrinsics, then intrinsics groups, then points (Theia's reversed
+// ordering, bundle_adjuster.cc:196-200), each block with Ceres' default per-block solver; then the cost there.
+int stage_inner_iterations(tba_context* c, double* inner_cost, bool* ok) {
+  DevProblem& P = c->P;
+  int rc = run_block_stage<kBlockCamera>(c);
+  if (rc) return rc;
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
+  rc = run_block_stage<kBlockGroup>(c);
+  if (rc) return rc;
+  if (P.n_pt > 0) {
+    PointLmOptions po;
+    const BlockLmOptions lo;
+    po.loss_type = c->opt.loss_function_type; po.loss_width = c->opt.robust_loss_width; po.max_num_iterations = lo.max_num_iterations;
+    po.function_tolerance = lo.function_tolerance; po.gradient_tolerance = lo.gradient_tolerance; po.parameter_tolerance = lo.parameter_tolerance;
+    po.initial_radius = lo.initial_radius; po.max_radius = lo.max_radius; po.min_radius = lo.min_radius; po.min_relative_decrease = lo.min_relative_decrease;
+    po.min_diag = lo.min_diag; po.max_diag = lo.max_diag; po.jacobi_scaling = 1; po.max_consecutive_invalid = lo.max_consecutive_invalid;
+    DevBuf<uint8_t> d_status;
+    DevBuf<double> d_cost2;
+    CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
+    CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
+    const DevProblem Q = candidate_view(P);
+    auto kfn = c->has_ext_models ? k_adjust_tracks<true> : k_adjust_tracks<false>;
+    LAUNCH(c, kfn, (P.n_pt + 63) / 64, 64, 0, Q, c->pt_slot.p, c->pt_len.p, po, d_status.p, d_cost2.p);
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));  // the scratch buffers go out of scope
+  }
+  // cost at the refined candidate
+  CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
+  if (P.n_tiles > 0) {
+    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
+  }
+  rc = allreduce_sum(c, c->scal2.p, 3);
+  if (rc) return rc;
+  double s3[3];
+  rc = read_scal(c, c->scal2.p, 3, s3);
+  if (rc) return rc;
+  *inner_cost = s3[0];
+  *ok = s3[2] == 0.0;
+  return TBA_OK;
+}
+
+// ||x - candidate|| over the non-constant blocks after the inner iterations (ParameterToleranceReached uses it).
+int stage_step_norm(tba_context* c, double* step_norm) {
+  DevProblem& P = c->P;
+  CUDA_OK(c, cudaMemsetAsync(c->scal2.p + 4, 0, 2 * sizeof(double), c->stream));
+  LAUNCH(c, k_xdiff, 256, 256, 0, P, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
+  int rc = allreduce_sum(c, c->scal2.p + 4, 2);
+  if (rc) return rc;
+  double s2[2];
+  rc = read_scal(c, c->scal2.p + 4, 2, s2);
+  if (rc) return rc;
+  *step_norm = std::sqrt(s2[0] + s2[1]);
+  return TBA_OK;
+}
+
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void push_iter(tba_summary* s, const tba_iteration& it) {
@@ -467,7 +611,6 @@ void push_iter(tba_summary* s, const tba_iteration& it) {
 }
 
 int check_options(tba_context* c, const tba_options* o) {
-  if (o->use_inner_iterations) { set_err(c, "use_inner_iterations=true is not implemented by the GPU engine (set it to false, as Theia's incremental/hybrid estimators do)"); return TBA_ERR_UNSUPPORTED; }
   if (o->linear_solver_type < TBA_DENSE_NORMAL_CHOLESKY || o->linear_solver_type > TBA_ITERATIVE_SCHUR) {
     set_err(c, "linear_solver_type %d unsupported: the GPU engine implements ITERATIVE_SCHUR, and the exact solver types (DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR) as the same LM step solved to the fp64 floor; CGNR is not implemented", o->linear_solver_type);
     return TBA_ERR_UNSUPPORTED;
@@ -759,6 +902,15 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
 #undef F
   }
   c->have_scale = false;
+  if (c->opt.use_inner_iterations) {
+    c->h_ext_const.assign(p->ext_const, p->ext_const + nc);
+    c->h_group_mask.assign(p->group_const_mask, p->group_const_mask + ng);
+    c->h_group_model.assign(p->group_model, p->group_model + ng);
+    CUDA_OK(c, c->d_ext_const.alloc((size_t)nc)); CUDA_OK(c, c->d_group_mask.alloc((size_t)ng));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_ext_const.p, p->ext_const, (size_t)nc, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_group_mask.p, p->group_const_mask, (size_t)ng * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
   c->uploaded = true;
   c->setup_seconds = now_s() - t0;
   return TBA_OK;
@@ -812,6 +964,8 @@ int tba_minimize(tba_context* c, tba_summary* s) {
   tba_iteration it;
   memset(&it, 0, sizeof it);
   int consecutive_invalid = 0;
+  bool inner_enabled = opt.use_inner_iterations != 0;
+  const double kInnerIterationTolerance = 1e-3;  // ceres::Solver::Options::inner_iteration_tolerance
 #define RC(expr) do { rc = (expr); if (rc) goto fail; } while (0)
   cudaEventRecord(ev0, c->stream);
   RC(stage_linearize(c, &x_cost, &fixed, &ok));
@@ -876,12 +1030,30 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     }
     consecutive_invalid = 0;
     if (!cand_ok) cand = 1.7976931348623157e308;
+    // DoInnerIterationsIfNeeded (N4)
+    bool inner_useful = false;
+    if (inner_enabled && cand_ok) {
+      double inner_cost = 0;
+      bool inner_ok = true;
+      RC(stage_inner_iterations(c, &inner_cost, &inner_ok));
+      if (inner_ok) {
+        mcc += cand - inner_cost;                       // the inner iterations' share is not credited to the trust-region step
+        inner_useful = inner_cost < x_cost;
+        inner_enabled = (1.0 - inner_cost / cand) > kInnerIterationTolerance;
+        cand = inner_cost;
+        RC(stage_step_norm(c, &step_norm));
+      } else {
+        // Ceres returns before adopting inner_iteration_x_: restore the trust-region candidate
+        RC(stage_backsub(c));
+        RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok));
+      }
+    }
     it.step_norm = step_norm;
     if (it.step_norm <= opt.parameter_tolerance * (xn + opt.parameter_tolerance)) { term = TBA_CONVERGENCE; msg = "Parameter tolerance reached."; break; }
     it.cost_change = x_cost - cand;
     if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) { term = TBA_CONVERGENCE; msg = "Function tolerance reached."; break; }
     it.relative_decrease = it.cost_change / mcc;
-    if (it.relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
+    if (inner_useful || it.relative_decrease > opt.min_relative_decrease) {  // IsStepSuccessful / HandleSuccessfulStep
       accept_candidate(c);
       RC(stage_xnorm(c, &xn));
       RC(stage_linearize(c, &x_cost, &fixed, &ok));

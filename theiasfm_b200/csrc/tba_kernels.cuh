@@ -1267,3 +1267,5 @@ __global__ void k_gradmax(DevProblem P, const double* __restrict__ g_cs, const d
 }
 
 }  // namespace tba
+
+#include "tba_inner.cuh"  // N4: observation passes of the inner iterations (uses DevProblem, block_sum, red_add from above)
