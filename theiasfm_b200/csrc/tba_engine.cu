@@ -133,7 +133,8 @@ struct tba_context {
   std::vector<int> h_group_model;
   DevBuf<uint8_t> d_ext_const, d_blk_active;
   DevBuf<uint32_t> d_group_mask;
-  DevBuf<double> d_blk_vals, d_blk_rec, d_blk_acc;
+  DevBuf<double> d_blk_vals, d_blk_rec, d_blk_acc, d_inner_cost2;
+  DevBuf<uint8_t> d_inner_status;
   int64_t inner_passes = 0;
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
@@ -563,14 +564,11 @@ int stage_inner_iterations(tba_context* c, double* inner_cost, bool* ok) {
     po.function_tolerance = lo.function_tolerance; po.gradient_tolerance = lo.gradient_tolerance; po.parameter_tolerance = lo.parameter_tolerance;
     po.initial_radius = lo.initial_radius; po.max_radius = lo.max_radius; po.min_radius = lo.min_radius; po.min_relative_decrease = lo.min_relative_decrease;
     po.min_diag = lo.min_diag; po.max_diag = lo.max_diag; po.jacobi_scaling = 1; po.max_consecutive_invalid = lo.max_consecutive_invalid;
-    DevBuf<uint8_t> d_status;
-    DevBuf<double> d_cost2;
-    CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
-    CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
+    CUDA_OK(c, c->d_inner_status.alloc((size_t)P.n_pt));  // no-ops: sized at upload
+    CUDA_OK(c, c->d_inner_cost2.alloc((size_t)P.n_pt * 2));
     const DevProblem Q = candidate_view(P);
     auto kfn = c->has_ext_models ? k_adjust_tracks<true> : k_adjust_tracks<false>;
-    LAUNCH(c, kfn, (P.n_pt + 63) / 64, 64, 0, Q, c->pt_slot.p, c->pt_len.p, po, d_status.p, d_cost2.p);
-    CUDA_OK(c, cudaStreamSynchronize(c->stream));  // the scratch buffers go out of scope
+    LAUNCH(c, kfn, (P.n_pt + 63) / 64, 64, 0, Q, c->pt_slot.p, c->pt_len.p, po, c->d_inner_status.p, c->d_inner_cost2.p);
   }
   // cost at the refined candidate
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
@@ -907,6 +905,13 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
     c->h_group_mask.assign(p->group_const_mask, p->group_const_mask + ng);
     c->h_group_model.assign(p->group_model, p->group_model + ng);
     CUDA_OK(c, c->d_ext_const.alloc((size_t)nc)); CUDA_OK(c, c->d_group_mask.alloc((size_t)ng));
+    // every buffer the inner iterations use is allocated here, never inside tba_minimize (no cudaMalloc between collectives)
+    CUDA_OK(c, c->d_blk_vals.alloc(std::max((size_t)nc * 6, (size_t)ng * 10)));
+    CUDA_OK(c, c->d_blk_active.alloc((size_t)std::max(nc, ng)));
+    CUDA_OK(c, c->d_blk_rec.alloc((size_t)nc * kCamRec));
+    CUDA_OK(c, c->d_blk_acc.alloc(std::max((size_t)nc * block_acc(kBlockCamera), (size_t)(ng == 1 ? 256 : 1) * ng * block_acc(kBlockGroup))));
+    CUDA_OK(c, c->d_inner_status.alloc((size_t)c->n_pt));
+    CUDA_OK(c, c->d_inner_cost2.alloc((size_t)c->n_pt * 2));
     CUDA_OK(c, cudaMemcpyAsync(c->d_ext_const.p, p->ext_const, (size_t)nc, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(c, cudaMemcpyAsync(c->d_group_mask.p, p->group_const_mask, (size_t)ng * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
