@@ -16,8 +16,8 @@ run() {  # run <seconds> <logname> <command...>
 # 1. the hardware-verified parity suite first, then everything that has never run on hardware (one file at a time so that
 #    one failure does not hide the others)
 run 600 parity python -m pytest tests/test_gpu_parity.py -q -m gpu -x
-for f in test_x_fountain_gpu test_x_fullsize_gpu test_x_matcher_gpu test_x_track_filter_gpu test_xx_camera_models_gpu \
-         test_xx_exact_schur_gpu test_xx_inner_iterations_gpu test_xx_track_estimator_gpu test_xx_two_view_gpu test_z_adapter_gpu; do
+for f in test_x_fountain_gpu test_x_fullsize_gpu test_xx_matcher_gpu test_x_track_filter_gpu test_xx_camera_models_gpu \
+         test_x_exact_schur_gpu test_xx_inner_iterations_gpu test_xx_track_estimator_gpu test_xx_two_view_gpu test_z_adapter_gpu; do
   run 420 "$f" python -m pytest "tests/$f.py" -q -m gpu
 done
 # 2. smoke + the bench line (default workload c3, N = 1)
