@@ -284,6 +284,11 @@ typedef struct tba_two_view_batch {
 } tba_two_view_batch;
 int tba_two_view_ba_batch(tba_context* ctx, tba_two_view_batch* batch, uint8_t* termination, double* initial_cost, double* final_cost,
                           int32_t* iterations);
+/* The same over n_devices GPUs of the box (0 = all visible): pairs are independent units, so the batch is split into contiguous
+ * ranges balanced by correspondence count and every range runs on its own device from its own host thread -- no collective.
+ * Its contexts (one per device, no NCCL) are created once per process. */
+int tba_two_view_ba_batch_multi(tba_two_view_batch* batch, int n_devices, uint8_t* termination, double* initial_cost, double* final_cost,
+                                int32_t* iterations);
 
 /* Re-load ext / intr / pt of an uploaded problem (same shape) without re-packing. */
 int tba_reset_parameters(tba_context* ctx, const tba_problem* problem);

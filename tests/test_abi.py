@@ -64,3 +64,18 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(engine.EngineError) as ei:
         engine.Engine()
     assert ei.value.code == _abi.ERR_NO_DEVICE
+
+
+def test_batched_entry_points_fail_loudly_without_a_gpu():
+    """No CPU fallback anywhere: without a CUDA device the batched N3 entry points return TBA_ERR_NO_DEVICE."""
+    from theiasfm_b200 import synthetic
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is present")
+    b = synthetic.make_two_view_batch(3, min_corr=10, max_corr=12, seed=1)
+    with pytest.raises(engine.EngineError):
+        engine.two_view_ba_batch_multi(b, n_devices=0)
+    before = b.points.copy()
+    st = b.as_struct()
+    term = (C.c_uint8 * 3)()
+    assert engine.lib().tba_two_view_ba_batch_multi(C.byref(st), 0, term, None, None, None) == _abi.ERR_NO_DEVICE
+    assert np.array_equal(b.points, before)

@@ -99,3 +99,19 @@ def test_single_process_multi_gpu_entry_point(world):
     import subprocess
     out = subprocess.run([sys.executable, "-c", _MULTI_SCRIPT % ROOT, str(world)], capture_output=True, text=True, timeout=180)
     assert out.returncode == 0 and "solve_multi ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_two_view_batch_sharded_over_gpus_is_bit_identical():
+    """Pairs are independent units: tba_two_view_ba_batch_multi splits the batch over the GPUs with no collective; every pair runs
+    the same single-thread LM wherever it lands, so the result equals the one-GPU result bit for bit."""
+    if engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    b = synthetic.make_two_view_batch(400, min_corr=40, max_corr=200, seed=12)
+    b1, b2 = b.copy(), b.copy()
+    eng = engine.Engine()
+    r1 = eng.two_view_ba_batch(b1)
+    eng.close()
+    r2 = engine.two_view_ba_batch_multi(b2, n_devices=2)
+    for a, c in zip(r1, r2):
+        assert np.array_equal(a, c)
+    assert np.array_equal(b1.ext2, b2.ext2) and np.array_equal(b1.points, b2.points) and np.array_equal(b1.intr2, b2.intr2)

@@ -1344,6 +1344,61 @@ int tba_two_view_ba_batch(tba_context* c, tba_two_view_batch* b, uint8_t* termin
   return TBA_OK;
 }
 
+// Pairs are independent: shard them over the devices of the box, one host thread and one (collective-free) context per device.
+namespace {
+std::mutex g_tv_mu;
+std::vector<tba_context*> g_tv_ctx;
+}  // namespace
+
+int tba_two_view_ba_batch_multi(tba_two_view_batch* b, int n_devices, uint8_t* termination, double* initial_cost, double* final_cost,
+                                int32_t* iterations) {
+  if (!b || !termination || b->n_pairs < 0 || (b->n_pairs > 0 && !b->pair_off)) return TBA_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(g_tv_mu);
+  const int avail = tba_device_count();
+  if (avail <= 0) return TBA_ERR_NO_DEVICE;
+  if (n_devices <= 0 || n_devices > avail) n_devices = avail;
+  n_devices = std::max(1, std::min(n_devices, std::max(b->n_pairs, 1)));
+  while ((int)g_tv_ctx.size() < n_devices) {
+    tba_context* cx = nullptr;
+    const int rc = tba_create((int)g_tv_ctx.size(), 0, 1, nullptr, &cx);
+    if (rc != TBA_OK) return rc;
+    g_tv_ctx.push_back(cx);
+  }
+  const int np = b->n_pairs;
+  if (np == 0) return TBA_OK;
+  // contiguous ranges balanced by correspondence count
+  std::vector<int> cut((size_t)n_devices + 1, np);
+  cut[0] = 0;
+  const int64_t total = b->pair_off[np] - b->pair_off[0];
+  for (int d = 1, p = 0; d < n_devices; ++d) {
+    const int64_t want = b->pair_off[0] + total * d / n_devices;
+    while (p < np && b->pair_off[p] < want) ++p;
+    cut[d] = std::max(p, cut[d - 1]);
+  }
+  std::vector<int> rcs((size_t)n_devices, TBA_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < n_devices; ++d)
+    th.emplace_back([&, d] {
+      const int p0 = cut[d], p1 = cut[d + 1];
+      if (p1 <= p0) return;
+      std::vector<int64_t> off((size_t)(p1 - p0) + 1);
+      const int64_t base = b->pair_off[p0];
+      for (int p = p0; p <= p1; ++p) off[(size_t)(p - p0)] = b->pair_off[p] - base;
+      tba_two_view_batch s = *b;
+      s.n_pairs = p1 - p0; s.pair_off = off.data();
+      s.ext1 = b->ext1 + (size_t)p0 * 6; s.ext2 = b->ext2 + (size_t)p0 * 6;
+      s.intr1 = b->intr1 + (size_t)p0 * TBA_INTR_STRIDE; s.intr2 = b->intr2 + (size_t)p0 * TBA_INTR_STRIDE;
+      s.model1 = b->model1 + p0; s.model2 = b->model2 + p0;
+      s.constant_intrinsics1 = b->constant_intrinsics1 + p0; s.constant_intrinsics2 = b->constant_intrinsics2 + p0;
+      s.xy1 = b->xy1 + (size_t)base * 2; s.xy2 = b->xy2 + (size_t)base * 2; s.points = b->points + (size_t)base * 4;
+      rcs[d] = tba_two_view_ba_batch(g_tv_ctx[d], &s, termination + p0, initial_cost ? initial_cost + p0 : nullptr,
+                                     final_cost ? final_cost + p0 : nullptr, iterations ? iterations + p0 : nullptr);
+    });
+  for (auto& t : th) t.join();
+  for (int d = 0; d < n_devices; ++d) if (rcs[d] != TBA_OK) return rcs[d];
+  return TBA_OK;
+}
+
 // --------------------------------------------------------------------------- single-process multi-GPU
 // The drop-in is called from ONE host thread (Theia's estimators); this entry point shards points + observations over
 // n_devices GPUs of the box, runs one rank per device on its own host thread (each with its own context, stream and

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch", "tba_two_view_ba_batch_multi",
 ]
 
 
@@ -60,6 +60,7 @@ def lib():
         L.tba_debug_pack.restype = C.c_int
         L.tba_adjust_tracks.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
         L.tba_estimate_tracks.argtypes = [C.c_void_p, C.POINTER(_abi.tba_options), C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+        L.tba_two_view_ba_batch_multi.argtypes = [C.POINTER(_abi.tba_two_view_batch), C.c_int, C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
         L.tba_two_view_ba_batch.argtypes = [C.c_void_p, C.POINTER(_abi.tba_two_view_batch), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
         L.tba_filter_tracks.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_uint8), dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
@@ -144,6 +145,19 @@ def debug_pack(problem):
         out["tile_nruns"] = out["tile_nruns"][:n_tiles]
         out["tile_flags"] = out["tile_flags"][:n_tiles]
     return out
+
+
+def two_view_ba_batch_multi(batch, n_devices=0):
+    """tba_two_view_ba_batch_multi: the batch sharded by pairs over n_devices GPUs (0 = all); updates the batch in place."""
+    n = max(batch.n_pairs, 1)
+    term = np.zeros(n, np.uint8); ic = np.zeros(n); fc = np.zeros(n); it = np.zeros(n, np.int32)
+    st = batch.as_struct()
+    rc = lib().tba_two_view_ba_batch_multi(C.byref(st), n_devices, term.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(ic), _dp(fc),
+                                           it.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise EngineError(rc, "tba_two_view_ba_batch_multi failed")
+    n = batch.n_pairs
+    return term[:n], ic[:n], fc[:n], it[:n]
 
 
 def solve_multi(problem, options=None, n_devices=0, max_iterations_logged=2048):
