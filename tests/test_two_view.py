@@ -1,5 +1,5 @@
 """N3: batched BundleAdjustTwoViews (bundle_adjust_two_views.cc:112-191).  The product's per-pair body
-(theiasfm_b200/csrc/tba_two_view.cuh, one instance per GPU thread in k_two_view_ba) is compiled for the host and run over
+(theiasfm_b200/csrc/tba_two_view.cuh; on the GPU one warp per pair, k_two_view_ba) is compiled for the host (one-lane team) and run over
 the batch layout; the checker is the oracle solving every pair as its own two-camera problem with the exact solver."""
 import ctypes as C
 import os

@@ -1,4 +1,4 @@
-"""N3 on the GPU, through the C-ABI: tba_two_view_ba_batch (batched BundleAdjustTwoViews, one thread per image pair) against
+"""N3 on the GPU, through the C-ABI: tba_two_view_ba_batch (batched BundleAdjustTwoViews, one warp per image pair) against
 the oracle solving every pair separately.  The per-pair body is checked on the host by tests/test_two_view.py; this file adds
 the kernel and the batch upload / download.  Never executed on hardware in round 1 (GPU budget spent)."""
 import numpy as np

@@ -1323,7 +1323,7 @@ int tba_two_view_ba_batch(tba_context* c, tba_two_view_batch* b, uint8_t* termin
   o.jacobi_scaling = 1; o.max_consecutive_invalid = 5;
   {
     auto kfn = ext_models ? k_two_view_ba<true> : k_two_view_ba<false>;
-    LAUNCH(c, kfn, (np + 31) / 32, 32, 0, B, o, d_term.p, d_cost2.p, d_it.p);
+    LAUNCH(c, kfn, (np + 3) / 4, 128, 0, B, o, d_term.p, d_cost2.p, d_it.p);  // 4 warps = 4 pairs per CTA
   }
   std::vector<double> hc((size_t)np * 2);
   std::vector<int> hit((size_t)np);

@@ -381,9 +381,10 @@ __global__ void k_adjust_tracks(DevProblem P, const long long* __restrict__ pt_s
 }
 
 // --------------------------------------------------------- N3: batched two-view bundle adjustment
-// BundleAdjustTwoViews for many image pairs at once: one thread runs the whole Levenberg-Marquardt of one pair
-// (tba_two_view.cuh).  Pairs are independent and of similar size (a few hundred correspondences), so thread-level
-// parallelism over pairs fills the machine when geometric verification hands over its thousands of pairs.
+// BundleAdjustTwoViews for many image pairs at once: one WARP runs the whole Levenberg-Marquardt of one pair
+// (tba_two_view.cuh, WarpTeam): the passes over the pair's few hundred correspondences are strided over the 32 lanes, the
+// 8x8 reduced system and every scalar are all-reduced by shuffles so that all lanes take the same decisions.  Pairs are
+// independent: geometric verification hands over thousands of them.
 struct TwoViewBatchDev {
   int n_pairs;
   const long long* off;       // [n_pairs + 1] into the correspondence arrays
@@ -396,18 +397,20 @@ struct TwoViewBatchDev {
 template <bool EXT>
 __global__ void k_two_view_ba(TwoViewBatchDev B, PointLmOptions o, uint8_t* __restrict__ termination, double* __restrict__ cost2,
                               int* __restrict__ iterations) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= B.n_pairs) return;
+  const int p = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);  // one warp per pair (WarpTeam)
+  if (p >= B.n_pairs) return;                                                  // warp-uniform
   TwoViewPair P;
   const long long b = B.off[p];
   P.ext1 = B.ext1 + (size_t)p * 6; P.ext2 = B.ext2 + (size_t)p * 6; P.k1 = B.k1 + (size_t)p * 10; P.k2 = B.k2 + (size_t)p * 10;
   P.model1 = B.model1[p]; P.model2 = B.model2[p]; P.free_f1 = B.const1[p] ? 0 : 1; P.free_f2 = B.const2[p] ? 0 : 1;
   P.n = (int)(B.off[p + 1] - b);
   P.pt = B.pt + (size_t)b * 4; P.xy1 = B.xy1 + (size_t)b * 2; P.xy2 = B.xy2 + (size_t)b * 2; P.sp = B.sp + (size_t)b * 4; P.pt_c = B.pt_c + (size_t)b * 4;
-  const PointLmResult r = two_view_lm<EXT>(P, o);
-  termination[p] = (uint8_t)r.termination;
-  cost2[2 * p] = r.initial_cost; cost2[2 * p + 1] = r.final_cost;
-  iterations[p] = r.iterations;
+  const PointLmResult r = two_view_lm<EXT, WarpTeam>(P, o);
+  if ((threadIdx.x & 31) == 0) {
+    termination[p] = (uint8_t)r.termination;
+    cost2[2 * p] = r.initial_cost; cost2[2 * p + 1] = r.final_cost;
+    iterations[p] = r.iterations;
+  }
 }
 
 // --------------------------------------------------------- per-point blocks

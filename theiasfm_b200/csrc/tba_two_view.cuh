@@ -2,7 +2,7 @@
 // self-contained per-pair Levenberg-Marquardt: camera 1 fixed; camera 2's six extrinsics free; each camera's focal length
 // free or its whole intrinsics block constant (.cc:71-108); every triangulated point (4-vector) free; two residual blocks per
 // point; no robust loss; DENSE_SCHUR; 200 iterations; Ceres' default tolerances (.cc:54-69).
-// Host/device: k_two_view_ba runs one instance per thread -- geometric verification issues one such problem per image pair
+// Host/device: k_two_view_ba runs one instance per WARP (WarpTeam below) -- geometric verification issues one such problem per image pair
 // (two_view_match_geometric_verification.cc:268-296), thousands of independent problems of a few hundred points -- and the
 // CPU test suite runs the same body against the oracle (tests/host_two_view.cc, tests/test_two_view.py).
 //
@@ -36,6 +36,53 @@ struct TwoViewPair {
 };
 
 constexpr int kTvC = 8;  // camera-side unknowns: ext2 (6), f1, f2
+
+// A "team" of lanes shares one pair: the loops over the pair's points are strided over the lanes and every sum / flag is
+// all-reduced, so that all lanes hold identical scalars and take identical decisions.  SerialTeam (1 lane) is what the host
+// tests run and what a thread-per-pair kernel would use; WarpTeam spreads a pair over the 32 lanes of a warp
+// (k_two_view_ba: one warp per image pair -- a few hundred correspondences give each lane a handful of points per pass).
+struct SerialTeam {
+  __host__ __device__ static int rank() { return 0; }
+  __host__ __device__ static int size() { return 1; }
+  __host__ __device__ static double sum(double v) { return v; }
+  __host__ __device__ static double max(double v) { return v; }
+  __host__ __device__ static bool all(bool v) { return v; }
+};
+struct WarpTeam {
+  __host__ __device__ static int rank() {
+#ifdef __CUDA_ARCH__
+    return threadIdx.x & 31;
+#else
+    return 0;
+#endif
+  }
+  __host__ __device__ static int size() {
+#ifdef __CUDA_ARCH__
+    return 32;
+#else
+    return 1;
+#endif
+  }
+  __host__ __device__ static double sum(double v) {
+#ifdef __CUDA_ARCH__
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);  // butterfly: every lane ends with the same bits
+#endif
+    return v;
+  }
+  __host__ __device__ static double max(double v) {
+#ifdef __CUDA_ARCH__
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+    return v;
+  }
+  __host__ __device__ static bool all(bool v) {
+#ifdef __CUDA_ARCH__
+    return __all_sync(0xffffffffu, v) != 0;
+#else
+    return v;
+#endif
+  }
+};
 
 // 8x8 SPD solve S x = b by Cholesky (S row-major, destroyed).
 __host__ __device__ inline bool spd8_solve(double* S, const double* b, double* x) {
@@ -95,16 +142,17 @@ __host__ __device__ inline bool tv_linearize(const TwoViewPair& P, const double*
 
 // Cost, gradient (camera side g_c, max |g| over everything), squared column norms of the camera columns; optionally the
 // Jacobi scales (iteration 0).  sc: current camera-side scales (all 1 when init_scale).
-template <bool EXT>
+template <bool EXT, class Team>
 __host__ __device__ inline bool tv_evaluate(const TwoViewPair& P, const double* rec1, const double* rec2, const PointLmOptions& o, bool init_scale,
-                                            double* sc, double* cost, double* gmax, double* diag_c /*[8] scaled col norms^2*/) {
+                                            const double* ext2v, const double* k1v, const double* k2v, double* sc, double* cost, double* gmax,
+                                            double* diag_c /*[8] scaled col norms^2*/) {
   double c = 0.0, gm = 0.0, gc[kTvC], cn[kTvC];
+  bool ok = true;
   for (int j = 0; j < kTvC; ++j) { gc[j] = 0.0; cn[j] = 0.0; }
-  for (int i = 0; i < P.n; ++i) {
+  for (int i = Team::rank(); i < P.n; i += Team::size()) {
     double r[4], Jc[4][kTvC], Jp[4][4], rho;
-    if (!tv_linearize<EXT>(P, rec1, P.ext2, rec2, P.k1, P.k2, P.pt + (size_t)i * 4, P.xy1 + (size_t)i * 2, P.xy2 + (size_t)i * 2, o.loss_type,
-                           o.loss_width, r, Jc, Jp, &rho))
-      return false;
+    if (!tv_linearize<EXT>(P, rec1, ext2v, rec2, k1v, k2v, P.pt + (size_t)i * 4, P.xy1 + (size_t)i * 2, P.xy2 + (size_t)i * 2, o.loss_type,
+                           o.loss_width, r, Jc, Jp, &rho)) { ok = false; break; }
     c += 0.5 * rho;
     for (int j = 0; j < kTvC; ++j) { double g = 0.0, n2 = 0.0; for (int a = 0; a < 4; ++a) { g += Jc[a][j] * r[a]; n2 += Jc[a][j] * Jc[a][j]; } gc[j] += g; cn[j] += n2; }
     for (int j = 0; j < 4; ++j) {
@@ -114,6 +162,9 @@ __host__ __device__ inline bool tv_evaluate(const TwoViewPair& P, const double* 
       if (init_scale) P.sp[(size_t)i * 4 + j] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(n2)) : 1.0;
     }
   }
+  if (!Team::all(ok)) return false;
+  c = Team::sum(c); gm = Team::max(gm);
+  for (int j = 0; j < kTvC; ++j) { gc[j] = Team::sum(gc[j]); cn[j] = Team::sum(cn[j]); }
   for (int j = 0; j < kTvC; ++j) gm = fmax(gm, fabs(gc[j]));
   if (init_scale) for (int j = 0; j < kTvC; ++j) sc[j] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(cn[j])) : 1.0;
   for (int j = 0; j < kTvC; ++j) diag_c[j] = cn[j] * sc[j] * sc[j];
@@ -121,17 +172,21 @@ __host__ __device__ inline bool tv_evaluate(const TwoViewPair& P, const double* 
   return true;
 }
 
-template <bool EXT>
+template <bool EXT, class Team = SerialTeam>
 __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const PointLmOptions& o) {
   PointLmResult res;
   res.initial_cost = res.final_cost = -1.0; res.iterations = 0; res.termination = 2;
   double rec1[kCamRec], rec2[kCamRec], rec2c[kCamRec];
+  // every lane keeps its own copy of the camera-side values (identical in all lanes); lane 0 writes them back at the end
+  double ext2v[6], k1v[10], k2v[10];
+  for (int j = 0; j < 6; ++j) ext2v[j] = P.ext2[j];
+  for (int j = 0; j < 10; ++j) { k1v[j] = P.k1[j]; k2v[j] = P.k2[j]; }
   cam_prep(P.ext1 + 3, rec1);
-  cam_prep(P.ext2 + 3, rec2);
+  cam_prep(ext2v + 3, rec2);
   const bool fr[kTvC] = {true, true, true, true, true, true, P.free_f1 != 0, P.free_f2 != 0};
   double sc[kTvC], diag_c[kTvC], cost, gmax;
   for (int j = 0; j < kTvC; ++j) sc[j] = 1.0;
-  if (!tv_evaluate<EXT>(P, rec1, rec2, o, true, sc, &cost, &gmax, diag_c)) return res;
+  if (!tv_evaluate<EXT, Team>(P, rec1, rec2, o, true, ext2v, k1v, k2v, sc, &cost, &gmax, diag_c)) return res;
   res.initial_cost = res.final_cost = cost;
   const int K1 = model_num_parameters(P.model1), K2 = model_num_parameters(P.model2);
   // ||x|| over the non-constant parameter blocks in ambient coordinates (camera 2 extrinsics, an intrinsics block whose focal
@@ -143,8 +198,12 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
     if (P.free_f2) for (int j = 0; j < K2; ++j) s += k2[j] * k2[j];
     return s;
   };
-  double xn2 = xnorm2_cam(P.ext2, P.k1, P.k2);
-  for (int i = 0; i < P.n * 4; ++i) xn2 += P.pt[i] * P.pt[i];
+  auto xnorm2_pts = [&]() {
+    double s = 0.0;
+    for (int i = Team::rank(); i < P.n; i += Team::size()) for (int a = 0; a < 4; ++a) s += P.pt[(size_t)i * 4 + a] * P.pt[(size_t)i * 4 + a];
+    return Team::sum(s);
+  };
+  double xn2 = xnorm2_cam(ext2v, k1v, k2v) + xnorm2_pts();
   double xnorm = sqrt(xn2);
   double radius = o.initial_radius, decrease = 2.0;
   int invalid = 0;
@@ -163,10 +222,10 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
     for (int j = 0; j < kTvC * kTvC; ++j) S[j] = 0.0;
     for (int j = 0; j < kTvC; ++j) rhs[j] = 0.0;
     bool valid = true;
-    for (int i = 0; i < P.n && valid; ++i) {
+    for (int i = Team::rank(); i < P.n && valid; i += Team::size()) {
       double r[4], Jc[4][kTvC], Jp[4][4], rho;
       const double* spi = P.sp + (size_t)i * 4;
-      if (!tv_linearize<EXT>(P, rec1, P.ext2, rec2, P.k1, P.k2, P.pt + (size_t)i * 4, P.xy1 + (size_t)i * 2, P.xy2 + (size_t)i * 2, o.loss_type,
+      if (!tv_linearize<EXT>(P, rec1, ext2v, rec2, k1v, k2v, P.pt + (size_t)i * 4, P.xy1 + (size_t)i * 2, P.xy2 + (size_t)i * 2, o.loss_type,
                              o.loss_width, r, Jc, Jp, &rho)) { valid = false; break; }
       for (int a = 0; a < 4; ++a) { for (int j = 0; j < kTvC; ++j) Jc[a][j] *= sc[j]; for (int j = 0; j < 4; ++j) Jp[a][j] *= spi[j]; }
       double A[10], Cinv[16];
@@ -196,7 +255,10 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
       }
     }
     double x[kTvC];
+    valid = Team::all(valid);
     if (valid) {
+      for (int j = 0; j < kTvC * kTvC; ++j) S[j] = Team::sum(S[j]);
+      for (int j = 0; j < kTvC; ++j) rhs[j] = Team::sum(rhs[j]);
       for (int j = 0; j < kTvC; ++j) {
         if (fr[j]) S[j * kTvC + j] += Dc[j] * Dc[j];
         else { for (int l = 0; l < kTvC; ++l) { S[j * kTvC + l] = 0.0; S[l * kTvC + j] = 0.0; } S[j * kTvC + j] = 1.0; rhs[j] = 0.0; }
@@ -207,16 +269,17 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
     double mcc = 0.0, dn2 = 0.0;
     double e2c[6], k1c[10], k2c[10];
     if (valid) {
-      for (int j = 0; j < 6; ++j) { const double d = -x[j] * sc[j]; e2c[j] = P.ext2[j] + d; dn2 += d * d; if (!isfinite(d)) valid = false; }
-      for (int j = 0; j < 10; ++j) { k1c[j] = P.k1[j]; k2c[j] = P.k2[j]; }
+      for (int j = 0; j < 6; ++j) { const double d = -x[j] * sc[j]; e2c[j] = ext2v[j] + d; dn2 += d * d; if (!isfinite(d)) valid = false; }
+      for (int j = 0; j < 10; ++j) { k1c[j] = k1v[j]; k2c[j] = k2v[j]; }
       if (P.free_f1) { const double d = -x[6] * sc[6]; k1c[0] += d; dn2 += d * d; if (!isfinite(d)) valid = false; }
       if (P.free_f2) { const double d = -x[7] * sc[7]; k2c[0] += d; dn2 += d * d; if (!isfinite(d)) valid = false; }
     }
-    for (int i = 0; i < P.n && valid; ++i) {
+    double dn2_pts = 0.0;
+    for (int i = Team::rank(); i < P.n && valid; i += Team::size()) {
       double r[4], Jc[4][kTvC], Jp[4][4], rho;
       const double* spi = P.sp + (size_t)i * 4;
       const double* X = P.pt + (size_t)i * 4;
-      if (!tv_linearize<EXT>(P, rec1, P.ext2, rec2, P.k1, P.k2, X, P.xy1 + (size_t)i * 2, P.xy2 + (size_t)i * 2, o.loss_type, o.loss_width, r, Jc, Jp,
+      if (!tv_linearize<EXT>(P, rec1, ext2v, rec2, k1v, k2v, X, P.xy1 + (size_t)i * 2, P.xy2 + (size_t)i * 2, o.loss_type, o.loss_width, r, Jc, Jp,
                              &rho)) { valid = false; break; }
       for (int a = 0; a < 4; ++a) { for (int j = 0; j < kTvC; ++j) Jc[a][j] *= sc[j]; for (int j = 0; j < 4; ++j) Jp[a][j] *= spi[j]; }
       double A[10], Cinv[16];
@@ -238,9 +301,12 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
         const double d = -yp[a] * spi[a];
         if (!isfinite(d)) valid = false;
         P.pt_c[(size_t)i * 4 + a] = X[a] + d;
-        dn2 += d * d;
+        dn2_pts += d * d;
       }
     }
+    valid = Team::all(valid);
+    mcc = Team::sum(mcc);
+    dn2 += Team::sum(dn2_pts);
     if (valid) valid = mcc > 0.0;
     if (!valid) {  // HandleInvalidStep
       if (++invalid >= o.max_consecutive_invalid) { res.termination = 2; break; }
@@ -253,7 +319,7 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
     cam_prep(e2c + 3, rec2c);
     double cand = 0.0;
     bool cand_ok = true;
-    for (int i = 0; i < P.n; ++i) {
+    for (int i = Team::rank(); i < P.n; i += Team::size()) {
       const double* X = P.pt_c + (size_t)i * 4;
       double r0, r1, rho[3];
       if (!reproject_any<EXT>(P.model1, P.ext1, rec1, k1c, X[0], X[1], X[2], X[3], P.xy1[(size_t)i * 2], P.xy1[(size_t)i * 2 + 1], r0, r1)) { cand_ok = false; break; }
@@ -263,6 +329,8 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
       loss_evaluate(o.loss_type, o.loss_width, r0 * r0 + r1 * r1, rho);
       cand += 0.5 * rho[0];
     }
+    cand_ok = Team::all(cand_ok);
+    cand = Team::sum(cand);
     if (!cand_ok) cand = DBL_MAX;
     // step norm in ambient coordinates of the non-constant blocks = ||delta|| (constant coordinates do not move)
     if (sqrt(dn2) <= o.parameter_tolerance * (xnorm + o.parameter_tolerance)) { res.termination = 0; break; }
@@ -270,14 +338,13 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
     if (fabs(cost_change) <= o.function_tolerance * cost) { res.termination = 0; break; }
     const double rho_q = cost_change / mcc;
     if (rho_q > o.min_relative_decrease) {  // HandleSuccessfulStep
-      for (int j = 0; j < 6; ++j) P.ext2[j] = e2c[j];
-      P.k1[0] = k1c[0]; P.k2[0] = k2c[0];
-      for (int i = 0; i < P.n * 4; ++i) P.pt[i] = P.pt_c[i];
+      for (int j = 0; j < 6; ++j) ext2v[j] = e2c[j];
+      k1v[0] = k1c[0]; k2v[0] = k2c[0];
+      for (int i = Team::rank(); i < P.n; i += Team::size()) for (int a = 0; a < 4; ++a) P.pt[(size_t)i * 4 + a] = P.pt_c[(size_t)i * 4 + a];
       for (int j = 0; j < kCamRec; ++j) rec2[j] = rec2c[j];
-      xn2 = xnorm2_cam(P.ext2, P.k1, P.k2);
-      for (int i = 0; i < P.n * 4; ++i) xn2 += P.pt[i] * P.pt[i];
+      xn2 = xnorm2_cam(ext2v, k1v, k2v) + xnorm2_pts();
       xnorm = sqrt(xn2);
-      if (!tv_evaluate<EXT>(P, rec1, rec2, o, false, sc, &cost, &gmax, diag_c)) { res.termination = 2; break; }
+      if (!tv_evaluate<EXT, Team>(P, rec1, rec2, o, false, ext2v, k1v, k2v, sc, &cost, &gmax, diag_c)) { res.termination = 2; break; }
       res.final_cost = cost;
       const double t = 2.0 * rho_q - 1.0;
       radius = fmin(o.max_radius, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
@@ -287,6 +354,10 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
       radius /= decrease; decrease *= 2.0;
       last_successful = false;
     }
+  }
+  if (Team::rank() == 0) {
+    for (int j = 0; j < 6; ++j) P.ext2[j] = ext2v[j];
+    P.k1[0] = k1v[0]; P.k2[0] = k2v[0];
   }
   return res;
 }
