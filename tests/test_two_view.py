@@ -31,6 +31,17 @@ def run_host(H, batch):
     return term, ic, fc, it
 
 
+def run_host_team(H, batch):
+    """The same body as a 4-lane team (host threads + barriers standing for the warp's shuffles)."""
+    n = batch.n_pairs
+    term = np.zeros(n, np.uint8); ic = np.zeros(n); fc = np.zeros(n); it = np.zeros(n, np.int32)
+    st = batch.as_struct()
+    dp = C.POINTER(C.c_double)
+    H.host_two_view_ba_batch_team(C.byref(st), term.ctypes.data_as(C.POINTER(C.c_uint8)), ic.ctypes.data_as(dp), fc.ctypes.data_as(dp),
+                                  it.ctypes.data_as(C.POINTER(C.c_int32)), 1)
+    return term, ic, fc, it
+
+
 def compare(b_host, res_host, b_or, res_or):
     th, ich, fch, ith = res_host
     to, ico, fco, ito = res_or
@@ -87,3 +98,20 @@ def test_degenerate_pairs(H, oracle):
     assert rh[0][0] == _abi.CONVERGENCE and rh[0][3] == _abi.CONVERGENCE
     for p in (0, 3):
         assert abs(rh[2][p] - ro[2][p]) <= 1e-7 * ro[2][p]
+
+
+def test_team_decomposition_matches_the_serial_body(H):
+    """k_two_view_ba spreads one pair over the 32 lanes of a warp; the decomposition (strided point loops, all-reduced sums and
+    flags, per-lane copies of the camera values, lane 0 writes back) is run here as a 4-lane team of host threads: every lane
+    takes the same decisions, and the result equals the one-lane run up to the order of the floating-point sums."""
+    b = synthetic.make_two_view_batch(5, min_corr=5, max_corr=60, seed=21, models=(_abi.MODEL_PINHOLE, _abi.MODEL_FISHEYE))
+    o1 = int(b.pair_off[1])
+    b.points[o1, :3] = b.ext2[1, :3]; b.points[o1, 3] = 1.0          # pair 1 fails at the initial evaluation (in one lane only)
+    bs, bt = b.copy(), b.copy()
+    ts, ics, fcs, its = run_host(H, bs)
+    tt, ict, fct, itt = run_host_team(H, bt)
+    assert np.array_equal(ts, tt) and ts[1] == _abi.FAILURE and (tt != 99).all()
+    ok = ts != _abi.FAILURE
+    assert np.allclose(ics[ok], ict[ok], rtol=1e-12) and np.allclose(fcs[ok], fct[ok], rtol=1e-9) and np.array_equal(its, itt)
+    assert np.abs(bs.ext2 - bt.ext2).max() <= 1e-9 and np.abs(bs.points - bt.points).max() <= 1e-8 * np.abs(bs.points).max()
+    assert np.abs(bs.intr2 - bt.intr2).max() <= 1e-9 * 800
