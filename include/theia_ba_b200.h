@@ -281,6 +281,11 @@ typedef struct tba_two_view_batch {
   const double* xy1;                     /* [n_corr * 2] FeatureCorrespondence::feature1 */
   const double* xy2;                     /* [n_corr * 2] feature2 */
   double* points;                        /* [n_corr * 4] in/out triangulated points */
+  /* optional post-BA inlier test of BundleAdjustRelativePose (two_view_match_geometric_verification.cc:294-312): inlier[i] = both
+   * cameras see point i at non-negative depth with squared reprojection error < final_max_reprojection_error_pixels^2 (:72-83).
+   * inlier == NULL: skipped. */
+  double final_max_reprojection_error_pixels;
+  uint8_t* inlier;                       /* [n_corr] out, optional */
 } tba_two_view_batch;
 int tba_two_view_ba_batch(tba_context* ctx, tba_two_view_batch* batch, uint8_t* termination, double* initial_cost, double* final_cost,
                           int32_t* iterations);

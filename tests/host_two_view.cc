@@ -72,6 +72,7 @@ extern "C" void host_two_view_ba_batch_team(tba_two_view_batch* b, unsigned char
     } else {
       r = tba::two_view_lm<true>(P, o);
     }
+    if (b->inlier) tba::two_view_inliers<true>(P, b->final_max_reprojection_error_pixels * b->final_max_reprojection_error_pixels, b->inlier + (size_t)b0);
     termination[p] = (unsigned char)r.termination; initial_cost[p] = r.initial_cost; final_cost[p] = r.final_cost; iterations[p] = r.iterations;
   }
 }

@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
                                                             _abi.MODEL_FOV, _abi.MODEL_DIVISION_UNDISTORTION)])
 def test_two_view_batch_matches_oracle(oracle, models):
     b = synthetic.make_two_view_batch(150, min_corr=40, max_corr=300, seed=8, models=models)
+    b.xy2[::17] += 6.0
+    b.final_max_reprojection_error_pixels = 2.0
     start = b.copy()
     bg, bo = b.copy(), b.copy()
     to, ico, fco, ito = oracle.two_view_ba_batch(bo)
@@ -29,4 +31,7 @@ def test_two_view_batch_matches_oracle(oracle, models):
     assert np.abs(bg.ext2[conv] - bo.ext2[conv]).max() <= 1e-5 * np.abs(bo.ext2).max()
     assert np.abs(bg.intr2[conv, 0] - bo.intr2[conv, 0]).max() <= 1e-5 * 800.0
     assert np.array_equal(bg.ext1, start.ext1) and np.array_equal(bg.intr2[:, 1:], start.intr2[:, 1:])
-    assert (fcg[conv] < 0.3 * icg[conv]).all()
+    assert (fcg[conv] < 0.6 * icg[conv]).all()
+    # post-BA inlier flags: equal except for correspondences whose error sits within rounding of the threshold
+    sel = np.repeat(conv, np.diff(b.pair_off))
+    assert (bg.inlier[sel] != bo.inlier[sel]).mean() < 1e-3 and bg.inlier[::17].mean() < 0.4

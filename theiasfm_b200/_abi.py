@@ -135,6 +135,8 @@ class tba_two_view_batch(C.Structure):
         ("xy1", C.POINTER(C.c_double)),
         ("xy2", C.POINTER(C.c_double)),
         ("points", C.POINTER(C.c_double)),
+        ("final_max_reprojection_error_pixels", C.c_double),
+        ("inlier", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -155,10 +157,14 @@ class TwoViewBatch:
         self.xy2 = np.ascontiguousarray(xy2, np.float64).reshape(-1, 2)
         self.points = np.ascontiguousarray(points, np.float64).reshape(-1, 4).copy()
         self.n_pairs = len(self.pair_off) - 1
+        self.final_max_reprojection_error_pixels = 0.0      # > 0: also compute self.inlier (post-BA reprojection test)
+        self.inlier = None
 
     def copy(self):
-        return TwoViewBatch(self.pair_off, self.ext1, self.ext2, self.intr1, self.intr2, self.model1, self.model2, self.const1,
-                            self.const2, self.xy1, self.xy2, self.points)
+        b = TwoViewBatch(self.pair_off, self.ext1, self.ext2, self.intr1, self.intr2, self.model1, self.model2, self.const1,
+                         self.const2, self.xy1, self.xy2, self.points)
+        b.final_max_reprojection_error_pixels = self.final_max_reprojection_error_pixels
+        return b
 
     def as_struct(self):
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
@@ -170,6 +176,10 @@ class TwoViewBatch:
         s.constant_intrinsics1 = self.const1.ctypes.data_as(C.POINTER(C.c_uint8))
         s.constant_intrinsics2 = self.const2.ctypes.data_as(C.POINTER(C.c_uint8))
         s.xy1, s.xy2, s.points = dp(self.xy1), dp(self.xy2), dp(self.points)
+        s.final_max_reprojection_error_pixels = self.final_max_reprojection_error_pixels
+        if self.final_max_reprojection_error_pixels > 0.0:
+            self.inlier = np.zeros(max(len(self.points), 1), np.uint8)
+            s.inlier = self.inlier.ctypes.data_as(C.POINTER(C.c_uint8))
         return s
 
 

@@ -1315,6 +1315,9 @@ int tba_two_view_ba_batch(tba_context* c, tba_two_view_batch* b, uint8_t* termin
   TwoViewBatchDev B;
   B.n_pairs = np; B.off = d_off.p; B.ext1 = d_ext1.p; B.ext2 = d_ext2.p; B.k1 = d_k1.p; B.k2 = d_k2.p; B.model1 = d_m1.p; B.model2 = d_m2.p;
   B.const1 = d_c1.p; B.const2 = d_c2.p; B.xy1 = d_xy1.p; B.xy2 = d_xy2.p; B.pt = d_pt.p; B.sp = d_sp.p; B.pt_c = d_ptc.p;
+  DevBuf<uint8_t> d_inl;
+  B.inlier = nullptr; B.sq_max_error = b->final_max_reprojection_error_pixels * b->final_max_reprojection_error_pixels;
+  if (b->inlier != nullptr) { CUDA_OK(c, d_inl.alloc((size_t)nc)); B.inlier = d_inl.p; }
   // SetSolverOptions of bundle_adjust_two_views.cc:54-69: everything but the solver type / iteration cap is Ceres' default
   PointLmOptions o;
   o.loss_type = TBA_LOSS_TRIVIAL; o.loss_width = 1.0; o.max_num_iterations = 200;
@@ -1334,6 +1337,7 @@ int tba_two_view_ba_batch(tba_context* c, tba_two_view_batch* b, uint8_t* termin
   CUDA_OK(c, cudaMemcpyAsync(b->intr1, d_k1.p, (size_t)np * 80, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaMemcpyAsync(b->intr2, d_k2.p, (size_t)np * 80, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaMemcpyAsync(b->points, d_pt.p, (size_t)nc * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (b->inlier != nullptr) CUDA_OK(c, cudaMemcpyAsync(b->inlier, d_inl.p, (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   c->d2h_bytes += (double)np * (1 + 16 + 4 + 48 + 160) + (double)nc * 32;
   for (int p = 0; p < np; ++p) {
@@ -1391,6 +1395,7 @@ int tba_two_view_ba_batch_multi(tba_two_view_batch* b, int n_devices, uint8_t* t
       s.model1 = b->model1 + p0; s.model2 = b->model2 + p0;
       s.constant_intrinsics1 = b->constant_intrinsics1 + p0; s.constant_intrinsics2 = b->constant_intrinsics2 + p0;
       s.xy1 = b->xy1 + (size_t)base * 2; s.xy2 = b->xy2 + (size_t)base * 2; s.points = b->points + (size_t)base * 4;
+      s.inlier = b->inlier ? b->inlier + (size_t)base : nullptr;
       rcs[d] = tba_two_view_ba_batch(g_tv_ctx[d], &s, termination + p0, initial_cost ? initial_cost + p0 : nullptr,
                                      final_cost ? final_cost + p0 : nullptr, iterations ? iterations + p0 : nullptr);
     });

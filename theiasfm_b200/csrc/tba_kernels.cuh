@@ -393,6 +393,7 @@ struct TwoViewBatchDev {
   const uint8_t* const1; const uint8_t* const2;  // constant_cameraN_intrinsics
   const double* xy1; const double* xy2;
   double* pt; double* sp; double* pt_c;
+  uint8_t* inlier; double sq_max_error;   // optional post-BA inlier flags (nullptr: skipped)
 };
 template <bool EXT>
 __global__ void k_two_view_ba(TwoViewBatchDev B, PointLmOptions o, uint8_t* __restrict__ termination, double* __restrict__ cost2,
@@ -406,6 +407,10 @@ __global__ void k_two_view_ba(TwoViewBatchDev B, PointLmOptions o, uint8_t* __re
   P.n = (int)(B.off[p + 1] - b);
   P.pt = B.pt + (size_t)b * 4; P.xy1 = B.xy1 + (size_t)b * 2; P.xy2 = B.xy2 + (size_t)b * 2; P.sp = B.sp + (size_t)b * 4; P.pt_c = B.pt_c + (size_t)b * 4;
   const PointLmResult r = two_view_lm<EXT, WarpTeam>(P, o);
+  if (B.inlier != nullptr) {
+    __syncwarp();  // lane 0's write-back of the refined camera values is visible to the warp
+    two_view_inliers<EXT, WarpTeam>(P, B.sq_max_error, B.inlier + (size_t)b);
+  }
   if ((threadIdx.x & 31) == 0) {
     termination[p] = (uint8_t)r.termination;
     cost2[2 * p] = r.initial_cost; cost2[2 * p + 1] = r.final_cost;

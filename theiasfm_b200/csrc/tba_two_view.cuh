@@ -362,4 +362,25 @@ __host__ __device__ inline PointLmResult two_view_lm(const TwoViewPair& P, const
   return res;
 }
 
+// AcceptableReprojectionError of two_view_match_geometric_verification.cc:72-83 for every correspondence of the pair, with the
+// refined cameras and points (the post-BA filter of BundleAdjustRelativePose, :294-312).
+template <bool EXT, class Team = SerialTeam>
+__host__ __device__ inline void two_view_inliers(const TwoViewPair& P, double sq_max_error, uint8_t* inlier) {
+  double rec1[kCamRec], rec2[kCamRec];
+  cam_prep(P.ext1 + 3, rec1);
+  cam_prep(P.ext2 + 3, rec2);
+  for (int i = Team::rank(); i < P.n; i += Team::size()) {
+    const double* X = P.pt + (size_t)i * 4;
+    double px, py, qz, a_sq;
+    bool ok = true;
+    project_pixel_any<EXT>(P.model1, P.ext1, rec1, P.k1, X[0], X[1], X[2], X[3], px, py, qz, a_sq);
+    const double dx1 = P.xy1[(size_t)i * 2] - px, dy1 = P.xy1[(size_t)i * 2 + 1] - py;
+    if (qz / X[3] < 0.0 || !(dx1 * dx1 + dy1 * dy1 < sq_max_error)) ok = false;
+    project_pixel_any<EXT>(P.model2, P.ext2, rec2, P.k2, X[0], X[1], X[2], X[3], px, py, qz, a_sq);
+    const double dx2 = P.xy2[(size_t)i * 2] - px, dy2 = P.xy2[(size_t)i * 2 + 1] - py;
+    if (qz / X[3] < 0.0 || !(dx2 * dx2 + dy2 * dy2 < sq_max_error)) ok = false;
+    inlier[i] = ok ? 1 : 0;
+  }
+}
+
 }  // namespace tba
