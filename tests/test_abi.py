@@ -27,6 +27,7 @@ def test_struct_layouts_match_header():
     engine.lib().tba_abi_sizes(sizes)
     assert list(sizes) == [C.sizeof(_abi.tba_options), C.sizeof(_abi.tba_problem), C.sizeof(_abi.tba_summary),
                            C.sizeof(_abi.tba_iteration)]
+    assert engine.lib().tba_abi_size_two_view_batch() == C.sizeof(_abi.tba_two_view_batch)
 
 
 def test_default_options_mirror_theia_defaults():

@@ -648,6 +648,8 @@ void tba_abi_sizes(int32_t* out /*[4]*/) {
   out[2] = (int32_t)sizeof(tba_summary); out[3] = (int32_t)sizeof(tba_iteration);
 }
 
+int32_t tba_abi_size_two_view_batch(void) { return (int32_t)sizeof(tba_two_view_batch); }
+
 int tba_nccl_unique_id(void* out_128_bytes) {
   std::lock_guard<std::mutex> lk(g_nccl_mu);
   std::string err;
