@@ -138,6 +138,7 @@ struct tba_context {
   int64_t inner_passes = 0;
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
+  bool exp_fast_seg = false;  // TBA_FAST_SEG=1: segmented reductions without key shuffles in k_linearize / the matvec (default off)
   bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
@@ -254,6 +255,10 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
     if (c->has_ext_models) {  // FISHEYE / FOV / DIVISION_UNDISTORTION present: the dual-number instantiation, all 10 columns
       auto kfn = k_linearize<0x3FFu, true>;
       LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p);
+    } else if (c->exp_fast_seg) {
+#define F(M) { auto kfn = k_linearize<M, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
     } else {
 #define F(M) LAUNCH(c, k_linearize<M>, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p)
       DISPATCH_IMASK(c->imask, F)
@@ -344,6 +349,10 @@ int launch_matvec(tba_context* c, const int* done) {
     const int pb = prof_begin(c);
     if (c->exp_bulkred) {
 #define F(M) { auto kfn = k_schur<M, 0, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    } else if (c->exp_fast_seg) {
+#define F(M) { auto kfn = k_schur<M, 0, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
     } else {
@@ -670,6 +679,7 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   c->device = device; c->rank = rank; c->world = world_size;
   tba_options_init(&c->opt);
   { const char* e = getenv("TBA_MATVEC_BULKRED"); c->exp_bulkred = e != nullptr && e[0] == '1'; }
+  { const char* e = getenv("TBA_FAST_SEG"); c->exp_fast_seg = e != nullptr && e[0] == '1'; }
   { const char* e = getenv("TBA_PACK_SORT"); c->exp_pack_sort = e != nullptr && e[0] == '1'; }
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&c->h_scal, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->h_st, sizeof(PcgState)) != cudaSuccess) {
@@ -896,6 +906,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
 #define F(M)                                                                                                        \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DISPATCH_IMASK(c->imask, F)

@@ -26,6 +26,8 @@ run 600 bench_c3 python bench.py
 # 3. the two compiled-in experiments: parity subset, then the bench line
 TBA_MATVEC_BULKRED=1 run 300 parity_bulkred python -m pytest tests/test_gpu_parity.py -q -m gpu -k "stage_parity or full_solve"
 TBA_MATVEC_BULKRED=1 run 400 bench_c3_bulkred python bench.py --no-cpu-baseline
+TBA_FAST_SEG=1 run 300 parity_fastseg python -m pytest tests/test_gpu_parity.py -q -m gpu -k "stage_parity or full_solve"
+TBA_FAST_SEG=1 run 400 bench_c3_fastseg python bench.py --no-cpu-baseline
 TBA_PACK_SORT=1 run 300 parity_packsort python -m pytest tests/test_gpu_parity.py -q -m gpu -k "stage_parity or full_solve"
 TBA_PACK_SORT=1 run 400 bench_c3_packsort python bench.py --no-cpu-baseline
 # 4. ncu: launch list of the bench command and one full capture of the matvec / linearise kernels
