@@ -43,3 +43,15 @@ def test_two_view_flattening_and_oracle_solve(adapter_test_bin):
     out = subprocess.run([adapter_test_bin, "twoview-oracle", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "twoview-oracle ok" in out.stdout
+
+
+@pytest.mark.parametrize("mode,marker", [("solve", "solve ok"), ("tracks", "tracks ok"), ("micro", "micro ok"), ("twoview", "twoview ok")])
+def test_adapters_end_to_end_against_a_mock_engine(oracle, mode, marker):
+    """The adapters' OWN logic end to end without a GPU: tests/adapter_test.cc's GPU modes linked against tests/mock_engine.c, a
+    stand-in for the C-ABI backed by the oracle (test infrastructure only).  Checks flattening, scatter back into the
+    Reconstruction, Theia's shallow intrinsics sharing, residency of the device problem, status mapping, default options."""
+    subprocess.check_call(["make", "-C", ADAPTER, "mock"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(ROOT, "tests", "adapter_test_mock"), mode, os.path.join(ROOT, "oracle", "libba_oracle.so")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert marker in out.stdout
