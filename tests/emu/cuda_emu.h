@@ -1,0 +1,255 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE: a minimal SIMT emulator so that theiasfm_b200/csrc/tba_engine.cu -- the engine's real host
+// code AND its real kernels -- can be compiled with g++ (-x c++ -DTBA_EMULATE -include this file) and run on a machine without a GPU
+// (tests/emu/Makefile -> tests/emu/libtheia_ba_b200_emu.so; `pytest -m gpu --emulate-engine`).
+//   * every CUDA thread of a block is a user-level fiber (own stack, hand-rolled x86-64 switch; ucontext elsewhere); blocks run one after the other, so `__shared__` is `static`;
+//   * __syncthreads / __syncwarp / __shfl_*_sync / __ballot_sync / __all_sync suspend the fiber until the whole block / warp (the
+//     lanes that have not exited) has arrived, then exchange the payloads -- the semantics the kernels rely on;
+//   * the TMA bulk copy + mbarrier PTX of the matvec is replaced by a memcpy + flag (tba_kernels.cuh, #ifdef TBA_EMULATE);
+//   * the CUDA runtime is malloc / memcpy; kernel launches are serialised by a mutex, so atomics are plain read-modify-writes;
+//   * TBA_EMU_DEVICES "devices" (default 1) share that one emulator; NCCL is tests/emu/emu_nccl.c (shared memory).
+// It checks control flow, indexing, reductions and the host glue -- not performance, not memory-model subtleties.
+#pragma once
+#include <execinfo.h>
+#include <ucontext.h>
+#include <unistd.h>
+
+#include <csignal>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;  // set by the scheduler before a fiber runs
+
+struct alignas(16) double2 { double x, y; };
+struct alignas(32) double4 { double x, y, z, w; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+
+using std::atan; using std::atan2; using std::cos; using std::fabs; using std::fmax; using std::fmin; using std::isfinite; using std::isinf; using std::isnan; using std::sin;
+using std::sqrt; using std::tan;
+
+// ---------------------------------------------------------------- runtime
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorEmu = 1 };
+typedef struct emu_stream* cudaStream_t;
+typedef struct emu_event* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = std::getenv("TBA_EMU_DEVICES"); *n = e ? std::atoi(e) : 1; return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+inline int emu_last_error = cudaSuccess;  // set by emu::launch on an invalid configuration, like cudaErrorInvalidConfiguration
+inline cudaError_t cudaPeekAtLastError() { return emu_last_error; }
+inline cudaError_t cudaGetLastError() { const int e = emu_last_error; emu_last_error = cudaSuccess; return e; }
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error (emulated)" : "invalid launch configuration (emulated)"; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+
+// ---------------------------------------------------------------- device intrinsics without synchronisation
+inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
+inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+
+// ---------------------------------------------------------------- fibers
+namespace emu {
+enum Wait { kRun = 0, kBlockBarrier = 1, kWarpOp = 2, kSpin = 3 };
+#if defined(__x86_64__)
+// Minimal context switch (callee-saved registers + stack pointer): glibc's swapcontext makes a sigprocmask system call per switch,
+// which dominated the emulation time.
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+    ".size emu_switch,.-emu_switch\n");
+#define EMU_FAST_SWITCH 1
+#endif
+struct Fiber {
+  ucontext_t ctx;
+  void* sp = nullptr;
+  char* stack = nullptr;
+  bool done = true;
+  Wait wait = kRun;
+  int op = 0;            // warp collective kind: 0 sync, 1 shfl (payload / src lane), 2 ballot, 3 all
+  uint64_t payload = 0;  // value contributed
+  int src = 0;           // shfl: lane to read from (already resolved; -1 = keep own)
+  uint64_t result = 0;
+};
+inline std::vector<Fiber> fibers;
+inline ucontext_t sched_ctx;
+inline void* sched_sp = nullptr;
+inline int cur = -1;
+inline const std::function<void()>* body = nullptr;
+inline std::vector<char> dyn_smem_buf;
+constexpr size_t kStack = 512 * 1024;
+
+#ifdef EMU_FAST_SWITCH
+inline void to_sched() { emu_switch(&fibers[cur].sp, sched_sp); }
+inline void to_fiber(Fiber& f) { emu_switch(&sched_sp, f.sp); }
+#else
+inline void to_sched() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
+inline void to_fiber(Fiber& f) { swapcontext(&sched_ctx, &f.ctx); }
+#endif
+inline void trampoline() {
+  (*body)();
+  fibers[cur].done = true;
+  to_sched();
+  std::abort();  // a finished fiber is never resumed
+}
+inline void suspend(Wait w) {
+  fibers[cur].wait = w;
+  to_sched();
+}
+template <class T> inline T* dyn_smem() { return reinterpret_cast<T*>(dyn_smem_buf.data()); }
+
+inline void run_block(unsigned nthreads) {
+  if (fibers.size() < nthreads) fibers.resize(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t) {
+    Fiber& f = fibers[t];
+    if (!f.stack) f.stack = (char*)std::malloc(kStack);
+#ifdef EMU_FAST_SWITCH
+    {  // frame emu_switch pops: r15 r14 r13 r12 rbx rbp, then `ret` into trampoline with rsp = 8 (mod 16) as after a call
+      uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
+      void** p = (void**)top;
+      *--p = nullptr;                      // trampoline's (never used) return address
+      *--p = (void*)(void (*)())trampoline;
+      for (int r = 0; r < 6; ++r) *--p = nullptr;
+      f.sp = p;
+    }
+#else
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = kStack; f.ctx.uc_link = &sched_ctx;
+    makecontext(&f.ctx, trampoline, 0);
+#endif
+    f.done = false; f.wait = kRun;
+  }
+  for (;;) {
+    bool progress = false, alive = false;
+    for (unsigned t = 0; t < nthreads; ++t) {
+      Fiber& f = fibers[t];
+      if (f.done) continue;
+      alive = true;
+      if (f.wait == kRun || f.wait == kSpin) {
+        cur = (int)t; threadIdx.x = t;
+        const Wait before = f.wait;
+        f.wait = kRun;
+        to_fiber(f);
+        if (f.done || f.wait != kSpin || before != kSpin) progress = true;
+      }
+    }
+    if (!alive) break;
+    // block barrier: every live thread waits
+    bool all_bar = true;
+    for (unsigned t = 0; t < nthreads; ++t) if (!fibers[t].done && fibers[t].wait != kBlockBarrier) { all_bar = false; break; }
+    if (all_bar) { for (unsigned t = 0; t < nthreads; ++t) if (!fibers[t].done) fibers[t].wait = kRun; progress = true; }
+    // warp collectives: every live lane of the warp waits
+    for (unsigned w0 = 0; w0 < nthreads; w0 += 32) {
+      const unsigned w1 = w0 + 32 < nthreads ? w0 + 32 : nthreads;
+      bool any_live = false, all_wait = true;
+      for (unsigned t = w0; t < w1; ++t) if (!fibers[t].done) { any_live = true; if (fibers[t].wait != kWarpOp) all_wait = false; }
+      if (!any_live || !all_wait) continue;
+      uint64_t ballot = 0; bool all = true;
+      for (unsigned t = w0; t < w1; ++t) if (!fibers[t].done) { if (fibers[t].payload) ballot |= 1ull << (t - w0); else all = false; }
+      for (unsigned t = w0; t < w1; ++t) {
+        Fiber& f = fibers[t];
+        if (f.done) continue;
+        if (f.op == 1) { const int s = f.src; f.result = (s >= 0 && w0 + s < w1 && !fibers[w0 + s].done) ? fibers[w0 + s].payload : f.payload; }
+        else if (f.op == 2) f.result = ballot;
+        else if (f.op == 3) f.result = all ? 1 : 0;
+      }
+      for (unsigned t = w0; t < w1; ++t) if (!fibers[t].done) fibers[t].wait = kRun;
+      progress = true;
+    }
+    if (!progress) {
+      // only spinners left that made no progress: a real deadlock would hang the GPU as well
+      bool only_spin = true;
+      for (unsigned t = 0; t < nthreads; ++t) if (!fibers[t].done && fibers[t].wait != kSpin) only_spin = false;
+      static int idle = 0;
+      if (!only_spin || ++idle > 1000000) { std::fprintf(stderr, "cuda_emu: deadlock in block %u\n", blockIdx.x); std::abort(); }
+    }
+  }
+}
+
+inline std::mutex launch_mu;  // one emulated device: the ranks of tba_solve_multi (one host thread each) take turns
+inline void segv_backtrace(int) {  // TBA_EMU_BACKTRACE=1: frames for `addr2line -e libtheia_ba_b200_emu.so`
+  void* fr[64];
+  const int n = backtrace(fr, 64);
+  backtrace_symbols_fd(fr, n, 2);
+  _exit(139);
+}
+template <class F>
+inline void launch(unsigned grid, unsigned block, size_t smem, F&& fn) {
+  static const bool traced = [] { if (std::getenv("TBA_EMU_BACKTRACE")) { std::signal(SIGSEGV, segv_backtrace); std::signal(SIGABRT, segv_backtrace); } return true; }();
+  (void)traced;
+  std::lock_guard<std::mutex> lk(launch_mu);
+  if (grid == 0 || block == 0 || block > 1024 || smem > 227 * 1024) {  // what the driver would refuse
+    std::fprintf(stderr, "cuda_emu: invalid launch configuration <<<%u, %u, %zu>>>\n", grid, block, smem);
+    emu_last_error = cudaErrorEmu;
+    return;
+  }
+  const std::function<void()> f = fn;
+  body = &f;
+  if (dyn_smem_buf.size() < smem + 256) dyn_smem_buf.resize(smem + 256);
+  gridDim.x = grid; blockDim.x = block;
+  for (unsigned b = 0; b < grid; ++b) { blockIdx.x = b; run_block(block); }
+  body = nullptr;
+}
+
+inline uint64_t warp_op(int op, uint64_t payload, int src) {
+  Fiber& f = fibers[cur];
+  f.op = op; f.payload = payload; f.src = src;
+  suspend(kWarpOp);
+  return fibers[cur].result;
+}
+}  // namespace emu
+
+inline void __syncthreads() { emu::suspend(emu::kBlockBarrier); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_op(0, 0, -1); }
+inline void emu_yield() { emu::suspend(emu::kSpin); }
+template <class T> inline uint64_t emu_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, ""); std::memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T emu_from(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
+template <class T> inline T __shfl_sync(unsigned, T v, int src_lane, int = 32) { return emu_from<T>(emu::warp_op(1, emu_bits(v), src_lane & 31)); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32) {
+  const int lane = threadIdx.x & 31; const int s = lane + (int)delta;
+  return emu_from<T>(emu::warp_op(1, emu_bits(v), s < 32 ? s : -1));
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta, int = 32) {
+  const int lane = threadIdx.x & 31; const int s = lane - (int)delta;
+  return emu_from<T>(emu::warp_op(1, emu_bits(v), s >= 0 ? s : -1));
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emu_from<T>(emu::warp_op(1, emu_bits(v), (threadIdx.x & 31) ^ m)); }
+inline unsigned __ballot_sync(unsigned, int pred) { return (unsigned)emu::warp_op(2, pred ? 1 : 0, -1); }
+inline int __all_sync(unsigned, int pred) { return (int)emu::warp_op(3, pred ? 1 : 0, -1); }

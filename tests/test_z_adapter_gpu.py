@@ -11,14 +11,17 @@ ADAPTER = os.path.join(ROOT, "adapter")
 
 
 @pytest.fixture(scope="module")
-def adapter_test_bin(oracle):
+def adapter_test_bin(oracle, request):
+    if request.config.getoption("--emulate-engine"):  # same driver and adapters, linked with the SIMT-emulated engine (tests/emu)
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu"), "adapter"], stdout=subprocess.DEVNULL)
+        return os.path.join(ROOT, "tests", "emu", "adapter_test_emu")
     subprocess.check_call(["make", "-C", ADAPTER], stdout=subprocess.DEVNULL)
     return os.path.join(ADAPTER, "adapter_test")
 
 
 @pytest.mark.gpu
 def test_adapter_end_to_end_against_oracle(adapter_test_bin):
-    out = subprocess.run([adapter_test_bin, "solve", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([adapter_test_bin, "solve", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "solve ok" in out.stdout
 
@@ -26,7 +29,7 @@ def test_adapter_end_to_end_against_oracle(adapter_test_bin):
 @pytest.mark.gpu
 def test_track_estimator_end_to_end_against_oracle(adapter_test_bin):
     """TrackEstimatorB200::EstimateAllTracks (batched estimate_track.cc) after a joint BA, against oracle_estimate_tracks."""
-    out = subprocess.run([adapter_test_bin, "tracks", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([adapter_test_bin, "tracks", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "tracks ok" in out.stdout
 
@@ -34,13 +37,13 @@ def test_track_estimator_end_to_end_against_oracle(adapter_test_bin):
 @pytest.mark.gpu
 def test_bundle_adjust_view_and_track_against_oracle(adapter_test_bin):
     """BundleAdjustViewB200 / BundleAdjustTrackB200 (bundle_adjustment.cc:82-107) against the oracle on the same flattening."""
-    out = subprocess.run([adapter_test_bin, "micro", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([adapter_test_bin, "micro", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "micro ok" in out.stdout
 
 
 @pytest.mark.gpu
 def test_bundle_adjust_two_views_against_oracle(adapter_test_bin):
-    out = subprocess.run([adapter_test_bin, "twoview", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([adapter_test_bin, "twoview", os.path.join(ROOT, "oracle", "libba_oracle.so")], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "twoview ok" in out.stdout

@@ -39,7 +39,12 @@ struct NcclApi {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string* err) {
     if (handle) return true;
+#ifdef TBA_EMULATE
+    const char* emu = getenv("TBA_EMU_NCCL");  // tests/emu/libemu_nccl.so (shared-memory stand-in, test infrastructure)
+    const char* names[] = {emu ? emu : "libemu_nccl.so", "libemu_nccl.so"};
+#else
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
+#endif
     for (const char* n : names) {
       handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (handle) break;
@@ -178,8 +183,21 @@ void set_err(tba_context* c, const char* fmt, ...) {
 
 // Every launch is checked: a rejected launch (bad configuration, missing shared-memory opt-in) must not turn into a
 // silently skipped kernel.
+#ifdef TBA_EMULATE  // CPU emulation build (tests/emu): blocks run one after the other, threads as fibers
+#define LAUNCH(c, kern, grid, block, smem, ...)                                              \
+  do {                                                                                       \
+    if ((unsigned)(grid) == 0u) break; /* see the CUDA variant */                            \
+    emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); }); \
+    if (cudaGetLastError() != cudaSuccess) {                                                 \
+      set_err(c, "kernel launch failed: invalid configuration at %s:%d (%s)", __FILE__, __LINE__, #kern); \
+      return TBA_ERR_CUDA;                                                                   \
+    }                                                                                        \
+    (c)->launches++;                                                                         \
+  } while (0)
+#else
 #define LAUNCH(c, kern, grid, block, smem, ...)                                                              \
   do {                                                                                                       \
+    if ((unsigned)(grid) == 0u) break; /* nothing to do (empty problem / empty set): a 0-block launch is an error */ \
     kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);                                             \
     const cudaError_t le__ = cudaPeekAtLastError();                                                          \
     if (le__ != cudaSuccess) {                                                                               \
@@ -188,6 +206,7 @@ void set_err(tba_context* c, const char* fmt, ...) {
     }                                                                                                        \
     (c)->launches++;                                                                                         \
   } while (0)
+#endif
 
 int prof_begin(tba_context* c) {
   if (!c->profiling) return -1;

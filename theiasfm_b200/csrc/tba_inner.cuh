@@ -46,7 +46,7 @@ __host__ __device__ inline bool block_obs_linearize(int model, const double* __r
   return true;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(TBA_EMULATE)
 struct BlockPassArgs {
   const double* ext;     // [n_cam][6]   values to evaluate with (block values already substituted by the host driver)
   const double* rec;     // [n_cam][kCamRec] for ext

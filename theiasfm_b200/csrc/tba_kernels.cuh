@@ -532,6 +532,17 @@ __device__ __forceinline__ void sym4_mul(const double* __restrict__ M, const dou
 }
 
 // ---------------------------------------------------- TMA (bulk async copy) helpers
+#ifdef TBA_EMULATE
+// CPU emulation build (tests/emu/cuda_emu.h): the bulk copy is a memcpy by the issuing lane, the mbarrier a flag the other lanes
+// poll (yielding to the fiber scheduler), the bulk reduction an in-place add.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { memcpy(dst, src, bytes); *bar += bytes; }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t) { while (*bar == 0) emu_yield(); }  // the issuing lane copied before the __syncwarp
+__device__ __forceinline__ void bulk_red_add_f64(double* dst, const double* src_smem, uint32_t bytes) { for (uint32_t i = 0; i < bytes / 8; ++i) dst[i] += src_smem[i]; }
+__device__ __forceinline__ void bulk_commit_and_wait_read() {}
+__device__ __forceinline__ void fence_proxy_async_smem() {}
+#else
 // cp.async.bulk global -> shared::cta completing on an mbarrier (SASS: UBLKCP + SYNCS.ARRIVE.TRANS64).
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -571,6 +582,8 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#endif  // TBA_EMULATE
+
 // --------------------------------------------- K2 implicit Schur complement
 // MODE 0: y += F^T (I - E M E^T) F xs                (PCG matvec; ImplicitSchurComplement::RightMultiply)
 // MODE 1: y += F^T (I - E M E^T) r                   (reduced rhs; ImplicitSchurComplement::ComputeRHS)
@@ -593,7 +606,11 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
   constexpr int NJ = 14 + 2 * NI;
   constexpr int WS = (NJ + 2) * 32;  // doubles per warp stage
   if (done_flag != nullptr && *done_flag) return;
+#ifdef TBA_EMULATE
+  double* s_dyn = emu::dyn_smem<double>();
+#else
   extern __shared__ __align__(128) double s_dyn[];
+#endif
   __shared__ double s_t[MAXP][4];
   __shared__ __align__(8) uint64_t s_bar[TILE / 32];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -834,7 +851,11 @@ __global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __r
   constexpr int NJ = 14 + 2 * NI;
   constexpr int NW = 4 * NI;
   constexpr int NS = NI * (NI + 1) / 2;
+#ifdef TBA_EMULATE
+  double* s_w = emu::dyn_smem<double>();
+#else
   extern __shared__ double s_w[];  // [nruns][NW] then [nruns] group ids (as int) and points
+#endif
   __shared__ double s_red[32];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nruns = P.tile_nruns[tile];

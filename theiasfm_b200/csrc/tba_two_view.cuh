@@ -50,33 +50,33 @@ struct SerialTeam {
 };
 struct WarpTeam {
   __host__ __device__ static int rank() {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(TBA_EMULATE)
     return threadIdx.x & 31;
 #else
     return 0;
 #endif
   }
   __host__ __device__ static int size() {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(TBA_EMULATE)
     return 32;
 #else
     return 1;
 #endif
   }
   __host__ __device__ static double sum(double v) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(TBA_EMULATE)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);  // butterfly: every lane ends with the same bits
 #endif
     return v;
   }
   __host__ __device__ static double max(double v) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(TBA_EMULATE)
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 #endif
     return v;
   }
   __host__ __device__ static bool all(bool v) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(TBA_EMULATE)
     return __all_sync(0xffffffffu, v) != 0;
 #else
     return v;

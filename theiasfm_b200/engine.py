@@ -11,7 +11,9 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtheia_ba_b200.so")
+# THEIA_BA_B200_LIB overrides where the C-ABI library is loaded from (an out-of-tree install; the test suite's emulation build,
+# which spawned rank processes must find too).  Whatever it names must export the full ABI: there is no CPU fallback.
+LIB_PATH = os.environ.get("THEIA_BA_B200_LIB") or os.path.join(_HERE, "libtheia_ba_b200.so")
 _LIB = None
 
 # every symbol include/theia_ba_b200.h declares
