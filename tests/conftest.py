@@ -28,6 +28,9 @@ def pytest_configure(config):
         from theiasfm_b200 import engine
         engine.LIB_PATH = os.path.join(emu, os.environ.get("TBA_EMU_LIBNAME", "libtheia_ba_b200_emu.so"))  # or the asan build, see tests/emu/Makefile
         engine._LIB = None
+        from theiasfm_b200 import matcher
+        matcher.LIB_PATH = os.path.join(emu, "libtheia_matcher_b200_emu.so")
+        matcher._LIB = None
         # spawned rank processes (test_y_multi_gpu) inherit these: two emulated devices, shared-memory NCCL stand-in
         os.environ["THEIA_BA_B200_LIB"] = engine.LIB_PATH
         os.environ["TBA_EMU_NCCL"] = os.path.join(emu, "libemu_nccl.so")
@@ -37,11 +40,11 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     if not (config.getoption("--mock-engine") or config.getoption("--emulate-engine")):
         return
-    skip = pytest.mark.skip(reason="needs the real CUDA engine (binary / multi-process / matcher library)")
+    skip = pytest.mark.skip(reason="needs the real CUDA engine or its emulation build (binary / multi-process / matcher library)")
     too_big = pytest.mark.skip(reason="full-size scene: hours under the SIMT emulator")
     emu_big = ("test_x_fullsize_gpu",)
     for item in items:
-        names = ("test_xx_matcher_gpu",) + (() if config.getoption("--emulate-engine") else ("test_z_adapter_gpu", "test_y_multi_gpu"))
+        names = () if config.getoption("--emulate-engine") else ("test_xx_matcher_gpu", "test_z_adapter_gpu", "test_y_multi_gpu")
         if any(k in item.nodeid for k in names):
             item.add_marker(skip)
         elif config.getoption("--emulate-engine") and any(k in item.nodeid for k in emu_big):

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -72,13 +73,25 @@ inline int emu_last_error = cudaSuccess;  // set by emu::launch on an invalid co
 inline cudaError_t cudaPeekAtLastError() { return emu_last_error; }
 inline cudaError_t cudaGetLastError() { const int e = emu_last_error; emu_last_error = cudaSuccess; return e; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error (emulated)" : "invalid launch configuration (emulated)"; }
-template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+inline std::mutex emu_attr_mu;
+inline std::map<const void*, size_t> emu_max_dyn_smem;  // kernel -> opted-in dynamic shared memory (default limit 48 KB)
+template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int attr, int v) {
+  if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+    if (v > 227 * 1024) return cudaErrorEmu;
+    std::lock_guard<std::mutex> lk(emu_attr_mu);
+    emu_max_dyn_smem[(const void*)f] = (size_t)v;
+  }
+  return cudaSuccess;
+}
 
 // ---------------------------------------------------------------- device intrinsics without synchronisation
 inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }  // volatile: no contraction into an FMA
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
@@ -211,11 +224,13 @@ inline void segv_backtrace(int) {  // TBA_EMU_BACKTRACE=1: frames for `addr2line
   _exit(139);
 }
 template <class F>
-inline void launch(unsigned grid, unsigned block, size_t smem, F&& fn) {
+inline void launch(const void* kernel, unsigned grid, unsigned block, size_t smem, F&& fn) {
   static const bool traced = [] { if (std::getenv("TBA_EMU_BACKTRACE")) { std::signal(SIGSEGV, segv_backtrace); std::signal(SIGABRT, segv_backtrace); } return true; }();
   (void)traced;
   std::lock_guard<std::mutex> lk(launch_mu);
-  if (grid == 0 || block == 0 || block > 1024 || smem > 227 * 1024) {  // what the driver would refuse
+  size_t smem_limit = 48 * 1024;
+  { std::lock_guard<std::mutex> la(emu_attr_mu); const auto opt = emu_max_dyn_smem.find(kernel); if (opt != emu_max_dyn_smem.end()) smem_limit = opt->second; }
+  if (grid == 0 || block == 0 || block > 1024 || smem > smem_limit) {  // what the driver would refuse
     std::fprintf(stderr, "cuda_emu: invalid launch configuration <<<%u, %u, %zu>>>\n", grid, block, smem);
     emu_last_error = cudaErrorEmu;
     return;

@@ -187,7 +187,7 @@ void set_err(tba_context* c, const char* fmt, ...) {
 #define LAUNCH(c, kern, grid, block, smem, ...)                                              \
   do {                                                                                       \
     if ((unsigned)(grid) == 0u) break; /* see the CUDA variant */                            \
-    emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); }); \
+    emu::launch((const void*)(kern), (unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); }); \
     if (cudaGetLastError() != cudaSuccess) {                                                 \
       set_err(c, "kernel launch failed: invalid configuration at %s:%d (%s)", __FILE__, __LINE__, #kern); \
       return TBA_ERR_CUDA;                                                                   \

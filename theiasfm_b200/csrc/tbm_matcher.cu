@@ -24,7 +24,11 @@ using tbm::top2_push;
 // L2::operator() evaluated term by term (distance.h:52-56).
 __global__ void __launch_bounds__(ROWS* SLICES) k_nn2(const float* __restrict__ A, int nA, const float* __restrict__ B, int nB, int dim,
                                                       int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d) {
+#ifdef TBA_EMULATE  // CPU emulation build (tests/emu)
+  float* smem = emu::dyn_smem<float>();
+#else
   extern __shared__ float smem[];
+#endif
   const int dimp = dim + 1;                 // padded row stride of the query tile: conflict-free column access
   float* sA = smem;                         // [ROWS][dimp]
   float* sB = smem + ROWS * dimp;           // [TJ][dim]
@@ -140,7 +144,12 @@ int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, 
       bj[dir].assign((size_t)nq, -1); bd[dir].assign((size_t)nq, 0.0f); sd[dir].assign((size_t)nq, 0.0f);
       if (nq == 0 || nc == 0) continue;
       if (dir == 1 && !options->keep_only_symmetric_matches) continue;
+#ifdef TBA_EMULATE
+      emu::launch((const void*)k_nn2, (unsigned)((nq + ROWS - 1) / ROWS), (unsigned)(ROWS * SLICES), smem,
+                  [&] { k_nn2(dir == 0 ? A : B, nq, dir == 0 ? B : A, nc, dim, d_bj[dir].p, d_bd[dir].p, d_sd[dir].p); });
+#else
       k_nn2<<<(nq + ROWS - 1) / ROWS, ROWS * SLICES, smem>>>(dir == 0 ? A : B, nq, dir == 0 ? B : A, nc, dim, d_bj[dir].p, d_bd[dir].p, d_sd[dir].p);
+#endif
       if (cudaPeekAtLastError() != cudaSuccess) return -3;
       if (cudaMemcpy(bj[dir].data(), d_bj[dir].p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
           cudaMemcpy(bd[dir].data(), d_bd[dir].p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
