@@ -52,6 +52,7 @@ class MockEngine:
         self.close()
         s = oracle_py.solve(self._w, self._opts)
         s.num_kernel_launches = 1
+        self._last = s
         return s
 
     def download(self, problem=None):
@@ -79,7 +80,10 @@ class MockEngine:
         pass
 
     def profile(self):
-        return dict(matvec_ms=0.0, matvec_launches=0, linearize_ms=0.0, linearize_launches=0, slots=0, observations=self._w.n_obs,
+        s = getattr(self, "_last", None)
+        n_it = s.num_iterations if s is not None else 0
+        n_mv = sum(it["linear_solver_iterations"] + 2 for it in s.iterations) if s is not None else 0
+        return dict(matvec_ms=0.0, matvec_launches=n_mv, linearize_ms=0.0, linearize_launches=n_it, slots=self._w.n_obs, observations=self._w.n_obs,
                     points=self._w.n_pt, doubles_per_obs=20)
 
     # staged hooks
