@@ -226,6 +226,7 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop(tw0, time.time())
     prof = eng.profile()
+    stages = eng.profile_stages()
     eng.set_profiling(False)
     iters = s.num_iterations - 1
     dev_s = sum(it["iteration_time_in_seconds"] for it in s.iterations)
@@ -291,7 +292,10 @@ def main():
                 # observation passes = linearisations + PCG matvecs + step evaluations, all ranks' shards together
                 "obs_passes_per_s": n_obs_total * (prof["linearize_launches"] + prof["matvec_launches"] + iters) / t_max,
                 "pcg_iterations": s.num_linear_solver_iterations, "initial_cost": s.initial_cost, "final_cost": s.final_cost,
-                "wall_seconds_timed_region": wall, "n_obs": n_obs_total}
+                "wall_seconds_timed_region": wall, "n_obs": n_obs_total,
+                # per-stage device time (CUDA events on the engine stream inside the timed region), ms per LM iteration
+                "stage_ms_per_step": {k: v["ms"] / iters for k, v in stages.items()},
+                "experiment_switches": {k: os.environ[k] for k in ("TBA_TRED", "TBA_MATVEC_BULKRED", "TBA_FAST_SEG", "TBA_PACK_SORT") if k in os.environ}}
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -86,6 +86,13 @@ class MockEngine:
         return dict(matvec_ms=0.0, matvec_launches=n_mv, linearize_ms=0.0, linearize_launches=n_it, slots=self._w.n_obs, observations=self._w.n_obs,
                     points=self._w.n_pt, doubles_per_obs=20)
 
+    def profile_stages(self):
+        p = self.profile()
+        z = {"ms": 0.0, "launches": p["linearize_launches"]}
+        out = {k: dict(z) for k in ("linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost")}
+        out["matvec"] = {"ms": 0.0, "launches": p["matvec_launches"]}
+        return out
+
     # staged hooks
     def linearize(self):
         return self._staged().linearize()

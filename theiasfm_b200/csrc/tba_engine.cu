@@ -127,7 +127,7 @@ struct tba_context {
   // optional per-kernel timing (CUDA events on the engine stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, int>> ev_spans[2];  // 0: matvec, 1: linearize ; indices into ev_pool
+  std::vector<std::pair<int, int>> ev_spans[7];  // 0: matvec, 1: linearize, 2: precond_ext, 3: precond_intr, 4: rhs, 5: back-substitution, 6: candidate cost ; indices into ev_pool
   // set by tba_solve_multi (which sees the whole problem) before tba_upload: global per-camera observation counts and the
   // global number of free points, so that the upload needs no collective
   const double* preset_cnt_cam = nullptr;
@@ -144,6 +144,7 @@ struct tba_context {
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
   bool exp_fast_seg = false;  // TBA_FAST_SEG=1: segmented reductions without key shuffles in k_linearize / the matvec (default off)
+  bool exp_tred = false;  // TBA_TRED=1: transposed RED emission (warp_red_rows) in k_linearize / k_precond_ext / rhs / matvec (round-2 experiment, default off)
   bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
@@ -274,6 +275,10 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
     if (c->has_ext_models) {  // FISHEYE / FOV / DIVISION_UNDISTORTION present: the dual-number instantiation, all 10 columns
       auto kfn = k_linearize<0x3FFu, true>;
       LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p);
+    } else if (c->exp_tred) {
+#define F(M) { auto kfn = k_linearize<M, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
     } else if (c->exp_fast_seg) {
 #define F(M) { auto kfn = k_linearize<M, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
       DISPATCH_IMASK(c->imask, F)
@@ -324,14 +329,24 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
   if (o.preconditioner_type != TBA_PRECOND_IDENTITY) {
     CUDA_OK(c, cudaMemsetAsync(c->Sblk.p, 0, nS * sizeof(double), c->stream));
     if (P.n_tiles > 0) {
-#define F(M) LAUNCH(c, k_precond_ext<M>, P.n_tiles, TILE, 0, P, c->Sblk.p)
-      DISPATCH_IMASK(c->imask, F)
+      const int pb_ext = prof_begin(c);
+      if (c->exp_tred) {
+#define F(M) { auto kfn = k_precond_ext<M, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->Sblk.p); }
+        DISPATCH_IMASK(c->imask, F)
 #undef F
+      } else {
+#define F(M) LAUNCH(c, k_precond_ext<M>, P.n_tiles, TILE, 0, P, c->Sblk.p)
+        DISPATCH_IMASK(c->imask, F)
+#undef F
+      }
+      prof_end(c, 2, pb_ext);
       if (c->NI > 0) {
         const size_t smem = (size_t)TILE * 4 * c->NI * sizeof(double) + 2 * TILE * sizeof(int);
+        const int pb_intr = prof_begin(c);
 #define F(M) LAUNCH(c, k_precond_intr<M>, P.n_tiles, TILE, smem, P, c->Sblk.p + (size_t)P.n_cam * 21)
         DISPATCH_IMASK(c->imask, F)
 #undef F
+        prof_end(c, 3, pb_intr);
       }
     }
     int rc = allreduce_sum(c, c->Sblk.p, nS);
@@ -342,9 +357,17 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
   // reduced rhs: y = F'(I - E M E') r, then b = sm .* y (k_pcg_init)
   CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
-#define F(M) { auto kfn = k_schur<M, 1>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr); }
-    DISPATCH_IMASK(c->imask, F)
+    const int pb_rhs = prof_begin(c);
+    if (c->exp_tred) {
+#define F(M) { auto kfn = k_schur<M, 1, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr); }
+      DISPATCH_IMASK(c->imask, F)
 #undef F
+    } else {
+#define F(M) { auto kfn = k_schur<M, 1>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    }
+    prof_end(c, 4, pb_rhs);
     if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   int rc = allreduce_sum(c, c->y.p, P.ncs);
@@ -366,7 +389,11 @@ int launch_matvec(tba_context* c, const int* done) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-    if (c->exp_bulkred) {
+    if (c->exp_tred) {
+#define F(M) { auto kfn = k_schur<M, 0, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    } else if (c->exp_bulkred) {
 #define F(M) { auto kfn = k_schur<M, 0, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
@@ -444,9 +471,11 @@ int stage_backsub(tba_context* c) {
   LAUNCH(c, k_cs_mul, VB, VT, 0, P.ncs, c->sm.p, c->x.p, c->xs.p);
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 16 * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
+    const int pb_bs = prof_begin(c);
 #define F(M) { auto kfn = k_schur<M, 2>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, nullptr, c->rep.p, nullptr); }
     DISPATCH_IMASK(c->imask, F)
 #undef F
+    prof_end(c, 5, pb_bs);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   // candidate = x + delta, step norm
@@ -460,8 +489,10 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
   DevProblem& P = c->P;
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
   if (P.n_tiles > 0) {
+    const int pb_cost = prof_begin(c);
     if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
     else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    prof_end(c, 6, pb_cost);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   int rc = allreduce_sum(c, c->scal2.p, 8);
@@ -699,6 +730,7 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   tba_options_init(&c->opt);
   { const char* e = getenv("TBA_MATVEC_BULKRED"); c->exp_bulkred = e != nullptr && e[0] == '1'; }
   { const char* e = getenv("TBA_FAST_SEG"); c->exp_fast_seg = e != nullptr && e[0] == '1'; }
+  { const char* e = getenv("TBA_TRED"); c->exp_tred = e != nullptr && e[0] == '1'; }
   { const char* e = getenv("TBA_PACK_SORT"); c->exp_pack_sort = e != nullptr && e[0] == '1'; }
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&c->h_scal, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->h_st, sizeof(PcgState)) != cudaSuccess) {
@@ -926,6 +958,8 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DISPATCH_IMASK(c->imask, F)
@@ -1161,7 +1195,8 @@ int tba_set_profiling(tba_context* c, int enable) {
   if (!c) return TBA_ERR_INVALID_ARGUMENT;
   cudaSetDevice(c->device);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-  c->ev_pool.clear(); c->ev_spans[0].clear(); c->ev_spans[1].clear();
+  c->ev_pool.clear();
+  for (auto& v : c->ev_spans) v.clear();
   c->real_matvecs = 0;
   c->profiling = enable != 0;
   return TBA_OK;
@@ -1180,6 +1215,21 @@ int tba_get_profile(tba_context* c, double* out) {
   }
   out[1] = (double)c->real_matvecs;  // early-exited launches (after convergence inside a batch) cost ~2 us and do no work
   out[4] = (double)c->n_slots; out[5] = (double)c->n_obs; out[6] = (double)c->n_pt; out[7] = (double)c->NJ;
+  return TBA_OK;
+}
+
+// Per-stage device times of the profiled minimise: out[2k] = total ms, out[2k + 1] = launches for stage k of
+// {0 matvec, 1 linearize, 2 precond_ext, 3 precond_intr, 4 reduced rhs, 5 back-substitution, 6 candidate cost}.
+int tba_get_profile_stages(tba_context* c, double* out) {
+  if (!c || !out) return TBA_ERR_INVALID_ARGUMENT;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < 7; ++w) {
+    double tot = 0;
+    for (auto& sp : c->ev_spans[w]) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_pool[sp.first], c->ev_pool[sp.second]); tot += ms; }
+    out[2 * w] = tot; out[2 * w + 1] = (double)c->ev_spans[w].size();
+  }
+  out[1] = (double)c->real_matvecs;
   return TBA_OK;
 }
 

@@ -102,6 +102,31 @@ __device__ __forceinline__ double seg_reduce_to(double v, int run_last, int lane
 
 __device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
 
+// Experiment TBA_TRED=1 ("transposed" RED emission).  A lane-per-observation RED of an N-double camera row touches 32
+// different 32-byte sectors per instruction (32 cameras), i.e. N x 32 sector operations at the L2 atomic units, which
+// is what bounds these kernels (profiles/: k_precond_ext 88 % lts throughput at one sector operation per RED).  Here
+// the warp first stages its 32 rows in shared memory ([32][N] doubles, lane-major) and then emits them element-major:
+// instruction k covers elements 32k..32k+31 of the staged [32*N] array, so consecutive lanes add to consecutive doubles
+// of the same row and one RED instruction covers about 32*8/32 = 8..11 sectors instead of 32 -- the same N RED
+// instructions per warp, about a third of the sector operations.  sbase[o] = element offset of observation o's row in
+// dst, < 0 for padding lanes.  The caller brackets the staging stores with __syncwarp().
+template <int N>
+__device__ __forceinline__ void warp_stage_row(double* __restrict__ stage, int* __restrict__ sbase, const double (&v)[N], int base, int lane) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) stage[lane * N + j] = v[j];
+  sbase[lane] = base;
+}
+template <int N>
+__device__ __forceinline__ void warp_red_rows(double* __restrict__ dst, const double* __restrict__ stage, const int* __restrict__ sbase, int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int e = k * 32 + lane;
+    const int o = e / N;
+    const int b = sbase[o];
+    if (b >= 0) red_add(dst + (size_t)b + (e - o * N), stage[e]);
+  }
+}
+
 // ------------------------------------------------------------ camera prep
 __global__ void k_cam_prep(int n_cam, const double* __restrict__ ext, double* __restrict__ rec) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,7 +165,7 @@ __device__ __forceinline__ size_t wslice(int tile, int warp, int rows) { return 
 // gradient / squared column norms (fp64 RED to global) and cost / failure counters (replicas).
 // Normal tiles: a point never straddles a warp -> per-point sums by warp-shuffle segmented reduction only, no
 // block barrier.  Long tiles (tracks > 32 observations): combined across warps in shared memory.
-template <uint32_t IMASK, bool EXT = false, bool FASTSEG = false>
+template <uint32_t IMASK, bool EXT = false, bool FASTSEG = false, bool TRED = false>
 __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
                                                     double* __restrict__ rep) {
   constexpr int NI = popcount10(IMASK);
@@ -238,7 +263,26 @@ __global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __rest
     }
   }
   // camera-side gradient and squared column norms: J_c = [-h Ja | Jw]
-  if (valid) {
+  if (TRED && !long_tile) {
+    // experimental (TBA_TRED=1): both 6-rows staged per warp in the (idle on normal tiles) s_acc area, emitted element-major
+    double gv[6], cv[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double c0 = -h * Ja[j], c1 = -h * Ja[3 + j];
+      gv[j] = c0 * r[0] + c1 * r[1];
+      cv[j] = c0 * c0 + c1 * c1;
+      gv[3 + j] = Jw[j] * r[0] + Jw[3 + j] * r[1];
+      cv[3 + j] = Jw[j] * Jw[j] + Jw[3 + j] * Jw[3 + j];
+    }
+    static_assert(MAXP * 14 >= (TILE / 32) * (2 * 32 * 6 + 16), "s_acc too small for the TRED staging");
+    double* stage = &s_acc[0][0] + warp * (2 * 32 * 6 + 16);
+    int* sbase = reinterpret_cast<int*>(stage + 2 * 32 * 6);
+    warp_stage_row<6>(stage, sbase, gv, valid ? cam * 6 : -1, lane);
+    warp_stage_row<6>(stage + 32 * 6, sbase, cv, valid ? cam * 6 : -1, lane);
+    __syncwarp();
+    warp_red_rows<6>(g_cs, stage, sbase, lane);
+    warp_red_rows<6>(cn_cs, stage + 32 * 6, sbase, lane);
+  } else if (valid) {
     double* gc = g_cs + (size_t)cam * 6;
     double* cc = cn_cs + (size_t)cam * 6;
 #pragma unroll
@@ -599,7 +643,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // Camera-side sums: fp64 RED.ADD to global; shared-intrinsics sums: warp reduce + RED to a replica row.
 // No block barrier on this path.  Long tiles (tracks > 32 observations) combine the per-point sums across warps in
 // shared memory (two block barriers).  Dynamic shared memory: TILE * (NJ + 2) doubles.
-template <uint32_t IMASK, int MODE, bool BULKRED = false, bool FASTSEG = false>
+template <uint32_t IMASK, int MODE, bool BULKRED = false, bool FASTSEG = false, bool TRED = false>
 __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 : 2) k_schur(DevProblem P, const double* __restrict__ xs, double* __restrict__ y,
                                                 double* __restrict__ rep, const int* __restrict__ done_flag) {
   constexpr int NI = popcount10(IMASK);
@@ -637,7 +681,7 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
   double xi[NI + 1];
   if (valid) {
     pl = P.slot_pt[slot] - p0;
-    grp = P.cam_group[cam];
+    grp = (TRED && P.single_group) ? 0 : P.cam_group[cam];  // TRED: no 32-sector gather when one group owns everything
     h = P.pt[(size_t)(p0 + pl) * 4 + 3];
     if (MODE != 1) {
       const double2* x2 = reinterpret_cast<const double2*>(xs + (size_t)cam * 6);
@@ -776,6 +820,35 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     }
     return;
   }
+  if (TRED) {
+    // experimental (TBA_TRED=1): camera-side contributions staged per warp and emitted element-major (warp_red_rows)
+    double yv[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) yv[j] = valid ? -h * (JA(j) * z0 + JA(3 + j) * z1) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) yv[3 + j] = valid ? JW(j) * z0 + JW(3 + j) * z1 : 0.0;
+    double yi[NI + 1];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) yi[j] = valid ? JI(j) * z0 + JI(NI + j) * z1 : 0.0;
+    __syncwarp();  // every lane has finished reading the J slice: its first 6.5 rows are reused as staging [32][6] + 32 ints
+    int* sbase = reinterpret_cast<int*>(sJ + 32 * 6);
+    warp_stage_row<6>(sJ, sbase, yv, valid ? cam * 6 : -1, lane);
+    __syncwarp();
+    warp_red_rows<6>(y, sJ, sbase, lane);
+    if (NI > 0) {
+      if (P.single_group) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const double v = warp_sum(yi[j]);
+          if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), yi[j]);
+      }
+    }
+    return;
+  }
   if (valid) {
     double* yc = y + (size_t)cam * 6;
 #pragma unroll
@@ -804,13 +877,55 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
 // ------------------------------------------- SCHUR_JACOBI preconditioner blocks
 // Extrinsics blocks: S_cc = sum_o J_c^T Q_o J_c with Q_o = I_2 - J_p M_p J_p^T (a view observes a track once).
 // Sc: [n_cam][21] upper triangle, unscaled (scaling + D^2 + inversion in k_precond_finish).
-template <uint32_t IMASK>
+template <uint32_t IMASK, bool TRED = false>
 __global__ void __launch_bounds__(TILE) k_precond_ext(DevProblem P, double* __restrict__ Sc) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t slot = (size_t)tile * TILE + tid;
   const int cam = P.slot_cam[slot];
+  if (TRED) {
+    // experimental (TBA_TRED=1): the 21 block entries of every observation staged per warp, emitted element-major
+    __shared__ double s_stage[TILE / 32][32 * 21];
+    __shared__ int s_base[TILE / 32][32];
+    double v[21];
+#pragma unroll
+    for (int j = 0; j < 21; ++j) v[j] = 0.0;
+    if (cam >= 0) {
+      const double* Jt = P.J + wslice(tile, warp, NJ) + lane;
+      double Ja[6], Jw[6], Jh[2];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) Ja[j] = Jt[j * 32];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) Jw[j] = Jt[(6 + j) * 32];
+      Jh[0] = Jt[12 * 32];
+      Jh[1] = Jt[13 * 32];
+      const int pt = P.slot_pt[slot];
+      const double h = P.pt[(size_t)pt * 4 + 3];
+      const double* M = P.Mp + (size_t)pt * 10;
+      const double jp0[4] = {Ja[0], Ja[1], Ja[2], Jh[0]}, jp1[4] = {Ja[3], Ja[4], Ja[5], Jh[1]};
+      double m0[4], m1[4];
+      sym4_mul(M, jp0, m0);
+      sym4_mul(M, jp1, m1);
+      const double q00 = 1.0 - (jp0[0] * m0[0] + jp0[1] * m0[1] + jp0[2] * m0[2] + jp0[3] * m0[3]);
+      const double q01 = -(jp0[0] * m1[0] + jp0[1] * m1[1] + jp0[2] * m1[2] + jp0[3] * m1[3]);
+      const double q11 = 1.0 - (jp1[0] * m1[0] + jp1[1] * m1[1] + jp1[2] * m1[2] + jp1[3] * m1[3]);
+      double c0[6], c1[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { c0[j] = -h * Ja[j]; c1[j] = -h * Ja[3 + j]; c0[3 + j] = Jw[j]; c1[3 + j] = Jw[3 + j]; }
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double qa0 = q00 * c0[a] + q01 * c1[a], qa1 = q01 * c0[a] + q11 * c1[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) { v[n] = qa0 * c0[b] + qa1 * c1[b]; ++n; }
+      }
+    }
+    warp_stage_row<21>(s_stage[warp], s_base[warp], v, cam >= 0 ? cam * 21 : -1, lane);
+    __syncwarp();
+    warp_red_rows<21>(Sc, s_stage[warp], s_base[warp], lane);
+    return;
+  }
   if (cam < 0) return;
   const double* Jt = P.J + wslice(tile, warp, NJ) + lane;
   double Ja[6], Jw[6], Jh[2];

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch", "tba_two_view_ba_batch_multi",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_get_profile_stages", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch", "tba_two_view_ba_batch_multi",
 ]
 
 
@@ -68,6 +68,7 @@ def lib():
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.tba_get_profile.argtypes = [C.c_void_p, dp]
+        L.tba_get_profile_stages.argtypes = [C.c_void_p, dp]
         _LIB = L
     return _LIB
 
@@ -293,6 +294,14 @@ class Engine:
         self._check(lib().tba_get_profile(self._h, _dp(out)))
         return dict(matvec_ms=out[0], matvec_launches=int(out[1]), linearize_ms=out[2], linearize_launches=int(out[3]),
                     slots=int(out[4]), observations=int(out[5]), points=int(out[6]), doubles_per_obs=int(out[7]))
+
+    STAGES = ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost")
+
+    def profile_stages(self):
+        """Per-stage device time of the profiled run: {stage: {"ms": total, "launches": n}} (tba_get_profile_stages)."""
+        out = np.zeros(14)
+        self._check(lib().tba_get_profile_stages(self._h, _dp(out)))
+        return {k: {"ms": float(out[2 * i]), "launches": int(out[2 * i + 1])} for i, k in enumerate(self.STAGES)}
 
     # ---- stage hooks (kernel-level parity tests)
     def linearize(self):

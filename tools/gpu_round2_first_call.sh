@@ -23,7 +23,11 @@ done
 # 2. smoke + the bench line (default workload c3, N = 1)
 run 300 smoke python -c "import __graft_entry__ as g; g.smoke()"
 run 600 bench_c3 python bench.py
-# 3. the two compiled-in experiments: parity subset, then the bench line
+# 3. the compiled-in experiments: parity subset, then the bench line (its "stage_ms_per_step" gives the per-kernel effect).
+#    TBA_TRED first: it is the one expected to matter most (a third of the L2 sector operations of every RED-bound kernel).
+TBA_TRED=1 run 300 parity_tred python -m pytest tests/test_gpu_parity.py -q -m gpu -k "stage_parity or full_solve"
+TBA_TRED=1 run 400 bench_c3_tred python bench.py --no-cpu-baseline
+TBA_TRED=1 TBA_PACK_SORT=1 run 400 bench_c3_tred_packsort python bench.py --no-cpu-baseline
 TBA_MATVEC_BULKRED=1 run 300 parity_bulkred python -m pytest tests/test_gpu_parity.py -q -m gpu -k "stage_parity or full_solve"
 TBA_MATVEC_BULKRED=1 run 400 bench_c3_bulkred python bench.py --no-cpu-baseline
 TBA_FAST_SEG=1 run 300 parity_fastseg python -m pytest tests/test_gpu_parity.py -q -m gpu -k "stage_parity or full_solve"
