@@ -82,15 +82,21 @@ class ClockSampler:
 def run_microbench(device):
     """fp64 FMA peak, fp64 RED rate and 48-byte gather rate of this GPU (theiasfm_b200/csrc/tba_microbench.cu), measured
     in a SEPARATE process before the solve so that it cannot disturb the timed region; None if anything goes wrong."""
-    code = ("import ctypes, json, sys; L = ctypes.CDLL(%r); out = (ctypes.c_double * 3)(); "
-            "rc = L.tba_microbench(%d, out); print(json.dumps({'rc': rc, 'v': list(out)}))"
-            % (os.path.join(ROOT, "theiasfm_b200", "libtheia_microbench_b200.so"), device))
+    code = ("import ctypes, json, sys; L = ctypes.CDLL(%r); out = (ctypes.c_double * 3)(); ex = (ctypes.c_double * 3)(); "
+            "rc = L.tba_microbench(%d, out); rx = L.tba_microbench_ex(%d, ex) if rc == 0 else -1; "
+            "print(json.dumps({'rc': rc, 'v': list(out), 'rx': rx, 'x': list(ex)}))"
+            % (os.path.join(ROOT, "theiasfm_b200", "libtheia_microbench_b200.so"), device, device))
     try:
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
         d = json.loads(r.stdout.strip().splitlines()[-1])
         if d["rc"] != 0:
             return None
+        ex = d.get("x") if d.get("rx") == 0 else None
         return {"fp64_fma_tflops": d["v"][0], "fp64_red_gops": d["v"][1], "gather48_grows": d["v"][2],
+                # design questions for the next kernel generation (NOTES.md section 3): REDs emitted element-major (6 lanes per
+                # 48-byte row), shared-memory fp64 atomicAdd (CAS loop), global REDs confined to a 1200-camera window per CTA
+                "fp64_red_rows_gops": ex[0] if ex else None, "fp64_smem_atomic_gops": ex[1] if ex else None,
+                "fp64_red_window_gops": ex[2] if ex else None,
                 "how": "tba_microbench: 8 DFMA chains/thread; RED.ADD.F64 and 3xLDG.128 gathers over a 60k-double vector, "
                        "32 distinct rows per warp; best of 5 after warm-up"}
     except Exception:  # noqa: BLE001 -- the micro-benchmark is optional evidence, never a reason to fail the bench
@@ -123,6 +129,78 @@ def cpu_baseline(steps, warmup=0):
             "linear_solver_iterations": s.num_linear_solver_iterations}
 
 
+SWITCHES = ("TBA_TRED", "TBA_MATVEC_BULKRED", "TBA_FAST_SEG", "TBA_PACK_SORT")
+VARIANTS = (("default", {}), ("tred", {"TBA_TRED": "1"}), ("fast_seg", {"TBA_FAST_SEG": "1"}), ("pack_sort", {"TBA_PACK_SORT": "1"}),
+            ("tred+pack_sort", {"TBA_TRED": "1", "TBA_PACK_SORT": "1"}), ("bulkred", {"TBA_MATVEC_BULKRED": "1"}))
+
+
+def experiments_child(workload, K, device):
+    """Runs in its OWN process (bench.py --experiments-child), after the measured solve of the parent is over: the same
+    workload solved once per compiled-in experiment switch (NOTES.md section 3; all default off), one JSON line per variant
+    with its per-stage device times and its per-iteration costs relative to the default kernels.  Diagnostics for the
+    next round's kernel work -- never part of `value` / `e2e`; a variant that fails only loses its own line."""
+    from theiasfm_b200 import engine
+    full = synthetic.make_config(workload)
+    init = full.copy()
+    ref = None
+    for name, env in VARIANTS:
+        for k in SWITCHES:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        line = {"variant": name}
+        try:
+            eng = engine.Engine(device=device)  # the switches are read when the context is created
+            eng.upload(full, engine.default_options(**solver_kwargs(K)))
+            eng.minimize()                      # warm-up
+            eng.reset_parameters(init)
+            eng.set_profiling(True)
+            s = eng.minimize()
+            st = eng.profile_stages()
+            eng.set_profiling(False)
+            eng.close()
+            iters = max(s.num_iterations - 1, 1)
+            costs = np.asarray(s.costs, dtype=np.float64)
+            if ref is None:
+                ref = costs
+            n = min(len(ref), len(costs))
+            line.update({"rc": int(s.rc), "ms_per_step": 1e3 * sum(it["iteration_time_in_seconds"] for it in s.iterations) / iters,
+                         "steps_run": iters, "pcg_iterations": int(s.num_linear_solver_iterations), "final_cost": float(s.final_cost),
+                         "max_rel_cost_diff_vs_default": float(np.max(np.abs(costs[:n] - ref[:n]) / ref[:n])) if n else None,
+                         "stage_ms_per_step": {k: v["ms"] / iters for k, v in st.items()},
+                         "matvec_ms_per_launch": st["matvec"]["ms"] / max(st["matvec"]["launches"], 1)})
+        except Exception as e:  # noqa: BLE001
+            line["error"] = "%s: %s" % (type(e).__name__, e)
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_experiments(workload, K, device, timeout=300):
+    """Parent side: spawn the child, keep whatever lines it managed to print."""
+    env = {k: v for k, v in os.environ.items() if k not in SWITCHES and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--experiments-child", "--workload", workload, "--steps", str(K), "--device", str(device)]
+    out, note = "", None
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        out = r.stdout
+        if r.returncode != 0:
+            note = "child exit code %d: %s" % (r.returncode, r.stderr.strip().splitlines()[-1] if r.stderr.strip() else "")
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        note = "child killed after %d s" % timeout
+    except Exception as e:  # noqa: BLE001 -- optional evidence, never a reason to fail the bench
+        note = "%s: %s" % (type(e).__name__, e)
+    res = {}
+    for ln in out.splitlines():
+        try:
+            d = json.loads(ln)
+            res[d.pop("variant")] = d
+        except Exception:  # noqa: BLE001
+            continue
+    if note:
+        res["note"] = note
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,7 +210,12 @@ def main():
     ap.add_argument("--workload", default="c3_10kcam", choices=list(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-experiments", action="store_true", help="skip the diagnostic pass over the compiled-in experiment switches")
+    ap.add_argument("--experiments-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.experiments_child:
+        return experiments_child(args.workload, args.steps, args.device)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -284,6 +367,10 @@ def main():
     cb = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         cb = cpu_baseline(3)
+    eng.close()
+    experiments = None
+    if world == 1 and rank == 0 and not args.no_experiments and not any(k in os.environ for k in SWITCHES):
+        experiments = run_experiments(args.workload, K, local_rank)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "obs/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t_max / iters, "steps_run": iters, "note": note, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -296,8 +383,8 @@ def main():
                 # per-stage device time (CUDA events on the engine stream inside the timed region), ms per LM iteration
                 "stage_ms_per_step": {k: v["ms"] / iters for k, v in stages.items()},
                 "experiment_switches": {k: os.environ[k] for k in ("TBA_TRED", "TBA_MATVEC_BULKRED", "TBA_FAST_SEG", "TBA_PACK_SORT") if k in os.environ}}
+        line["experiments"] = experiments
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

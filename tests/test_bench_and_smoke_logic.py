@@ -27,10 +27,12 @@ def test_bench_line_has_every_contract_field():
 import bench
 bench.run_microbench = lambda d: {"fp64_fma_tflops": 37.0, "fp64_red_gops": 200.0, "gather48_grows": 50.0, "how": "mock"}
 sys.argv = ["bench.py", "--workload", "c1_50cam", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]
+bench.run_experiments = lambda w, k, d: {"default": {"rc": 0}}
 bench.main()
 """)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["experiments"] == {"default": {"rc": 0}} and set(line["stage_ms_per_step"]) >= {"matvec", "linearize", "precond_ext", "rhs"}
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert key in line, key
@@ -44,3 +46,28 @@ def test_smoke_logic():
     out = _run("import __graft_entry__ as g\ng.smoke()\n")
     assert out.returncode == 0, out.stderr[-2000:]
     assert "smoke ok" in out.stdout
+
+
+def test_bench_experiments_child_logic():
+    """The diagnostic pass over the experiment switches (bench.py --experiments-child): one JSON line per variant."""
+    out = _run("""
+import bench
+bench.experiments_child("c1_50cam", 2, 0)
+""")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [json.loads(ln) for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert [d["variant"] for d in lines] == [v[0] for v in __import__("bench").VARIANTS]
+    for d in lines:
+        assert "error" not in d, d
+        assert d["rc"] == 0 and d["steps_run"] == 2 and d["max_rel_cost_diff_vs_default"] <= 1e-12
+        assert set(d["stage_ms_per_step"]) >= {"matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost"}
+
+
+def test_bench_experiments_parent_survives_a_failing_child():
+    """Without a GPU the real child cannot create an engine: every variant reports its error (or the child dies), the parent
+    returns a dictionary either way and never raises."""
+    sys.path.insert(0, ROOT)
+    import bench
+    res = bench.run_experiments("c1_50cam", 1, 0, timeout=240)
+    assert isinstance(res, dict) and res
+    assert all(("error" in v) for k, v in res.items() if k != "note") or "note" in res

@@ -41,6 +41,45 @@ __global__ void k_gather(const double* __restrict__ x, unsigned n_rows, int reps
   out[gid] = acc;
 }
 
+// Round-2 design questions, measured for free by the round-end bench run (tba_microbench_ex):
+// k_red_rows: the element-major ("transposed", TBA_TRED) emission -- lanes 6q..6q+5 of a warp add to the 6 consecutive doubles
+// of one random 48-byte row (2 sectors), i.e. 32 elements cover ~11 sectors instead of 32.  G elements/s, comparable to k_red.
+__global__ void k_red_rows(double* y, unsigned n_rows, int reps) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u, warp = gid >> 5;
+  const unsigned q = lane / 6u, j = lane - q * 6u;  // lanes 30, 31: a sixth row (2 of its elements)
+  for (int k = 0; k < reps; ++k) {
+    const unsigned row = ((warp * 6u + q) * 2654435761u + (unsigned)k * 40503u) % n_rows;
+    atomicAdd(y + (size_t)row * 6 + j, 1.0);
+  }
+}
+// k_smem_atomic: shared-memory fp64 atomicAdd (compiles to a CAS loop) to random slots of a 2048-double window per CTA,
+// flushed once at the end: would a shared-memory camera-window accumulator beat global REDs?  G ops/s.
+__global__ void k_smem_atomic(double* out, int reps) {
+  __shared__ double win[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) win[i] = 0.0;
+  __syncthreads();
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < reps; ++k) {
+    const unsigned idx = (gid * 2654435761u + (unsigned)k * 40503u) & 2047u;
+    atomicAdd(&win[idx], 1.0);
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) acc += win[i];
+  out[gid] = acc;
+}
+// k_red_win: the same global REDs as k_red but every CTA confined to a window of 1200 rows x 6 doubles that slides with
+// the CTA index (TBA_PACK_SORT locality: concurrent CTAs hit the same few thousand addresses).  G ops/s.
+__global__ void k_red_win(double* y, unsigned n, int reps) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned win = 7200u, base = (unsigned)(((unsigned long long)blockIdx.x * (n - win)) / gridDim.x);
+  for (int k = 0; k < reps; ++k) {
+    const unsigned idx = base + (gid * 2654435761u + (unsigned)k * 40503u) % win;
+    atomicAdd(y + idx, 1.0);
+  }
+}
+
 float time_ms(cudaEvent_t e0, cudaEvent_t e1) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); return ms; }
 
 }  // namespace
@@ -70,6 +109,45 @@ extern "C" int tba_microbench(int device, double* out3) {
     const double t2 = time_ms(e0, e1) * 1e-3;
     if (rep == 0) continue;
     const double v0 = (double)nthreads * iters * 8 * 2 / t0 * 1e-12, v1 = (double)nthreads * reps / t1 * 1e-9, v2 = (double)nthreads * reps / t2 * 1e-9;
+    if (v0 > best[0]) best[0] = v0;
+    if (v1 > best[1]) best[1] = v1;
+    if (v2 > best[2]) best[2] = v2;
+  }
+  const cudaError_t err = cudaDeviceSynchronize();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out); cudaFree(d_y);
+  if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) return -3;
+  out3[0] = best[0]; out3[1] = best[1]; out3[2] = best[2];
+  return 0;
+}
+
+// out[0] = element-major RED rate (k_red_rows), out[1] = shared-memory fp64 atomicAdd rate (k_smem_atomic),
+// out[2] = windowed global RED rate (k_red_win); all in G operations/s, best of 5 after a warm-up.  Diagnostics only.
+extern "C" int tba_microbench_ex(int device, double* out3) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -5;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 16, threads = 256;
+  const size_t nthreads = (size_t)blocks * threads;
+  const unsigned n_y = 60000;
+  double *d_out = nullptr, *d_y = nullptr;
+  if (cudaMalloc(&d_out, nthreads * sizeof(double)) != cudaSuccess || cudaMalloc(&d_y, (size_t)n_y * sizeof(double)) != cudaSuccess) return -3;
+  cudaMemset(d_y, 0, (size_t)n_y * sizeof(double));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = 64;
+  double best[3] = {0, 0, 0};
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0); k_red_rows<<<blocks, threads>>>(d_y, n_y / 6, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double t0 = time_ms(e0, e1) * 1e-3;
+    cudaEventRecord(e0); k_smem_atomic<<<blocks, threads>>>(d_out, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double t1 = time_ms(e0, e1) * 1e-3;
+    cudaEventRecord(e0); k_red_win<<<blocks, threads>>>(d_y, n_y, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double t2 = time_ms(e0, e1) * 1e-3;
+    if (rep == 0) continue;
+    const double v0 = (double)nthreads * reps / t0 * 1e-9, v1 = (double)nthreads * reps / t1 * 1e-9, v2 = (double)nthreads * reps / t2 * 1e-9;
     if (v0 > best[0]) best[0] = v0;
     if (v1 > best[1]) best[1] = v1;
     if (v2 > best[2]) best[2] = v2;

@@ -36,9 +36,9 @@ TBA_PACK_SORT=1 run 300 parity_packsort python -m pytest tests/test_gpu_parity.p
 TBA_PACK_SORT=1 run 400 bench_c3_packsort python bench.py --no-cpu-baseline
 # 4. ncu: launch list of the bench command and one full capture of the matvec / linearise kernels
 run 600 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-experiments
 run 600 ncu_full_schur ncu --set full --clock-control none --import-source on -k regex:k_schur -s 4 -c 2 -o "$OUT/r2_schur" -f \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-experiments
 run 600 ncu_full_linearize ncu --set full --clock-control none --import-source on -k regex:k_linearize -s 1 -c 1 -o "$OUT/r2_linearize" -f \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-experiments
 cat "$OUT/summary.txt"
