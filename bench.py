@@ -171,6 +171,44 @@ def experiments_child(workload, K, device):
         except Exception as e:  # noqa: BLE001
             line["error"] = "%s: %s" % (type(e).__name__, e)
         print(json.dumps(line), flush=True)
+    # secondary path (BASELINE.json configs[4]): the CUDA-core brute-force matcher on a sample of config 5's
+    # image pairs (5k x 5k SIFT-128 each, ratio test + symmetric intersection); host buffers in, match lists out
+    line = {"variant": "matcher_sample"}
+    try:
+        import ctypes as C
+        from theiasfm_b200 import matcher
+        rng = np.random.default_rng(0)
+        n_img, n, dim = 4, int(os.environ.get("TBA_BENCH_MATCHER_N", "5000")), 128  # the variable only shrinks the CPU test of this code
+        base = np.abs(rng.normal(size=(n, dim)))
+        # every image sees the same features in its own order, with noise: the ratio test keeps most true matches
+        desc = np.concatenate([base[rng.permutation(n)] + 0.05 * rng.normal(size=(n, dim)) for _ in range(n_img)]).astype(np.float32)
+        desc /= np.linalg.norm(desc, axis=1, keepdims=True)
+        off = (np.arange(n_img + 1) * n).astype(np.int64)
+        pr = np.array([(i, j) for i in range(n_img) for j in range(i + 1, n_img)], np.int32)
+        cap = len(pr) * n + 1
+        out = (matcher.tbm_match * cap)()
+        moff = np.zeros(len(pr) + 1, np.int64)
+        ok = np.zeros(len(pr), np.uint8)
+        opt = matcher.default_options()
+        L = matcher.lib()
+
+        def call():
+            return L.tbm_match_all(device, desc.ctypes.data_as(C.POINTER(C.c_float)), off.ctypes.data_as(C.POINTER(C.c_int64)), n_img, dim,
+                                   pr.ctypes.data_as(C.POINTER(C.c_int32)), len(pr), C.byref(opt), out, cap,
+                                   moff.ctypes.data_as(C.POINTER(C.c_int64)), ok.ctypes.data_as(C.POINTER(C.c_uint8)))
+        rc = call()  # warm-up
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            rc = call()
+        dt = (time.perf_counter() - t0) / reps
+        line.update({"rc": int(rc), "images": n_img, "descriptors_per_image": n, "dim": dim, "pairs": int(len(pr)), "seconds_per_call": dt,
+                     "pairs_per_s": len(pr) / dt, "matches": int(moff[-1]),
+                     "distance_evaluations_per_s": len(pr) * float(n) * n / dt,
+                     "note": "end to end through tbm_match_all with host buffers (H2D, top-2 kernel, D2H, host ratio test / intersection)"})
+    except Exception as e:  # noqa: BLE001
+        line["error"] = "%s: %s" % (type(e).__name__, e)
+    print(json.dumps(line), flush=True)
     return 0
 
 

@@ -38,7 +38,7 @@ struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;  // set by the scheduler before a fiber runs
 
 struct alignas(16) double2 { double x, y; };
-struct alignas(32) double4 { double x, y, z, w; };
+struct alignas(16) double4 { double x, y, z, w; };  // CUDA 12: __align__(16), two 128-bit accesses
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 
@@ -54,7 +54,13 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cu
 enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = std::getenv("TBA_EMU_DEVICES"); *n = e ? std::atoi(e) : 1; return cudaSuccess; }
-template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
+// 256-byte aligned like the real allocator (vector accesses of the kernels rely on it), zero-filled like calloc was
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
+  const size_t bytes = ((n ? n : 1) + 255) & ~(size_t)255;
+  *p = (T*)std::aligned_alloc(256, bytes);
+  if (*p) std::memset((void*)*p, 0, bytes);
+  return *p ? cudaSuccess : cudaErrorEmu;
+}
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }

@@ -51,12 +51,20 @@ def test_smoke_logic():
 def test_bench_experiments_child_logic():
     """The diagnostic pass over the experiment switches (bench.py --experiments-child): one JSON line per variant."""
     out = _run("""
-import bench
+import bench, os, subprocess
+# the matcher sample runs through the SIMT-emulation build of the matcher library (tests/emu), shrunk to 48 descriptors per image
+emu = os.path.join(%r, "tests", "emu")
+subprocess.check_call(["make", "-C", emu, "libtheia_matcher_b200_emu.so"], stdout=subprocess.DEVNULL)
+from theiasfm_b200 import matcher
+matcher.LIB_PATH = os.path.join(emu, "libtheia_matcher_b200_emu.so")
+os.environ["TBA_BENCH_MATCHER_N"] = "48"
 bench.experiments_child("c1_50cam", 2, 0)
-""")
+""" % ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [json.loads(ln) for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
-    assert [d["variant"] for d in lines] == [v[0] for v in __import__("bench").VARIANTS]
+    assert [d["variant"] for d in lines] == [v[0] for v in __import__("bench").VARIANTS] + ["matcher_sample"]
+    m = lines.pop()
+    assert "error" not in m and m["rc"] == 0 and m["pairs"] == 6 and m["matches"] > 0, m
     for d in lines:
         assert "error" not in d, d
         assert d["rc"] == 0 and d["steps_run"] == 2 and d["max_rel_cost_diff_vs_default"] <= 1e-12
@@ -70,4 +78,4 @@ def test_bench_experiments_parent_survives_a_failing_child():
     import bench
     res = bench.run_experiments("c1_50cam", 1, 0, timeout=240)
     assert isinstance(res, dict) and res
-    assert all(("error" in v) for k, v in res.items() if k != "note") or "note" in res
+    assert all(("error" in v or v.get("rc") != 0) for k, v in res.items() if k != "note") or "note" in res
