@@ -20,7 +20,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
+#include <numeric>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -133,6 +135,11 @@ inline void* sched_sp = nullptr;
 inline int cur = -1;
 inline const std::function<void()>* body = nullptr;
 inline std::vector<char> dyn_smem_buf;
+inline int sched_order_mode() {
+  const char* e = std::getenv("TBA_EMU_ORDER");
+  if (!e) return 0;
+  return e[0] == 'r' && e[1] == 'e' ? 1 : e[0] == 'r' && e[1] == 'a' ? 2 : 0;
+}
 constexpr size_t kStack = 512 * 1024;
 
 #ifdef EMU_FAST_SWITCH
@@ -175,9 +182,21 @@ inline void run_block(unsigned nthreads) {
 #endif
     f.done = false; f.wait = kRun;
   }
+  // TBA_EMU_ORDER=reverse|random: the order in which the runnable fibers of a block (and the blocks of a grid) are resumed.  A kernel that
+  // is correct on the GPU cannot depend on it; a missing __syncthreads() / __syncwarp() between a producer and a consumer does
+  // (ascending order hides "low thread writes, high thread reads", descending order the opposite, random order both sometimes).
+  static const int order_mode = sched_order_mode();
+  static thread_local std::vector<unsigned> perm;
+  static thread_local uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)(std::getenv("TBA_EMU_SEED") ? std::atoll(std::getenv("TBA_EMU_SEED")) : 1);
   for (;;) {
     bool progress = false, alive = false;
-    for (unsigned t = 0; t < nthreads; ++t) {
+    if (order_mode == 2) {
+      perm.resize(nthreads);
+      for (unsigned i = 0; i < nthreads; ++i) perm[i] = i;
+      for (unsigned i = nthreads; i > 1; --i) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(perm[i - 1], perm[rng % i]); }
+    }
+    for (unsigned i = 0; i < nthreads; ++i) {
+      const unsigned t = order_mode == 0 ? i : order_mode == 1 ? nthreads - 1 - i : perm[i];
       Fiber& f = fibers[t];
       if (f.done) continue;
       alive = true;
@@ -245,7 +264,13 @@ inline void launch(const void* kernel, unsigned grid, unsigned block, size_t sme
   body = &f;
   if (dyn_smem_buf.size() < smem + 256) dyn_smem_buf.resize(smem + 256);
   gridDim.x = grid; blockDim.x = block;
-  for (unsigned b = 0; b < grid; ++b) { blockIdx.x = b; run_block(block); }
+  const int order_mode = sched_order_mode();
+  for (unsigned i = 0; i < grid; ++i) {
+    // reverse: last block first; random: a fixed odd stride through the grid (a permutation when coprime with the grid size)
+    unsigned b = order_mode == 1 ? grid - 1 - i : i;
+    if (order_mode == 2) { unsigned stride = 7919u; while (std::gcd(stride, grid) != 1u) ++stride; b = (unsigned)(((uint64_t)i * stride + 3u) % grid); }
+    blockIdx.x = b; run_block(block);
+  }
   body = nullptr;
 }
 

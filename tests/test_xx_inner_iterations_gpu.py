@@ -36,9 +36,24 @@ def test_theia_default_options_match_the_oracle(oracle, name, solver):
     assert abs(sg.num_iterations - so.num_iterations) <= 3
     n = min(len(sg.costs), len(so.costs), 4)
     assert np.all(np.abs(sg.costs[:n] - so.costs[:n]) <= 1e-5 * so.costs[:n])
-    assert abs(sg.final_cost - so.final_cost) <= 2e-2 * so.final_cost
+    # Sensitivity measured by running the ENGINE itself with a different rounding (tests/emu FMA-contracted build vs the plain build, both
+    # against the oracle): every case stays within 5e-5 (final cost) / 3e-5 (parameters) after 12 iterations, EXCEPT all-free RADTAN
+    # intrinsics with the inexact PCG (eta = 0.1), where a 1e-6 difference at iteration 3 grows to 7e-4 at iteration 4 and to 5.6 % in the
+    # final cost (1.6e-2 in the parameters) at iteration 12 -- with the exact step (SPARSE_SCHUR) the same scene stays within 3e-6.
+    chaotic = name == "radtan_per_camera" and solver == _abi.ITERATIVE_SCHUR
+    assert abs(sg.final_cost - so.final_cost) <= (0.15 if chaotic else 2e-2) * so.final_cost
     assert sg.final_cost < 0.05 * sg.initial_cost and sg.costs[1] < 0.2 * sg.costs[0]
-    assert rel_err(pg.ext, po.ext) < 1e-2
+    assert rel_err(pg.ext, po.ext) < (0.1 if chaotic else 1e-2)
+    if chaotic:  # the part of the trajectory that IS reproducible, compared tightly: 4 iterations (measured: 7e-4 cost, 8e-5 parameters)
+        kw["max_num_iterations"] = 4
+        po4, pg4 = p.copy(), p.copy()
+        so4 = oracle.solve(po4, oracle.default_options(**kw))
+        eng = engine.Engine()
+        sg4 = eng.solve(pg4, engine.default_options(**kw))
+        eng.close()
+        assert sg4.rc == 0 and sg4.num_iterations == so4.num_iterations
+        assert abs(sg4.final_cost - so4.final_cost) <= 5e-3 * so4.final_cost
+        assert rel_err(pg4.ext, po4.ext) < 1e-3 and rel_err(pg4.pt, po4.pt) < 1e-3 and rel_err(pg4.intr, po4.intr) < 1e-3
     assert np.array_equal(pg.ext[1], p.ext[1]) and np.array_equal(pg.ext[2, :3], p.ext[2, :3]) and np.array_equal(pg.pt[[4, 9]], p.pt[[4, 9]])
 
 
