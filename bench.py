@@ -79,28 +79,38 @@ class ClockSampler:
                 "power_w_max": max([float(r[4]) for r in rows if r[4].replace(".", "").isdigit()], default=None)}
 
 
-def run_microbench(device):
-    """fp64 FMA peak, fp64 RED rate and 48-byte gather rate of this GPU (theiasfm_b200/csrc/tba_microbench.cu), measured
-    in a SEPARATE process before the solve so that it cannot disturb the timed region; None if anything goes wrong."""
-    code = ("import ctypes, json, sys; L = ctypes.CDLL(%r); out = (ctypes.c_double * 3)(); ex = (ctypes.c_double * 3)(); "
-            "rc = L.tba_microbench(%d, out); rx = L.tba_microbench_ex(%d, ex) if rc == 0 else -1; "
-            "print(json.dumps({'rc': rc, 'v': list(out), 'rx': rx, 'x': list(ex)}))"
-            % (os.path.join(ROOT, "theiasfm_b200", "libtheia_microbench_b200.so"), device, device))
+def _microbench_call(symbol, n_out, device):
+    code = ("import ctypes, json; L = ctypes.CDLL(%r); out = (ctypes.c_double * %d)(); rc = L.%s(%d, out); "
+            "print(json.dumps({'rc': rc, 'v': list(out)}))"
+            % (os.path.join(ROOT, "theiasfm_b200", "libtheia_microbench_b200.so"), n_out, symbol, device))
     try:
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
         d = json.loads(r.stdout.strip().splitlines()[-1])
-        if d["rc"] != 0:
-            return None
-        ex = d.get("x") if d.get("rx") == 0 else None
-        return {"fp64_fma_tflops": d["v"][0], "fp64_red_gops": d["v"][1], "gather48_grows": d["v"][2],
-                # design questions for the next kernel generation (NOTES.md section 3): REDs emitted element-major (6 lanes per
-                # 48-byte row), shared-memory fp64 atomicAdd (CAS loop), global REDs confined to a 1200-camera window per CTA
-                "fp64_red_rows_gops": ex[0] if ex else None, "fp64_smem_atomic_gops": ex[1] if ex else None,
-                "fp64_red_window_gops": ex[2] if ex else None,
-                "how": "tba_microbench: 8 DFMA chains/thread; RED.ADD.F64 and 3xLDG.128 gathers over a 60k-double vector, "
-                       "32 distinct rows per warp; best of 5 after warm-up"}
-    except Exception:  # noqa: BLE001 -- the micro-benchmark is optional evidence, never a reason to fail the bench
+        return d["v"] if d["rc"] == 0 else None
+    except Exception:  # noqa: BLE001 -- the micro-benchmarks are optional evidence, never a reason to fail the bench
         return None
+
+
+def run_microbench(device):
+    """fp64 FMA peak, fp64 RED rate and 48-byte gather rate of this GPU (theiasfm_b200/csrc/tba_microbench.cu), measured
+    in SEPARATE processes before the solve so that they cannot disturb the timed region; None if anything goes wrong.
+    The second call (tba_microbench_ex) answers design questions for the next kernel generation and may fail on its own."""
+    v = _microbench_call("tba_microbench", 3, device)
+    if v is None:
+        return None
+    ex = _microbench_call("tba_microbench_ex", 6, device)
+    return {"fp64_fma_tflops": v[0], "fp64_red_gops": v[1], "gather48_grows": v[2],
+            # design questions for the next kernel generation (NOTES.md section 3): REDs emitted element-major (6 lanes per
+            # 48-byte row), shared-memory fp64 atomicAdd (CAS loop), global REDs confined to a 1200-camera window per CTA
+            "fp64_red_rows_gops": ex[0] if ex else None, "fp64_smem_atomic_gops": ex[1] if ex else None,
+            "fp64_red_window_gops": ex[2] if ex else None,
+            # gather strategies for the 48-byte camera rows, G rows/s like gather48_grows (the shipped 3 x LDG.128 lane-per-row):
+            # chunk-major loads transposed through shared memory, 64-byte padded rows with one 256-bit + one 128-bit load,
+            # element-major 64-bit loads
+            "gather48_coop_grows": ex[3] if ex else None, "gather64_ld256_grows": ex[4] if ex else None,
+            "gather48_elem_grows": ex[5] if ex else None,
+            "how": "tba_microbench: 8 DFMA chains/thread; RED.ADD.F64 and 3xLDG.128 gathers over a 60k-double vector, "
+                   "32 distinct rows per warp; best of 5 after warm-up"}
 
 
 def load_peaks():

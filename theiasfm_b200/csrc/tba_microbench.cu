@@ -80,6 +80,65 @@ __global__ void k_red_win(double* y, unsigned n, int reps) {
   }
 }
 
+// Gather strategies for the matvec's 48-byte camera rows (k_gather above = the shipped one: 3 x LDG.128 per lane, lane-per-row).
+// k_gather_coop: chunk-major -- lane l of load k fetches 16-byte chunk 32k + l of the warp's 32 rows (3 lanes cover one row: ~21 sectors
+// per instruction instead of 32), transposed back through shared memory (3 x STS.128 + 3 x LDS.128 per lane).
+__global__ void k_gather_coop(const double* __restrict__ x, unsigned n_rows, int reps, double* out) {
+  __shared__ __align__(16) double s_rows[8][32 * 6];
+  __shared__ unsigned s_row[8][32];
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int k = 0; k < reps; ++k) {
+    s_row[w][lane] = (gid * 2654435761u + (unsigned)k * 40503u) % n_rows;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned e = c * 32u + lane, o = e / 3u, part = e - o * 3u;
+      const double2 v = __ldg(reinterpret_cast<const double2*>(x + (size_t)s_row[w][o] * 6) + part);
+      *reinterpret_cast<double2*>(&s_rows[w][e * 2]) = v;
+    }
+    __syncwarp();
+    const double2* r = reinterpret_cast<const double2*>(&s_rows[w][lane * 6]);
+    const double2 a = r[0], b = r[1], c2 = r[2];
+    acc += a.x + a.y + b.x + b.y + c2.x + c2.y;
+    __syncwarp();
+  }
+  out[gid] = acc;
+}
+// k_gather_256: rows padded to 64 bytes (8 doubles, 64-byte aligned): one 256-bit load (sm_100 LDG.E.ENL2.256) + one 128-bit load
+// per lane, 2 sectors of ONE 128-byte line per row.
+__global__ void k_gather_256(const double* __restrict__ x8, unsigned n_rows, int reps, double* out) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  for (int k = 0; k < reps; ++k) {
+    const unsigned row = (gid * 2654435761u + (unsigned)k * 40503u) % n_rows;
+    const double* p = x8 + (size_t)row * 8;
+    double a, b, c, d;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+    const double2 e = __ldg(reinterpret_cast<const double2*>(p + 4));
+    acc += a + b + c + d + e.x + e.y;
+  }
+  out[gid] = acc;
+}
+// k_gather_elem: element-major 64-bit loads (6 x LDG.64: lane l of load k fetches double 32k + l of the warp's 32 rows), no transposition
+// back (the sum does not need it): isolates the load side of the chunk-major idea.
+__global__ void k_gather_elem(const double* __restrict__ x, unsigned n_rows, int reps, double* out) {
+  __shared__ unsigned s_row[8][32];
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int k = 0; k < reps; ++k) {
+    s_row[w][lane] = (gid * 2654435761u + (unsigned)k * 40503u) % n_rows;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const unsigned e = c * 32u + lane, o = e / 6u;
+      acc += __ldg(x + (size_t)s_row[w][o] * 6 + (e - o * 6u));
+    }
+    __syncwarp();
+  }
+  out[gid] = acc;
+}
+
 float time_ms(cudaEvent_t e0, cudaEvent_t e1) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); return ms; }
 
 }  // namespace
@@ -122,8 +181,10 @@ extern "C" int tba_microbench(int device, double* out3) {
 }
 
 // out[0] = element-major RED rate (k_red_rows), out[1] = shared-memory fp64 atomicAdd rate (k_smem_atomic),
-// out[2] = windowed global RED rate (k_red_win); all in G operations/s, best of 5 after a warm-up.  Diagnostics only.
-extern "C" int tba_microbench_ex(int device, double* out3) {
+// out[2] = windowed global RED rate (k_red_win), all in G operations/s; out[3..5] = 48-byte row gather rates in G rows/s of
+// k_gather_coop / k_gather_256 / k_gather_elem (compare with tba_microbench's out[2]); best of 5 after a warm-up.  Diagnostics only.
+extern "C" int tba_microbench_ex(int device, double* out6) {
+  double* out3 = out6;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -5;
   if (cudaSetDevice(device) != cudaSuccess) return -3;
@@ -138,8 +199,23 @@ extern "C" int tba_microbench_ex(int device, double* out3) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int reps = 64;
-  double best[3] = {0, 0, 0};
+  double best[6] = {0, 0, 0, 0, 0, 0};
+  double* d_x8 = nullptr;
+  if (cudaMalloc(&d_x8, (size_t)(n_y / 6) * 8 * sizeof(double)) != cudaSuccess) return -3;
+  cudaMemset(d_x8, 0, (size_t)(n_y / 6) * 8 * sizeof(double));
   for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0); k_gather_coop<<<blocks, threads>>>(d_y, n_y / 6, reps, d_out); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double g0 = time_ms(e0, e1) * 1e-3;
+    cudaEventRecord(e0); k_gather_256<<<blocks, threads>>>(d_x8, n_y / 6, reps, d_out); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double g1 = time_ms(e0, e1) * 1e-3;
+    cudaEventRecord(e0); k_gather_elem<<<blocks, threads>>>(d_y, n_y / 6, reps, d_out); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    const double g2 = time_ms(e0, e1) * 1e-3;
+    if (rep > 0) {
+      const double w0 = (double)nthreads * reps / g0 * 1e-9, w1 = (double)nthreads * reps / g1 * 1e-9, w2 = (double)nthreads * reps / g2 * 1e-9;
+      if (w0 > best[3]) best[3] = w0;
+      if (w1 > best[4]) best[4] = w1;
+      if (w2 > best[5]) best[5] = w2;
+    }
     cudaEventRecord(e0); k_red_rows<<<blocks, threads>>>(d_y, n_y / 6, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
     const double t0 = time_ms(e0, e1) * 1e-3;
     cudaEventRecord(e0); k_smem_atomic<<<blocks, threads>>>(d_out, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
@@ -154,8 +230,8 @@ extern "C" int tba_microbench_ex(int device, double* out3) {
   }
   const cudaError_t err = cudaDeviceSynchronize();
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(d_out); cudaFree(d_y);
+  cudaFree(d_out); cudaFree(d_y); cudaFree(d_x8);
   if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) return -3;
-  out3[0] = best[0]; out3[1] = best[1]; out3[2] = best[2];
+  for (int i = 0; i < 6; ++i) out3[i] = best[i];
   return 0;
 }
