@@ -139,9 +139,11 @@ def cpu_baseline(steps, warmup=0):
             "linear_solver_iterations": s.num_linear_solver_iterations}
 
 
-SWITCHES = ("TBA_TRED", "TBA_MATVEC_BULKRED", "TBA_FAST_SEG", "TBA_PACK_SORT")
+SWITCHES = ("TBA_TRED", "TBA_MATVEC_BULKRED", "TBA_FAST_SEG", "TBA_PACK_SORT", "TBA_LIN_OCC")
 VARIANTS = (("default", {}), ("tred", {"TBA_TRED": "1"}), ("fast_seg", {"TBA_FAST_SEG": "1"}), ("pack_sort", {"TBA_PACK_SORT": "1"}),
-            ("tred+pack_sort", {"TBA_TRED": "1", "TBA_PACK_SORT": "1"}), ("bulkred", {"TBA_MATVEC_BULKRED": "1"}))
+            ("tred+pack_sort", {"TBA_TRED": "1", "TBA_PACK_SORT": "1"}),
+            ("tred+fast_seg", {"TBA_TRED": "1", "TBA_FAST_SEG": "1"}),
+            ("lin_occ3", {"TBA_LIN_OCC": "3"}), ("tred+lin_occ3", {"TBA_TRED": "1", "TBA_LIN_OCC": "3"}), ("bulkred", {"TBA_MATVEC_BULKRED": "1"}))
 
 
 def experiments_child(workload, K, device):
@@ -430,7 +432,7 @@ def main():
                 "wall_seconds_timed_region": wall, "n_obs": n_obs_total,
                 # per-stage device time (CUDA events on the engine stream inside the timed region), ms per LM iteration
                 "stage_ms_per_step": {k: v["ms"] / iters for k, v in stages.items()},
-                "experiment_switches": {k: os.environ[k] for k in ("TBA_TRED", "TBA_MATVEC_BULKRED", "TBA_FAST_SEG", "TBA_PACK_SORT") if k in os.environ}}
+                "experiment_switches": {k: os.environ[k] for k in SWITCHES if k in os.environ}}
         line["experiments"] = experiments
         print(json.dumps(line))
     if world > 1:

@@ -16,9 +16,12 @@ VARIANTS = {
     "fast_seg": {"TBA_FAST_SEG": "1"},
     "pack_sort": {"TBA_PACK_SORT": "1"},
     "tred+pack_sort": {"TBA_TRED": "1", "TBA_PACK_SORT": "1"},
+    "tred+fast_seg": {"TBA_TRED": "1", "TBA_FAST_SEG": "1"},
+    "lin_occ3": {"TBA_LIN_OCC": "3"},
+    "tred+lin_occ3": {"TBA_TRED": "1", "TBA_LIN_OCC": "3"},
     "bulkred": {"TBA_MATVEC_BULKRED": "1"},
 }
-ALL = ("TBA_TRED", "TBA_FAST_SEG", "TBA_PACK_SORT", "TBA_MATVEC_BULKRED")
+ALL = ("TBA_TRED", "TBA_FAST_SEG", "TBA_PACK_SORT", "TBA_MATVEC_BULKRED", "TBA_LIN_OCC")
 
 
 @pytest.fixture

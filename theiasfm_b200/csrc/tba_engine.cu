@@ -145,6 +145,7 @@ struct tba_context {
   bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
   bool exp_fast_seg = false;  // TBA_FAST_SEG=1: segmented reductions without key shuffles in k_linearize / the matvec (default off)
   bool exp_tred = false;  // TBA_TRED=1: transposed RED emission (warp_red_rows) in k_linearize / k_precond_ext / rhs / matvec (round-2 experiment, default off)
+  bool exp_lin_occ = false;  // TBA_LIN_OCC=3: k_linearize compiled for 3 CTAs/SM (80 registers, ~130 bytes of spills) instead of 2 (128 registers) (default off)
   bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
@@ -275,6 +276,18 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
     if (c->has_ext_models) {  // FISHEYE / FOV / DIVISION_UNDISTORTION present: the dual-number instantiation, all 10 columns
       auto kfn = k_linearize<0x3FFu, true>;
       LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p);
+    } else if (c->exp_lin_occ && c->exp_tred) {
+#define F(M) { auto kfn = k_linearize<M, false, false, true, 3>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    } else if (c->exp_lin_occ) {
+#define F(M) { auto kfn = k_linearize<M, false, false, false, 3>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    } else if (c->exp_tred && c->exp_fast_seg) {
+#define F(M) { auto kfn = k_linearize<M, false, true, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
     } else if (c->exp_tred) {
 #define F(M) { auto kfn = k_linearize<M, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
       DISPATCH_IMASK(c->imask, F)
@@ -389,7 +402,11 @@ int launch_matvec(tba_context* c, const int* done) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-    if (c->exp_tred) {
+    if (c->exp_tred && c->exp_fast_seg) {
+#define F(M) { auto kfn = k_schur<M, 0, false, true, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    } else if (c->exp_tred) {
 #define F(M) { auto kfn = k_schur<M, 0, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
@@ -730,6 +747,7 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   tba_options_init(&c->opt);
   { const char* e = getenv("TBA_MATVEC_BULKRED"); c->exp_bulkred = e != nullptr && e[0] == '1'; }
   { const char* e = getenv("TBA_FAST_SEG"); c->exp_fast_seg = e != nullptr && e[0] == '1'; }
+  { const char* e = getenv("TBA_LIN_OCC"); c->exp_lin_occ = e != nullptr && e[0] == '3'; }
   { const char* e = getenv("TBA_TRED"); c->exp_tred = e != nullptr && e[0] == '1'; }
   { const char* e = getenv("TBA_PACK_SORT"); c->exp_pack_sort = e != nullptr && e[0] == '1'; }
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -959,6 +977,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

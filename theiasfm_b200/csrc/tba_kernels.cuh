@@ -165,8 +165,8 @@ __device__ __forceinline__ size_t wslice(int tile, int warp, int rows) { return 
 // gradient / squared column norms (fp64 RED to global) and cost / failure counters (replicas).
 // Normal tiles: a point never straddles a warp -> per-point sums by warp-shuffle segmented reduction only, no
 // block barrier.  Long tiles (tracks > 32 observations): combined across warps in shared memory.
-template <uint32_t IMASK, bool EXT = false, bool FASTSEG = false, bool TRED = false>
-__global__ void __launch_bounds__(TILE) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
+template <uint32_t IMASK, bool EXT = false, bool FASTSEG = false, bool TRED = false, int MINB = 1>
+__global__ void __launch_bounds__(TILE, MINB) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
                                                     double* __restrict__ rep) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
