@@ -224,7 +224,7 @@ def experiments_child(workload, K, device):
     return 0
 
 
-def run_experiments(workload, K, device, timeout=300):
+def run_experiments(workload, K, device, timeout=180):
     """Parent side: spawn the child, keep whatever lines it managed to print."""
     env = {k: v for k, v in os.environ.items() if k not in SWITCHES and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     cmd = [sys.executable, os.path.abspath(__file__), "--experiments-child", "--workload", workload, "--steps", str(K), "--device", str(device)]

@@ -19,8 +19,9 @@ VARIANTS = {
     "tred+fast_seg": {"TBA_TRED": "1", "TBA_FAST_SEG": "1"},
     "lin_occ3": {"TBA_LIN_OCC": "3"},
     "tred+lin_occ3": {"TBA_TRED": "1", "TBA_LIN_OCC": "3"},
-    "bulkred": {"TBA_MATVEC_BULKRED": "1"},
 }
+# the TMA bulk-reduction matvec (cp.reduce.async.bulk) is the only switch with new PTX: its cases come last in the file
+BULKRED = {"bulkred": {"TBA_MATVEC_BULKRED": "1"}}
 ALL = ("TBA_TRED", "TBA_FAST_SEG", "TBA_PACK_SORT", "TBA_MATVEC_BULKRED", "TBA_LIN_OCC")
 
 
@@ -28,7 +29,7 @@ ALL = ("TBA_TRED", "TBA_FAST_SEG", "TBA_PACK_SORT", "TBA_MATVEC_BULKRED", "TBA_L
 def variant_engine(request, monkeypatch):
     for k in ALL:
         monkeypatch.delenv(k, raising=False)
-    for k, v in VARIANTS[request.param].items():
+    for k, v in {**VARIANTS, **BULKRED}[request.param].items():
         monkeypatch.setenv(k, v)
     e = engine.Engine()  # the switches are read when the context is created
     yield e
@@ -68,3 +69,11 @@ def test_switch_long_tracks(variant_engine, oracle):
     """Long tiles (tracks > 32 observations) take the plain RED path in k_linearize and the staged one elsewhere."""
     from test_gpu_parity import test_long_tracks_use_the_cta_level_path as body
     body(variant_engine, oracle)
+
+
+@pytest.mark.parametrize("variant_engine", list(BULKRED), indirect=True)
+def test_bulkred_stage_and_solve_parity(variant_engine, oracle):
+    from test_gpu_parity import test_stage_parity as stage_body
+    stage_body(variant_engine, oracle, "radtan_per_camera", True, _abi.LOSS_HUBER)
+    stage_body(variant_engine, oracle, "pinhole_shared", False, _abi.LOSS_TRIVIAL)
+    test_switch_full_solve_parity(variant_engine, oracle, "pinhole_shared", _abi.LOSS_TRIVIAL)
