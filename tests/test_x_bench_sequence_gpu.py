@@ -1,6 +1,6 @@
 """The engine call sequence bench.py's timed region makes (bench.py:211-229): upload -> minimize (warm-up) -> reset_parameters ->
 upload -> reset_parameters -> set_profiling -> minimize -> profile.  The warm-up must leave no trace: the timed minimise starts
-from the initial estimate and reproduces a fresh solve bit for bit; the profile counters describe what ran."""
+from the initial estimate and reproduces a fresh solve (to the rounding of the unordered fp64 REDs); the profile counters describe what ran."""
 import numpy as np
 import pytest
 
@@ -35,8 +35,12 @@ def test_warmup_reset_timed_sequence_matches_a_fresh_solve():
     eng.set_profiling(False)
     eng.download()
     eng.close()
-    assert s.num_iterations == s0.num_iterations and np.array_equal(s.costs, s0.costs)
-    assert np.array_equal(shard.pt, fresh.pt) and np.array_equal(shard.ext, fresh.ext) and np.array_equal(shard.intr, fresh.intr)
+    # Two solves on the GPU agree only up to the order of the fp64 RED accumulations (not reproducible run to run): measured with the
+    # emulator's random scheduling order (TBA_EMU_ORDER=random; the ascending order hid it and an exact comparison passed there) the costs
+    # differ in the 12th digit here and by <= 1e-10 on a 100k-observation scene; a warm-up that leaked state would be off by far more.
+    assert s.num_iterations == s0.num_iterations and np.all(np.abs(s.costs - s0.costs) <= 1e-9 * s0.costs)
+    for a, b in ((shard.pt, fresh.pt), (shard.ext, fresh.ext), (shard.intr, fresh.intr)):
+        assert np.abs(a - b).max() <= 1e-7 * np.abs(b).max()
     assert prof["observations"] == p.n_obs and prof["points"] == p.n_pt and prof["slots"] >= p.n_obs
     assert prof["linearize_launches"] == s.num_iterations          # one linearisation per evaluated point incl. the initial one
     assert prof["matvec_launches"] >= sum(it["linear_solver_iterations"] for it in s.iterations)   # + the rhs / residual products
