@@ -60,11 +60,18 @@ inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = std::getenv("TBA
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
   const size_t bytes = ((n ? n : 1) + 255) & ~(size_t)255;
   *p = (T*)std::aligned_alloc(256, bytes);
-  if (*p) std::memset((void*)*p, 0, bytes);
+  // cudaMalloc does NOT zero memory: TBA_EMU_POISON=1 fills every allocation with 0xFF bytes (NaN doubles, -1 ints) so that a kernel
+  // relying on zero-initialised buffers without a cudaMemset fails here as it would (sooner or later) on the GPU
+  static const bool poison = std::getenv("TBA_EMU_POISON") != nullptr;
+  if (*p) std::memset((void*)*p, poison ? 0xFF : 0, bytes);
   return *p ? cudaSuccess : cudaErrorEmu;
 }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
-template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) {
+  *p = (T*)std::calloc(n ? n : 1, 1);
+  if (*p && std::getenv("TBA_EMU_POISON")) std::memset((void*)*p, 0xFF, n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorEmu;
+}
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
@@ -127,6 +134,7 @@ struct Fiber {
   int op = 0;            // warp collective kind: 0 sync, 1 shfl (payload / src lane), 2 ballot, 3 all
   uint64_t payload = 0;  // value contributed
   int src = 0;           // shfl: lane to read from (already resolved; -1 = keep own)
+  int line = 0;          // source line of the collective's call site (TBA_EMU_STRICT: all lanes of one collective must agree)
   uint64_t result = 0;
 };
 inline std::vector<Fiber> fibers;
@@ -219,6 +227,19 @@ inline void run_block(unsigned nthreads) {
       bool any_live = false, all_wait = true;
       for (unsigned t = w0; t < w1; ++t) if (!fibers[t].done) { any_live = true; if (fibers[t].wait != kWarpOp) all_wait = false; }
       if (!any_live || !all_wait) continue;
+      static const bool strict = std::getenv("TBA_EMU_STRICT") != nullptr;
+      if (strict) {  // the lanes of one warp collective must come from ONE call site with ONE operation: on the GPU lanes that reach
+                     // different *_sync call sites under a full mask do not exchange data with each other (undefined / deadlock)
+        int op0 = -1, line0 = -1;
+        for (unsigned t = w0; t < w1; ++t) if (!fibers[t].done) {
+          if (op0 < 0) { op0 = fibers[t].op; line0 = fibers[t].line; }
+          else if (fibers[t].op != op0 || fibers[t].line != line0) {
+            std::fprintf(stderr, "cuda_emu: divergent warp collective in block %u warp %u: op %d line %d vs op %d line %d\n", blockIdx.x, w0 / 32, op0,
+                         line0, fibers[t].op, fibers[t].line);
+            std::abort();
+          }
+        }
+      }
       uint64_t ballot = 0; bool all = true;
       for (unsigned t = w0; t < w1; ++t) if (!fibers[t].done) { if (fibers[t].payload) ballot |= 1ull << (t - w0); else all = false; }
       for (unsigned t = w0; t < w1; ++t) {
@@ -274,28 +295,28 @@ inline void launch(const void* kernel, unsigned grid, unsigned block, size_t sme
   body = nullptr;
 }
 
-inline uint64_t warp_op(int op, uint64_t payload, int src) {
+inline uint64_t warp_op(int op, uint64_t payload, int src, int line = 0) {
   Fiber& f = fibers[cur];
-  f.op = op; f.payload = payload; f.src = src;
+  f.op = op; f.payload = payload; f.src = src; f.line = line;
   suspend(kWarpOp);
   return fibers[cur].result;
 }
 }  // namespace emu
 
 inline void __syncthreads() { emu::suspend(emu::kBlockBarrier); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_op(0, 0, -1); }
+inline void __syncwarp(unsigned = 0xffffffffu, int line = __builtin_LINE()) { emu::warp_op(0, 0, -1, line); }
 inline void emu_yield() { emu::suspend(emu::kSpin); }
 template <class T> inline uint64_t emu_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, ""); std::memcpy(&b, &v, sizeof(T)); return b; }
 template <class T> inline T emu_from(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
-template <class T> inline T __shfl_sync(unsigned, T v, int src_lane, int = 32) { return emu_from<T>(emu::warp_op(1, emu_bits(v), src_lane & 31)); }
-template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32) {
+template <class T> inline T __shfl_sync(unsigned, T v, int src_lane, int = 32, int line = __builtin_LINE()) { return emu_from<T>(emu::warp_op(1, emu_bits(v), src_lane & 31, line)); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32, int line = __builtin_LINE()) {
   const int lane = threadIdx.x & 31; const int s = lane + (int)delta;
-  return emu_from<T>(emu::warp_op(1, emu_bits(v), s < 32 ? s : -1));
+  return emu_from<T>(emu::warp_op(1, emu_bits(v), s < 32 ? s : -1, line));
 }
-template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta, int = 32) {
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta, int = 32, int line = __builtin_LINE()) {
   const int lane = threadIdx.x & 31; const int s = lane - (int)delta;
-  return emu_from<T>(emu::warp_op(1, emu_bits(v), s >= 0 ? s : -1));
+  return emu_from<T>(emu::warp_op(1, emu_bits(v), s >= 0 ? s : -1, line));
 }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emu_from<T>(emu::warp_op(1, emu_bits(v), (threadIdx.x & 31) ^ m)); }
-inline unsigned __ballot_sync(unsigned, int pred) { return (unsigned)emu::warp_op(2, pred ? 1 : 0, -1); }
-inline int __all_sync(unsigned, int pred) { return (int)emu::warp_op(3, pred ? 1 : 0, -1); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32, int line = __builtin_LINE()) { return emu_from<T>(emu::warp_op(1, emu_bits(v), (threadIdx.x & 31) ^ m, line)); }
+inline unsigned __ballot_sync(unsigned, int pred, int line = __builtin_LINE()) { return (unsigned)emu::warp_op(2, pred ? 1 : 0, -1, line); }
+inline int __all_sync(unsigned, int pred, int line = __builtin_LINE()) { return (int)emu::warp_op(3, pred ? 1 : 0, -1, line); }

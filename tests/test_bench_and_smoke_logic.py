@@ -79,3 +79,37 @@ def test_bench_experiments_parent_survives_a_failing_child():
     res = bench.run_experiments("c1_50cam", 1, 0, timeout=240)
     assert isinstance(res, dict) and res
     assert all(("error" in v or v.get("rc") != 0) for k, v in res.items() if k != "note") or "note" in res
+
+
+def test_bench_main_and_experiments_child_against_the_emulated_engine():
+    """The same two entry points through the REAL ctypes binding and the real engine code (tests/emu SIMT-emulation build) instead of the
+    mock: catches attribute / signature drift between engine.py and what bench.py expects (it did: minimize()'s summary had no rc)."""
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["make", "-C", emu], stdout=subprocess.DEVNULL)
+    code = """
+import sys, os, json
+sys.path.insert(0, %r)
+import torch
+torch.cuda.set_device = lambda d: None
+torch.cuda.synchronize = lambda *a, **k: None
+from theiasfm_b200 import engine, matcher
+engine.LIB_PATH = os.path.join(%r, "libtheia_ba_b200_emu.so"); engine._LIB = None
+matcher.LIB_PATH = os.path.join(%r, "libtheia_matcher_b200_emu.so"); matcher._LIB = None
+os.environ["TBA_BENCH_MATCHER_N"] = "32"
+import bench
+bench.run_microbench = lambda d: None
+bench.run_experiments = lambda w, k, d: {"skipped": True}
+sys.argv = ["bench.py", "--workload", "c1_50cam", "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-e2e"]
+bench.main()
+bench.experiments_child("c1_50cam", 1, 0)
+""" % (ROOT, emu, emu)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [json.loads(ln) for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    main, child = lines[0], lines[1:]
+    assert main["steps_run"] == 1 and main["gpu_launches"] > 0 and set(main["stage_ms_per_step"]) == set(__import__("bench").VARIANTS and
+                                                                                                      ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost"))
+    assert [d["variant"] for d in child] == [v[0] for v in __import__("bench").VARIANTS] + ["matcher_sample"]
+    for d in child:
+        assert "error" not in d and d["rc"] == 0, d
+    assert all(d["max_rel_cost_diff_vs_default"] <= 1e-9 for d in child[:-1])

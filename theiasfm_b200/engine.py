@@ -238,7 +238,9 @@ class Engine:
     def minimize(self):
         s = self._new_summary()
         self._check(lib().tba_minimize(self._h, C.byref(s)))
-        return Summary(s, self._iters)
+        out = Summary(s, self._iters)
+        out.rc = 0  # a failure raised above; same attribute as the summary of solve()
+        return out
 
     def download(self, problem=None):
         problem = problem or self._problem
