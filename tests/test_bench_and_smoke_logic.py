@@ -113,3 +113,18 @@ bench.experiments_child("c1_50cam", 1, 0)
     for d in child:
         assert "error" not in d and d["rc"] == 0, d
     assert all(d["max_rel_cost_diff_vs_default"] <= 1e-9 for d in child[:-1])
+
+
+def test_smoke_against_the_emulated_engine():
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["make", "-C", emu], stdout=subprocess.DEVNULL)
+    code = """
+import sys, os
+sys.path.insert(0, %r)
+from theiasfm_b200 import engine
+engine.LIB_PATH = os.path.join(%r, "libtheia_ba_b200_emu.so"); engine._LIB = None
+import __graft_entry__ as g
+g.smoke()
+""" % (ROOT, emu)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "smoke ok" in out.stdout, out.stderr[-2000:]
