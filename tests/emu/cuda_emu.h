@@ -286,10 +286,12 @@ inline void launch(const void* kernel, unsigned grid, unsigned block, size_t sme
   if (dyn_smem_buf.size() < smem + 256) dyn_smem_buf.resize(smem + 256);
   gridDim.x = grid; blockDim.x = block;
   const int order_mode = sched_order_mode();
+  static const bool poison_smem = std::getenv("TBA_EMU_POISON") != nullptr;
   for (unsigned i = 0; i < grid; ++i) {
     // reverse: last block first; random: a fixed odd stride through the grid (a permutation when coprime with the grid size)
     unsigned b = order_mode == 1 ? grid - 1 - i : i;
     if (order_mode == 2) { unsigned stride = 7919u; while (std::gcd(stride, grid) != 1u) ++stride; b = (unsigned)(((uint64_t)i * stride + 3u) % grid); }
+    if (poison_smem && smem) std::memset(dyn_smem_buf.data(), 0xFF, smem);  // shared memory is not zeroed at block start either
     blockIdx.x = b; run_block(block);
   }
   body = nullptr;
