@@ -41,7 +41,9 @@ void FlattenTwoViewProblem(const TwoViewBundleAdjustmentOptions& options, const 
     f->id_of_group.push_back(static_cast<CameraIntrinsicsGroupId>(i));
     f->group_model.push_back(static_cast<int32_t>(cams[i]->GetCameraIntrinsicsModelType()));
     for (int j = 0; j < TBA_INTR_STRIDE; ++j) f->intr.push_back(j < K ? cams[i]->intrinsics()[j] : 0.0);
-    const bool all_const = shared ? (const_intr[0] && const_intr[1]) : const_intr[i];
+    // shared block: AddCameraParametersToProblem runs for both cameras on the SAME parameter block and
+    // SetParameterBlockConstant from either call sticks (bundle_adjust_two_views.cc:96-108): constant if EITHER flag is set
+    const bool all_const = shared ? (const_intr[0] || const_intr[1]) : const_intr[i];
     const uint32_t all = (1u << K) - 1u;
     f->group_const_mask.push_back(all_const ? all : (all & ~1u));  // focal length (index 0) is the only free one (.cc:96-108)
   }

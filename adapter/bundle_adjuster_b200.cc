@@ -303,6 +303,11 @@ int BundleAdjusterB200::SetOutlierTracksToUnestimated(const double max_inlier_re
   }
   int removed = 0;
   for (size_t q = 0; q < resident_tracks_.size(); ++q) {
+    // Only tracks added through AddTrack are resident with ALL their estimated views (bundle_adjuster.cc:141-180); a track
+    // that came in through AddView alone carries only the observations of the optimised views, so its statistics here would be
+    // those of a subset (the reference evaluates a track over all of its estimated views,
+    // set_outlier_tracks_to_unestimated.cc:62-136): such tracks are left alone.
+    if (optimized_tracks_.count(resident_tracks_[q]) == 0) continue;
     Track* track = reconstruction_->MutableTrack(resident_tracks_[q]);
     if (track == nullptr || !track->IsEstimated()) continue;  // :77-79: only estimated tracks are examined
     if (status[q] != 0) { track->SetEstimated(false); ++removed; }  // :100-101,111-112,121-122

@@ -297,6 +297,8 @@ int tba_two_view_ba_batch_multi(tba_two_view_batch* batch, int n_devices, uint8_
 
 /* Re-load ext / intr / pt of an uploaded problem (same shape) without re-packing. */
 int tba_reset_parameters(tba_context* ctx, const tba_problem* problem);
+/* Change Solver::Options::max_num_iterations (bundle_adjustment.h:110) of an uploaded problem without re-packing. */
+int tba_set_max_iterations(tba_context* ctx, int32_t max_num_iterations);
 
 /* Per-kernel device timing (CUDA events on the engine stream) for the roofline report:
  * out[0..3] = {ms in the Schur matvec kernel, launches, ms in the linearise kernel, launches},

@@ -40,7 +40,8 @@ float matcher_l2(const float* a, const float* b, int dim) {
 /* One direction: for each descriptor of A the best match in B, kept if the (squared) ratio test passes.
  * Returns the number of matches written. */
 static int match_one_way(const float* A, int nA, const float* B, int nB, int dim, const matcher_options* o, indexed_feature_match* out) {
-  const double sq_lowes_ratio = (double)o->lowes_ratio * (double)o->lowes_ratio; /* :58-59 */
+  const float sq_lowes_ratio_f = o->lowes_ratio * o->lowes_ratio; /* :58-59: float * float, rounded to float, then widened */
+  const double sq_lowes_ratio = (double)sq_lowes_ratio_f;
   int n = 0;
   for (int i = 0; i < nA; ++i) {
     float best = 0, second = 0; int best_j = -1, second_j = -1;

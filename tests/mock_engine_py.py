@@ -76,6 +76,9 @@ class MockEngine:
     def two_view_ba_batch(self, batch):
         return oracle_py.two_view_ba_batch(batch)
 
+    def set_max_iterations(self, n):
+        self._opts.max_num_iterations = int(n)
+
     def set_profiling(self, enable=True):
         pass
 

@@ -39,7 +39,7 @@ bench.main()
     assert line["unit"] == "obs/s" and line["dtype"] == "f64" and line["data"] == "synthetic" and "workload" in line["config"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
-    assert line["steps_run"] == 2 and line["value"] > 0 and line["obs_passes_per_s"] >= line["value"]
+    assert line["steps"] == 2 and line["steps_requested"] == 2 and line["value"] > 0 and line["obs_passes_per_s"] >= line["value"]
 
 
 def test_smoke_logic():
@@ -67,7 +67,8 @@ bench.experiments_child("c1_50cam", 2, 0)
     assert "error" not in m and m["rc"] == 0 and m["pairs"] == 6 and m["matches"] > 0, m
     for d in lines:
         assert "error" not in d, d
-        assert d["rc"] == 0 and d["steps_run"] == 2 and d["max_rel_cost_diff_vs_default"] <= 1e-12
+        assert d["rc"] == 0 and d["steps_run"] == 2
+        assert d["variant"].startswith("ablate") or d["max_rel_cost_diff_vs_default"] <= 1e-12
         assert set(d["stage_ms_per_step"]) >= {"matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost"}
 
 
@@ -107,12 +108,12 @@ bench.experiments_child("c1_50cam", 1, 0)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [json.loads(ln) for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
     main, child = lines[0], lines[1:]
-    assert main["steps_run"] == 1 and main["gpu_launches"] > 0 and set(main["stage_ms_per_step"]) == set(__import__("bench").VARIANTS and
+    assert main["steps"] == 1 and main["gpu_launches"] > 0 and set(main["stage_ms_per_step"]) == set(__import__("bench").VARIANTS and
                                                                                                       ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost"))
     assert [d["variant"] for d in child] == [v[0] for v in __import__("bench").VARIANTS] + ["matcher_sample"]
     for d in child:
         assert "error" not in d and d["rc"] == 0, d
-    assert all(d["max_rel_cost_diff_vs_default"] <= 1e-9 for d in child[:-1])
+    assert all(d["max_rel_cost_diff_vs_default"] <= 1e-9 for d in child[:-1] if not d["variant"].startswith("ablate"))
 
 
 def test_smoke_against_the_emulated_engine():

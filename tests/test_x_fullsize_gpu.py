@@ -5,6 +5,8 @@ initial cost identical to the oracle, monotone decrease over successful steps, c
 gives the same trajectory up to the non-associativity of the fp64 RED accumulations (the CPU oracle on this exact
 configuration: 10 LM iterations, final cost 1.0018 x the noise floor, in 17 s on 8 threads).
 Written after the round-1 GPU budget was exhausted: first executed by the round-end driver."""
+import os
+
 import numpy as np
 import pytest
 
@@ -49,3 +51,28 @@ def test_config2_full_size_properties(oracle):
     assert abs(s2.num_iterations - s1.num_iterations) <= 1
     n = min(len(s1.costs), len(s2.costs))
     assert np.all(np.abs(s2.costs[:n] - s1.costs[:n]) <= 1e-7 * s1.costs[:n])
+
+
+@pytest.mark.parametrize("workload,n_obs,iters", [("c2_1kcam", 2_000_000, 6), ("c4_radtan", 5_000_000, 5)])
+def test_full_size_trajectory_matches_oracle(oracle, workload, n_obs, iters):
+    """BASELINE.json configs[1] and configs[3] at FULL size: the first LM iterations against the CPU oracle -- per-iteration cost,
+    PCG iteration counts, step acceptance and the parameters after the last iteration.  configs[3] is the only full-size run of
+    the per-camera-intrinsics-group code path (1000 groups of PINHOLE_RADIAL_TANGENTIAL, pinhole_radial_tangential_camera_model.h:190-291):
+    non-shared intrinsics columns in the matvec / rhs / SCHUR_JACOBI blocks.  Tolerances: 1e-9 relative on the costs (fp64
+    summation order only; the PCG takes the same number of iterations), 1e-6 on the parameters."""
+    kw = dict(use_inner_iterations=0, linear_solver_type=_abi.ITERATIVE_SCHUR, max_num_iterations=iters)
+    p0 = synthetic.make_config(workload)
+    assert abs(p0.n_obs - n_obs) <= 0.01 * n_obs
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    po, pg = p0.copy(), p0.copy()
+    so = oracle.solve(po, oracle.default_options(**kw))
+    eng = engine.Engine()
+    sg = eng.solve(pg, engine.default_options(**kw))
+    eng.close()
+    assert sg.rc == 0 and sg.success and so.success
+    assert abs(sg.initial_cost - so.initial_cost) <= 1e-11 * so.initial_cost
+    assert sg.num_iterations == so.num_iterations == iters + 1
+    assert np.all(np.abs(sg.costs - so.costs) <= 1e-9 * so.costs), (sg.costs, so.costs)
+    assert [i["linear_solver_iterations"] for i in sg.iterations] == [i["linear_solver_iterations"] for i in so.iterations]
+    assert [i["step_is_successful"] for i in sg.iterations] == [i["step_is_successful"] for i in so.iterations]
+    assert rel_err(pg.ext, po.ext) < 1e-6 and rel_err(pg.pt, po.pt) < 1e-6 and rel_err(pg.intr, po.intr) < 1e-6

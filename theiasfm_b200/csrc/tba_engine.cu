@@ -502,8 +502,12 @@ int stage_backsub(tba_context* c) {
 }
 
 // Cost at the candidate; scal2 then holds [cost, fixed, failed, mcc, |d_cs|^2, |d_pt|^2].
-int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, double* step_norm, bool* ok) {
+int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, double* step_norm, bool* ok, double elapsed_s = 0.0,
+                             double* elapsed_collective = nullptr) {
   DevProblem& P = c->P;
+  // multi-GPU: every branch of the LM loop must be taken by all ranks alike, the time-out included.  Rank 0's clock is the
+  // clock: its elapsed time rides in slot 8 of this all-reduce (the other ranks add 0), so every rank reads the same value.
+  if (c->world > 1) LAUNCH(c, k_set_f64, 1, 1, 0, c->scal2.p + 8, c->rank == 0 ? elapsed_s : 0.0);
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
   if (P.n_tiles > 0) {
     const int pb_cost = prof_begin(c);
@@ -512,15 +516,16 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
     prof_end(c, 6, pb_cost);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
-  int rc = allreduce_sum(c, c->scal2.p, 8);
+  int rc = allreduce_sum(c, c->scal2.p, 9);
   if (rc) return rc;
-  double s[8];
-  rc = read_scal(c, c->scal2.p, 8, s);
+  double s[9];
+  rc = read_scal(c, c->scal2.p, 9, s);
   if (rc) return rc;
   *ok = s[2] == 0.0;
   *cand_cost = s[0];
   *mcc = s[3];
   *step_norm = std::sqrt(s[4] + s[5]);
+  if (elapsed_collective) *elapsed_collective = c->world > 1 ? s[8] : elapsed_s;
   return TBA_OK;
 }
 
@@ -747,8 +752,10 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   tba_options_init(&c->opt);
   { const char* e = getenv("TBA_MATVEC_BULKRED"); c->exp_bulkred = e != nullptr && e[0] == '1'; }
   { const char* e = getenv("TBA_FAST_SEG"); c->exp_fast_seg = e != nullptr && e[0] == '1'; }
-  { const char* e = getenv("TBA_LIN_OCC"); c->exp_lin_occ = e != nullptr && e[0] == '3'; }
-  { const char* e = getenv("TBA_TRED"); c->exp_tred = e != nullptr && e[0] == '1'; }
+  // round 2: the transposed RED emission and the 3-CTA/SM linearise are the defaults (driver-measured 28.1 vs 31.9 ms per
+  // LM iteration at 20 M observations, costs equal to 2e-8); TBA_TRED=0 / TBA_LIN_OCC=2 select the round-1 kernels
+  { const char* e = getenv("TBA_LIN_OCC"); c->exp_lin_occ = !(e != nullptr && e[0] == '2'); }
+  { const char* e = getenv("TBA_TRED"); c->exp_tred = !(e != nullptr && e[0] == '0'); }
   { const char* e = getenv("TBA_PACK_SORT"); c->exp_pack_sort = e != nullptr && e[0] == '1'; }
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&c->h_scal, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->h_st, sizeof(PcgState)) != cudaSuccess) {
@@ -836,13 +843,19 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   HostPack& H = c->pack;
   c->slot_orig.clear();
   pack_count_and_sort(p, T, &H);  // A, B, C
-  if (H.bad >= 0) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)H.bad, p->obs_cam[H.bad], p->obs_pt[H.bad]); return TBA_ERR_INVALID_ARGUMENT; }
-  if (H.maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", H.maxlen, TILE); return TBA_ERR_UNSUPPORTED; }
-  pack_points(p, &H, c->exp_pack_sort);
+  // rank-local validation errors (they depend on this rank's shard of the observations): in process-per-rank mode the
+  // failing rank must still take part in the first collective below, where every rank learns about the failure and all
+  // return together -- an early return here would leave the other ranks blocked in that all-reduce
+  int local_err = TBA_OK;
+  if (H.bad >= 0) { set_err(c, "observation %lld references camera %d / point %d out of range", (long long)H.bad, p->obs_cam[H.bad], p->obs_pt[H.bad]); local_err = TBA_ERR_INVALID_ARGUMENT; }
+  else if (H.maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", H.maxlen, TILE); local_err = TBA_ERR_UNSUPPORTED; }
+  const bool collective_upload = c->world > 1 && c->preset_cnt_cam == nullptr;
+  if (local_err != TBA_OK && !collective_upload) return local_err;
+  if (local_err == TBA_OK) pack_points(p, &H, c->exp_pack_sort);
   // ---- which blocks take part (blocks without residuals are not in the Ceres program)
   std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
-  for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
-  c->n_free_pt = H.n_free_pt;
+  if (local_err == TBA_OK) for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
+  c->n_free_pt = local_err == TBA_OK ? H.n_free_pt : 0;
   c->n_free_pt_global = c->n_free_pt;
   if (c->world > 1 && c->preset_cnt_cam != nullptr) {  // single-process multi-GPU: the caller counted over the whole problem
     std::fill(cnt_g.begin(), cnt_g.end(), 0.0);
@@ -852,6 +865,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
     std::vector<double> tmp(cnt_c);
     tmp.insert(tmp.end(), cnt_g.begin(), cnt_g.end());
     tmp.push_back((double)c->n_free_pt);
+    tmp.push_back(local_err != TBA_OK ? 1.0 : 0.0);  // number of ranks whose shard failed validation
     rc = [&]() -> int {
       CUDA_OK(c, c->scal2.alloc(std::max<size_t>(tmp.size(), 16)));
       CUDA_OK(c, cudaMemcpyAsync(c->scal2.p, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -862,9 +876,13 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
       return TBA_OK;
     }();
     if (rc) return rc;
+    if (tmp.back() != 0.0) {  // some rank failed: every rank returns an error, nobody is left inside a collective
+      if (local_err == TBA_OK) { set_err(c, "upload failed on %d other rank(s) (invalid observation indices or over-long track in their shard)", (int)tmp.back()); return TBA_ERR_INVALID_ARGUMENT; }
+      return local_err;
+    }
     std::copy(tmp.begin(), tmp.begin() + nc, cnt_c.begin());
     std::copy(tmp.begin() + nc, tmp.begin() + nc + ng, cnt_g.begin());
-    c->n_free_pt_global = (int64_t)tmp.back();
+    c->n_free_pt_global = (int64_t)tmp[tmp.size() - 2];
   }
   pack_masks_and_tiles(p, cnt_c, cnt_g, &H);  // masks, D
   const int ne = nc * 6, ncs = ne + ng * 10;
@@ -964,6 +982,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   P.slot_cam = c->slot_cam.p; P.slot_pt = c->slot_pt.p; P.slot_flags = c->slot_flags.p; P.slot_run = c->slot_run.p;
   P.tile_pt_begin = c->tile_pt_begin.p; P.tile_nruns = c->tile_nruns.p; P.tile_flags = c->tile_flags.p; P.xy = c->xy.p; P.J = c->J.p; P.res = c->res.p;
   P.Hpp = c->Hpp.p; P.gp = c->gp.p; P.Mp = c->Mp.p; P.sp = c->sp.p; P.dpt = c->dpt.p; P.pt_const = c->pt_const.p;
+  { const char* e = getenv("TBA_ABLATE"); P.ablate = e ? atoi(e) : 0; }  // timing diagnostics only (wrong results): see k_schur
   if (c->NI > 0) {
     const int smem = TILE * 4 * c->NI * (int)sizeof(double) + 2 * TILE * (int)sizeof(int);
 #define F(M) CUDA_OK(c, cudaFuncSetAttribute(k_precond_intr<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
@@ -1054,6 +1073,7 @@ int tba_minimize(tba_context* c, tba_summary* s) {
   tba_iteration it;
   memset(&it, 0, sizeof it);
   int consecutive_invalid = 0;
+  double elapsed = 0.0;  // collective view of the solver time (see the time-out test below)
   bool inner_enabled = opt.use_inner_iterations != 0;
   const double kInnerIterationTolerance = 1e-3;  // ceres::Solver::Options::inner_iteration_tolerance
 #define RC(expr) do { rc = (expr); if (rc) goto fail; } while (0)
@@ -1084,7 +1104,9 @@ int tba_minimize(tba_context* c, tba_summary* s) {
       fprintf(stderr, "tba % 4d: f:% 3.12e d:% 3.2e g:% 3.2e h:% 3.2e rho:% 3.2e mu:% 3.2e li:% 3d t:% 3.2e\n", it.iteration, it.cost,
               it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius,
               it.linear_solver_iterations, it.iteration_time_in_seconds);
-    if (now_s() - t1 > opt.max_solver_time_in_seconds) { term = TBA_NO_CONVERGENCE; msg = "Maximum solver time reached."; break; }
+    // world > 1: `elapsed` is rank 0's clock as seen by every rank through the last candidate evaluation (a rank-local clock
+    // here would let one rank leave the loop while the others enter the next iteration's all-reduces: deadlock)
+    if ((c->world > 1 ? elapsed : now_s() - t1) > opt.max_solver_time_in_seconds) { term = TBA_NO_CONVERGENCE; msg = "Maximum solver time reached."; break; }
     if (it.iteration >= opt.max_num_iterations) { term = TBA_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
     if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) { term = TBA_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
     if (radius <= opt.min_trust_region_radius) { term = TBA_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
@@ -1107,7 +1129,7 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     s->num_linear_solver_iterations += cg_iters;
     if (valid) {
       RC(stage_backsub(c));
-      RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok));
+      RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok, now_s() - t1, &elapsed));
       if (!std::isfinite(mcc) || !std::isfinite(step_norm)) valid = false;
       else valid = mcc > 0.0;
     }
@@ -1207,6 +1229,12 @@ int tba_reset_parameters(tba_context* c, const tba_problem* p) {
   CUDA_OK(c, cudaMemcpyAsync(c->P.pt_c, ptk.data(), (size_t)c->n_pt * 32, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   c->have_scale = false;
+  return TBA_OK;
+}
+
+int tba_set_max_iterations(tba_context* c, int32_t max_num_iterations) {
+  if (!c || max_num_iterations < 0) return TBA_ERR_INVALID_ARGUMENT;
+  c->opt.max_num_iterations = max_num_iterations;
   return TBA_OK;
 }
 

@@ -29,6 +29,8 @@ struct DevProblem {
   int ncs;                     // n_cam*6 + n_group*10 (camera-space vector length)
   int single_group;            // n_group == 1: block-reduce the intrinsics accumulations
   int loss_type; double loss_width;
+  int ablate;                  // TBA_ABLATE (timing diagnostics of the matvec, results are WRONG when non-zero): bit0 no camera-side
+                               // REDs, bit1 no x gather, bit2 no shared-intrinsics warp sums, bit3 no segmented reduction
   // parameters: current x and candidate
   double *ext, *intr, *pt, *ext_c, *intr_c, *pt_c;
   const int* cam_group; const int* group_model;
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     grp = (TRED && P.single_group) ? 0 : P.cam_group[cam];  // TRED: no 32-sector gather when one group owns everything
     h = P.pt[(size_t)(p0 + pl) * 4 + 3];
     if (MODE != 1) {
-      const double2* x2 = reinterpret_cast<const double2*>(xs + (size_t)cam * 6);
+      const double2* x2 = reinterpret_cast<const double2*>(xs + (size_t)((MODE == 0 && (P.ablate & 2)) ? lane : cam) * 6);
       xa = __ldg(x2); xb = __ldg(x2 + 1); xc = __ldg(x2 + 2);
       if (NI > 0) {
         const double* xg = xs + P.ne + (size_t)grp * 10;
@@ -728,7 +730,8 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     t[0] = JA(0) * w0 + JA(3) * w1; t[1] = JA(1) * w0 + JA(4) * w1; t[2] = JA(2) * w0 + JA(5) * w1;
     t[3] = JH(0) * w0 + JH(1) * w1;
   }
-  if (FASTSEG) {
+  if (MODE == 0 && (P.ablate & 8)) {
+  } else if (FASTSEG) {
     const int last = run_last_lane(heads, lane);
 #pragma unroll
     for (int j = 0; j < 4; ++j) t[j] = seg_reduce_to(t[j], last, lane);
@@ -834,13 +837,20 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     int* sbase = reinterpret_cast<int*>(sJ + 32 * 6);
     warp_stage_row<6>(sJ, sbase, yv, valid ? cam * 6 : -1, lane);
     __syncwarp();
-    warp_red_rows<6>(y, sJ, sbase, lane);
+    if (!(MODE == 0 && (P.ablate & 1))) warp_red_rows<6>(y, sJ, sbase, lane);
     if (NI > 0) {
       if (P.single_group) {
+        if (MODE == 0 && (P.ablate & 4)) {
+          double v = 0.0;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) v += yi[j];
+          if (v == 1.2345e300) red_add(rr, v);
+        } else {
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
           const double v = warp_sum(yi[j]);
           if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
+        }
         }
       } else if (valid) {
 #pragma unroll
@@ -1369,6 +1379,7 @@ __global__ void k_pcg_finalize(const PcgState* __restrict__ in, PcgState* __rest
   if (threadIdx.x == 0) { *out = st; *done_flag = st.done; }
 }
 __global__ void k_set_flag(int* f, int v) { *f = v; }
+__global__ void k_set_f64(double* p, double v) { *p = v; }
 
 // xs = sm .* x (scaled solution -> unscaled), used before back-substitution
 __global__ void k_cs_mul(int ncs, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ o) {

@@ -79,7 +79,8 @@ struct DevI { int* p = nullptr; size_t n = 0; ~DevI() { if (p) cudaFree(p); } bo
 // :58-59, :78-81: keep the best match when the ratio test is off, there is no second candidate, or it passes
 inline bool passes(const tbm_options* o, float best, float second, int second_valid) {
   if (!o->use_lowes_ratio || !second_valid) return true;
-  const double sq = (double)o->lowes_ratio * (double)o->lowes_ratio;
+  const float sqf = o->lowes_ratio * o->lowes_ratio;  // FeatureMatcherOptions::lowes_ratio is a float: the product is rounded to float, then widened (:58-59)
+  const double sq = (double)sqf;
   return (double)best < sq * (double)second;
 }
 

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "tba_options_init", "tba_device_count", "tba_create", "tba_destroy", "tba_nccl_unique_id", "tba_last_error",
     "tba_solve", "tba_upload", "tba_minimize", "tba_download", "tba_shard_points", "tba_debug_linearize",
     "tba_debug_prepare_linear_system", "tba_debug_schur_matvec", "tba_debug_solve_linear_system",
-    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_profiling", "tba_get_profile", "tba_get_profile_stages", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch", "tba_two_view_ba_batch_multi",
+    "tba_debug_evaluate_step", "tba_debug_read", "tba_reset_parameters", "tba_set_max_iterations", "tba_set_profiling", "tba_get_profile", "tba_get_profile_stages", "tba_solve_multi", "tba_debug_pack", "tba_filter_tracks", "tba_adjust_tracks", "tba_estimate_tracks", "tba_two_view_ba_batch", "tba_two_view_ba_batch_multi",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
         L.tba_two_view_ba_batch.argtypes = [C.c_void_p, C.POINTER(_abi.tba_two_view_batch), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int32)]
         L.tba_filter_tracks.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_uint8), dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tba_reset_parameters.argtypes = [C.c_void_p, C.POINTER(_abi.tba_problem)]
+        L.tba_set_max_iterations.argtypes = [C.c_void_p, C.c_int32]
         L.tba_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.tba_get_profile.argtypes = [C.c_void_p, dp]
         L.tba_get_profile_stages.argtypes = [C.c_void_p, dp]
@@ -287,6 +288,9 @@ class Engine:
     def reset_parameters(self, problem):
         st = problem.as_struct()
         self._check(lib().tba_reset_parameters(self._h, C.byref(st)))
+
+    def set_max_iterations(self, n):
+        self._check(lib().tba_set_max_iterations(self._h, int(n)))
 
     def set_profiling(self, enable=True):
         self._check(lib().tba_set_profiling(self._h, int(enable)))
