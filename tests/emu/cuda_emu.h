@@ -88,6 +88,13 @@ inline int emu_last_error = cudaSuccess;  // set by emu::launch on an invalid co
 inline cudaError_t cudaPeekAtLastError() { return emu_last_error; }
 inline cudaError_t cudaGetLastError() { const int e = emu_last_error; emu_last_error = cudaSuccess; return e; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error (emulated)" : "invalid launch configuration (emulated)"; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+// a small "GPU" (TBA_EMU_SMS multiprocessors, default 3): persistent kernels then give every warp a range of several slices
+inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {
+  const char* e = getenv("TBA_EMU_SMS");
+  *v = attr == cudaDevAttrMultiProcessorCount ? (e ? atoi(e) : 3) : 0;
+  return cudaSuccess;
+}
 inline std::mutex emu_attr_mu;
 inline std::map<const void*, size_t> emu_max_dyn_smem;  // kernel -> opted-in dynamic shared memory (default limit 48 KB)
 template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int attr, int v) {

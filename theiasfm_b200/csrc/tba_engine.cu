@@ -142,11 +142,11 @@ struct tba_context {
   DevBuf<uint8_t> d_inner_status;
   int64_t inner_passes = 0;
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
-  bool exp_pack_sort = false;  // TBA_PACK_SORT=1: experimental locality ordering of points (default off)
-  bool exp_fast_seg = false;  // TBA_FAST_SEG=1: segmented reductions without key shuffles in k_linearize / the matvec (default off)
-  bool exp_tred = false;  // TBA_TRED=1: transposed RED emission (warp_red_rows) in k_linearize / k_precond_ext / rhs / matvec (round-2 experiment, default off)
-  bool exp_lin_occ = false;  // TBA_LIN_OCC=3: k_linearize compiled for 3 CTAs/SM (80 registers, ~130 bytes of spills) instead of 2 (128 registers) (default off)
-  bool exp_bulkred = false;  // TBA_MATVEC_BULKRED=1: experimental TMA bulk-reduction matvec (round-2 experiment, default off)
+  bool exp_tred = true;     // transposed RED emission (warp_red_rows) in k_linearize / k_precond_ext / rhs / matvec; TBA_TRED=0: the round-1 lane-per-row REDs
+  bool exp_lin_occ = true;  // k_linearize compiled for 3 CTAs/SM (80 registers, ~130 bytes of spills); TBA_LIN_OCC=2: 2 CTAs/SM, 128 registers
+  bool stream_schur = true; // persistent streaming k_schur_stream over the normal tiles; TBA_MATVEC=tile: the tile-per-CTA k_schur everywhere
+  int n_normal_tiles = 0;   // tiles whose tracks fit a warp slice (they precede the long tiles)
+  int n_sm = 148;
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
   // host mirrors
@@ -277,22 +277,14 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
       auto kfn = k_linearize<0x3FFu, true>;
       LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p);
     } else if (c->exp_lin_occ && c->exp_tred) {
-#define F(M) { auto kfn = k_linearize<M, false, false, true, 3>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+#define F(M) { auto kfn = k_linearize<M, false, true, 3>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
     } else if (c->exp_lin_occ) {
-#define F(M) { auto kfn = k_linearize<M, false, false, false, 3>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else if (c->exp_tred && c->exp_fast_seg) {
-#define F(M) { auto kfn = k_linearize<M, false, true, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
+#define F(M) { auto kfn = k_linearize<M, false, false, 3>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
     } else if (c->exp_tred) {
-#define F(M) { auto kfn = k_linearize<M, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else if (c->exp_fast_seg) {
 #define F(M) { auto kfn = k_linearize<M, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, lin_g(c), lin_cn(c), c->rep.p); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
@@ -328,6 +320,36 @@ int stage_gradient_max_norm(tba_context* c, double* gmax) {
   rc = read_scal(c, c->gmax.p, 2, g);
   if (rc) return rc;
   *gmax = std::max(g[0], g[1]);
+  return TBA_OK;
+}
+
+// One pass of the implicit Schur operator (MODE 0 matvec, 1 reduced rhs, 2 back-substitution) over every tile: the persistent
+// streaming kernel over the normal tiles, the tile-per-CTA kernel over the long tiles (tracks of 33..256 observations).
+template <int MODE>
+int launch_schur(tba_context* c, const double* xs, double* y, const int* done) {
+  DevProblem& P = c->P;
+  int first_tile = 0;
+  if (c->stream_schur && c->exp_tred && c->n_normal_tiles > 0) {
+    const int n_slices = c->n_normal_tiles * (TILE / 32);
+#define F(M) { using Cfg = StreamCfg<M, MODE>; auto kfn = k_schur_stream<M, MODE>; \
+               const int grid = std::max(1, std::min(c->n_sm, (n_slices + Cfg::NW - 1) / Cfg::NW)); \
+               LAUNCH(c, kfn, grid, Cfg::NW * 32, Cfg::SMEM, P, xs, y, c->rep.p, done, n_slices); }
+    DISPATCH_IMASK(c->imask, F)
+#undef F
+    first_tile = c->n_normal_tiles;
+  }
+  const int rest = P.n_tiles - first_tile;
+  if (rest > 0) {
+    if (c->exp_tred || MODE == 2) {
+#define F(M) { auto kfn = k_schur<M, MODE, true>; LAUNCH(c, kfn, rest, TILE, schur_smem(c), P, xs, y, c->rep.p, done, first_tile); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    } else {
+#define F(M) { auto kfn = k_schur<M, MODE, false>; LAUNCH(c, kfn, rest, TILE, schur_smem(c), P, xs, y, c->rep.p, done, first_tile); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+    }
+  }
   return TBA_OK;
 }
 
@@ -371,15 +393,7 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
   CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
     const int pb_rhs = prof_begin(c);
-    if (c->exp_tred) {
-#define F(M) { auto kfn = k_schur<M, 1, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else {
-#define F(M) { auto kfn = k_schur<M, 1>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    }
+    { const int rc1 = launch_schur<1>(c, nullptr, c->y.p, nullptr); if (rc1) return rc1; }
     prof_end(c, 4, pb_rhs);
     if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
@@ -402,27 +416,8 @@ int launch_matvec(tba_context* c, const int* done) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-    if (c->exp_tred && c->exp_fast_seg) {
-#define F(M) { auto kfn = k_schur<M, 0, false, true, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else if (c->exp_tred) {
-#define F(M) { auto kfn = k_schur<M, 0, false, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else if (c->exp_bulkred) {
-#define F(M) { auto kfn = k_schur<M, 0, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else if (c->exp_fast_seg) {
-#define F(M) { auto kfn = k_schur<M, 0, false, true>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    } else {
-#define F(M) { auto kfn = k_schur<M, 0>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, c->y.p, c->rep.p, done); }
-      DISPATCH_IMASK(c->imask, F)
-#undef F
-    }
+    const int rc = launch_schur<0>(c, c->xs.p, c->y.p, done);
+    if (rc) return rc;
     prof_end(c, 0, pb);
     if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
@@ -489,9 +484,7 @@ int stage_backsub(tba_context* c) {
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 16 * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
     const int pb_bs = prof_begin(c);
-#define F(M) { auto kfn = k_schur<M, 2>; LAUNCH(c, kfn, P.n_tiles, TILE, schur_smem(c), P, c->xs.p, nullptr, c->rep.p, nullptr); }
-    DISPATCH_IMASK(c->imask, F)
-#undef F
+    { const int rc2 = launch_schur<2>(c, c->xs.p, nullptr, nullptr); if (rc2) return rc2; }
     prof_end(c, 5, pb_bs);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
@@ -750,14 +743,12 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   tba_context* c = new tba_context();
   c->device = device; c->rank = rank; c->world = world_size;
   tba_options_init(&c->opt);
-  { const char* e = getenv("TBA_MATVEC_BULKRED"); c->exp_bulkred = e != nullptr && e[0] == '1'; }
-  { const char* e = getenv("TBA_FAST_SEG"); c->exp_fast_seg = e != nullptr && e[0] == '1'; }
+  { const char* e = getenv("TBA_MATVEC"); c->stream_schur = !(e != nullptr && e[0] == 't'); }
   // round 2: the transposed RED emission and the 3-CTA/SM linearise are the defaults (driver-measured 28.1 vs 31.9 ms per
   // LM iteration at 20 M observations, costs equal to 2e-8); TBA_TRED=0 / TBA_LIN_OCC=2 select the round-1 kernels
   { const char* e = getenv("TBA_LIN_OCC"); c->exp_lin_occ = !(e != nullptr && e[0] == '2'); }
   { const char* e = getenv("TBA_TRED"); c->exp_tred = !(e != nullptr && e[0] == '0'); }
-  { const char* e = getenv("TBA_PACK_SORT"); c->exp_pack_sort = e != nullptr && e[0] == '1'; }
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&c->h_scal, 64 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->h_st, sizeof(PcgState)) != cudaSuccess) {
     delete c;
     return TBA_ERR_CUDA;
@@ -851,7 +842,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   else if (H.maxlen > TILE) { set_err(c, "track with %d observations exceeds the engine limit of %d per track", H.maxlen, TILE); local_err = TBA_ERR_UNSUPPORTED; }
   const bool collective_upload = c->world > 1 && c->preset_cnt_cam == nullptr;
   if (local_err != TBA_OK && !collective_upload) return local_err;
-  if (local_err == TBA_OK) pack_points(p, &H, c->exp_pack_sort);
+  if (local_err == TBA_OK) pack_points(p, &H);
   // ---- which blocks take part (blocks without residuals are not in the Ceres program)
   std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
   if (local_err == TBA_OK) for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
@@ -992,17 +983,19 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   {
     const int smem = (int)schur_smem(c);
 #define F(M)                                                                                                        \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 0>::SMEM)); \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 1>::SMEM)); \
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 2>::SMEM));
     DISPATCH_IMASK(c->imask, F)
 #undef F
   }
+  c->n_normal_tiles = 0;
+  for (int t = 0; t < n_tiles; ++t) c->n_normal_tiles += (tile_flags[t] & 1) ? 0 : 1;
   c->have_scale = false;
   if (c->opt.use_inner_iterations) {
     c->h_ext_const.assign(p->ext_const, p->ext_const + nc);
@@ -1654,7 +1647,7 @@ int tba_debug_pack(const tba_problem* p, int64_t cap_slots, int64_t* sizes_out, 
   pack_count_and_sort(p, 4, &H);
   if (H.bad >= 0) return TBA_ERR_INVALID_ARGUMENT;
   if (H.maxlen > TILE) return TBA_ERR_UNSUPPORTED;
-  { const char* e = getenv("TBA_PACK_SORT"); pack_points(p, &H, e != nullptr && e[0] == '1'); }
+  pack_points(p, &H);
   std::vector<double> cnt_c(p->n_cam, 0.0), cnt_g(p->n_group, 0.0);
   for (int i = 0; i < p->n_cam; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
   pack_masks_and_tiles(p, cnt_c, cnt_g, &H);

@@ -167,7 +167,7 @@ __device__ __forceinline__ size_t wslice(int tile, int warp, int rows) { return 
 // gradient / squared column norms (fp64 RED to global) and cost / failure counters (replicas).
 // Normal tiles: a point never straddles a warp -> per-point sums by warp-shuffle segmented reduction only, no
 // block barrier.  Long tiles (tracks > 32 observations): combined across warps in shared memory.
-template <uint32_t IMASK, bool EXT = false, bool FASTSEG = false, bool TRED = false, int MINB = 1>
+template <uint32_t IMASK, bool EXT = false, bool TRED = false, int MINB = 1>
 __global__ void __launch_bounds__(TILE, MINB) k_linearize(DevProblem P, double* __restrict__ g_cs, double* __restrict__ cn_cs,
                                                     double* __restrict__ rep) {
   constexpr int NI = popcount10(IMASK);
@@ -242,14 +242,8 @@ __global__ void __launch_bounds__(TILE, MINB) k_linearize(DevProblem P, double* 
     for (int a = 0; a < 4; ++a) acc[10 + a] = jp0[a] * r[0] + jp1[a] * r[1];
     const int prev = __shfl_up_sync(0xffffffffu, pl, 1);
     const bool head = valid && (lane == 0 || prev != pl);
-    if (FASTSEG) {
-      const int last = run_last_lane(__ballot_sync(0xffffffffu, lane == 0 || prev != pl), lane);
 #pragma unroll
-      for (int j = 0; j < 14; ++j) acc[j] = seg_reduce_to(acc[j], last, lane);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 14; ++j) acc[j] = seg_reduce(acc[j], pl, lane);
-    }
+    for (int j = 0; j < 14; ++j) acc[j] = seg_reduce(acc[j], pl, lane);
     if (head) {
       if (long_tile) {
 #pragma unroll
@@ -581,10 +575,12 @@ __device__ __forceinline__ void sym4_mul(const double* __restrict__ M, const dou
 #ifdef TBA_EMULATE
 // CPU emulation build (tests/emu/cuda_emu.h): the bulk copy is a memcpy by the issuing lane, the mbarrier a flag the other lanes
 // poll (yielding to the fiber scheduler), the bulk reduction an in-place add.
+// *bar counts the completed phases: the issuing lane's sequence "expect_tx, bulk copy, bulk copy ..." runs without a yield in
+// between, so a phase is complete as soon as its expect_tx is visible; wait(parity) passes once phase `parity` is over.
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { memcpy(dst, src, bytes); *bar += bytes; }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t) { while (*bar == 0) emu_yield(); }  // the issuing lane copied before the __syncwarp
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t) { *bar += 1; }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while ((*bar & 1u) == parity) emu_yield(); }
 __device__ __forceinline__ void bulk_red_add_f64(double* dst, const double* src_smem, uint32_t bytes) { for (uint32_t i = 0; i < bytes / 8; ++i) dst[i] += src_smem[i]; }
 __device__ __forceinline__ void bulk_commit_and_wait_read() {}
 __device__ __forceinline__ void fence_proxy_async_smem() {}
@@ -645,9 +641,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // Camera-side sums: fp64 RED.ADD to global; shared-intrinsics sums: warp reduce + RED to a replica row.
 // No block barrier on this path.  Long tiles (tracks > 32 observations) combine the per-point sums across warps in
 // shared memory (two block barriers).  Dynamic shared memory: TILE * (NJ + 2) doubles.
-template <uint32_t IMASK, int MODE, bool BULKRED = false, bool FASTSEG = false, bool TRED = false>
+template <uint32_t IMASK, int MODE, bool TRED = true>
 __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 : 2) k_schur(DevProblem P, const double* __restrict__ xs, double* __restrict__ y,
-                                                double* __restrict__ rep, const int* __restrict__ done_flag) {
+                                                double* __restrict__ rep, const int* __restrict__ done_flag, int tile0) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
   constexpr int WS = (NJ + 2) * 32;  // doubles per warp stage
@@ -659,7 +655,7 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
 #endif
   __shared__ double s_t[MAXP][4];
   __shared__ __align__(8) uint64_t s_bar[TILE / 32];
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = tile0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* sJ = s_dyn + (size_t)warp * WS;  // [NJ][32]
   double* sR = sJ + NJ * 32;               // [2][32]
   if (lane == 0) {
@@ -731,10 +727,6 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     t[3] = JH(0) * w0 + JH(1) * w1;
   }
   if (MODE == 0 && (P.ablate & 8)) {
-  } else if (FASTSEG) {
-    const int last = run_last_lane(heads, lane);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = seg_reduce_to(t[j], last, lane);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) t[j] = seg_reduce(t[j], pl, lane);
@@ -790,41 +782,8 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
     if (lane == 0) red_add(rr + 23, mcc);
     return;
   }
-  if (BULKRED) {
-    // experimental: stage the lane's 6 camera-side contributions in its own 48-byte row of the (now consumed) residual /
-    // padding area of the warp stage, then one TMA bulk reduction per observation
-    double yv[6];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) yv[j] = valid ? -h * (JA(j) * z0 + JA(3 + j) * z1) : 0.0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) yv[3 + j] = valid ? JW(j) * z0 + JW(3 + j) * z1 : 0.0;
-    double yi[NI + 1];
-#pragma unroll
-    for (int j = 0; j < NI; ++j) yi[j] = valid ? JI(j) * z0 + JI(NI + j) * z1 : 0.0;
-    __syncwarp();  // every lane has finished reading the J slice: rows 0..5 of the slice are reused as staging [32][6]
-    double* stage = sJ + lane * 6;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) stage[j] = yv[j];
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (valid) bulk_red_add_f64(y + (size_t)cam * 6, stage, 48);
-    bulk_commit_and_wait_read();
-    if (NI > 0) {
-      if (P.single_group) {
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const double v = warp_sum(yi[j]);
-          if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
-        }
-      } else if (valid) {
-#pragma unroll
-        for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), yi[j]);
-      }
-    }
-    return;
-  }
   if (TRED) {
-    // experimental (TBA_TRED=1): camera-side contributions staged per warp and emitted element-major (warp_red_rows)
+    // camera-side contributions staged per warp and emitted element-major (warp_red_rows); TBA_TRED=0: one RED per lane and row element
     double yv[6];
 #pragma unroll
     for (int j = 0; j < 3; ++j) yv[j] = valid ? -h * (JA(j) * z0 + JA(3 + j) * z1) : 0.0;
@@ -882,6 +841,269 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
 #undef JW
 #undef JH
 #undef JI
+}
+
+// --------------------------------------------- K2s: persistent streaming implicit Schur complement (round 2)
+// Same three operators as k_schur (MODE 0 matvec, 1 reduced rhs, 2 back-substitution) over the NORMAL tiles, restructured
+// around what the round-1 captures showed: the tile-per-CTA kernel is latency bound (one TMA round trip + two levels of
+// dependent gathers per 32 observations and CTA lifetime), not bandwidth or issue bound.
+//   * persistent CTAs (one per SM), every WARP owns a contiguous range of warp slices and a private ring of NS TMA stages:
+//     one stage = the slice's compact Jacobian [NJ][32] (+ residuals [2][32]) + its camera / point index rows, fetched by
+//     three or four cp.async.bulk copies that complete on the stage's mbarrier.  Slices i+1 .. i+NS-1 are in flight
+//     while slice i is processed; the warp re-arms a stage as soon as it has consumed it (no block barrier anywhere);
+//   * the camera-side gathers (x block of the observing camera, h and M_p of the point) of slice i+1 are issued BEFORE the
+//     arithmetic of slice i and consumed one iteration later (software pipelining through registers);
+//   * per-point sums by ballot-driven segmented shuffle reduction; camera-side sums staged in the consumed stage and emitted
+//     element-major (warp_red_rows); sums shared by every observation (shared intrinsics, model cost change) are kept in
+//     registers across the whole range and leave the warp once, at the end.
+__device__ __forceinline__ int run_last_lane_dev(unsigned heads, int lane) {
+#ifdef TBA_EMULATE
+  return run_last_lane(heads, lane);
+#else
+  const unsigned above = lane >= 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  return above == 0u ? 31 : __ffs(above) - 2;
+#endif
+}
+
+// element-major emission of staged [32][N] rows whose N elements go to the (non-contiguous) columns of IMASK
+template <uint32_t IMASK, int N>
+__device__ __forceinline__ void warp_red_rows_cols(double* __restrict__ dst, const double* __restrict__ stage, const int* __restrict__ sbase, int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int e = k * 32 + lane;
+    const int o = e / N, j = e - o * N;
+    const int b = sbase[o];
+    int col = 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q) if (q == j) col = nth_bit(IMASK, q);
+    if (b >= 0) red_add(dst + (size_t)b + col, stage[e]);
+  }
+}
+
+template <uint32_t IMASK, int MODE>
+struct StreamCfg {
+  static constexpr int NI = popcount10(IMASK);
+  static constexpr int NJ = 14 + 2 * NI;
+  static constexpr int STG = NJ * 32 + (MODE != 0 ? 64 : 0) + 32;  // doubles per stage: J | [res] | cam ids (32 int) + point ids (32 int)
+  static constexpr int NS = 3;                                      // ring depth
+  // warps per CTA: what fits 220 KB of dynamic shared memory with NS stages, at most 12 (384 threads leave 168 registers per
+  // thread: the software-pipelined gathers of the next slice live in registers next to the current slice's)
+  static constexpr int NW = (220 * 1024 / (NS * STG * 8)) > 12 ? 12 : (220 * 1024 / (NS * STG * 8));
+  static constexpr size_t SMEM = (size_t)NW * NS * STG * 8 + (size_t)NW * NS * 8;
+};
+
+template <uint32_t IMASK, int MODE>
+__global__ void __launch_bounds__(StreamCfg<IMASK, MODE>::NW * 32, 1)
+k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__ y, double* __restrict__ rep,
+               const int* __restrict__ done_flag, int n_slices) {
+  using Cfg = StreamCfg<IMASK, MODE>;
+  constexpr int NI = Cfg::NI, NJ = Cfg::NJ, STG = Cfg::STG, NS = Cfg::NS, NW = Cfg::NW;
+  if (done_flag != nullptr && *done_flag) return;
+#ifdef TBA_EMULATE
+  double* s_dyn = emu::dyn_smem<double>();
+#else
+  extern __shared__ __align__(128) double s_dyn[];
+#endif
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * NW + warp, GW = gridDim.x * NW;
+  const int s_begin = (int)((long long)n_slices * gw / GW), s_end = (int)((long long)n_slices * (gw + 1) / GW);
+  if (s_begin >= s_end) return;  // warp-uniform; no block-level synchronisation exists in this kernel
+  double* ring = s_dyn + (size_t)warp * NS * STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)NW * NS * STG) + warp * NS;
+  constexpr uint32_t jbytes = NJ * 32 * 8, rbytes = (MODE != 0) ? 2 * 32 * 8 : 0;
+  auto issue = [&](int stage, int slice) {  // lane 0 only
+    double* st = ring + (size_t)stage * STG;
+    mbar_expect_tx(&bars[stage], jbytes + rbytes + 256);
+    bulk_g2s(st, P.J + (size_t)slice * NJ * 32, jbytes, &bars[stage]);
+    if (MODE != 0) bulk_g2s(st + NJ * 32, P.res + (size_t)slice * 64, rbytes, &bars[stage]);
+    int* idx = reinterpret_cast<int*>(st + NJ * 32 + (MODE != 0 ? 64 : 0));
+    bulk_g2s(idx, P.slot_cam + (size_t)slice * 32, 128, &bars[stage]);
+    bulk_g2s(idx + 32, P.slot_pt + (size_t)slice * 32, 128, &bars[stage]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) mbar_init(&bars[k], 1);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (s_begin + k < s_end) issue(k, s_begin + k);
+  }
+  __syncwarp();
+  // intrinsics x of the single shared group: one uniform load for the whole kernel
+  double xi_u[NI + 1];
+  if (NI > 0 && MODE != 1 && P.single_group) {
+#pragma unroll
+    for (int j = 0; j < NI; ++j) xi_u[j] = __ldg(xs + P.ne + nth_bit(IMASK, j));
+  }
+  double yi_acc[NI + 1];  // shared-intrinsics sums of this lane over the whole range
+#pragma unroll
+  for (int j = 0; j < NI; ++j) yi_acc[j] = 0.0;
+  double mcc_acc = 0.0;
+  // ---- registers of the slice being prefetched ("n" = next)
+  int cam_n = -1, pt_n = 0, grp_n = 0;
+  unsigned heads_n = 0xffffffffu;
+  double2 xa_n = make_double2(0.0, 0.0), xb_n = xa_n, xc_n = xa_n;
+  double xi_n[NI + 1];
+  double h_n = 0.0;
+  double2 m01_n = xa_n, m23_n = xa_n, m45_n = xa_n, m67_n = xa_n, m89_n = xa_n;
+  uint8_t flag_n = 0;
+  auto prefetch = [&](int slice, int it) {
+    const int stage = it % NS;
+    mbar_wait(&bars[stage], (uint32_t)((it / NS) & 1));
+    const int* idx = reinterpret_cast<const int*>(ring + (size_t)stage * STG + NJ * 32 + (MODE != 0 ? 64 : 0));
+    cam_n = idx[lane];
+    pt_n = idx[32 + lane];
+    const bool valid = cam_n >= 0;
+    const int key = valid ? pt_n : -1 - lane;
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || prev != key;
+    heads_n = __ballot_sync(0xffffffffu, head);
+    if (valid) {
+      h_n = __ldg(P.pt + (size_t)pt_n * 4 + 3);
+      if (MODE != 1) {
+        const double2* x2 = reinterpret_cast<const double2*>(xs + (size_t)((MODE == 0 && (P.ablate & 2)) ? lane : cam_n) * 6);
+        xa_n = __ldg(x2); xb_n = __ldg(x2 + 1); xc_n = __ldg(x2 + 2);
+      }
+      if (NI > 0 && !P.single_group) {
+        grp_n = __ldg(P.cam_group + cam_n);
+        if (MODE != 1) {
+          const double* xg = xs + P.ne + (size_t)grp_n * 10;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) xi_n[j] = __ldg(xg + nth_bit(IMASK, j));
+        }
+      }
+      if (head) {
+        const double2* M2 = reinterpret_cast<const double2*>(P.Mp + (size_t)pt_n * 10);
+        m01_n = __ldg(M2); m23_n = __ldg(M2 + 1); m45_n = __ldg(M2 + 2); m67_n = __ldg(M2 + 3); m89_n = __ldg(M2 + 4);
+      }
+      if (MODE == 2) flag_n = P.slot_flags[(size_t)slice * 32 + lane];
+    }
+  };
+  prefetch(s_begin, 0);
+  for (int s = s_begin, it = 0; s < s_end; ++s, ++it) {
+    // ---- take over the prefetched registers, start the prefetch of the next slice
+    const int cam = cam_n, pt = pt_n, grp = grp_n;
+    const unsigned heads = heads_n;
+    const double2 xa = xa_n, xb = xb_n, xc = xc_n, m01 = m01_n, m23 = m23_n, m45 = m45_n, m67 = m67_n, m89 = m89_n;
+    const double h = h_n;
+    const uint8_t flag = flag_n;
+    double xi[NI + 1];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) xi[j] = (NI > 0 && MODE != 1) ? (P.single_group ? xi_u[j] : xi_n[j]) : 0.0;
+    const bool valid = cam >= 0;
+    if (s + 1 < s_end) prefetch(s + 1, it + 1);
+    // ---- slice s: its stage landed (waited for by its prefetch)
+    const int stage = it % NS;
+    double* sJ = ring + (size_t)stage * STG;
+    const double* sR = sJ + NJ * 32;
+    const double* Jt = sJ + lane;
+#define JA(j) Jt[(j) * 32]
+#define JW(j) Jt[(6 + (j)) * 32]
+#define JH(j) Jt[(12 + (j)) * 32]
+#define JI(j) Jt[(14 + (j)) * 32]
+    double w0 = 0.0, w1 = 0.0, r0 = 0.0, r1 = 0.0;
+    double ja[6], jh[2];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ja[j] = JA(j);
+    jh[0] = JH(0); jh[1] = JH(1);
+    if (valid) {
+      if (MODE != 0) { r0 = sR[lane]; r1 = sR[32 + lane]; }
+      if (MODE != 1) {
+        w0 = -h * (ja[0] * xa.x + ja[1] * xa.y + ja[2] * xb.x) + JW(0) * xb.y + JW(1) * xc.x + JW(2) * xc.y;
+        w1 = -h * (ja[3] * xa.x + ja[4] * xa.y + ja[5] * xb.x) + JW(3) * xb.y + JW(4) * xc.x + JW(5) * xc.y;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) { w0 += JI(j) * xi[j]; w1 += JI(NI + j) * xi[j]; }
+      }
+      if (MODE == 1) { w0 = r0; w1 = r1; }
+      if (MODE == 2) { w0 = r0 - w0; w1 = r1 - w1; }
+    }
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    if (valid) {
+      t[0] = ja[0] * w0 + ja[3] * w1; t[1] = ja[1] * w0 + ja[4] * w1; t[2] = ja[2] * w0 + ja[5] * w1;
+      t[3] = jh[0] * w0 + jh[1] * w1;
+    }
+    if (!(MODE == 0 && (P.ablate & 8))) {
+      const int last = run_last_lane_dev(heads, lane);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = seg_reduce_to(t[j], last, lane);
+    }
+    double u0 = m01.x * t[0] + m01.y * t[1] + m23.x * t[2] + m23.y * t[3];
+    double u1 = m01.y * t[0] + m45.x * t[1] + m45.y * t[2] + m67.x * t[3];
+    double u2 = m23.x * t[0] + m45.y * t[1] + m67.y * t[2] + m89.x * t[3];
+    double u3 = m23.y * t[0] + m67.x * t[1] + m89.x * t[2] + m89.y * t[3];
+    const bool head = (heads >> lane) & 1u;
+    if (MODE == 2 && head && valid) {
+      double2* d = reinterpret_cast<double2*>(P.dpt + (size_t)pt * 4);
+      d[0] = make_double2(-u0, -u1);
+      d[1] = make_double2(-u2, -u3);
+    }
+    const int hl = run_head_lane(heads, lane);
+    u0 = __shfl_sync(0xffffffffu, u0, hl); u1 = __shfl_sync(0xffffffffu, u1, hl);
+    u2 = __shfl_sync(0xffffffffu, u2, hl); u3 = __shfl_sync(0xffffffffu, u3, hl);
+    double z0 = 0.0, z1 = 0.0;
+    if (valid) {
+      z0 = w0 - (ja[0] * u0 + ja[1] * u1 + ja[2] * u2 + jh[0] * u3);
+      z1 = w1 - (ja[3] * u0 + ja[4] * u1 + ja[5] * u2 + jh[1] * u3);
+    }
+    if (MODE == 2) {
+      // model residual m = J * step = -(F xs + E u) = -(r - z); contribution -m.(r + m/2)
+      if (valid && !(flag & 1)) {
+        const double m0 = -(r0 - z0), m1 = -(r1 - z1);
+        mcc_acc += -(m0 * (r0 + 0.5 * m0) + m1 * (r1 + 0.5 * m1));
+      }
+    } else {
+      double yv[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) yv[j] = valid ? -h * (ja[j] * z0 + ja[3 + j] * z1) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) yv[3 + j] = valid ? JW(j) * z0 + JW(3 + j) * z1 : 0.0;
+      double yi[NI + 1];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) yi[j] = valid ? JI(j) * z0 + JI(NI + j) * z1 : 0.0;
+      __syncwarp();  // every lane has finished reading the J slice: its first rows are reused as staging [32][6] + 32 ints
+      int* sbase = reinterpret_cast<int*>(sJ + 32 * 6);
+      warp_stage_row<6>(sJ, sbase, yv, valid ? cam * 6 : -1, lane);
+      __syncwarp();
+      if (!(MODE == 0 && (P.ablate & 1))) warp_red_rows<6>(y, sJ, sbase, lane);
+      if (NI > 0) {
+        if (P.single_group) {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) yi_acc[j] += yi[j];
+        } else {
+          // per-group intrinsics rows: staged behind the extrinsics rows ([32][NI] doubles + 32 ints) and emitted element-major
+          static_assert(32 * 6 + 16 + 32 * NI + 16 <= NJ * 32, "stage too small for the intrinsics staging");
+          double* si = sJ + 32 * 6 + 16;
+          int* sibase = reinterpret_cast<int*>(si + 32 * NI);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < NI; ++j) si[lane * NI + j] = yi[j];
+          sibase[lane] = valid ? P.ne + grp * 10 : -1;
+          __syncwarp();
+          if (!(MODE == 0 && (P.ablate & 1))) warp_red_rows_cols<IMASK, (NI > 0 ? NI : 1)>(y, si, sibase, lane);
+        }
+      }
+    }
+#undef JA
+#undef JW
+#undef JH
+#undef JI
+    // ---- the stage is consumed: re-arm it for slice s + NS
+    __syncwarp();
+    if (lane == 0 && s + NS < s_end) {
+      fence_proxy_async_smem();  // generic-proxy accesses of the stage (reads, staging stores) before the async-proxy refill
+      issue(stage, s + NS);
+    }
+  }
+  // ---- sums that leave the warp once
+  double* rr = rep + (size_t)(gw & (NREP - 1)) * REPW;
+  if (MODE == 2) {
+    const double m = warp_sum(mcc_acc);
+    if (lane == 0) red_add(rr + 23, m);
+  } else if (NI > 0 && P.single_group) {
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const double v = warp_sum(yi_acc[j]);
+      if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
+    }
+  }
 }
 
 // ------------------------------------------- SCHUR_JACOBI preconditioner blocks

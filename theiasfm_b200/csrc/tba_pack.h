@@ -161,9 +161,7 @@ inline void pack_count_and_sort(const tba_problem* p, int T, HostPack* H) {
 
 // Packed points = points that have observations (zero-observation points are left untouched): first the points whose
 // track fits one warp slice (<= 32 observations) in caller order, then the long tracks.
-// sort_by_anchor (experimental, TBA_PACK_SORT=1, default off): order the short-track points by their lowest camera index
-// so that neighbouring tiles touch neighbouring cameras (a locality experiment for round 2; any order is valid).
-inline void pack_points(const tba_problem* p, HostPack* H, bool sort_by_anchor = false) {
+inline void pack_points(const tba_problem* p, HostPack* H) {
   const int np = p->n_pt;
   H->pk2caller.clear();
   H->pk2caller.reserve((size_t)np);
@@ -175,15 +173,6 @@ inline void pack_points(const tba_problem* p, HostPack* H, bool sort_by_anchor =
     if (n == 0) continue;
     if (n <= 32) H->pk2caller.push_back(q); else long_pts.push_back(q);
     H->n_free_pt += p->pt_const[q] ? 0 : 1;
-  }
-  if (sort_by_anchor) {
-    std::vector<int> anchor((size_t)np, 0);
-    for (int q : H->pk2caller) {
-      int a = p->obs_cam[H->order[H->off[q]]];
-      for (int64_t k = H->off[q] + 1; k < H->off[(size_t)q + 1]; ++k) a = std::min(a, (int)p->obs_cam[H->order[k]]);
-      anchor[q] = a;
-    }
-    std::stable_sort(H->pk2caller.begin(), H->pk2caller.end(), [&](int a, int b) { return anchor[a] < anchor[b]; });
   }
   H->n_long = (int)long_pts.size();
   H->pk2caller.insert(H->pk2caller.end(), long_pts.begin(), long_pts.end());
