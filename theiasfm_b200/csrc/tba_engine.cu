@@ -120,6 +120,8 @@ struct tba_context {
   // camera space: [g | cn | scal(16)] is one allreduce buffer
   DevBuf<double> lin;       // g_cs[ncs] | cn_cs[ncs] | scal[16]
   DevBuf<double> mask, blk_free, sm, D2, Sblk /*[n_cam*21 | n_group*55]*/, Minv_c, Minv_i;
+  DevBuf<double> z2;  // z = Minv r of the PCG (z holds q = S p)
+  int last_cg_iters = 6;  // CG iterations of the previous linear solve: size of the first enqueued batch
   DevBuf<double> b, x, r, p, z, xs, y, part /*3 x VB*/, gmax, flag, scal2 /*16*/, rep /*NREP x REPW*/;
   DevBuf<PcgState> st;      // [2]
   DevBuf<int> done_flag;
@@ -412,14 +414,15 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
 
 const int* st_done(const PcgState* st) { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(st) + offsetof(PcgState, done)); }
 
-int launch_matvec(tba_context* c, const int* done) {
+// defer_fold: the caller folds the shared-intrinsics replica rows itself (k_pcg_a / k_pcg_reset_bz; one GPU only)
+int launch_matvec(tba_context* c, const int* done, bool defer_fold = false) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
     const int rc = launch_schur<0>(c, c->xs.p, c->y.p, done);
     if (rc) return rc;
     prof_end(c, 0, pb);
-    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
+    if (P.single_group && !defer_fold) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   return allreduce_sum(c, c->y.p, P.ncs);
 }
@@ -443,25 +446,34 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
   const int ident = o.preconditioner_type == TBA_PRECOND_IDENTITY;
   int cur = 0;  // index of the valid state
   int it = 0;
-  const int batch = 8;
+  // Three vector kernels per iteration (k_pcg_c, k_pcg_a, k_pcg_b; tba_kernels.cuh) around the matvec.  One GPU and one shared
+  // intrinsics group: k_pcg_a folds the matvec's replica rows itself (no k_fold launch).  The host enqueues the number of
+  // iterations the previous solve needed (+2) before it looks at the device-side state; surplus iterations early-exit.
+  const bool fold_in_a = c->world == 1 && P.single_group && P.n_tiles > 0;
+  double* fold_rep = fold_in_a ? c->rep.p : nullptr;
+  LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
+         part_Q, part_rho, ident, 1, nullptr);
+  cur ^= 1;
+  int batch = std::max(4, std::min(c->last_cg_iters + 2, 64));
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       ++it;
-      LAUNCH(c, k_pcg_v1, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_Q, c->Minv_c.p, c->Minv_i.p, c->r.p, c->z.p, part_rho, ident);
-      cur ^= 1;
-      LAUNCH(c, k_pcg_v2, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_rho, c->z.p, c->sm.p, c->p.p, c->xs.p, c->y.p);
+      LAUNCH(c, k_pcg_c, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_Q, part_rho, c->z2.p, c->sm.p, c->p.p, c->xs.p, c->y.p, nullptr);
       cur ^= 1;
       // every kernel of an iteration (matvec included) early-exits through the device-side state
-      int rc = launch_matvec(c, st_done(st + cur));
+      int rc = launch_matvec(c, st_done(st + cur), fold_in_a);
       if (rc) return rc;
-      LAUNCH(c, k_pcg_v3, VB, VT, 0, P.ncs, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq);
-      LAUNCH(c, k_pcg_v4, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, part_Q);
+      LAUNCH(c, k_pcg_a, VB, VT, 0, P.ncs, P.ne, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq, fold_rep);
+      LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
+             part_Q, part_rho, ident, 0, fold_rep);
       cur ^= 1;
       if (o.cg_residual_reset_period > 0 && it % o.cg_residual_reset_period == 0) {
         LAUNCH(c, k_pcg_reset_a, VB, VT, 0, P.ncs, st + cur, c->x.p, c->sm.p, c->xs.p, c->y.p);
-        rc = launch_matvec(c, st_done(st + cur));
+        rc = launch_matvec(c, st_done(st + cur), fold_in_a);
         if (rc) return rc;
-        LAUNCH(c, k_pcg_reset_b, VB, VT, 0, P.ncs, st + cur, c->y.p, c->sm.p, c->D2.p, c->x.p, c->b.p, c->r.p, part_Q);
+        LAUNCH(c, k_pcg_reset_bz, VB, VT, 0, P, st + cur, c->y.p, c->sm.p, c->D2.p, c->x.p, c->b.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
+               part_Q, part_rho, ident, fold_rep);
+        if (fold_in_a) LAUNCH(c, k_zero_rep_cols, 4, 256, 0, c->rep.p);
       }
     }
     LAUNCH(c, k_pcg_finalize, 1, 32, 0, st + cur, st + (cur ^ 1), part_Q, c->done_flag.p);
@@ -470,7 +482,9 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     if (c->h_st->done) break;
     if (it > o.max_linear_solver_iterations + batch) { set_err(c, "PCG did not terminate"); return TBA_ERR_CUDA; }
+    batch = 4;
   }
+  c->last_cg_iters = c->h_st->iters;
   *iters = c->h_st->iters;
   *status = c->h_st->status;
   c->real_matvecs += c->h_st->iters + (o.cg_residual_reset_period > 0 ? c->h_st->iters / o.cg_residual_reset_period : 0);
@@ -932,7 +946,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(pt_slot, (size_t)npd); ALLOC(pt_len, (size_t)npd); ALLOC(pt_stat, (size_t)npd);
   ALLOC(lin, 2 * (size_t)ncs + 16); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
   ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
-  ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
+  ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(z2, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
   ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(rep, (size_t)NREP * REPW);
 #undef ALLOC
 #define H2D(buf, src, n)                                                                                      \

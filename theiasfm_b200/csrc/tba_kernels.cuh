@@ -1417,102 +1417,7 @@ __global__ void k_pcg_init_state(PcgState* st, const double* __restrict__ part, 
   *st = s;
 }
 
-// V1: [Q-test of the previous iteration]; z = Minv r; partial rho = r.z
-__global__ void __launch_bounds__(VT) k_pcg_v1(DevProblem P, const PcgState* __restrict__ in, PcgState* __restrict__ out,
-                                               const double* __restrict__ part_Q, const double* __restrict__ Minv_c,
-                                               const double* __restrict__ Minv_i, const double* __restrict__ r,
-                                               double* __restrict__ z, double* __restrict__ part_rho, int identity_precond) {
-  __shared__ double s_red[32];
-  PcgState st = *in;
-  if (!st.done && st.pending_q) {
-    const double Q1 = -sum_partials(part_Q, s_red);
-    const double zeta = st.iters * (Q1 - st.Q0) / Q1;
-    st.Q1 = Q1;
-    st.pending_q = 0;
-    if (zeta < st.eta && st.iters >= st.min_iters) { st.done = 1; st.status = 0; }
-    else {
-      st.Q0 = Q1;
-      if (st.iters >= st.max_iters) { st.done = 1; st.status = 1; }
-      else st.iters += 1;
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
-  if (st.done) return;
-  double acc = 0.0;
-  const int nblk = P.n_cam + P.n_group;
-  for (int blk = blockIdx.x * VT + threadIdx.x; blk < nblk; blk += VB * VT) {
-    if (blk < P.n_cam) {
-      const double* M = Minv_c + (size_t)blk * 36;
-      const double* rr = r + (size_t)blk * 6;
-      double* zz = z + (size_t)blk * 6;
-      double rv[6];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) rv[a] = rr[a];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        double s = rv[a];
-        if (!identity_precond) {
-          s = 0.0;
-#pragma unroll
-          for (int b = 0; b < 6; ++b) s += M[a * 6 + b] * rv[b];
-        }
-        zz[a] = s;
-        acc += rv[a] * s;
-      }
-    } else {
-      const int g = blk - P.n_cam;
-      const double* M = Minv_i + (size_t)g * 100;
-      const double* rr = r + P.ne + (size_t)g * 10;
-      double* zz = z + P.ne + (size_t)g * 10;
-      double rv[10];
-#pragma unroll
-      for (int a = 0; a < 10; ++a) rv[a] = rr[a];
-#pragma unroll
-      for (int a = 0; a < 10; ++a) {
-        double s = rv[a];
-        if (!identity_precond) {
-          s = 0.0;
-#pragma unroll
-          for (int b = 0; b < 10; ++b) s += M[a * 10 + b] * rv[b];
-        }
-        zz[a] = s;
-        acc += rv[a] * s;
-      }
-    }
-  }
-  const double s = block_sum(acc, s_red);
-  if (threadIdx.x == 0) part_rho[blockIdx.x] = s;
-}
-
-// V2: rho, beta; p = z + beta p; xs = sm .* p; y = 0
-__global__ void __launch_bounds__(VT) k_pcg_v2(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
-                                               const double* __restrict__ part_rho, const double* __restrict__ z,
-                                               const double* __restrict__ sm, double* __restrict__ p, double* __restrict__ xs,
-                                               double* __restrict__ y) {
-  __shared__ double s_red[32];
-  PcgState st = *in;
-  if (!st.done) {
-    const double rho = sum_partials(part_rho, s_red);
-    st.last_rho = st.rho;
-    st.rho = rho;
-    if (zero_or_inf(rho)) { st.done = 1; st.status = 2; }
-    else if (st.iters > 1) {
-      st.beta = rho / st.last_rho;
-      if (zero_or_inf(st.beta)) { st.done = 1; st.status = 2; }
-    } else st.beta = 0.0;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
-  if (st.done) return;
-  const bool first = st.iters == 1;
-  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
-    const double pv = first ? z[i] : z[i] + st.beta * p[i];
-    p[i] = pv;
-    xs[i] = sm[i] * pv;
-    y[i] = 0.0;
-  }
-}
-
-// V3: q = sm .* y + D2 .* p (stored in z); partial pq = p.q
+// q = sm .* y + D2 .* p; partial pq = p.q  (kept for tba_debug_schur_matvec)
 __global__ void __launch_bounds__(VT) k_pcg_v3(int ncs, const PcgState* __restrict__ in, const double* __restrict__ y,
                                                const double* __restrict__ sm, const double* __restrict__ D2,
                                                const double* __restrict__ p, double* __restrict__ q,
@@ -1529,14 +1434,141 @@ __global__ void __launch_bounds__(VT) k_pcg_v3(int ncs, const PcgState* __restri
   if (threadIdx.x == 0) part_pq[blockIdx.x] = s;
 }
 
-// V4: alpha = rho / pq; x += alpha p; r -= alpha q; partial x.(b + r)
-__global__ void __launch_bounds__(VT) k_pcg_v4(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
-                                               const double* __restrict__ part_pq, const double* __restrict__ p,
-                                               const double* __restrict__ q, const double* __restrict__ b,
-                                               double* __restrict__ x, double* __restrict__ r, double* __restrict__ part_Q) {
+// ---- round 2: three vector kernels per CG iteration instead of four (plus the separate fold) -------------------------------
+//   C: [Q-test of the previous iteration]; rho, beta; p = z + beta p; xs = sm .* p; y = 0        (k_pcg_c)
+//      matvec
+//   A: [fold of the shared-intrinsics replica rows into y]; q = sm .* y + D2 .* p; partial p.q   (k_pcg_a)
+//   B: alpha = rho / pq; x += alpha p; r -= alpha q; partial x.(b + r); z = Minv r; partial r.z  (k_pcg_b, per parameter block)
+// The same operations in the same order as the round-1 sequence k_pcg_v1 .. v4; the partial sums of x.(b + r) are grouped per
+// parameter block now (they were grouped per element stride), i.e. equal up to fp64 summation order.
+
+// z = Minv r for one parameter block (camera: 6, intrinsics group: 10); returns r.z
+__device__ __forceinline__ double pcg_precondition_block(const DevProblem& P, int blk, const double* __restrict__ Minv_c,
+                                                         const double* __restrict__ Minv_i, const double* __restrict__ r,
+                                                         double* __restrict__ z, int identity_precond) {
+  double acc = 0.0;
+  if (blk < P.n_cam) {
+    const double* M = Minv_c + (size_t)blk * 36;
+    const double* rr = r + (size_t)blk * 6;
+    double* zz = z + (size_t)blk * 6;
+    double rv[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) rv[a] = rr[a];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = rv[a];
+      if (!identity_precond) {
+        s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) s += M[a * 6 + b] * rv[b];
+      }
+      zz[a] = s;
+      acc += rv[a] * s;
+    }
+  } else {
+    const int g = blk - P.n_cam;
+    const double* M = Minv_i + (size_t)g * 100;
+    const double* rr = r + P.ne + (size_t)g * 10;
+    double* zz = z + P.ne + (size_t)g * 10;
+    double rv[10];
+#pragma unroll
+    for (int a = 0; a < 10; ++a) rv[a] = rr[a];
+#pragma unroll
+    for (int a = 0; a < 10; ++a) {
+      double s = rv[a];
+      if (!identity_precond) {
+        s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 10; ++b) s += M[a * 10 + b] * rv[b];
+      }
+      zz[a] = s;
+      acc += rv[a] * s;
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void pcg_q_test(PcgState& st, const double* __restrict__ part_Q, double* s_red) {
+  if (!st.done && st.pending_q) {
+    const double Q1 = -sum_partials(part_Q, s_red);
+    const double zeta = st.iters * (Q1 - st.Q0) / Q1;
+    st.Q1 = Q1;
+    st.pending_q = 0;
+    if (zeta < st.eta && st.iters >= st.min_iters) { st.done = 1; st.status = 0; }
+    else {
+      st.Q0 = Q1;
+      if (st.iters >= st.max_iters) { st.done = 1; st.status = 1; }
+      else st.iters += 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                              const double* __restrict__ part_Q, const double* __restrict__ part_rho,
+                                              const double* __restrict__ z, const double* __restrict__ sm, double* __restrict__ p,
+                                              double* __restrict__ xs, double* __restrict__ y, int* __restrict__ done_flag) {
   __shared__ double s_red[32];
   PcgState st = *in;
+  pcg_q_test(st, part_Q, s_red);
   if (!st.done) {
+    const double rho = sum_partials(part_rho, s_red);
+    st.last_rho = st.rho;
+    st.rho = rho;
+    if (zero_or_inf(rho)) { st.done = 1; st.status = 2; }
+    else if (st.iters > 1) {
+      st.beta = rho / st.last_rho;
+      if (zero_or_inf(st.beta)) { st.done = 1; st.status = 2; }
+    } else st.beta = 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *out = st; if (done_flag) *done_flag = st.done; }
+  if (st.done) return;
+  const bool first = st.iters == 1;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double pv = first ? z[i] : z[i] + st.beta * p[i];
+    p[i] = pv;
+    xs[i] = sm[i] * pv;
+    y[i] = 0.0;
+  }
+}
+
+// fold_rep != nullptr (one GPU, one shared intrinsics group): the replica rows of the matvec are folded into y[ne ..] here,
+// in the fixed row order of k_fold, by every CTA (they all need the value) -- CTA 0 stores it and re-zeroes the replicas.
+__global__ void __launch_bounds__(VT) k_pcg_a(int ncs, int ne, const PcgState* __restrict__ in, double* __restrict__ y,
+                                              const double* __restrict__ sm, const double* __restrict__ D2,
+                                              const double* __restrict__ p, double* __restrict__ q, double* __restrict__ part_pq,
+                                              const double* __restrict__ fold_rep) {
+  __shared__ double s_red[32];
+  __shared__ double s_fold[10];
+  if (in->done) return;
+  if (fold_rep != nullptr) {
+    if (threadIdx.x < 10) {
+      double v = y[ne + threadIdx.x];
+      for (int r = 0; r < NREP; ++r) v += fold_rep[(size_t)r * REPW + threadIdx.x];
+      s_fold[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+  double acc = 0.0;
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+    const double yv = (fold_rep != nullptr && i >= ne && i < ne + 10) ? s_fold[i - ne] : y[i];
+    const double qv = sm[i] * yv + D2[i] * p[i];
+    q[i] = qv;
+    acc += p[i] * qv;
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part_pq[blockIdx.x] = s;
+}
+// (the replicas are re-zeroed by the kernel that runs after every CTA of k_pcg_a has read them: k_pcg_b)
+
+__global__ void __launch_bounds__(VT) k_pcg_b(DevProblem P, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                              const double* __restrict__ part_pq, const double* __restrict__ p,
+                                              const double* __restrict__ q, const double* __restrict__ b, double* __restrict__ x,
+                                              double* __restrict__ r, double* __restrict__ z, const double* __restrict__ Minv_c,
+                                              const double* __restrict__ Minv_i, double* __restrict__ part_Q,
+                                              double* __restrict__ part_rho, int identity_precond, int first, double* __restrict__ zero_rep) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  if (!first && !st.done) {
     const double pq = sum_partials(part_pq, s_red);
     st.pq = pq;
     if (pq <= 0.0 || isinf(pq)) { st.done = 1; st.status = 1; }
@@ -1547,16 +1579,68 @@ __global__ void __launch_bounds__(VT) k_pcg_v4(int ncs, const PcgState* __restri
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
-  if (st.done) return;
-  double acc = 0.0;
-  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
-    const double xv = x[i] + st.alpha * p[i];
-    const double rv = r[i] - st.alpha * q[i];
-    x[i] = xv; r[i] = rv;
-    acc += xv * (b[i] + rv);
+  if (zero_rep != nullptr && !first) {  // the replica columns folded by k_pcg_a
+    for (int i = blockIdx.x * VT + threadIdx.x; i < NREP * 10; i += VB * VT) zero_rep[(size_t)(i / 10) * REPW + (i % 10)] = 0.0;
   }
-  const double s = block_sum(acc, s_red);
-  if (threadIdx.x == 0) part_Q[blockIdx.x] = s;
+  if (st.done) return;
+  double accQ = 0.0, accR = 0.0;
+  const int nblk = P.n_cam + P.n_group;
+  for (int blk = blockIdx.x * VT + threadIdx.x; blk < nblk; blk += VB * VT) {
+    const int i0 = blk < P.n_cam ? blk * 6 : P.ne + (blk - P.n_cam) * 10, n = blk < P.n_cam ? 6 : 10;
+    if (!first) {
+      for (int a = 0; a < n; ++a) {
+        const int i = i0 + a;
+        const double xv = x[i] + st.alpha * p[i];
+        const double rv = r[i] - st.alpha * q[i];
+        x[i] = xv; r[i] = rv;
+        accQ += xv * (b[i] + rv);
+      }
+    }
+    accR += pcg_precondition_block(P, blk, Minv_c, Minv_i, r, z, identity_precond);
+  }
+  const double sQ = block_sum(accQ, s_red);
+  const double sR = block_sum(accR, s_red);
+  if (threadIdx.x == 0) { if (!first) part_Q[blockIdx.x] = sQ; part_rho[blockIdx.x] = sR; }
+}
+
+// Residual reset, second half, with the preconditioner applied to the fresh residual: r = b - (sm.*y + D2.*x); partial x.(b + r);
+// z = Minv r; partial r.z (per parameter block)
+__global__ void __launch_bounds__(VT) k_pcg_reset_bz(DevProblem P, const PcgState* __restrict__ in, double* __restrict__ y,
+                                                     const double* __restrict__ sm, const double* __restrict__ D2,
+                                                     const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
+                                                     double* __restrict__ z, const double* __restrict__ Minv_c,
+                                                     const double* __restrict__ Minv_i, double* __restrict__ part_Q,
+                                                     double* __restrict__ part_rho, int identity_precond, const double* __restrict__ fold_rep) {
+  __shared__ double s_red[32];
+  __shared__ double s_fold[10];
+  if (in->done) return;
+  if (fold_rep != nullptr) {
+    if (threadIdx.x < 10) {
+      double v = y[P.ne + threadIdx.x];
+      for (int rr = 0; rr < NREP; ++rr) v += fold_rep[(size_t)rr * REPW + threadIdx.x];
+      s_fold[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+  double accQ = 0.0, accR = 0.0;
+  const int nblk = P.n_cam + P.n_group;
+  for (int blk = blockIdx.x * VT + threadIdx.x; blk < nblk; blk += VB * VT) {
+    const int i0 = blk < P.n_cam ? blk * 6 : P.ne + (blk - P.n_cam) * 10, n = blk < P.n_cam ? 6 : 10;
+    for (int a = 0; a < n; ++a) {
+      const int i = i0 + a;
+      const double yv = (fold_rep != nullptr && i >= P.ne && i < P.ne + 10) ? s_fold[i - P.ne] : y[i];
+      const double rv = b[i] - (sm[i] * yv + D2[i] * x[i]);
+      r[i] = rv;
+      accQ += x[i] * (b[i] + rv);
+    }
+    accR += pcg_precondition_block(P, blk, Minv_c, Minv_i, r, z, identity_precond);
+  }
+  const double sQ = block_sum(accQ, s_red);
+  const double sR = block_sum(accR, s_red);
+  if (threadIdx.x == 0) { part_Q[blockIdx.x] = sQ; part_rho[blockIdx.x] = sR; }
+}
+__global__ void k_zero_rep_cols(double* __restrict__ rep) {  // re-zero the 10 folded replica columns (after k_pcg_reset_bz)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NREP * 10; i += gridDim.x * blockDim.x) rep[(size_t)(i / 10) * REPW + (i % 10)] = 0.0;
 }
 
 // Residual reset (every cg_residual_reset_period iterations): xs = sm .* x, y = 0 ... matvec ... r = b - (sm.*y + D2.*x)
@@ -1565,22 +1649,6 @@ __global__ void __launch_bounds__(VT) k_pcg_reset_a(int ncs, const PcgState* __r
   if (in->done) return;
   for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) { xs[i] = sm[i] * x[i]; y[i] = 0.0; }
 }
-__global__ void __launch_bounds__(VT) k_pcg_reset_b(int ncs, const PcgState* __restrict__ in, const double* __restrict__ y,
-                                                    const double* __restrict__ sm, const double* __restrict__ D2,
-                                                    const double* __restrict__ x, const double* __restrict__ b,
-                                                    double* __restrict__ r, double* __restrict__ part_Q) {
-  __shared__ double s_red[32];
-  if (in->done) return;
-  double acc = 0.0;
-  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
-    const double rv = b[i] - (sm[i] * y[i] + D2[i] * x[i]);
-    r[i] = rv;
-    acc += x[i] * (b[i] + rv);
-  }
-  const double s = block_sum(acc, s_red);
-  if (threadIdx.x == 0) part_Q[blockIdx.x] = s;
-}
-
 // Finalise a batch: run the pending Q-test so that `done`/`iters` are current, publish the flag.
 __global__ void k_pcg_finalize(const PcgState* __restrict__ in, PcgState* __restrict__ out, const double* __restrict__ part_Q,
                                int* __restrict__ done_flag) {
