@@ -1,7 +1,6 @@
-"""The compiled-in experiment switches (NOTES.md section 3; all default off) against the oracle: TBA_TRED (element-major RED
-emission in k_linearize / k_precond_ext / reduced rhs / matvec), TBA_FAST_SEG, TBA_PACK_SORT, TBA_MATVEC_BULKRED.  They only
-change the ORDER of fp64 sums (and, for the pack switch, of points), so the default tolerances of tests/test_gpu_parity.py apply
-unchanged.  Named to run last: none of these kernels ships as the default path."""
+"""The kernel-selection switches against the oracle: TBA_MATVEC=tile (the tile-per-CTA Schur kernels instead of the persistent
+streaming ones; they remain the shipped path for tracks of more than 32 observations), TBA_TRED=0 (lane-per-row REDs), TBA_LIN_OCC=2.
+They only change the ORDER of fp64 sums, so the default tolerances of tests/test_gpu_parity.py apply unchanged."""
 import numpy as np
 import pytest
 
@@ -12,24 +11,19 @@ from theiasfm_b200 import _abi, engine
 pytestmark = pytest.mark.gpu
 
 VARIANTS = {
-    "tred": {"TBA_TRED": "1"},
-    "fast_seg": {"TBA_FAST_SEG": "1"},
-    "pack_sort": {"TBA_PACK_SORT": "1"},
-    "tred+pack_sort": {"TBA_TRED": "1", "TBA_PACK_SORT": "1"},
-    "tred+fast_seg": {"TBA_TRED": "1", "TBA_FAST_SEG": "1"},
-    "lin_occ3": {"TBA_LIN_OCC": "3"},
-    "tred+lin_occ3": {"TBA_TRED": "1", "TBA_LIN_OCC": "3"},
+    "tile_kernels": {"TBA_MATVEC": "tile"},                                        # tile-per-CTA k_schur everywhere (round-1 structure, TRED)
+    "tile_no_tred": {"TBA_MATVEC": "tile", "TBA_TRED": "0"},                       # lane-per-row REDs
+    "r1_kernels": {"TBA_MATVEC": "tile", "TBA_TRED": "0", "TBA_LIN_OCC": "2"},     # the round-1 defaults
+    "lin_occ2": {"TBA_LIN_OCC": "2"},
 }
-# the TMA bulk-reduction matvec (cp.reduce.async.bulk) is the only switch with new PTX: its cases come last in the file
-BULKRED = {"bulkred": {"TBA_MATVEC_BULKRED": "1"}}
-ALL = ("TBA_TRED", "TBA_FAST_SEG", "TBA_PACK_SORT", "TBA_MATVEC_BULKRED", "TBA_LIN_OCC")
+ALL = ("TBA_TRED", "TBA_MATVEC", "TBA_LIN_OCC", "TBA_ABLATE")
 
 
 @pytest.fixture
 def variant_engine(request, monkeypatch):
     for k in ALL:
         monkeypatch.delenv(k, raising=False)
-    for k, v in {**VARIANTS, **BULKRED}[request.param].items():
+    for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)
     e = engine.Engine()  # the switches are read when the context is created
     yield e
@@ -64,16 +58,8 @@ def test_switch_stage_parity(variant_engine, oracle):
     stage_body(variant_engine, oracle, "pinhole_shared", False, _abi.LOSS_TRIVIAL)
 
 
-@pytest.mark.parametrize("variant_engine", ["tred", "fast_seg", "tred+pack_sort"], indirect=True)
+@pytest.mark.parametrize("variant_engine", ["tile_kernels", "tile_no_tred"], indirect=True)
 def test_switch_long_tracks(variant_engine, oracle):
     """Long tiles (tracks > 32 observations) take the plain RED path in k_linearize and the staged one elsewhere."""
     from test_gpu_parity import test_long_tracks_use_the_cta_level_path as body
     body(variant_engine, oracle)
-
-
-@pytest.mark.parametrize("variant_engine", list(BULKRED), indirect=True)
-def test_bulkred_stage_and_solve_parity(variant_engine, oracle):
-    from test_gpu_parity import test_stage_parity as stage_body
-    stage_body(variant_engine, oracle, "radtan_per_camera", True, _abi.LOSS_HUBER)
-    stage_body(variant_engine, oracle, "pinhole_shared", False, _abi.LOSS_TRIVIAL)
-    test_switch_full_solve_parity(variant_engine, oracle, "pinhole_shared", _abi.LOSS_TRIVIAL)

@@ -57,44 +57,53 @@ __host__ __device__ constexpr int nth_bit(uint32_t m, int j) {
   return 0;
 }
 
-// Rotation matrix and left Jacobian of SO(3) for one camera.
-__host__ __device__ inline void cam_prep(const double* __restrict__ w, double* __restrict__ rec) {
-  const double w0 = w[0], w1 = w[1], w2 = w[2];
-  const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
-  double* R = rec;
-  double* L = rec + 9;
+// Rotation matrix and left Jacobian of SO(3) for one camera, in two steps so that kernels can gather a COMPACT record
+// (the angle-axis w from ext + four scalars = 56 bytes instead of the 160-byte matrix record) and rebuild R and J_l in
+// registers with exactly the arithmetic cam_prep itself uses (bit-identical values everywhere):
+//   s4 = {c, S, B, Cc}:  c = cos(th), S = sin(th)/th, B = (1 - cos th)/th^2 = 2 sin^2(th/2)/th^2, Cc = (th - sin th)/th^3;
+//   R   = c I + S [w]x + B w w^T,     J_l = (1 - Cc th^2) I + B [w]x + Cc w w^T;
+//   first-order branch of ceres::AngleAxisRotatePoint (th^2 <= DBL_EPSILON): s4 = {1, 1, 0, 0}, R = I + [w]x, J_l = I
+//   (B == 0 identifies it: B ~ 1/2 whenever the Rodrigues branch runs).
+__host__ __device__ inline void cam_scalars(const double* __restrict__ w, double s4[4]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   if (th2 > DBL_EPSILON) {
     const double th = sqrt(th2);
     double s, c;
     sincos(th, &s, &c);
-    const double ti = 1.0 / th;
-    const double k0 = w0 * ti, k1 = w1 * ti, k2 = w2 * ti;
-    const double oc = 1.0 - c;
-    R[0] = c + oc * k0 * k0;      R[1] = oc * k0 * k1 - s * k2; R[2] = oc * k0 * k2 + s * k1;
-    R[3] = oc * k1 * k0 + s * k2; R[4] = c + oc * k1 * k1;      R[5] = oc * k1 * k2 - s * k0;
-    R[6] = oc * k2 * k0 - s * k1; R[7] = oc * k2 * k1 + s * k0; R[8] = c + oc * k2 * k2;
-    // J_l = I + B [w]x + Cc [w]x^2,  B = (1-cos)/th^2 = 2 sin^2(th/2)/th^2,  Cc = (th - sin)/th^3
     const double sh = sin(0.5 * th);
-    const double B = 2.0 * sh * sh / th2;
-    double Cc;
-    if (th < 0.05) {
-      Cc = 1.0 / 6.0 - th2 * (1.0 / 120.0 - th2 * (1.0 / 5040.0 - th2 * (1.0 / 362880.0 - th2 / 39916800.0)));
-    } else {
-      Cc = (th - s) / (th2 * th);
-    }
-    // [w]x^2 = w w^T - th2 I
-    L[0] = 1.0 + Cc * (w0 * w0 - th2); L[1] = -B * w2 + Cc * w0 * w1;     L[2] = B * w1 + Cc * w0 * w2;
-    L[3] = B * w2 + Cc * w1 * w0;      L[4] = 1.0 + Cc * (w1 * w1 - th2); L[5] = -B * w0 + Cc * w1 * w2;
-    L[6] = -B * w1 + Cc * w2 * w0;     L[7] = B * w0 + Cc * w2 * w1;      L[8] = 1.0 + Cc * (w2 * w2 - th2);
-    rec[18] = 0.0;
+    s4[0] = c;
+    s4[1] = s / th;
+    s4[2] = 2.0 * sh * sh / th2;
+    if (th < 0.05) s4[3] = 1.0 / 6.0 - th2 * (1.0 / 120.0 - th2 * (1.0 / 5040.0 - th2 * (1.0 / 362880.0 - th2 / 39916800.0)));
+    else s4[3] = (th - s) / (th2 * th);
   } else {
-    R[0] = 1.0; R[1] = -w2; R[2] = w1;
-    R[3] = w2;  R[4] = 1.0; R[5] = -w0;
-    R[6] = -w1; R[7] = w0;  R[8] = 1.0;
-    L[0] = 1.0; L[1] = 0.0; L[2] = 0.0; L[3] = 0.0; L[4] = 1.0; L[5] = 0.0; L[6] = 0.0; L[7] = 0.0; L[8] = 1.0;
-    rec[18] = 1.0;
+    s4[0] = 1.0; s4[1] = 1.0; s4[2] = 0.0; s4[3] = 0.0;
   }
+}
+__host__ __device__ inline void cam_rec_expand(const double w0, const double w1, const double w2, const double c, const double S,
+                                               const double B, const double Cc, double* __restrict__ rec) {
+  double* R = rec;
+  double* L = rec + 9;
+  const double Sw0 = S * w0, Sw1 = S * w1, Sw2 = S * w2;
+  const double B01 = B * w0 * w1, B02 = B * w0 * w2, B12 = B * w1 * w2;
+  R[0] = c + B * w0 * w0; R[1] = B01 - Sw2;       R[2] = B02 + Sw1;
+  R[3] = B01 + Sw2;       R[4] = c + B * w1 * w1; R[5] = B12 - Sw0;
+  R[6] = B02 - Sw1;       R[7] = B12 + Sw0;       R[8] = c + B * w2 * w2;
+  const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+  const double d = 1.0 - Cc * th2;
+  const double Bw0 = B * w0, Bw1 = B * w1, Bw2 = B * w2;
+  const double C01 = Cc * w0 * w1, C02 = Cc * w0 * w2, C12 = Cc * w1 * w2;
+  L[0] = d + Cc * w0 * w0; L[1] = C01 - Bw2;        L[2] = C02 + Bw1;
+  L[3] = C01 + Bw2;        L[4] = d + Cc * w1 * w1; L[5] = C12 - Bw0;
+  L[6] = C02 - Bw1;        L[7] = C12 + Bw0;        L[8] = d + Cc * w2 * w2;
+  rec[18] = B == 0.0 ? 1.0 : 0.0;  // first-order branch
   rec[19] = 0.0;
+}
+__host__ __device__ inline void cam_prep(const double* __restrict__ w, double* __restrict__ rec, double* __restrict__ s4_out = nullptr) {
+  double s4[4];
+  cam_scalars(w, s4);
+  cam_rec_expand(w[0], w[1], w[2], s4[0], s4[1], s4[2], s4[3], rec);
+  if (s4_out) { s4_out[0] = s4[0]; s4_out[1] = s4[1]; s4_out[2] = s4[2]; s4_out[3] = s4[3]; }
 }
 
 // ceres::LossFunction::Evaluate for the six types create_loss_function.cc:42-71 maps to.

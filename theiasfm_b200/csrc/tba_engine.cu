@@ -107,7 +107,7 @@ struct tba_context {
   int n_pt_caller = 0;
   std::vector<int> pk2caller;  // packed point -> caller point id
   // parameters and packed problem
-  DevBuf<double> ext, intr, pt, ext_c, intr_c, pt_c, cam_rec, cam_rec_c, xy, J, res, Hpp, gp, Mp, sp, dpt;
+  DevBuf<double> ext, intr, pt, ext_c, intr_c, pt_c, cam_rec, cam_rec_c, cam_s4, cam_s4_c, xy, J, res, Hpp, gp, Mp, sp, dpt;
   DevBuf<int> cam_group, group_model, slot_cam, slot_pt, tile_pt_begin, tile_nruns;
   DevBuf<uint8_t> slot_flags, pt_const, tile_flags;
   void* stage = nullptr;  // pinned host staging for the packed observation arrays
@@ -272,7 +272,7 @@ int read_scal(tba_context* c, const double* dev, int n, double* out) {
 int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
   DevProblem& P = c->P;
   CUDA_OK(c, cudaMemsetAsync(c->lin.p, 0, (2 * (size_t)P.ncs + 16) * sizeof(double), c->stream));
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec, P.cam_s4);
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
     if (c->has_ext_models) {  // FISHEYE / FOV / DIVISION_UNDISTORTION present: the dual-number instantiation, all 10 columns
@@ -515,11 +515,11 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
   // multi-GPU: every branch of the LM loop must be taken by all ranks alike, the time-out included.  Rank 0's clock is the
   // clock: its elapsed time rides in slot 8 of this all-reduce (the other ranks add 0), so every rank reads the same value.
   if (c->world > 1) LAUNCH(c, k_set_f64, 1, 1, 0, c->scal2.p + 8, c->rank == 0 ? elapsed_s : 0.0);
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c, P.cam_s4_c);
   if (P.n_tiles > 0) {
     const int pb_cost = prof_begin(c);
-    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
-    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_s4_c, P.intr_c, P.pt_c, c->rep.p); }
+    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_s4_c, P.intr_c, P.pt_c, c->rep.p); }
     prof_end(c, 6, pb_cost);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
@@ -555,13 +555,14 @@ void accept_candidate(tba_context* c) {
   std::swap(P.intr, P.intr_c);
   std::swap(P.pt, P.pt_c);
   std::swap(P.cam_rec, P.cam_rec_c);
+  std::swap(P.cam_s4, P.cam_s4_c);
 }
 
 // ---- N4: inner iterations -------------------------------------------------------------------------------
 // The candidate buffers seen as "the problem": kernels that read P.ext / P.intr / P.pt / P.cam_rec then work on the candidate.
 DevProblem candidate_view(const DevProblem& P) {
   DevProblem Q = P;
-  Q.ext = P.ext_c; Q.intr = P.intr_c; Q.pt = P.pt_c; Q.cam_rec = P.cam_rec_c;
+  Q.ext = P.ext_c; Q.intr = P.intr_c; Q.pt = P.pt_c; Q.cam_rec = P.cam_rec_c; Q.cam_s4 = P.cam_s4_c;
   return Q;
 }
 
@@ -608,7 +609,7 @@ int run_block_stage(tba_context* c) {
     CUDA_OK(c, cudaMemcpyAsync(c->d_blk_vals.p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(c, cudaMemcpyAsync(c->d_blk_active.p, active.data(), (size_t)nb, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(c, cudaMemsetAsync(c->d_blk_acc.p, 0, acc.size() * 8, c->stream));
-    if (KIND == kBlockCamera) LAUNCH(c, k_cam_prep, (nb + 127) / 128, 128, 0, nb, c->d_blk_vals.p, c->d_blk_rec.p);
+    if (KIND == kBlockCamera) LAUNCH(c, k_cam_prep, (nb + 127) / 128, 128, 0, nb, c->d_blk_vals.p, c->d_blk_rec.p, (double*)nullptr);
     if (P.n_tiles > 0 && pass == 0) {
       auto kfn = c->has_ext_models ? k_block_pass<KIND, true, false> : k_block_pass<KIND, false, false>;
       LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, A);
@@ -642,7 +643,7 @@ int stage_inner_iterations(tba_context* c, double* inner_cost, bool* ok) {
   DevProblem& P = c->P;
   int rc = run_block_stage<kBlockCamera>(c);
   if (rc) return rc;
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c, P.cam_s4_c);
   rc = run_block_stage<kBlockGroup>(c);
   if (rc) return rc;
   if (P.n_pt > 0) {
@@ -661,8 +662,8 @@ int stage_inner_iterations(tba_context* c, double* inner_cost, bool* ok) {
   // cost at the refined candidate
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
-    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
-    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_s4_c, P.intr_c, P.pt_c, c->rep.p); }
+    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_s4_c, P.intr_c, P.pt_c, c->rep.p); }
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   rc = allreduce_sum(c, c->scal2.p, 3);
@@ -937,7 +938,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   c->h2d_bytes = 0; c->d2h_bytes = 0; c->launches = 0;
 #define ALLOC(buf, n) CUDA_OK(c, c->buf.alloc(n))
   ALLOC(ext, (size_t)ne); ALLOC(ext_c, (size_t)ne); ALLOC(intr, (size_t)ng * 10); ALLOC(intr_c, (size_t)ng * 10);
-  ALLOC(pt, (size_t)npd * 4); ALLOC(pt_c, (size_t)npd * 4); ALLOC(cam_rec, (size_t)nc * kCamRec); ALLOC(cam_rec_c, (size_t)nc * kCamRec);
+  ALLOC(pt, (size_t)npd * 4); ALLOC(pt_c, (size_t)npd * 4); ALLOC(cam_rec, (size_t)nc * kCamRec); ALLOC(cam_rec_c, (size_t)nc * kCamRec); ALLOC(cam_s4, (size_t)nc * 4); ALLOC(cam_s4_c, (size_t)nc * 4);
   ALLOC(xy, (size_t)n_slots * 2); ALLOC(J, (size_t)n_slots * c->NJ); ALLOC(res, (size_t)n_slots * 2);
   ALLOC(Hpp, (size_t)npd * 10); ALLOC(gp, (size_t)npd * 4); ALLOC(Mp, (size_t)npd * 10); ALLOC(sp, (size_t)npd * 4); ALLOC(dpt, (size_t)npd * 4);
   ALLOC(cam_group, (size_t)nc); ALLOC(group_model, (size_t)ng); ALLOC(slot_cam, (size_t)n_slots); ALLOC(slot_pt, (size_t)n_slots);
@@ -983,7 +984,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   P.n_cam = nc; P.n_group = ng; P.n_pt = npd; P.n_tiles = n_tiles; P.ne = ne; P.ncs = ncs; P.single_group = ng == 1;
   P.loss_type = options->loss_function_type; P.loss_width = options->robust_loss_width;
   P.ext = c->ext.p; P.intr = c->intr.p; P.pt = c->pt.p; P.ext_c = c->ext_c.p; P.intr_c = c->intr_c.p; P.pt_c = c->pt_c.p;
-  P.cam_group = c->cam_group.p; P.group_model = c->group_model.p; P.cam_rec = c->cam_rec.p; P.cam_rec_c = c->cam_rec_c.p;
+  P.cam_group = c->cam_group.p; P.group_model = c->group_model.p; P.cam_rec = c->cam_rec.p; P.cam_rec_c = c->cam_rec_c.p; P.cam_s4 = c->cam_s4.p; P.cam_s4_c = c->cam_s4_c.p;
   P.slot_cam = c->slot_cam.p; P.slot_pt = c->slot_pt.p; P.slot_flags = c->slot_flags.p; P.slot_run = c->slot_run.p;
   P.tile_pt_begin = c->tile_pt_begin.p; P.tile_nruns = c->tile_nruns.p; P.tile_flags = c->tile_flags.p; P.xy = c->xy.p; P.J = c->J.p; P.res = c->res.p;
   P.Hpp = c->Hpp.p; P.gp = c->gp.p; P.Mp = c->Mp.p; P.sp = c->sp.p; P.dpt = c->dpt.p; P.pt_const = c->pt_const.p;
@@ -1303,7 +1304,7 @@ int tba_filter_tracks(tba_context* c, double max_inlier_reprojection_error, doub
   DevBuf<uint8_t> d_status;
   CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
   // the per-camera rotation records must describe the CURRENT extrinsics
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec, P.cam_s4);
   if (P.n_pt > 0) {
     auto kfn = c->has_ext_models ? k_filter_tracks<true> : k_filter_tracks<false>;
     LAUNCH(c, kfn, (P.n_pt + 127) / 128, 128, 0, P, c->pt_slot.p, c->pt_len.p, max_sq, cos_min, d_status.p, c->pt_stat.p);
@@ -1371,7 +1372,7 @@ int tba_adjust_tracks(tba_context* c, const tba_options* options, uint8_t* statu
   DevBuf<double> d_cost2;
   CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
   CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec, P.cam_s4);
   if (P.n_pt > 0) {
     auto kfn = c->has_ext_models ? k_adjust_tracks<true> : k_adjust_tracks<false>;
     LAUNCH(c, kfn, (P.n_pt + 63) / 64, 64, 0, P, c->pt_slot.p, c->pt_len.p, point_lm_options(*options), d_status.p, d_cost2.p);
@@ -1398,7 +1399,7 @@ int tba_estimate_tracks(tba_context* c, const tba_options* ba_options, double ma
   DevBuf<double> d_cost2;
   CUDA_OK(c, d_status.alloc((size_t)P.n_pt));
   CUDA_OK(c, d_cost2.alloc((size_t)P.n_pt * 2));
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec, P.cam_s4);
   // the rays live in the Jacobian store (NJ >= 14 doubles per slot; re-linearised by the next tba_minimize anyway)
   double* ray = P.J;
   if (c->n_slots > 0) LAUNCH(c, k_track_rays, (unsigned)((c->n_slots + 255) / 256), 256, 0, P, (long long)c->n_slots, ray);
@@ -1748,10 +1749,10 @@ int tba_debug_evaluate_step(tba_context* c, double* candidate_cost) {
   CUDA_OK(c, cudaSetDevice(c->device));
   DevProblem& P = c->P;
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 3 * sizeof(double), c->stream));
-  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c);
+  LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext_c, P.cam_rec_c, P.cam_s4_c);
   if (P.n_tiles > 0) {
-    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
-    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_rec_c, P.intr_c, P.pt_c, c->rep.p); }
+    if (c->has_ext_models) { auto kfn = k_cost<true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_s4_c, P.intr_c, P.pt_c, c->rep.p); }
+    else { auto kfn = k_cost<false>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, P.ext_c, P.cam_s4_c, P.intr_c, P.pt_c, c->rep.p); }
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
   int rc = allreduce_sum(c, c->scal2.p, 3);

@@ -36,6 +36,8 @@ struct DevProblem {
   const int* cam_group; const int* group_model;
   double* cam_rec;             // [n_cam][kCamRec] for x
   double* cam_rec_c;           // ... for the candidate
+  double* cam_s4;              // [n_cam][4] compact rotation scalars for x (cam_scalars)
+  double* cam_s4_c;            // ... for the candidate
   // observation slots (tile-major, point-sorted)
   const int* slot_cam;         // -1 = padding
   const int* slot_pt;          // packed point id
@@ -130,9 +132,20 @@ __device__ __forceinline__ void warp_red_rows(double* __restrict__ dst, const do
 }
 
 // ------------------------------------------------------------ camera prep
-__global__ void k_cam_prep(int n_cam, const double* __restrict__ ext, double* __restrict__ rec) {
+// rec: the full [kCamRec] record (R | J_l) for the kernels that run rarely; s4 (optional): the four scalars the hot
+// per-observation kernels gather instead (k_linearize, k_cost rebuild R and J_l from ext + s4 in registers).
+__global__ void k_cam_prep(int n_cam, const double* __restrict__ ext, double* __restrict__ rec, double* __restrict__ s4 = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n_cam) cam_prep(ext + (size_t)c * 6 + 3, rec + (size_t)c * kCamRec);
+  if (c < n_cam) cam_prep(ext + (size_t)c * 6 + 3, rec + (size_t)c * kCamRec, s4 ? s4 + (size_t)c * 4 : nullptr);
+}
+// The observing camera's parameters through vector gathers: ext[6] (3 x 128 bit) + s4[4] (2 x 128 bit), expanded in registers.
+__device__ __forceinline__ void gather_camera(const double* __restrict__ ext, const double* __restrict__ s4, int cam, double Cw[6], double rec[kCamRec]) {
+  const double2* e2 = reinterpret_cast<const double2*>(ext + (size_t)cam * 6);
+  const double2 e0 = __ldg(e2), e1 = __ldg(e2 + 1), e3 = __ldg(e2 + 2);
+  const double2* q2 = reinterpret_cast<const double2*>(s4 + (size_t)cam * 4);
+  const double2 q0 = __ldg(q2), q1 = __ldg(q2 + 1);
+  Cw[0] = e0.x; Cw[1] = e0.y; Cw[2] = e1.x; Cw[3] = e1.y; Cw[4] = e3.x; Cw[5] = e3.y;
+  cam_rec_expand(e1.y, e3.x, e3.y, q0.x, q0.y, q1.x, q1.y, rec);
 }
 
 // ---------------------------------------------------- replicated scalar accumulators
@@ -199,7 +212,9 @@ __global__ void __launch_bounds__(TILE, MINB) k_linearize(DevProblem P, double* 
     const double* xyw = P.xy + wslice(tile, warp, 2) + lane;
     const double x = xyw[0], y = xyw[32];
     double rho0 = 0.0;
-    const bool ok = linearize_obs_any<IMASK, EXT>(P.group_model[grp], P.ext + (size_t)cam * 6, P.cam_rec + (size_t)cam * kCamRec,
+    double Cw[6], rec[kCamRec];
+    gather_camera(P.ext, P.cam_s4, cam, Cw, rec);
+    const bool ok = linearize_obs_any<IMASK, EXT>(P.group_model[grp], Cw, rec,
                                          P.intr + (size_t)grp * 10, X.x, X.y, X.z, X.w, x, y, P.loss_type, P.loss_width,
                                          r, rho0, Ja, Jw, Jh, Ji);
     const bool is_fixed = (P.slot_flags[slot] & 1) != 0;
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_linearize(DevProblem P, double* 
 
 // ------------------------------------------------------- K3 cost at candidate
 template <bool EXT = false>
-__global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __restrict__ ext, const double* __restrict__ rec,
+__global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __restrict__ ext, const double* __restrict__ s4,
                                                const double* __restrict__ intr, const double* __restrict__ pt,
                                                double* __restrict__ rep) {
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -342,7 +357,9 @@ __global__ void __launch_bounds__(TILE) k_cost(DevProblem P, const double* __res
     const double4 X = *reinterpret_cast<const double4*>(pt + (size_t)p * 4);
     const double* xyw = P.xy + wslice(tile, warp, 2) + lane;
     double r0, r1;
-    if (!reproject_any<EXT>(P.group_model[grp], ext + (size_t)cam * 6, rec + (size_t)cam * kCamRec, intr + (size_t)grp * 10, X.x, X.y,
+    double Cw[6], rec[kCamRec];
+    gather_camera(ext, s4, cam, Cw, rec);
+    if (!reproject_any<EXT>(P.group_model[grp], Cw, rec, intr + (size_t)grp * 10, X.x, X.y,
                    X.z, X.w, xyw[0], xyw[32], r0, r1)) {
       failed = 1.0;
     } else {
@@ -599,16 +616,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// Never a silent hang: a bulk copy that does not land within ~2 s (4e9 SM cycles) is a bug -- report it and abort the kernel
+// (the launch then fails with a CUDA error that the engine returns to the caller).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("tba: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
 }
 
 // Bulk reduction shared -> global (TMA): dst[0..bytes) += src[0..bytes) element-wise in fp64, asynchronously.
@@ -1000,10 +1029,21 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
 #define JH(j) Jt[(12 + (j)) * 32]
 #define JI(j) Jt[(14 + (j)) * 32]
     double w0 = 0.0, w1 = 0.0, r0 = 0.0, r1 = 0.0;
-    double ja[6], jh[2];
+    // the whole row set of this lane in registers: every element of J is read from shared memory exactly once
+    double ja[6], jh[2], jw[6], ji[2 * NI + 1];
 #pragma unroll
     for (int j = 0; j < 6; ++j) ja[j] = JA(j);
     jh[0] = JH(0); jh[1] = JH(1);
+    if (MODE != 2) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) jw[j] = JW(j);
+#pragma unroll
+      for (int j = 0; j < 2 * NI; ++j) ji[j] = JI(j);
+    }
+#undef JW
+#undef JI
+#define JW(j) (MODE != 2 ? jw[j] : Jt[(6 + (j)) * 32])
+#define JI(j) (MODE != 2 ? ji[j] : Jt[(14 + (j)) * 32])
     if (valid) {
       if (MODE != 0) { r0 = sR[lane]; r1 = sR[32 + lane]; }
       if (MODE != 1) {
