@@ -305,10 +305,10 @@ int tba_set_max_iterations(tba_context* ctx, int32_t max_num_iterations);
  * out[4..7] = {observation slots, observations, packed points, doubles stored per observation}. */
 int tba_set_profiling(tba_context* ctx, int enable);
 int tba_get_profile(tba_context* ctx, double* out8);
-/* Per-stage breakdown of the same profiled run: out14[2k] = total ms, out14[2k+1] = launches, k over
+/* Per-stage breakdown of the same profiled run: out16[2k] = total ms, out16[2k+1] = launches, k over
  * {Schur matvec, linearise, extrinsics preconditioner blocks, intrinsics preconditioner blocks, reduced rhs,
- *  back-substitution, candidate cost}. */
-int tba_get_profile_stages(tba_context* ctx, double* out14);
+ *  back-substitution, candidate cost, fused prepare (rhs + both preconditioner block families in one pass over J)}. */
+int tba_get_profile_stages(tba_context* ctx, double* out16);
 
 /* Contiguous point range [begin,end) owned by `rank` of `world_size`
  * (balanced by observation count given per-point counts). */

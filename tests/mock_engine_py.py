@@ -92,7 +92,7 @@ class MockEngine:
     def profile_stages(self):
         p = self.profile()
         z = {"ms": 0.0, "launches": p["linearize_launches"]}
-        out = {k: dict(z) for k in ("linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost")}
+        out = {k: dict(z) for k in ("linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost", "prepare_fused")}
         out["matvec"] = {"ms": 0.0, "launches": p["matvec_launches"]}
         return out
 

@@ -129,7 +129,7 @@ struct tba_context {
   // optional per-kernel timing (CUDA events on the engine stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, int>> ev_spans[7];  // 0: matvec, 1: linearize, 2: precond_ext, 3: precond_intr, 4: rhs, 5: back-substitution, 6: candidate cost ; indices into ev_pool
+  std::vector<std::pair<int, int>> ev_spans[8];  // 0: matvec, 1: linearize, 2: precond_ext, 3: precond_intr, 4: rhs, 5: back-substitution, 6: candidate cost, 7: fused prepare (rhs + both preconditioner block families) ; indices into ev_pool
   // set by tba_solve_multi (which sees the whole problem) before tba_upload: global per-camera observation counts and the
   // global number of free points, so that the upload needs no collective
   const double* preset_cnt_cam = nullptr;
@@ -363,16 +363,33 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
   LAUNCH(c, k_cs_diag, VB, VT, 0, P.ncs, lin_cn(c), c->sm.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, c->D2.p);
   if (P.n_pt > 0) LAUNCH(c, k_point_blocks, (P.n_pt + 255) / 256, 256, 0, P, radius, o.min_lm_diagonal, o.max_lm_diagonal, c->flag.p);
   const size_t nS = (size_t)P.n_cam * 21 + (size_t)P.n_group * 55;
-  if (o.preconditioner_type != TBA_PRECOND_IDENTITY) {
-    CUDA_OK(c, cudaMemsetAsync(c->Sblk.p, 0, nS * sizeof(double), c->stream));
-    if (P.n_tiles > 0) {
+  const bool precond = o.preconditioner_type != TBA_PRECOND_IDENTITY;
+  if (precond) CUDA_OK(c, cudaMemsetAsync(c->Sblk.p, 0, nS * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
+  if (P.n_tiles > 0) {
+    // normal tiles: ONE streaming pass over J for the reduced rhs and both families of SCHUR_JACOBI blocks (k_prepare_stream);
+    // long tiles (and TBA_MATVEC=tile / IDENTITY preconditioner): the three tile kernels
+    int first_tile = 0;
+    if (c->stream_schur && c->exp_tred && precond && c->n_normal_tiles > 0) {
+      const int n_slices = c->n_normal_tiles * (TILE / 32);
+      const int pb = prof_begin(c);
+#define F(M) { using Cfg = PrepCfg<M>; auto kfn = k_prepare_stream<M>; \
+               const int grid = std::max(1, std::min(c->n_sm, (n_slices + Cfg::NW - 1) / Cfg::NW)); \
+               LAUNCH(c, kfn, grid, Cfg::NW * 32, Cfg::SMEM, P, c->y.p, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->rep.p, n_slices); }
+      DISPATCH_IMASK(c->imask, F)
+#undef F
+      prof_end(c, 7, pb);
+      first_tile = c->n_normal_tiles;
+    }
+    const int rest = P.n_tiles - first_tile;
+    if (rest > 0 && precond) {
       const int pb_ext = prof_begin(c);
       if (c->exp_tred) {
-#define F(M) { auto kfn = k_precond_ext<M, true>; LAUNCH(c, kfn, P.n_tiles, TILE, 0, P, c->Sblk.p); }
+#define F(M) { auto kfn = k_precond_ext<M, true>; LAUNCH(c, kfn, rest, TILE, 0, P, c->Sblk.p, first_tile); }
         DISPATCH_IMASK(c->imask, F)
 #undef F
       } else {
-#define F(M) LAUNCH(c, k_precond_ext<M>, P.n_tiles, TILE, 0, P, c->Sblk.p)
+#define F(M) LAUNCH(c, k_precond_ext<M>, rest, TILE, 0, P, c->Sblk.p, first_tile)
         DISPATCH_IMASK(c->imask, F)
 #undef F
       }
@@ -380,24 +397,29 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
       if (c->NI > 0) {
         const size_t smem = (size_t)TILE * 4 * c->NI * sizeof(double) + 2 * TILE * sizeof(int);
         const int pb_intr = prof_begin(c);
-#define F(M) LAUNCH(c, k_precond_intr<M>, P.n_tiles, TILE, smem, P, c->Sblk.p + (size_t)P.n_cam * 21)
+#define F(M) LAUNCH(c, k_precond_intr<M>, rest, TILE, smem, P, c->Sblk.p + (size_t)P.n_cam * 21, first_tile)
         DISPATCH_IMASK(c->imask, F)
 #undef F
         prof_end(c, 3, pb_intr);
       }
     }
+    if (rest > 0) {
+      const int pb_rhs = prof_begin(c);
+      if (first_tile == 0) { const int rc1 = launch_schur<1>(c, nullptr, c->y.p, nullptr); if (rc1) return rc1; }
+      else {
+#define F(M) { auto kfn = k_schur<M, 1, true>; LAUNCH(c, kfn, rest, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr, first_tile); }
+        DISPATCH_IMASK(c->imask, F)
+#undef F
+      }
+      prof_end(c, 4, pb_rhs);
+    }
+    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
+  }
+  if (precond) {
     int rc = allreduce_sum(c, c->Sblk.p, nS);
     if (rc) return rc;
     LAUNCH(c, k_precond_finish, (P.n_cam + P.n_group + 63) / 64, 64, 0, P, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->sm.p,
            c->D2.p, c->Minv_c.p, c->Minv_i.p, c->flag.p);
-  }
-  // reduced rhs: y = F'(I - E M E') r, then b = sm .* y (k_pcg_init)
-  CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
-  if (P.n_tiles > 0) {
-    const int pb_rhs = prof_begin(c);
-    { const int rc1 = launch_schur<1>(c, nullptr, c->y.p, nullptr); if (rc1) return rc1; }
-    prof_end(c, 4, pb_rhs);
-    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   int rc = allreduce_sum(c, c->y.p, P.ncs);
   if (rc) return rc;
@@ -1005,7 +1027,8 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   CUDA_OK(c, cudaFuncSetAttribute(k_schur<M, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 0>::SMEM)); \
   CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 1>::SMEM)); \
-  CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 2>::SMEM));
+  CUDA_OK(c, cudaFuncSetAttribute(k_schur_stream<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<M, 2>::SMEM)); \
+  CUDA_OK(c, cudaFuncSetAttribute(k_prepare_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrepCfg<M>::SMEM));
     DISPATCH_IMASK(c->imask, F)
 #undef F
   }
@@ -1274,12 +1297,13 @@ int tba_get_profile(tba_context* c, double* out) {
 }
 
 // Per-stage device times of the profiled minimise: out[2k] = total ms, out[2k + 1] = launches for stage k of
-// {0 matvec, 1 linearize, 2 precond_ext, 3 precond_intr, 4 reduced rhs, 5 back-substitution, 6 candidate cost}.
+// {0 matvec, 1 linearize, 2 precond_ext, 3 precond_intr, 4 reduced rhs, 5 back-substitution, 6 candidate cost,
+//  7 fused prepare (rhs + both preconditioner block families in one pass)}.
 int tba_get_profile_stages(tba_context* c, double* out) {
   if (!c || !out) return TBA_ERR_INVALID_ARGUMENT;
   CUDA_OK(c, cudaSetDevice(c->device));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  for (int w = 0; w < 7; ++w) {
+  for (int w = 0; w < 8; ++w) {
     double tot = 0;
     for (auto& sp : c->ev_spans[w]) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_pool[sp.first], c->ev_pool[sp.second]); tot += ms; }
     out[2 * w] = tot; out[2 * w + 1] = (double)c->ev_spans[w].size();

@@ -1146,14 +1146,271 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
   }
 }
 
+// --------------------------------------------- K2p: everything the LM iteration needs from J besides the matvec, in ONE pass
+// Fuses, over the normal tiles and with the streaming structure of k_schur_stream (per-warp TMA ring, pipelined gathers):
+//   * the reduced right-hand side  y += F^T (I - E M E^T) r                          (k_schur MODE 1),
+//   * the SCHUR_JACOBI extrinsics blocks  Sc[cam] += J_c^T Q_o J_c,  Q_o = I_2 - J_p M_p J_p^T   (k_precond_ext),
+//   * the SCHUR_JACOBI intrinsics blocks  Si[g] += sum_o J_i^T J_i - sum_(p,g) W^T M_p W,  W = sum_{o in p and g} J_p^T J_i
+//     (k_precond_intr; the per-(point, group) sums W by ballot-driven segmented shuffle reduction instead of shared-memory
+//     atomics; with one shared group every lane keeps its share of Si in registers until the end of its range).
+// Three sweeps over the 3.2 GB linearisation (5.7 ms at 20 M observations in round 1) become one.
+// Long tiles keep the three tile kernels (engine: stage_prepare).
+template <uint32_t IMASK>
+struct PrepCfg {
+  static constexpr int NI = popcount10(IMASK);
+  static constexpr int NJ = 14 + 2 * NI;
+  static constexpr int NSI = NI * (NI + 1) / 2;
+  static constexpr int STG = NJ * 32 + 64 + 32;
+  static constexpr int NS = 3;
+  static constexpr int NWMAX = NI <= 4 ? 10 : 6;  // register budget: NI <= 4: 192 registers per thread, else 255
+  static constexpr int NW = (216 * 1024 / (NS * STG * 8)) > NWMAX ? NWMAX : (216 * 1024 / (NS * STG * 8));
+  static constexpr size_t SMEM = (size_t)NW * NS * STG * 8 + (size_t)NW * NS * 8 + (size_t)NW * (NSI + 1) * 8;
+};
+
+template <uint32_t IMASK>
+__global__ void __launch_bounds__(PrepCfg<IMASK>::NW * 32, 1)
+k_prepare_stream(DevProblem P, double* __restrict__ y, double* __restrict__ Sc, double* __restrict__ Si, double* __restrict__ rep, int n_slices) {
+  using Cfg = PrepCfg<IMASK>;
+  constexpr int NI = Cfg::NI, NJ = Cfg::NJ, STG = Cfg::STG, NS = Cfg::NS, NW = Cfg::NW, NSI = Cfg::NSI;
+#ifdef TBA_EMULATE
+  double* s_dyn = emu::dyn_smem<double>();
+#else
+  extern __shared__ __align__(128) double s_dyn[];
+#endif
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * NW + warp, GW = gridDim.x * NW;
+  const int s_begin = (int)((long long)n_slices * gw / GW), s_end = (int)((long long)n_slices * (gw + 1) / GW);
+  double* ring = s_dyn + (size_t)warp * NS * STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)NW * NS * STG) + warp * NS;
+  double* s_si = s_dyn + (size_t)NW * NS * STG + (size_t)NW * NS;  // [NW][NSI + 1] end-of-kernel partials of the shared-group block
+  constexpr uint32_t jbytes = NJ * 32 * 8, rbytes = 2 * 32 * 8;
+  auto issue = [&](int stage, int slice) {  // lane 0 only
+    double* st = ring + (size_t)stage * STG;
+    mbar_expect_tx(&bars[stage], jbytes + rbytes + 256);
+    bulk_g2s(st, P.J + (size_t)slice * NJ * 32, jbytes, &bars[stage]);
+    bulk_g2s(st + NJ * 32, P.res + (size_t)slice * 64, rbytes, &bars[stage]);
+    int* idx = reinterpret_cast<int*>(st + NJ * 32 + 64);
+    bulk_g2s(idx, P.slot_cam + (size_t)slice * 32, 128, &bars[stage]);
+    bulk_g2s(idx + 32, P.slot_pt + (size_t)slice * 32, 128, &bars[stage]);
+  };
+  if (lane == 0 && s_begin < s_end) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) mbar_init(&bars[k], 1);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (s_begin + k < s_end) issue(k, s_begin + k);
+  }
+  __syncwarp();
+  double yi_acc[NI + 1], si_acc[NSI + 1];
+#pragma unroll
+  for (int j = 0; j < NI; ++j) yi_acc[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < NSI; ++j) si_acc[j] = 0.0;
+  // ---- registers of the slice being prefetched
+  int cam_n = -1, pt_n = 0, grp_n = 0;
+  unsigned heads_n = 0xffffffffu, rheads_n = 0xffffffffu;
+  double h_n = 0.0;
+  double2 m01_n = make_double2(0.0, 0.0), m23_n = m01_n, m45_n = m01_n, m67_n = m01_n, m89_n = m01_n;
+  auto prefetch = [&](int it) {
+    const int stage = it % NS;
+    mbar_wait(&bars[stage], (uint32_t)((it / NS) & 1));
+    const int* idx = reinterpret_cast<const int*>(ring + (size_t)stage * STG + NJ * 32 + 64);
+    cam_n = idx[lane];
+    pt_n = idx[32 + lane];
+    const bool valid = cam_n >= 0;
+    grp_n = 0;
+    if (valid && NI > 0 && !P.single_group) grp_n = __ldg(P.cam_group + cam_n);
+    const int key = valid ? pt_n : -1 - lane;
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const int prevg = __shfl_up_sync(0xffffffffu, grp_n, 1);
+    const bool head = lane == 0 || prev != key;
+    heads_n = __ballot_sync(0xffffffffu, head);
+    rheads_n = __ballot_sync(0xffffffffu, head || prevg != grp_n);  // (point, group) runs
+    if (valid) {
+      h_n = __ldg(P.pt + (size_t)pt_n * 4 + 3);
+      const double2* M2 = reinterpret_cast<const double2*>(P.Mp + (size_t)pt_n * 10);  // every lane: Q_o needs M_p
+      m01_n = __ldg(M2); m23_n = __ldg(M2 + 1); m45_n = __ldg(M2 + 2); m67_n = __ldg(M2 + 3); m89_n = __ldg(M2 + 4);
+    }
+  };
+  if (s_begin < s_end) prefetch(0);
+  for (int s = s_begin, it = 0; s < s_end; ++s, ++it) {
+    const int cam = cam_n, grp = grp_n;
+    const unsigned heads = heads_n, rheads = rheads_n;
+    const double M[10] = {m01_n.x, m01_n.y, m23_n.x, m23_n.y, m45_n.x, m45_n.y, m67_n.x, m67_n.y, m89_n.x, m89_n.y};
+    const double h = h_n;
+    const bool valid = cam >= 0;
+    if (s + 1 < s_end) prefetch(it + 1);
+    const int stage = it % NS;
+    double* sJ = ring + (size_t)stage * STG;
+    const double* sR = sJ + NJ * 32;
+    const double* Jt = sJ + lane;
+    double ja[6], jh[2], jw[6], ji[2 * NI + 1];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { ja[j] = Jt[j * 32]; jw[j] = Jt[(6 + j) * 32]; }
+    jh[0] = Jt[12 * 32]; jh[1] = Jt[13 * 32];
+#pragma unroll
+    for (int j = 0; j < 2 * NI; ++j) ji[j] = Jt[(14 + j) * 32];
+    double r0 = 0.0, r1 = 0.0;
+    if (valid) { r0 = sR[lane]; r1 = sR[32 + lane]; }
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { ja[j] = 0.0; jw[j] = 0.0; }
+      jh[0] = jh[1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2 * NI; ++j) ji[j] = 0.0;
+    }
+    __syncwarp();  // every lane holds its rows: the stage is free for staging from here on
+    const int last = run_last_lane_dev(heads, lane);
+    const int hl = run_head_lane(heads, lane);
+    // ---------------- reduced rhs (MODE 1 of k_schur): w = r
+    {
+      double t[4] = {ja[0] * r0 + ja[3] * r1, ja[1] * r0 + ja[4] * r1, ja[2] * r0 + ja[5] * r1, jh[0] * r0 + jh[1] * r1};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = seg_reduce_to(t[j], last, lane);
+      double u[4];
+      sym4_mul(M, t, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = __shfl_sync(0xffffffffu, u[j], hl);
+      const double z0 = r0 - (ja[0] * u[0] + ja[1] * u[1] + ja[2] * u[2] + jh[0] * u[3]);
+      const double z1 = r1 - (ja[3] * u[0] + ja[4] * u[1] + ja[5] * u[2] + jh[1] * u[3]);
+      double yv[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { yv[j] = -h * (ja[j] * z0 + ja[3 + j] * z1); yv[3 + j] = jw[j] * z0 + jw[3 + j] * z1; }
+      int* sbase = reinterpret_cast<int*>(sJ + 32 * 6);
+      warp_stage_row<6>(sJ, sbase, yv, valid ? cam * 6 : -1, lane);
+      __syncwarp();
+      warp_red_rows<6>(y, sJ, sbase, lane);
+      if (NI > 0) {
+        if (P.single_group) {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) yi_acc[j] += ji[j] * z0 + ji[NI + j] * z1;
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) red_add(y + P.ne + (size_t)grp * 10 + nth_bit(IMASK, j), ji[j] * z0 + ji[NI + j] * z1);
+        }
+      }
+      __syncwarp();
+    }
+    // ---------------- extrinsics blocks: 21 entries per observation, staged and emitted in three groups of seven columns
+    {
+      const double jp0[4] = {ja[0], ja[1], ja[2], jh[0]}, jp1[4] = {ja[3], ja[4], ja[5], jh[1]};
+      double m0[4], m1[4];
+      sym4_mul(M, jp0, m0);
+      sym4_mul(M, jp1, m1);
+      const double q00 = 1.0 - (jp0[0] * m0[0] + jp0[1] * m0[1] + jp0[2] * m0[2] + jp0[3] * m0[3]);
+      const double q01 = -(jp0[0] * m1[0] + jp0[1] * m1[1] + jp0[2] * m1[2] + jp0[3] * m1[3]);
+      const double q11 = 1.0 - (jp1[0] * m1[0] + jp1[1] * m1[1] + jp1[2] * m1[2] + jp1[3] * m1[3]);
+      double c0[6], c1[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { c0[j] = -h * ja[j]; c1[j] = -h * ja[3 + j]; c0[3 + j] = jw[j]; c1[3 + j] = jw[3 + j]; }
+      double v[21];
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double qa0 = q00 * c0[a] + q01 * c1[a], qa1 = q01 * c0[a] + q11 * c1[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) { v[n] = qa0 * c0[b] + qa1 * c1[b]; ++n; }
+      }
+      int* sbase = reinterpret_cast<int*>(sJ + 32 * 7);
+#pragma unroll
+      for (int g3 = 0; g3 < 3; ++g3) {
+        const double vv[7] = {v[7 * g3], v[7 * g3 + 1], v[7 * g3 + 2], v[7 * g3 + 3], v[7 * g3 + 4], v[7 * g3 + 5], v[7 * g3 + 6]};
+        warp_stage_row<7>(sJ, sbase, vv, valid ? cam * 21 + 7 * g3 : -1, lane);
+        __syncwarp();
+        warp_red_rows<7>(Sc, sJ, sbase, lane);
+        __syncwarp();
+      }
+    }
+    // ---------------- intrinsics blocks
+    if (NI > 0) {
+      // W = sum over the (point, group) run of J_p^T J_i  (4 x NI), on the run's head lane
+      const int rlast = run_last_lane_dev(rheads, lane);
+      const bool rhead = (rheads >> lane) & 1u;
+      double W[4 * NI + 1];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double p0 = a < 3 ? ja[a] : jh[0], p1 = a < 3 ? ja[3 + a] : jh[1];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) W[a * NI + j] = seg_reduce_to(p0 * ji[j] + p1 * ji[NI + j], rlast, lane);
+      }
+      double sub[NSI + 1];
+#pragma unroll
+      for (int j = 0; j < NSI; ++j) sub[j] = 0.0;
+      if (rhead && valid) {
+        double MW[4][NI + 1];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const double t4[4] = {W[0 * NI + j], W[1 * NI + j], W[2 * NI + j], W[3 * NI + j]};
+          double u4[4];
+          sym4_mul(M, t4, u4);
+          MW[0][j] = u4[0]; MW[1][j] = u4[1]; MW[2][j] = u4[2]; MW[3][j] = u4[3];
+        }
+        int n = 0;
+#pragma unroll
+        for (int a = 0; a < NI; ++a)
+#pragma unroll
+          for (int b = a; b < NI; ++b) {
+            sub[n] = W[0 * NI + a] * MW[0][b] + W[1 * NI + a] * MW[1][b] + W[2 * NI + a] * MW[2][b] + W[3 * NI + a] * MW[3][b];
+            ++n;
+          }
+      }
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < NI; ++a)
+#pragma unroll
+        for (int b = a; b < NI; ++b) {
+          const double acc = ji[a] * ji[b] + ji[NI + a] * ji[NI + b];  // 0 on padding lanes
+          if (P.single_group) si_acc[n] += acc - sub[n];
+          else if (valid) {
+            const int ia = nth_bit(IMASK, a), ib = nth_bit(IMASK, b);
+            const int idx = ia * 10 - ia * (ia - 1) / 2 + (ib - ia);
+            red_add(Si + (size_t)grp * 55 + idx, acc - sub[n]);
+          }
+          ++n;
+        }
+    }
+    __syncwarp();
+    if (lane == 0 && s + NS < s_end) {
+      fence_proxy_async_smem();
+      issue(stage, s + NS);
+    }
+  }
+  // ---- sums that leave the warp once
+  if (NI > 0 && P.single_group) {
+    double* rr = rep + (size_t)(gw & (NREP - 1)) * REPW;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const double vsum = warp_sum(yi_acc[j]);
+      if (lane == 0) red_add(rr + nth_bit(IMASK, j), vsum);
+    }
+#pragma unroll
+    for (int j = 0; j < NSI; ++j) {
+      const double vsum = warp_sum(si_acc[j]);
+      if (lane == 0) s_si[warp * (NSI + 1) + j] = vsum;
+    }
+    __syncthreads();  // the only block barrier of the kernel: every thread reaches it (no early exit above)
+    if ((int)threadIdx.x < NSI) {
+      double vsum = 0.0;
+      for (int w = 0; w < NW; ++w) vsum += s_si[w * (NSI + 1) + threadIdx.x];
+      // position of entry n in the 10x10 upper triangle
+      int n = 0, idx = 0;
+      for (int a = 0; a < NI; ++a)
+        for (int b = a; b < NI; ++b) {
+          if (n == (int)threadIdx.x) { const int ia = nth_bit(IMASK, a), ib = nth_bit(IMASK, b); idx = ia * 10 - ia * (ia - 1) / 2 + (ib - ia); }
+          ++n;
+        }
+      red_add(Si + idx, vsum);
+    }
+  }
+}
+
 // ------------------------------------------- SCHUR_JACOBI preconditioner blocks
 // Extrinsics blocks: S_cc = sum_o J_c^T Q_o J_c with Q_o = I_2 - J_p M_p J_p^T (a view observes a track once).
 // Sc: [n_cam][21] upper triangle, unscaled (scaling + D^2 + inversion in k_precond_finish).
 template <uint32_t IMASK, bool TRED = false>
-__global__ void __launch_bounds__(TILE) k_precond_ext(DevProblem P, double* __restrict__ Sc) {
+__global__ void __launch_bounds__(TILE) k_precond_ext(DevProblem P, double* __restrict__ Sc, int tile0) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = tile0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t slot = (size_t)tile * TILE + tid;
   const int cam = P.slot_cam[slot];
   if (TRED) {
@@ -1233,7 +1490,7 @@ __global__ void __launch_bounds__(TILE) k_precond_ext(DevProblem P, double* __re
 // Intrinsics blocks: S_gg = sum_o J_i^T J_i - sum_(p,g) W^T M_p W, W = sum_{o in p and g} J_p^T J_i.
 // Si: [n_group][55] upper triangle over the padded 10 parameter indices.  Dynamic smem: runs x 4 x NI doubles.
 template <uint32_t IMASK>
-__global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __restrict__ Si) {
+__global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __restrict__ Si, int tile0) {
   constexpr int NI = popcount10(IMASK);
   constexpr int NJ = 14 + 2 * NI;
   constexpr int NW = 4 * NI;
@@ -1244,7 +1501,7 @@ __global__ void __launch_bounds__(TILE) k_precond_intr(DevProblem P, double* __r
   extern __shared__ double s_w[];  // [nruns][NW] then [nruns] group ids (as int) and points
 #endif
   __shared__ double s_red[32];
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = tile0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nruns = P.tile_nruns[tile];
   int* s_grp = reinterpret_cast<int*>(s_w + (size_t)TILE * NW);
   int* s_pt = s_grp + TILE;

@@ -301,11 +301,11 @@ class Engine:
         return dict(matvec_ms=out[0], matvec_launches=int(out[1]), linearize_ms=out[2], linearize_launches=int(out[3]),
                     slots=int(out[4]), observations=int(out[5]), points=int(out[6]), doubles_per_obs=int(out[7]))
 
-    STAGES = ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost")
+    STAGES = ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost", "prepare_fused")
 
     def profile_stages(self):
         """Per-stage device time of the profiled run: {stage: {"ms": total, "launches": n}} (tba_get_profile_stages)."""
-        out = np.zeros(14)
+        out = np.zeros(16)
         self._check(lib().tba_get_profile_stages(self._h, _dp(out)))
         return {k: {"ms": float(out[2 * i]), "launches": int(out[2 * i + 1])} for i, k in enumerate(self.STAGES)}
 
