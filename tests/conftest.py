@@ -55,4 +55,7 @@ def pytest_collection_modifyitems(config, items):
 def oracle():
     from oracle import oracle_py
     oracle_py.build()
+    # the GPU boxes are shared hosts with 128 logical CPUs: a 128-thread OpenMP team there spends its time in barrier spins whenever
+    # a neighbour is busy (a 20 s test file took 20 min in round 2); the checker does not need more than 32 threads
+    oracle_py.set_num_threads(min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8))
     return oracle_py

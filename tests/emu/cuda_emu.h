@@ -312,6 +312,8 @@ inline uint64_t warp_op(int op, uint64_t payload, int src, int line = 0) {
 }
 }  // namespace emu
 
+inline void __threadfence() {}
+inline void __threadfence_system() {}
 inline void __syncthreads() { emu::suspend(emu::kBlockBarrier); }
 inline void __syncwarp(unsigned = 0xffffffffu, int line = __builtin_LINE()) { emu::warp_op(0, 0, -1, line); }
 inline void emu_yield() { emu::suspend(emu::kSpin); }

@@ -63,7 +63,7 @@ def test_full_size_trajectory_matches_oracle(oracle, workload, n_obs, iters):
     kw = dict(use_inner_iterations=0, linear_solver_type=_abi.ITERATIVE_SCHUR, max_num_iterations=iters)
     p0 = synthetic.make_config(workload)
     assert abs(p0.n_obs - n_obs) <= 0.01 * n_obs
-    oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    oracle.set_num_threads(min(32, len(os.sched_getaffinity(0))))
     po, pg = p0.copy(), p0.copy()
     so = oracle.solve(po, oracle.default_options(**kw))
     eng = engine.Engine()

@@ -7,6 +7,7 @@
 // TBA_ERR_NO_DEVICE / TBA_ERR_CUDA when there is no usable GPU.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -36,6 +37,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;  // optional (peer-memory setup)
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string* err) {
     if (handle) return true;
@@ -55,6 +57,7 @@ struct NcclApi {
     CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
     GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
     if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { *err = "libnccl is missing symbols"; return false; }
     return true;
   }
@@ -148,6 +151,16 @@ struct tba_context {
   bool exp_lin_occ = true;  // k_linearize compiled for 3 CTAs/SM (80 registers, ~130 bytes of spills); TBA_LIN_OCC=2: 2 CTAs/SM, 128 registers
   bool stream_schur = true; // persistent streaming k_schur_stream over the normal tiles; TBA_MATVEC=tile: the tile-per-CTA k_schur everywhere
   int n_normal_tiles = 0;   // tiles whose tracks fit a warp slice (they precede the long tiles)
+  // fused matvec + all-reduce over peer memory (P2pDev, tba_kernels.cuh): world > 1, every peer reachable, TBA_P2P != 0
+  bool p2p_enabled = true, p2p_ok = false, p2p_use = false;
+  size_t p2p_cap = 0;
+  double* p2p_inbox = nullptr;                // local inbox [2][world][cap]
+  unsigned long long* p2p_flags = nullptr;    // local flags [world]
+  int* p2p_ctr = nullptr;
+  std::vector<void*> p2p_opened;              // peer mappings opened with cudaIpcOpenMemHandle
+  DevBuf<double*> p2p_inbox_ptrs;
+  DevBuf<unsigned long long*> p2p_flag_ptrs;
+  unsigned long long p2p_seq = 0;
   int n_sm = 148;
   int64_t real_matvecs = 0;  // matvec launches that did work (not early-exited after PCG convergence)
   double x_cost = 0, fixed_cost = 0;
@@ -325,17 +338,124 @@ int stage_gradient_max_norm(tba_context* c, double* gmax) {
   return TBA_OK;
 }
 
+// ---- peer-memory setup for the fused matvec + all-reduce (collective: every rank calls it from tba_upload) -------------
+void p2p_release(tba_context* c) {
+#ifndef TBA_EMULATE
+  for (void* q : c->p2p_opened) cudaIpcCloseMemHandle(q);
+#endif
+  c->p2p_opened.clear();
+  if (c->p2p_inbox) cudaFree(c->p2p_inbox);
+  if (c->p2p_flags) cudaFree(c->p2p_flags);
+  if (c->p2p_ctr) cudaFree(c->p2p_ctr);
+  c->p2p_inbox = nullptr; c->p2p_flags = nullptr; c->p2p_ctr = nullptr; c->p2p_cap = 0; c->p2p_ok = false;
+}
+
+#ifndef TBA_EMULATE
+struct P2pInfo {
+  long long pid;
+  int device, ok;
+  double* inbox;
+  unsigned long long* flags;
+  cudaIpcMemHandle_t h_inbox, h_flags;
+};
+#endif
+
+// Allocates the inbox for `ncs` doubles per slot and exchanges the mappings.  On any failure on any rank every rank falls
+// back to the NCCL all-reduce (p2p_ok = false); never an error.
+int p2p_setup(tba_context* c, int ncs) {
+#ifdef TBA_EMULATE
+  (void)ncs; c->p2p_ok = false; return TBA_OK;  // the SIMT emulation has no peer mappings: NCCL stand-in
+#else
+  if (c->world == 1 || !c->p2p_enabled || g_nccl.AllGather == nullptr) { c->p2p_ok = false; return TBA_OK; }
+  const size_t cap = ((size_t)ncs + 1) / 2 * 2;
+  if (c->p2p_ok && cap <= c->p2p_cap) return TBA_OK;  // (ncs is a global property: every rank takes the same branch)
+  p2p_release(c);
+  const int W = c->world;
+  int ok = 1;
+  if (cudaMalloc(&c->p2p_inbox, 2 * (size_t)W * cap * sizeof(double)) != cudaSuccess) { c->p2p_inbox = nullptr; ok = 0; }
+  if (cudaMalloc(&c->p2p_flags, (size_t)W * sizeof(unsigned long long)) != cudaSuccess) { c->p2p_flags = nullptr; ok = 0; }
+  if (cudaMalloc(&c->p2p_ctr, sizeof(int)) != cudaSuccess) { c->p2p_ctr = nullptr; ok = 0; }
+  cudaGetLastError();
+  P2pInfo mine;
+  memset(&mine, 0, sizeof mine);
+  mine.pid = (long long)getpid(); mine.device = c->device; mine.inbox = c->p2p_inbox; mine.flags = c->p2p_flags;
+  if (ok) {
+    CUDA_OK(c, cudaMemsetAsync(c->p2p_flags, 0, (size_t)W * sizeof(unsigned long long), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(c->p2p_ctr, 0, sizeof(int), c->stream));
+    if (cudaIpcGetMemHandle(&mine.h_inbox, c->p2p_inbox) != cudaSuccess || cudaIpcGetMemHandle(&mine.h_flags, c->p2p_flags) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  mine.ok = ok;
+  // all-gather the descriptors (device buffers, NCCL)
+  DevBuf<char> d_send, d_recv;
+  CUDA_OK(c, d_send.alloc(sizeof(P2pInfo)));
+  CUDA_OK(c, d_recv.alloc(sizeof(P2pInfo) * (size_t)W));
+  CUDA_OK(c, cudaMemcpyAsync(d_send.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(c, g_nccl.AllGather(d_send.p, d_recv.p, sizeof(P2pInfo), ncclChar, c->comm, c->stream));
+  std::vector<P2pInfo> all((size_t)W);
+  CUDA_OK(c, cudaMemcpyAsync(all.data(), d_recv.p, sizeof(P2pInfo) * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  std::vector<double*> inbox((size_t)W, nullptr);
+  std::vector<unsigned long long*> flags((size_t)W, nullptr);
+  for (int q = 0; q < W && ok; ++q) {
+    if (!all[q].ok) { ok = 0; break; }
+    if (q == c->rank) { inbox[q] = c->p2p_inbox; flags[q] = c->p2p_flags; continue; }
+    if (all[q].pid == mine.pid) {  // rank threads of one process (tba_solve_multi): plain peer access
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c->device, all[q].device) != cudaSuccess || !can) { ok = 0; cudaGetLastError(); break; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(all[q].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; }
+      cudaGetLastError();
+      inbox[q] = all[q].inbox; flags[q] = all[q].flags;
+    } else {                       // one process per GPU: CUDA IPC mappings (peer access enabled lazily by the runtime)
+      void *pi = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pi, all[q].h_inbox, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      c->p2p_opened.push_back(pi);
+      if (cudaIpcOpenMemHandle(&pf, all[q].h_flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      c->p2p_opened.push_back(pf);
+      inbox[q] = (double*)pi; flags[q] = (unsigned long long*)pf;
+    }
+  }
+  // every rank must agree (a min-reduction of the success flags through the existing all-reduce)
+  {
+    CUDA_OK(c, c->scal2.alloc(16));
+    const double v = ok ? 0.0 : 1.0;
+    CUDA_OK(c, cudaMemcpyAsync(c->scal2.p, &v, 8, cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(c, g_nccl.AllReduce(c->scal2.p, c->scal2.p, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    double failed = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&failed, c->scal2.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (failed != 0.0) { p2p_release(c); return TBA_OK; }
+  }
+  CUDA_OK(c, c->p2p_inbox_ptrs.alloc((size_t)W));
+  CUDA_OK(c, c->p2p_flag_ptrs.alloc((size_t)W));
+  CUDA_OK(c, cudaMemcpyAsync(c->p2p_inbox_ptrs.p, inbox.data(), (size_t)W * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->p2p_flag_ptrs.p, flags.data(), (size_t)W * sizeof(unsigned long long*), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->p2p_cap = cap; c->p2p_seq = 0; c->p2p_ok = true;
+  return TBA_OK;
+#endif
+}
+
+P2pDev p2p_none() { return P2pDev(); }
+// The descriptor of the NEXT exchange (advances the sequence number): the matvec launch and its consumer get the same one.
+P2pDev p2p_next(tba_context* c) {
+  P2pDev d;
+  d.world = c->world; d.rank = c->rank; d.seq = ++c->p2p_seq; d.cap = c->p2p_cap;
+  d.inbox = c->p2p_inbox_ptrs.p; d.flags = c->p2p_flag_ptrs.p; d.ctr = c->p2p_ctr;
+  return d;
+}
+
 // One pass of the implicit Schur operator (MODE 0 matvec, 1 reduced rhs, 2 back-substitution) over every tile: the persistent
 // streaming kernel over the normal tiles, the tile-per-CTA kernel over the long tiles (tracks of 33..256 observations).
 template <int MODE>
-int launch_schur(tba_context* c, const double* xs, double* y, const int* done) {
+int launch_schur(tba_context* c, const double* xs, double* y, const int* done, const P2pDev& pp = P2pDev()) {
   DevProblem& P = c->P;
   int first_tile = 0;
   if (c->stream_schur && c->exp_tred && c->n_normal_tiles > 0) {
     const int n_slices = c->n_normal_tiles * (TILE / 32);
 #define F(M) { using Cfg = StreamCfg<M, MODE>; auto kfn = k_schur_stream<M, MODE>; \
                const int grid = std::max(1, std::min(c->n_sm, (n_slices + Cfg::NW - 1) / Cfg::NW)); \
-               LAUNCH(c, kfn, grid, Cfg::NW * 32, Cfg::SMEM, P, xs, y, c->rep.p, done, n_slices); }
+               LAUNCH(c, kfn, grid, Cfg::NW * 32, Cfg::SMEM, P, xs, y, c->rep.p, done, n_slices, pp); }
     DISPATCH_IMASK(c->imask, F)
 #undef F
     first_tile = c->n_normal_tiles;
@@ -436,14 +556,19 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
 
 const int* st_done(const PcgState* st) { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(st) + offsetof(PcgState, done)); }
 
-// defer_fold: the caller folds the shared-intrinsics replica rows itself (k_pcg_a / k_pcg_reset_bz; one GPU only)
-int launch_matvec(tba_context* c, const int* done, bool defer_fold = false) {
+// The fused path is available when the whole problem runs through the streaming kernel (no long tiles, the default kernels).
+bool p2p_matvec_possible(const tba_context* c) { return c->p2p_ok && c->p2p_use; }
+
+// defer_fold: the caller folds the shared-intrinsics replica rows itself (k_pcg_a / k_pcg_reset_bz; one GPU only).
+// pp (world > 1): the matvec kernel itself pushes the partial sums to the peers; no fold launch, no NCCL call.
+int launch_matvec(tba_context* c, const int* done, bool defer_fold = false, const P2pDev& pp = P2pDev()) {
   DevProblem& P = c->P;
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
-    const int rc = launch_schur<0>(c, c->xs.p, c->y.p, done);
+    const int rc = launch_schur<0>(c, c->xs.p, c->y.p, done, pp);
     if (rc) return rc;
     prof_end(c, 0, pb);
+    if (pp.world > 1) return TBA_OK;
     if (P.single_group && !defer_fold) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   return allreduce_sum(c, c->y.p, P.ncs);
@@ -473,6 +598,8 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
   // iterations the previous solve needed (+2) before it looks at the device-side state; surplus iterations early-exit.
   const bool fold_in_a = c->world == 1 && P.single_group && P.n_tiles > 0;
   double* fold_rep = fold_in_a ? c->rep.p : nullptr;
+  const bool p2p = p2p_matvec_possible(c);  // multi-GPU: the matvec pushes its partial sums to the peers, k_pcg_a sums the inbox
+  int* zero_ctr = p2p ? c->p2p_ctr : nullptr;
   LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
          part_Q, part_rho, ident, 1, nullptr);
   cur ^= 1;
@@ -480,21 +607,23 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       ++it;
-      LAUNCH(c, k_pcg_c, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_Q, part_rho, c->z2.p, c->sm.p, c->p.p, c->xs.p, c->y.p, nullptr);
+      LAUNCH(c, k_pcg_c, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_Q, part_rho, c->z2.p, c->sm.p, c->p.p, c->xs.p, c->y.p, nullptr, zero_ctr);
       cur ^= 1;
       // every kernel of an iteration (matvec included) early-exits through the device-side state
-      int rc = launch_matvec(c, st_done(st + cur), fold_in_a);
+      const P2pDev pp = p2p ? p2p_next(c) : p2p_none();
+      int rc = launch_matvec(c, st_done(st + cur), fold_in_a, pp);
       if (rc) return rc;
-      LAUNCH(c, k_pcg_a, VB, VT, 0, P.ncs, P.ne, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq, fold_rep);
+      LAUNCH(c, k_pcg_a, VB, VT, 0, P.ncs, P.ne, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq, fold_rep, pp);
       LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
              part_Q, part_rho, ident, 0, fold_rep);
       cur ^= 1;
       if (o.cg_residual_reset_period > 0 && it % o.cg_residual_reset_period == 0) {
-        LAUNCH(c, k_pcg_reset_a, VB, VT, 0, P.ncs, st + cur, c->x.p, c->sm.p, c->xs.p, c->y.p);
-        rc = launch_matvec(c, st_done(st + cur), fold_in_a);
+        LAUNCH(c, k_pcg_reset_a, VB, VT, 0, P.ncs, st + cur, c->x.p, c->sm.p, c->xs.p, c->y.p, zero_ctr);
+        const P2pDev pr = p2p ? p2p_next(c) : p2p_none();
+        rc = launch_matvec(c, st_done(st + cur), fold_in_a, pr);
         if (rc) return rc;
         LAUNCH(c, k_pcg_reset_bz, VB, VT, 0, P, st + cur, c->y.p, c->sm.p, c->D2.p, c->x.p, c->b.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
-               part_Q, part_rho, ident, fold_rep);
+               part_Q, part_rho, ident, fold_rep, pr);
         if (fold_in_a) LAUNCH(c, k_zero_rep_cols, 4, 256, 0, c->rep.p);
       }
     }
@@ -781,6 +910,7 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   c->device = device; c->rank = rank; c->world = world_size;
   tba_options_init(&c->opt);
   { const char* e = getenv("TBA_MATVEC"); c->stream_schur = !(e != nullptr && e[0] == 't'); }
+  { const char* e = getenv("TBA_P2P"); c->p2p_enabled = !(e != nullptr && e[0] == '0'); }
   // round 2: the transposed RED emission and the 3-CTA/SM linearise are the defaults (driver-measured 28.1 vs 31.9 ms per
   // LM iteration at 20 M observations, costs equal to 2e-8); TBA_TRED=0 / TBA_LIN_OCC=2 select the round-1 kernels
   { const char* e = getenv("TBA_LIN_OCC"); c->exp_lin_occ = !(e != nullptr && e[0] == '2'); }
@@ -809,6 +939,7 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
 void tba_destroy(tba_context* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  p2p_release(c);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -1034,6 +1165,23 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   }
   c->n_normal_tiles = 0;
   for (int t = 0; t < n_tiles; ++t) c->n_normal_tiles += (tile_flags[t] & 1) ? 0 : 1;
+  {
+    // multi-GPU: peer-memory inbox for the fused matvec + all-reduce; used only if EVERY rank runs its whole shard through the
+    // streaming kernel (a rank with long tiles or without tiles would not push) -- agreed on collectively, here
+    const int rcp = p2p_setup(c, ncs);
+    if (rcp) return rcp;
+    c->p2p_use = false;
+    if (c->world > 1 && c->p2p_ok) {
+      const double mine = (c->stream_schur && c->exp_tred && c->n_normal_tiles > 0 && c->n_normal_tiles == n_tiles) ? 0.0 : 1.0;
+      double others = 0.0;
+      CUDA_OK(c, cudaMemcpyAsync(c->scal2.p, &mine, 8, cudaMemcpyHostToDevice, c->stream));
+      const int r2 = allreduce_sum(c, c->scal2.p, 1);
+      if (r2) return r2;
+      CUDA_OK(c, cudaMemcpyAsync(&others, c->scal2.p, 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      c->p2p_use = others == 0.0;
+    }
+  }
   c->have_scale = false;
   if (c->opt.use_inner_iterations) {
     c->h_ext_const.assign(p->ext_const, p->ext_const + nc);

@@ -872,6 +872,61 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
 #undef JI
 }
 
+// --------------------------------------------- fused matvec + all-reduce over NVLink peer memory (multi-GPU)
+// Every rank owns an "inbox" [2][world][cap] in its own HBM that all peers can write (CUDA IPC / peer access).  The CTA of
+// k_schur_stream<., 0> that finishes LAST on a rank folds the replica rows and then STORES the rank's complete partial y into
+// slot `rank` of every peer's inbox (buffer seq & 1) -- 16-byte stores over NVLink, no separate collective launch -- and
+// releases flags[rank] = seq on every peer.  The consumer (k_pcg_a / k_pcg_reset_bz) acquires the `world` flags of its own
+// inbox and sums the slots in rank order: the same bits on every rank (the replicated PCG state stays in lockstep) and
+// run-to-run reproducible for a given world size.  Two buffers suffice: a rank can be at most one exchange ahead of a peer,
+// because exchange k+1 needs the sums of exchange k, to which every peer contributed after it consumed exchange k-1.
+struct P2pDev {
+  int world = 1, rank = 0;
+  unsigned long long seq = 0;
+  size_t cap = 0;                        // doubles per slot
+  double* const* inbox = nullptr;        // [world] base pointers of the ranks' inboxes (inbox[rank] is the local one)
+  unsigned long long* const* flags = nullptr;  // [world] base pointers of the ranks' flag arrays ([world] each)
+  int* ctr = nullptr;                    // local count of finished CTAs (zeroed before every matvec by k_pcg_c / k_pcg_reset_a)
+};
+#ifdef TBA_EMULATE
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return *p; }
+__device__ __forceinline__ double ld_cg(const double* p) { return *p; }
+#else
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+#endif
+// Consumer side: wait for the `world` flags of the local inbox (threads 0 .. world-1), then a block barrier.
+__device__ __forceinline__ void p2p_wait(const P2pDev& pp) {
+  if ((int)threadIdx.x < pp.world) {
+    const unsigned long long* f = pp.flags[pp.rank] + threadIdx.x;
+#ifndef TBA_EMULATE
+    const long long t0 = clock64();
+#endif
+    while (ld_acquire_sys(f) < pp.seq) {
+#ifdef TBA_EMULATE
+      emu_yield();
+#else
+      if (clock64() - t0 > 20000000000ll) { printf("tba: rank %d waited 10 s for the partial sums of rank %d (exchange %llu)\n", pp.rank, (int)threadIdx.x, pp.seq); __trap(); }
+#endif
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double p2p_sum(const P2pDev& pp, int i) {
+  const double* base = pp.inbox[pp.rank] + (size_t)(pp.seq & 1ull) * pp.world * pp.cap + i;
+  double v = 0.0;
+  for (int q = 0; q < pp.world; ++q) v += ld_cg(base + (size_t)q * pp.cap);
+  return v;
+}
+
 // --------------------------------------------- K2s: persistent streaming implicit Schur complement (round 2)
 // Same three operators as k_schur (MODE 0 matvec, 1 reduced rhs, 2 back-substitution) over the NORMAL tiles, restructured
 // around what the round-1 captures showed: the tile-per-CTA kernel is latency bound (one TMA round trip + two levels of
@@ -924,7 +979,7 @@ struct StreamCfg {
 template <uint32_t IMASK, int MODE>
 __global__ void __launch_bounds__(StreamCfg<IMASK, MODE>::NW * 32, 1)
 k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__ y, double* __restrict__ rep,
-               const int* __restrict__ done_flag, int n_slices) {
+               const int* __restrict__ done_flag, int n_slices, P2pDev pp) {
   using Cfg = StreamCfg<IMASK, MODE>;
   constexpr int NI = Cfg::NI, NJ = Cfg::NJ, STG = Cfg::STG, NS = Cfg::NS, NW = Cfg::NW;
   if (done_flag != nullptr && *done_flag) return;
@@ -936,7 +991,7 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * NW + warp, GW = gridDim.x * NW;
   const int s_begin = (int)((long long)n_slices * gw / GW), s_end = (int)((long long)n_slices * (gw + 1) / GW);
-  if (s_begin >= s_end) return;  // warp-uniform; no block-level synchronisation exists in this kernel
+  const bool active = s_begin < s_end;  // warp-uniform; idle warps fall through to the end (the multi-GPU epilogue has block barriers)
   double* ring = s_dyn + (size_t)warp * NS * STG;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)NW * NS * STG) + warp * NS;
   constexpr uint32_t jbytes = NJ * 32 * 8, rbytes = (MODE != 0) ? 2 * 32 * 8 : 0;
@@ -949,7 +1004,7 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
     bulk_g2s(idx, P.slot_cam + (size_t)slice * 32, 128, &bars[stage]);
     bulk_g2s(idx + 32, P.slot_pt + (size_t)slice * 32, 128, &bars[stage]);
   };
-  if (lane == 0) {
+  if (lane == 0 && active) {
 #pragma unroll
     for (int k = 0; k < NS; ++k) mbar_init(&bars[k], 1);
 #pragma unroll
@@ -1006,7 +1061,7 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
       if (MODE == 2) flag_n = P.slot_flags[(size_t)slice * 32 + lane];
     }
   };
-  prefetch(s_begin, 0);
+  if (active) prefetch(s_begin, 0);
   for (int s = s_begin, it = 0; s < s_end; ++s, ++it) {
     // ---- take over the prefetched registers, start the prefetch of the next slice
     const int cam = cam_n, pt = pt_n, grp = grp_n;
@@ -1134,7 +1189,8 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
   }
   // ---- sums that leave the warp once
   double* rr = rep + (size_t)(gw & (NREP - 1)) * REPW;
-  if (MODE == 2) {
+  if (!active) {
+  } else if (MODE == 2) {
     const double m = warp_sum(mcc_acc);
     if (lane == 0) red_add(rr + 23, m);
   } else if (NI > 0 && P.single_group) {
@@ -1142,6 +1198,35 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
     for (int j = 0; j < NI; ++j) {
       const double v = warp_sum(yi_acc[j]);
       if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
+    }
+  }
+  // ---- multi-GPU: the CTA that finishes last on this rank folds and pushes the rank's complete partial y to every peer
+  if (MODE == 0 && pp.world > 1) {
+    __shared__ int s_last;
+    __threadfence();  // this thread's REDs are performed before its CTA is counted
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(pp.ctr, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (NI > 0 && P.single_group && threadIdx.x < 10) {  // k_fold: replica columns 0..9 -> y[ne ..], replicas re-zeroed
+        double v = ld_cg(y + P.ne + threadIdx.x);
+        for (int r = 0; r < NREP; ++r) { v += ld_cg(rep + (size_t)r * REPW + threadIdx.x); rep[(size_t)r * REPW + threadIdx.x] = 0.0; }
+        y[P.ne + threadIdx.x] = v;
+      }
+      __syncthreads();
+      const size_t slot = ((size_t)(pp.seq & 1ull) * pp.world + pp.rank) * pp.cap;
+      const int n2 = (P.ncs + 1) / 2;  // 16-byte stores; cap is even and the slot is padded
+      for (int q = 0; q < pp.world; ++q) {
+        double2* dst = reinterpret_cast<double2*>(pp.inbox[q] + slot);
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+          const double a = ld_cg(y + 2 * i), b = 2 * i + 1 < P.ncs ? ld_cg(y + 2 * i + 1) : 0.0;
+          dst[i] = make_double2(a, b);
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if ((int)threadIdx.x < pp.world) st_release_sys(pp.flags[threadIdx.x] + pp.rank, pp.seq);
     }
   }
 }
@@ -1803,9 +1888,10 @@ __device__ __forceinline__ void pcg_q_test(PcgState& st, const double* __restric
 __global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
                                               const double* __restrict__ part_Q, const double* __restrict__ part_rho,
                                               const double* __restrict__ z, const double* __restrict__ sm, double* __restrict__ p,
-                                              double* __restrict__ xs, double* __restrict__ y, int* __restrict__ done_flag) {
+                                              double* __restrict__ xs, double* __restrict__ y, int* __restrict__ done_flag, int* __restrict__ zero_ctr) {
   __shared__ double s_red[32];
   PcgState st = *in;
+  if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_ctr = 0;  // finished-CTA counter of the next matvec
   pcg_q_test(st, part_Q, s_red);
   if (!st.done) {
     const double rho = sum_partials(part_rho, s_red);
@@ -1833,10 +1919,11 @@ __global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restric
 __global__ void __launch_bounds__(VT) k_pcg_a(int ncs, int ne, const PcgState* __restrict__ in, double* __restrict__ y,
                                               const double* __restrict__ sm, const double* __restrict__ D2,
                                               const double* __restrict__ p, double* __restrict__ q, double* __restrict__ part_pq,
-                                              const double* __restrict__ fold_rep) {
+                                              const double* __restrict__ fold_rep, P2pDev pp) {
   __shared__ double s_red[32];
   __shared__ double s_fold[10];
   if (in->done) return;
+  if (pp.world > 1) p2p_wait(pp);  // the matvec of every rank has pushed its partial sums into the local inbox
   if (fold_rep != nullptr) {
     if (threadIdx.x < 10) {
       double v = y[ne + threadIdx.x];
@@ -1847,7 +1934,7 @@ __global__ void __launch_bounds__(VT) k_pcg_a(int ncs, int ne, const PcgState* _
   }
   double acc = 0.0;
   for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
-    const double yv = (fold_rep != nullptr && i >= ne && i < ne + 10) ? s_fold[i - ne] : y[i];
+    const double yv = pp.world > 1 ? p2p_sum(pp, i) : ((fold_rep != nullptr && i >= ne && i < ne + 10) ? s_fold[i - ne] : y[i]);
     const double qv = sm[i] * yv + D2[i] * p[i];
     q[i] = qv;
     acc += p[i] * qv;
@@ -1907,10 +1994,11 @@ __global__ void __launch_bounds__(VT) k_pcg_reset_bz(DevProblem P, const PcgStat
                                                      const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
                                                      double* __restrict__ z, const double* __restrict__ Minv_c,
                                                      const double* __restrict__ Minv_i, double* __restrict__ part_Q,
-                                                     double* __restrict__ part_rho, int identity_precond, const double* __restrict__ fold_rep) {
+                                                     double* __restrict__ part_rho, int identity_precond, const double* __restrict__ fold_rep, P2pDev pp) {
   __shared__ double s_red[32];
   __shared__ double s_fold[10];
   if (in->done) return;
+  if (pp.world > 1) p2p_wait(pp);
   if (fold_rep != nullptr) {
     if (threadIdx.x < 10) {
       double v = y[P.ne + threadIdx.x];
@@ -1925,7 +2013,7 @@ __global__ void __launch_bounds__(VT) k_pcg_reset_bz(DevProblem P, const PcgStat
     const int i0 = blk < P.n_cam ? blk * 6 : P.ne + (blk - P.n_cam) * 10, n = blk < P.n_cam ? 6 : 10;
     for (int a = 0; a < n; ++a) {
       const int i = i0 + a;
-      const double yv = (fold_rep != nullptr && i >= P.ne && i < P.ne + 10) ? s_fold[i - P.ne] : y[i];
+      const double yv = pp.world > 1 ? p2p_sum(pp, i) : ((fold_rep != nullptr && i >= P.ne && i < P.ne + 10) ? s_fold[i - P.ne] : y[i]);
       const double rv = b[i] - (sm[i] * yv + D2[i] * x[i]);
       r[i] = rv;
       accQ += x[i] * (b[i] + rv);
@@ -1942,7 +2030,9 @@ __global__ void k_zero_rep_cols(double* __restrict__ rep) {  // re-zero the 10 f
 
 // Residual reset (every cg_residual_reset_period iterations): xs = sm .* x, y = 0 ... matvec ... r = b - (sm.*y + D2.*x)
 __global__ void __launch_bounds__(VT) k_pcg_reset_a(int ncs, const PcgState* __restrict__ in, const double* __restrict__ x,
-                                                    const double* __restrict__ sm, double* __restrict__ xs, double* __restrict__ y) {
+                                                    const double* __restrict__ sm, double* __restrict__ xs, double* __restrict__ y,
+                                                    int* __restrict__ zero_ctr) {
+  if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_ctr = 0;
   if (in->done) return;
   for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) { xs[i] = sm[i] * x[i]; y[i] = 0.0; }
 }
