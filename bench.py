@@ -300,13 +300,152 @@ def run_experiments(workload, K, device, timeout=180):
     return res
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: BruteForceFeatureMatcher on 5k x 5k SIFT-128 image pairs.
+MATCHER_METRIC = ("image pairs/s = matched image pairs / time (BruteForceFeatureMatcher::MatchImagePair semantics: 5000 x 5000 SIFT-128 "
+                  "descriptors per pair, squared L2, Lowe ratio 0.8, symmetric, min 30 matches)")
+MATCHER_N, MATCHER_DIM = 5000, 128
+
+
+def matcher_scene(n_img, n=MATCHER_N, seed=20240613):
+    """SIFT-like images: every image sees the same physical features (non-negative unit descriptors) in its own order with noise,
+    plus 20 % unrelated descriptors: the ratio test keeps most true matches and rejects the rest."""
+    rng = np.random.default_rng(seed)
+    n_true = int(0.8 * n)
+    base = np.abs(rng.normal(size=(n_true, MATCHER_DIM))).astype(np.float32)
+    sets = []
+    for _ in range(n_img):
+        s = base[rng.permutation(n_true)] + 0.05 * np.abs(rng.normal(size=(n_true, MATCHER_DIM))).astype(np.float32)
+        s = np.concatenate([s, np.abs(rng.normal(size=(n - n_true, MATCHER_DIM))).astype(np.float32)])
+        s = s[rng.permutation(n)]
+        sets.append(np.ascontiguousarray(s / np.linalg.norm(s, axis=1, keepdims=True), np.float32))
+    return sets
+
+
+def matcher_cpu_pairs_per_s(sets, n_pairs=2):
+    """The CPU restatement of MatchImagePair (oracle/matcher_oracle.c, one thread: the reference runs one pair per pool thread)."""
+    import ctypes as C
+    from theiasfm_b200 import matcher
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libmatcher_oracle.so"], stdout=subprocess.DEVNULL)
+    M = C.CDLL(os.path.join(ROOT, "oracle", "libmatcher_oracle.so"))
+    o = matcher.default_options()
+    fp = C.POINTER(C.c_float)
+    out = (matcher.tbm_match * len(sets[0]))()
+    n = C.c_int()
+    t0 = time.perf_counter()
+    for p in range(n_pairs):
+        a, b = sets[p % len(sets)], sets[(p + 1) % len(sets)]
+        M.matcher_match_image_pair(a.ctypes.data_as(fp), len(a), b.ctypes.data_as(fp), len(b), MATCHER_DIM, C.byref(o), out, C.byref(n))
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt
+
+
+def matcher_main(args):
+    """python bench.py --workload c5_matcher [--gpus N]: a "step" = this rank's share of all image pairs of a 48-image sample of
+    config 5 (1128 pairs of 5000 x 5000 descriptors) through tbm_match_all; pairs are independent units, sharded round-robin over
+    the ranks with no collective (descriptors replicated) -- strong scaling over a fixed pair list."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 0)
+    n_img = int(os.environ.get("TBA_BENCH_MATCHER_IMAGES", "48"))
+    n_desc = int(os.environ.get("TBA_BENCH_MATCHER_N", str(MATCHER_N)))
+    config = {"workload": "c5_matcher: %d-image sample of config 5 (10k images x 5k SIFT-128): all %d image pairs, %d x %d descriptors per pair, "
+                          "ratio 0.8, symmetric, min 30 matches" % (n_img, n_img * (n_img - 1) // 2, n_desc, n_desc),
+              "parallelism": "image pairs sharded round-robin over %d GPU(s), descriptors replicated, no collective" % world,
+              "l2_policy": "every step re-uploads the descriptors and streams %d candidate tiles per query block; the distance matrices are never stored" % ((n_desc + 127) // 128)}
+    sets = matcher_scene(n_img, n_desc)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, dt = matcher_cpu_pairs_per_s(sets, 3)
+        line = {"impl": "reference", "metric": MATCHER_METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * dt / 3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                                    "sample": "3 image pairs of the same scene through oracle/matcher_oracle.c (one thread), %.2f s" % dt},
+                "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    import torch
+    import torch.distributed as dist
+    from theiasfm_b200 import matcher
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(local_rank)
+
+    def allred(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t[0])
+    all_pairs = [(i, j) for i in range(n_img) for j in range(i + 1, n_img)]
+    mine = all_pairs[rank::world]
+    opt = matcher.default_options()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(W):
+        rc, res, ok = matcher.match_all(sets, mine, opt, device=local_rank)
+        assert rc == 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tw0 = time.time()
+    t0 = time.perf_counter()
+    gemm_ms = exact_ms = h2d_ms = 0.0
+    n_matches = 0
+    for _ in range(K):
+        rc, res, ok = matcher.match_all(sets, mine, opt, device=local_rank)
+        assert rc == 0
+        tm = matcher.last_timing()
+        gemm_ms += tm["gemm_ms"]; exact_ms += tm["exact_ms"]; h2d_ms += tm["h2d_ms"]
+        n_matches = sum(len(r) for r in res)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = allred(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop(tw0, time.time())
+    dev_s = allred(1e-3 * (gemm_ms + exact_ms), dist.ReduceOp.MAX if world > 1 else None)
+    gemm_s = allred(1e-3 * gemm_ms, dist.ReduceOp.MAX if world > 1 else None)
+    pairs_total = len(all_pairs) * K
+    n_matches = allred(float(n_matches), dist.ReduceOp.SUM if world > 1 else None)
+    flops = 2.0 * n_desc * n_desc * MATCHER_DIM * 2 * len(all_pairs) * K  # both directions of every pair
+    peak = 1414.5
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_src = "fallback"
+    if os.path.exists(pk):
+        with open(pk) as f:
+            peak = float(json.load(f)["bf16_tflops_sustained"]); peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    achieved = flops / gemm_s / 1e12 / world if gemm_s > 0 else 0.0   # per GPU
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt = matcher_cpu_pairs_per_s(sets, 2)
+        cb = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port", "sample": "2 image pairs of the same scene through oracle/matcher_oracle.c (one thread), %.2f s" % dt}
+    if rank == 0:
+        line = {"metric": MATCHER_METRIC, "value": pairs_total / dev_s if dev_s > 0 else 0.0, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core ranking, exact f32 decision)",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": pairs_total / wall, "unit": "pairs/s", "h2d_bytes_per_step": float(n_img * n_desc * MATCHER_DIM * 4) * world,
+                        "d2h_bytes_per_step": float(len(all_pairs) * 2 * n_desc * 12), "seconds": wall},
+                "gpu_launches": int(K * 3 * max(1, (len(mine) * 2 * n_desc + (4 << 20) - 1) // (4 << 20))) * world,
+                "roofline": {"kernel": "k_nn_candidates (TF32 tcgen05.mma distance GEMM + fused top-8 epilogue from TMEM)", "bound": "tensor", "achieved": achieved,
+                             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "algorithmic flops 2*n1*n2*128 per direction on the TF32 path (nominal dense TF32 = half the bf16 rate the peak is quoted for); per GPU",
+                             "gemm_seconds": gemm_s, "exact_seconds": allred(1e-3 * exact_ms, dist.ReduceOp.MAX if world > 1 else None)},
+                "cpu_baseline": cb, "matches_per_step": n_matches, "distance_evaluations_per_s": 2.0 * n_desc * n_desc * pairs_total / dev_s if dev_s > 0 else 0.0}
+        print(json.dumps(line))
+    elif world > 1:
+        allred(1e-3 * exact_ms, dist.ReduceOp.MAX)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3_10kcam", choices=list(synthetic.CONFIGS))
+    ap.add_argument("--workload", default="c3_10kcam", choices=list(synthetic.CONFIGS) + ["c5_matcher"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-experiments", action="store_true", help="skip the diagnostic pass over the compiled-in experiment switches")
@@ -315,6 +454,8 @@ def main():
     args = ap.parse_args()
     if args.experiments_child:
         return experiments_child(args.workload, args.steps, args.device)
+    if args.workload == "c5_matcher":
+        return matcher_main(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -7,8 +7,9 @@
  * Semantics are MatchImagePair's, per pair: squared float L2 (distance.h:52-56), best of image 2 for every descriptor of
  * image 1 (ties: lower index), kept if !use_lowes_ratio || best < ratio^2 * second (:78-81, double arithmetic on
  * float distances), early "not enough matches" exits (:84-86, :116), symmetric filtering through IntersectMatches
- * (feature_matcher_utils.cc:48-71).  Round 1: correctness-first CUDA-core kernel (bit-exact float summation order);
- * the tcgen05 distance GEMM is round-2 work.
+ * (feature_matcher_utils.cc:48-71).  128-dimensional descriptors (SIFT): a TF32 tcgen05 distance GEMM with a fused top-8
+ * epilogue selects candidates, an exact float pass (the reference's summation order) decides -- theiasfm_b200/csrc/tbm_matcher_tc.cuh;
+ * other dimensions / TBM_PATH=exact: the round-1 CUDA-core kernel (bit-exact float summation order throughout).
  */
 #ifndef THEIA_MATCHER_B200_H_
 #define THEIA_MATCHER_B200_H_
@@ -49,6 +50,10 @@ int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, 
 int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const float* f_second_d, int32_t n1, int f_second_valid,
                           const int32_t* r_best_j, const float* r_best_d, const float* r_second_d, int32_t n2, int r_second_valid,
                           const tbm_options* options, tbm_match* matches /* capacity n1 */, int32_t* n_matches);
+
+/* Device times (CUDA events, ms) of the last tbm_match_all on the tensor-core path: {candidate GEMM kernel (tcgen05), exact
+ * re-evaluation kernel, host-to-device copy of the descriptors, 0}.  All zero after a call that took the CUDA-core path. */
+void tbm_debug_last_timing(double* out4);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="needs the real CUDA engine or its emulation build (binary / multi-process / matcher library)")
     too_big = pytest.mark.skip(reason="full-size scene: hours under the SIMT emulator")
-    emu_big = ("test_x_fullsize_gpu",)
+    emu_big = ("test_x_fullsize_gpu", "test_tensor_core_path_equals")
     for item in items:
         names = () if config.getoption("--emulate-engine") else ("test_xx_matcher_gpu", "test_z_adapter_gpu", "test_y_multi_gpu")
         if any(k in item.nodeid for k in names):

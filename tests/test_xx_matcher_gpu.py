@@ -49,3 +49,30 @@ def test_random_descriptors_match_oracle_exactly():
             ok_o, exp = _oracle_match(sets[i], sets[j], **kw)
             assert ok[p] == ok_o and res[p] == exp, (kw, i, j)
     assert sum(len(r) for r in res) > 1000
+
+
+def test_tensor_core_path_equals_the_exact_kernel_at_sift_size(monkeypatch):
+    """dim 128 goes through the tcgen05 / TMA candidate pass + exact re-evaluation (tbm_matcher_tc.cuh); TBM_PATH=exact forces the
+    round-1 CUDA-core kernel (bit-exact float order), the checker here: the match lists -- indices AND distances -- must be identical
+    at SIFT-like sizes (non-negative unit descriptors, thousands per image, sizes that are not multiples of the 128-row tiles), with
+    and without the ratio test, including an image matched against itself (zero distances, exact ties)."""
+    rng = np.random.default_rng(5)
+    base = np.abs(rng.normal(size=(3000, 128))).astype(np.float32)
+    sets = []
+    for n in (3000, 2500, 129, 4097):
+        idx = rng.permutation(3000)[:min(n, 3000)]
+        s = base[idx] + 0.08 * np.abs(rng.normal(size=(len(idx), 128))).astype(np.float32)
+        if n > 3000:
+            s = np.concatenate([s, np.abs(rng.normal(size=(n - 3000, 128))).astype(np.float32)])
+        sets.append(np.ascontiguousarray(s / np.linalg.norm(s, axis=1, keepdims=True), np.float32))
+    sets[2][7] = sets[2][3]  # duplicate descriptors: equal distances, the lower index must win
+    pairs = [(0, 1), (1, 0), (0, 3), (2, 3), (3, 2), (2, 2), (1, 1)]
+    for kw in (dict(), dict(use_lowes_ratio=0, min_num_feature_matches=0, keep_only_symmetric_matches=0)):
+        monkeypatch.delenv("TBM_PATH", raising=False)
+        rc_t, res_t, ok_t = matcher.match_all(sets, pairs, matcher.default_options(**kw))
+        monkeypatch.setenv("TBM_PATH", "exact")
+        rc_e, res_e, ok_e = matcher.match_all(sets, pairs, matcher.default_options(**kw))
+        assert rc_t == 0 and rc_e == 0 and ok_t == ok_e
+        for p in range(len(pairs)):
+            assert res_t[p] == res_e[p], (kw, pairs[p], len(res_t[p]), len(res_e[p]))
+    assert sum(len(r) for r in res_t) > 5000

@@ -104,7 +104,16 @@ __device__ __forceinline__ double seg_reduce_to(double v, int run_last, int lane
   return v;
 }
 
-__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
+// fp64 reduction into GLOBAL memory without a return value.  Written as the PTX `red` itself: left to the compiler, atomicAdd
+// becomes ATOMG (with its round trip back to the SM) as soon as the kernel also contains a __threadfence -- the multi-GPU
+// epilogue of k_schur_stream made every matvec 13 % slower that way (round 2, GPU call 4: RED wavefronts 0, ATOMG instead).
+__device__ __forceinline__ void red_add(double* p, double v) {
+#ifdef TBA_EMULATE
+  atomicAdd(p, v);
+#else
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#endif
+}
 
 // Experiment TBA_TRED=1 ("transposed" RED emission).  A lane-per-observation RED of an N-double camera row touches 32
 // different 32-byte sectors per instruction (32 cameras), i.e. N x 32 sector operations at the L2 atomic units, which

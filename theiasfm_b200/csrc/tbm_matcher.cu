@@ -9,6 +9,12 @@
 
 #include "../../include/theia_matcher_b200.h"
 #include "tbm_top2.h"
+#ifndef TBA_EMULATE
+#include "tbm_matcher_tc.cuh"   // tcgen05 / TMA path (sm_100a); the SIMT emulation build keeps the exact CUDA-core kernel only
+#endif
+#include <cstdlib>
+
+static double g_last_timing[4] = {0, 0, 0, 0};  // ms: candidate GEMM kernel, exact re-evaluation kernel, H2D of the descriptors, unused
 
 namespace {
 
@@ -90,6 +96,8 @@ extern "C" {
 
 void tbm_options_init(tbm_options* o) { o->keep_only_symmetric_matches = 1; o->use_lowes_ratio = 1; o->lowes_ratio = 0.8f; o->min_num_feature_matches = 30; }
 
+void tbm_debug_last_timing(double* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_last_timing[i]; }
+
 int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const float* f_second_d, int32_t n1, int f_second_valid,
                           const int32_t* r_best_j, const float* r_best_d, const float* r_second_d, int32_t n2, int r_second_valid,
                           const tbm_options* o, tbm_match* matches, int32_t* n_matches) {
@@ -113,12 +121,142 @@ int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const 
   return n >= o->min_num_feature_matches;  // :116
 }
 
+#ifndef TBA_EMULATE
+// Tensor-core path (dim == 128): all pairs of a chunk in ONE launch of k_nn_candidates + ONE launch of k_exact_top2, one
+// device-to-host copy per chunk, then MatchImagePair's ratio test / early exits / IntersectMatches per pair on the host.
+static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_t n_img, const int32_t* pairs, int64_t n_pairs,
+                        const tbm_options* options, tbm_match* matches, int64_t cap, int64_t* match_off, uint8_t* pair_ok) {
+  using namespace tbm_tc;
+  const int64_t total = img_off[n_img];
+  if (total >= (int64_t)1 << 31) return -1;
+  cudaEvent_t ev[6];
+  for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return -3;
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]); } } ev_guard{ev};
+  g_last_timing[0] = g_last_timing[1] = g_last_timing[2] = g_last_timing[3] = 0.0;
+  cudaEventRecord(ev[0]);
+  int n_sm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  DevF d_desc, d_nrm, d_bd, d_sd;
+  DevI d_cand, d_bj, d_qrow, d_brow0;
+  if (!d_desc.alloc((size_t)(total > 0 ? total : 1) * DIM) || !d_nrm.alloc((size_t)(total > 0 ? total : 1))) return -3;
+  if (total > 0 && cudaMemcpy(d_desc.p, descriptors, (size_t)total * DIM * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+  cudaEventRecord(ev[1]);
+  if (total > 0) {
+    k_row_norms<<<(unsigned)((total + 255) / 256), 256>>>(d_desc.p, total, d_nrm.p);
+    if (cudaPeekAtLastError() != cudaSuccess) return -3;
+  }
+  CUtensorMap map;
+  if (total > 0 && !make_desc_map(&map, d_desc.p, total)) return -3;
+  if (cudaFuncSetAttribute(k_nn_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
+  struct DevItems { WorkItem* p = nullptr; size_t n = 0; ~DevItems() { if (p) cudaFree(p); } } d_items;
+  std::vector<WorkItem> items;
+  std::vector<int> h_qrow, h_brow0, h_bj;
+  std::vector<float> h_bd, h_sd;
+  std::vector<tbm_match> tmp;
+  const bool sym = options->keep_only_symmetric_matches != 0;
+  int64_t written = 0;
+  bool overflow = false;
+  const int64_t kChunkQueries = (int64_t)4 << 20;  // queries per chunk (both directions): bounds the device / host staging
+  for (int64_t p0 = 0; p0 < n_pairs;) {
+    // ---- chunk [p0, p1): as many pairs as fit the query budget
+    int64_t p1 = p0, nq_chunk = 0;
+    while (p1 < n_pairs) {
+      const int a = pairs[2 * p1], b = pairs[2 * p1 + 1];
+      if (a < 0 || a >= n_img || b < 0 || b >= n_img) return -1;
+      const int64_t n1 = img_off[a + 1] - img_off[a], n2 = img_off[b + 1] - img_off[b];
+      const int64_t add = n1 + (sym ? n2 : 0);
+      if (p1 > p0 && nq_chunk + add > kChunkQueries) break;
+      nq_chunk += add; ++p1;
+    }
+    items.clear(); h_qrow.resize((size_t)nq_chunk); h_brow0.resize((size_t)nq_chunk);
+    std::vector<int64_t> q_off((size_t)(p1 - p0) * 2 + 1, 0);
+    int64_t qo = 0;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int a = pairs[2 * p], b = pairs[2 * p + 1];
+      for (int dir = 0; dir < 2; ++dir) {
+        q_off[(size_t)(p - p0) * 2 + dir] = qo;
+        if (dir == 1 && !sym) continue;
+        const int qa = dir == 0 ? a : b, cb = dir == 0 ? b : a;
+        const int nq = (int)(img_off[qa + 1] - img_off[qa]), nc = (int)(img_off[cb + 1] - img_off[cb]);
+        for (int i = 0; i < nq; ++i) { h_qrow[(size_t)qo + i] = (int)img_off[qa] + i; h_brow0[(size_t)qo + i] = (int)img_off[cb]; }
+        if (nc > 0)
+          for (int m0 = 0; m0 < nq; m0 += BM) {
+            WorkItem w;
+            w.a_row0 = (int)img_off[qa] + m0; w.a_rows = nq - m0 < BM ? nq - m0 : BM; w.b_row0 = (int)img_off[cb]; w.b_rows = nc; w.out_row0 = qo + m0;
+            items.push_back(w);
+          }
+        qo += nq;
+      }
+    }
+    q_off.back() = qo;
+    if (nq_chunk > 0) {
+      if (!d_cand.alloc((size_t)nq_chunk * KC) || !d_bj.alloc((size_t)nq_chunk) || !d_bd.alloc((size_t)nq_chunk) || !d_sd.alloc((size_t)nq_chunk) ||
+          !d_qrow.alloc((size_t)nq_chunk) || !d_brow0.alloc((size_t)nq_chunk)) return -3;
+      if (cudaMemset(d_cand.p, 0xFF, (size_t)nq_chunk * KC * sizeof(int)) != cudaSuccess) return -3;  // -1: no candidate (empty other image)
+      if (cudaMemcpy(d_qrow.p, h_qrow.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(d_brow0.p, h_brow0.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+      if (!items.empty()) {
+        if (d_items.n < items.size()) { if (d_items.p) cudaFree(d_items.p); d_items.p = nullptr; d_items.n = 0;
+          if (cudaMalloc(&d_items.p, items.size() * sizeof(WorkItem)) != cudaSuccess) return -3; d_items.n = items.size(); }
+        if (cudaMemcpy(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+        const int grid = (int)(items.size() < (size_t)n_sm ? items.size() : (size_t)n_sm);
+        cudaEventRecord(ev[2]);
+        k_nn_candidates<<<grid, THREADS, kSmemBytes>>>(map, d_items.p, (int)items.size(), d_nrm.p, d_cand.p);
+        if (cudaPeekAtLastError() != cudaSuccess) return -3;
+        cudaEventRecord(ev[3]);
+      }
+      cudaEventRecord(ev[4]);
+      k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256>>>(d_desc.p, d_qrow.p, d_brow0.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p);
+      if (cudaPeekAtLastError() != cudaSuccess) return -3;
+      cudaEventRecord(ev[5]);
+      h_bj.resize((size_t)nq_chunk); h_bd.resize((size_t)nq_chunk); h_sd.resize((size_t)nq_chunk);
+      if (cudaMemcpy(h_bj.data(), d_bj.p, (size_t)nq_chunk * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(h_bd.data(), d_bd.p, (size_t)nq_chunk * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(h_sd.data(), d_sd.p, (size_t)nq_chunk * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+      float ms = 0;
+      if (!items.empty() && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) g_last_timing[0] += ms;
+      if (cudaEventElapsedTime(&ms, ev[4], ev[5]) == cudaSuccess) g_last_timing[1] += ms;
+    }
+    // ---- MatchImagePair's decisions, per pair
+    static const int kNone = -1; static const float kZero = 0.0f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int a = pairs[2 * p], b = pairs[2 * p + 1];
+      const int n1 = (int)(img_off[a + 1] - img_off[a]), n2 = (int)(img_off[b + 1] - img_off[b]);
+      const int64_t f0 = q_off[(size_t)(p - p0) * 2], r0 = q_off[(size_t)(p - p0) * 2 + 1];
+      tmp.resize((size_t)(n1 > 0 ? n1 : 1));
+      int32_t nm = 0;
+      const int* fbj = n1 > 0 ? h_bj.data() + f0 : &kNone; const float* fbd = n1 > 0 ? h_bd.data() + f0 : &kZero; const float* fsd = n1 > 0 ? h_sd.data() + f0 : &kZero;
+      const bool have_r = sym && n2 > 0;
+      const int* rbj = have_r ? h_bj.data() + r0 : &kNone; const float* rbd = have_r ? h_bd.data() + r0 : &kZero; const float* rsd = have_r ? h_sd.data() + r0 : &kZero;
+      pair_ok[p] = (uint8_t)tbm_debug_postprocess(fbj, fbd, fsd, n1, n2 >= 2, rbj, rbd, rsd, have_r ? n2 : 0, n1 >= 2, options, tmp.data(), &nm);
+      match_off[p] = written;
+      if (written + nm > cap || !matches) overflow = true;
+      else memcpy(matches + written, tmp.data(), (size_t)nm * sizeof(tbm_match));
+      written += nm;
+    }
+    p0 = p1;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+  { float ms = 0; if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) g_last_timing[2] = ms; }
+  match_off[n_pairs] = written;
+  return overflow ? -1 : 0;
+}
+#endif
+
 int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, int32_t n_img, int32_t dim, const int32_t* pairs,
                   int64_t n_pairs, const tbm_options* options, tbm_match* matches, int64_t cap, int64_t* match_off, uint8_t* pair_ok) {
   if (!descriptors || !img_off || !pairs || !options || !match_off || !pair_ok || n_img < 0 || dim <= 0 || dim > 512 || n_pairs < 0) return -1;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return -5; }
   if (cudaSetDevice(device) != cudaSuccess) return -3;
+#ifndef TBA_EMULATE
+  {
+    // dim 128 (SIFT): the tensor-core path.  TBM_PATH=exact forces the CUDA-core kernel (the bit-exact checker of round 1).
+    const char* e = getenv("TBM_PATH");
+    for (int i = 0; i < n_img; ++i) if (img_off[i + 1] < img_off[i]) return -1;
+    if (dim == tbm_tc::DIM && !(e != nullptr && e[0] == 'e')) return match_all_tc(descriptors, img_off, n_img, pairs, n_pairs, options, matches, cap, match_off, pair_ok);
+  }
+#endif
   const int64_t total = img_off[n_img];
   int64_t max_n = 0;
   for (int i = 0; i < n_img; ++i) { if (img_off[i + 1] < img_off[i]) return -1; max_n = img_off[i + 1] - img_off[i] > max_n ? img_off[i + 1] - img_off[i] : max_n; }

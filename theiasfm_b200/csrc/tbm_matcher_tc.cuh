@@ -1,0 +1,318 @@
+// tbm_matcher_tc.cuh -- tensor-core path of the brute-force matcher (sm_100a only).
+//
+// Replaces the hot loop of BruteForceFeatureMatcher::MatchImagePair
+// (src/theia/matching/brute_force_feature_matcher.cc:64-82 forward, :93-112 reverse; L2::operator() distance.h:52-56):
+// for every descriptor of one image the two nearest descriptors of the other image in squared L2.
+//
+// Two passes per (image pair, direction):
+//   1. k_nn_candidates (this file): ||x - y||^2 = ||x||^2 + ||y||^2 - 2 x.y with the 128-dimensional dot products as a TF32
+//      tcgen05.mma GEMM -- a 128-query block of image A (resident in shared memory) against 128-candidate tiles of image B
+//      streamed by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32 accumulators double-buffered in TMEM -- and a fused
+//      epilogue that reads the accumulator tile back with tcgen05.ld and keeps, per query row, the KC smallest scores
+//      ||y||^2 - 2 x.y in registers across all candidate tiles.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected
+//      lane) + TMEM allocation, 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs over a list of work items.
+//   2. k_exact_top2: the KC candidates of every query are re-evaluated EXACTLY -- float, term by term in the reference's
+//      order without fused multiply-add, like the round-1 kernel k_nn2 -- and the best two (ties: lower index) are kept.
+// TF32 only ranks candidates; every distance that leaves the GPU, every ratio test and every tie-break is computed from
+// the exact values, so the match lists equal the CPU oracle's unless the true nearest / second-nearest neighbour is not
+// among the KC = 8 best TF32 scores (tests/test_xx_matcher_gpu.py counts such cases: none).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <cstdint>
+#include <cstdio>
+
+namespace tbm_tc {
+
+constexpr int BM = 128;        // query rows per work item (= TMEM lanes)
+constexpr int BN = 128;        // candidate rows per tile (= accumulator columns)
+constexpr int DIM = 128;       // descriptor length (SIFT); 4 swizzle atoms of 32 floats
+constexpr int KC = 8;          // candidates kept per query
+constexpr int ATOM_BYTES = BM * 128;              // one 128-row x 128-byte swizzle-atom panel
+constexpr int TILE_BYTES = 4 * ATOM_BYTES;        // 64 KB: a 128 x 128 float tile
+constexpr int NSTAGE = 2;
+constexpr int THREADS = 192;
+
+struct WorkItem {
+  int a_row0;    // global row of the first query of this block
+  int a_rows;    // valid query rows (1..128)
+  int b_row0;    // global row of the first candidate of image B
+  int b_rows;    // number of candidates
+  long long out_row0;  // first row of this block in the candidate-index output
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ bool bar_try(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_addr(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  if (bar_try(b, parity)) return;
+  const long long t0 = clock64();
+  while (!bar_try(b, parity)) {
+    if (clock64() - t0 > 4000000000ll) { printf("tbm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, TF32 inputs, fp32 accumulation
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused with swizzled K-major layouts): 1
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 bytes
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, K-major both, N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct __align__(8) Ctl {
+  uint64_t a_full, a_empty, b_full[NSTAGE], b_empty[NSTAGE], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+// sorted insertion into the KC smallest (value, index) pairs of this thread
+__device__ __forceinline__ void keep_smallest(float (&v)[KC], int (&id)[KC], float s, int j) {
+  if (!(s < v[KC - 1])) return;
+  v[KC - 1] = s; id[KC - 1] = j;
+#pragma unroll
+  for (int k = KC - 1; k > 0; --k) {
+    if (v[k] < v[k - 1]) { const float tv = v[k]; v[k] = v[k - 1]; v[k - 1] = tv; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
+  }
+}
+
+// ------------------------------------------------------------------ pass 1: TF32 candidates
+// desc_map: the concatenated descriptor matrix [total_rows][128] float as a 2-D tensor map, box = 32 floats x 128 rows, SWIZZLE_128B.
+// nrm[r] = ||descriptor r||^2 (float).  cand[(out_row0 + m) * KC + k] = global row of the k-th best candidate of query m (-1: none).
+__global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_constant__ CUtensorMap desc_map, const WorkItem* __restrict__ items,
+                                                              int n_items, const float* __restrict__ nrm, int* __restrict__ cand) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte-swizzled operand panels must start on 1024-byte boundaries (of the shared-memory address)
+  uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                  // 4 atom panels of the query block
+  uint8_t* sB = smem + TILE_BYTES;                     // NSTAGE x 4 atom panels of candidate tiles
+  float* sN = reinterpret_cast<float*>(smem + TILE_BYTES * (1 + NSTAGE));  // [2][BN] squared norms of the tile being drained
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    bar_init(&ctl->a_full, 1); bar_init(&ctl->a_empty, 1);
+    for (int s = 0; s < NSTAGE; ++s) { bar_init(&ctl->b_full[s], 1); bar_init(&ctl->b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { bar_init(&ctl->acc_full[a], 1); bar_init(&ctl->acc_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&ctl->tmem_base)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t bt = 0, itc = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++itc) {
+        const WorkItem w = items[it];
+        bar_wait(&ctl->a_empty, (itc & 1) ^ 1);          // the MMAs of the previous item have read sA
+        bar_expect_tx(&ctl->a_full, TILE_BYTES);
+        for (int a = 0; a < 4; ++a) tma_load_2d(sA + a * ATOM_BYTES, &desc_map, a * 32, w.a_row0, &ctl->a_full);
+        const int n_tiles = (w.b_rows + BN - 1) / BN;
+        for (int t = 0; t < n_tiles; ++t, ++bt) {
+          const int s = bt % NSTAGE;
+          bar_wait(&ctl->b_empty[s], ((bt / NSTAGE) & 1) ^ 1);
+          bar_expect_tx(&ctl->b_full[s], TILE_BYTES);
+          for (int a = 0; a < 4; ++a) tma_load_2d(sB + (size_t)s * TILE_BYTES + a * ATOM_BYTES, &desc_map, a * 32, w.b_row0 + t * BN, &ctl->b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t bt = 0, itc = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++itc) {
+        const WorkItem w = items[it];
+        bar_wait(&ctl->a_full, itc & 1);
+        const int n_tiles = (w.b_rows + BN - 1) / BN;
+        for (int t = 0; t < n_tiles; ++t, ++bt) {
+          const int s = bt % NSTAGE, acc = bt & 1;
+          bar_wait(&ctl->b_full[s], (bt / NSTAGE) & 1);
+          bar_wait(&ctl->acc_empty[acc], ((bt >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB + (size_t)s * TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle atom
+              tc_mma_tf32(tmem + acc * BN, make_desc(a0 + a * ATOM_BYTES + k * 32), make_desc(b0 + a * ATOM_BYTES + k * 32), kIdesc, (a | k) != 0);
+          tc_commit(&ctl->b_empty[s]);      // the stage can be refilled once these MMAs have read it
+          tc_commit(&ctl->acc_full[acc]);   // ... and the accumulator is complete
+        }
+        tc_commit(&ctl->a_empty);
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, TMEM lane quarter (warp % 4) =====================
+    const int q = warp & 3;                 // warps 2,3,4,5 -> quarters 2,3,0,1
+    const int row = q * 32 + lane;          // query row of this thread inside the block
+    const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+    uint32_t bt = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem w = items[it];
+      float v[KC]; int id[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) { v[k] = __int_as_float(0x7f800000); id[k] = -1; }
+      const int n_tiles = (w.b_rows + BN - 1) / BN;
+      for (int t = 0; t < n_tiles; ++t, ++bt) {
+        const int acc = bt & 1;
+        // squared norms of this tile's candidates (one per epilogue thread), double-buffered in shared memory
+        const int col_row = t * BN + et;
+        sN[acc * BN + et] = col_row < w.b_rows ? __ldg(nrm + w.b_row0 + col_row) : __int_as_float(0x7f800000);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        bar_wait(&ctl->acc_full[acc], (bt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          const float4* n4 = reinterpret_cast<const float4*>(sN + acc * BN + c0);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 nn = n4[c >> 2];
+            const int j = w.b_row0 + t * BN + c0 + c;
+            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c]), nn.x), j);
+            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c + 1]), nn.y), j + 1);
+            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c + 2]), nn.z), j + 2);
+            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c + 3]), nn.w), j + 3);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&ctl->acc_empty[acc]);
+      }
+      if (row < w.a_rows) {
+        int* o = cand + (size_t)(w.out_row0 + row) * KC;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) o[k] = id[k];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+}
+
+// ||d||^2 of every descriptor row (float, plain left-to-right sum: only used to RANK candidates)
+__global__ void k_row_norms(const float* __restrict__ d, long long n_rows, float* __restrict__ nrm) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const float4* p = reinterpret_cast<const float4*>(d + r * DIM);
+  float s = 0.0f;
+#pragma unroll 8
+  for (int k = 0; k < DIM / 4; ++k) { const float4 x = __ldg(p + k); s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
+  nrm[r] = s;
+}
+
+// ------------------------------------------------------------------ pass 2: exact top-2 among the candidates
+// One thread per (query, candidate): the exact squared distance -- float, term by term, no fused multiply-add: L2::operator()
+// (distance.h:52-56) as the oracle and k_nn2 evaluate it; then thread 0 of the query picks the best two (ties: lower index).
+// q_row[i] = global descriptor row of query i, b_row0[i] = first row of the candidate image (indices are reported relative to it).
+__global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
+                                                    const int* __restrict__ cand, long long n_q, int* __restrict__ best_j,
+                                                    float* __restrict__ best_d, float* __restrict__ second_d) {
+  __shared__ float s_d[32][KC];
+  __shared__ int s_j[32][KC];
+  const int ql = threadIdx.x / KC, c = threadIdx.x % KC;
+  const long long qi = (long long)blockIdx.x * 32 + ql;
+  float dist = 0.0f;
+  int j = -1;
+  if (qi < n_q) {
+    j = cand[qi * KC + c];
+    if (j >= 0) {
+      const float* a = d + (size_t)q_row[qi] * DIM;
+      const float* b = d + (size_t)j * DIM;
+      float s = 0.0f;
+      for (int k = 0; k < DIM; ++k) {
+        const float df = __fsub_rn(a[k], b[k]);
+        s = __fadd_rn(s, __fmul_rn(df, df));
+      }
+      dist = s;
+      j -= b_row0[qi];
+    }
+  }
+  s_d[ql][c] = dist; s_j[ql][c] = j;
+  __syncthreads();
+  if (c == 0 && qi < n_q) {
+    int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
+    for (int k = 0; k < KC; ++k) {
+      const int jj = s_j[ql][k]; const float dd = s_d[ql][k];
+      if (jj < 0) continue;
+      if (bj < 0 || dd < bd || (dd == bd && jj < bj)) { sj = bj; sd = bd; bj = jj; bd = dd; }
+      else if (sj < 0 || dd < sd || (dd == sd && jj < sj)) { sj = jj; sd = dd; }
+    }
+    best_j[qi] = bj; best_d[qi] = bd; second_d[qi] = sj >= 0 ? sd : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------ host helpers
+inline bool make_desc_map(CUtensorMap* map, const float* d_desc, long long n_rows) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return false;
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)DIM, (cuuint64_t)n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)DIM * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_desc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr size_t kSmemBytes = (size_t)TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float) + sizeof(Ctl) + 1024;
+
+}  // namespace tbm_tc

@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtheia_matcher_b200.so")
 _LIB = None
-EXPORTED_SYMBOLS = ["tbm_options_init", "tbm_match_all", "tbm_debug_postprocess"]
+EXPORTED_SYMBOLS = ["tbm_options_init", "tbm_match_all", "tbm_debug_postprocess", "tbm_debug_last_timing"]
 
 
 class tbm_match(C.Structure):
@@ -32,8 +32,17 @@ def lib():
                                     C.POINTER(tbm_match), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]
         L.tbm_debug_postprocess.argtypes = [ip, fp, fp, C.c_int32, C.c_int, ip, fp, fp, C.c_int32, C.c_int, C.POINTER(tbm_options),
                                             C.POINTER(tbm_match), ip]
+        L.tbm_debug_last_timing.argtypes = [C.POINTER(C.c_double)]
+        L.tbm_debug_last_timing.restype = None
         _LIB = L
     return _LIB
+
+
+def last_timing():
+    """{gemm_ms, exact_ms, h2d_ms} of the last match_all on the tensor-core path (CUDA events)."""
+    out = (C.c_double * 4)()
+    lib().tbm_debug_last_timing(out)
+    return {"gemm_ms": out[0], "exact_ms": out[1], "h2d_ms": out[2]}
 
 
 def default_options(**kw):
