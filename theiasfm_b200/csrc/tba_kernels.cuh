@@ -639,6 +639,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Never a silent hang: a bulk copy that does not land within ~2 s (4e9 SM cycles) is a bug -- report it and abort the kernel
 // (the launch then fails with a CUDA error that the engine returns to the caller).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef TBA_MBAR_SIMPLE
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+  return;
+#endif
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -1098,7 +1110,10 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
 #pragma unroll
     for (int j = 0; j < 6; ++j) ja[j] = JA(j);
     jh[0] = JH(0); jh[1] = JH(1);
-    if (MODE != 2) {
+#ifndef TBA_STREAM_CACHE_J
+#define TBA_STREAM_CACHE_J 0
+#endif
+    if (TBA_STREAM_CACHE_J && MODE != 2) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) jw[j] = JW(j);
 #pragma unroll
@@ -1106,8 +1121,8 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
     }
 #undef JW
 #undef JI
-#define JW(j) (MODE != 2 ? jw[j] : Jt[(6 + (j)) * 32])
-#define JI(j) (MODE != 2 ? ji[j] : Jt[(14 + (j)) * 32])
+#define JW(j) ((TBA_STREAM_CACHE_J && MODE != 2) ? jw[j] : Jt[(6 + (j)) * 32])
+#define JI(j) ((TBA_STREAM_CACHE_J && MODE != 2) ? ji[j] : Jt[(14 + (j)) * 32])
     if (valid) {
       if (MODE != 0) { r0 = sR[lane]; r1 = sR[32 + lane]; }
       if (MODE != 1) {

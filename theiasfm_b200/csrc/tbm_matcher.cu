@@ -137,7 +137,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   DevF d_desc, d_nrm, d_bd, d_sd;
-  DevI d_cand, d_bj, d_qrow, d_brow0;
+  DevI d_cand, d_bj, d_qrow, d_brow0, d_brows;
   if (!d_desc.alloc((size_t)(total > 0 ? total : 1) * DIM) || !d_nrm.alloc((size_t)(total > 0 ? total : 1))) return -3;
   if (total > 0 && cudaMemcpy(d_desc.p, descriptors, (size_t)total * DIM * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
   cudaEventRecord(ev[1]);
@@ -150,7 +150,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   if (cudaFuncSetAttribute(k_nn_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
   struct DevItems { WorkItem* p = nullptr; size_t n = 0; ~DevItems() { if (p) cudaFree(p); } } d_items;
   std::vector<WorkItem> items;
-  std::vector<int> h_qrow, h_brow0, h_bj;
+  std::vector<int> h_qrow, h_brow0, h_brows, h_bj;
   std::vector<float> h_bd, h_sd;
   std::vector<tbm_match> tmp;
   const bool sym = options->keep_only_symmetric_matches != 0;
@@ -168,7 +168,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
       if (p1 > p0 && nq_chunk + add > kChunkQueries) break;
       nq_chunk += add; ++p1;
     }
-    items.clear(); h_qrow.resize((size_t)nq_chunk); h_brow0.resize((size_t)nq_chunk);
+    items.clear(); h_qrow.resize((size_t)nq_chunk); h_brow0.resize((size_t)nq_chunk); h_brows.resize((size_t)nq_chunk);
     std::vector<int64_t> q_off((size_t)(p1 - p0) * 2 + 1, 0);
     int64_t qo = 0;
     for (int64_t p = p0; p < p1; ++p) {
@@ -178,7 +178,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
         if (dir == 1 && !sym) continue;
         const int qa = dir == 0 ? a : b, cb = dir == 0 ? b : a;
         const int nq = (int)(img_off[qa + 1] - img_off[qa]), nc = (int)(img_off[cb + 1] - img_off[cb]);
-        for (int i = 0; i < nq; ++i) { h_qrow[(size_t)qo + i] = (int)img_off[qa] + i; h_brow0[(size_t)qo + i] = (int)img_off[cb]; }
+        for (int i = 0; i < nq; ++i) { h_qrow[(size_t)qo + i] = (int)img_off[qa] + i; h_brow0[(size_t)qo + i] = (int)img_off[cb]; h_brows[(size_t)qo + i] = nc; }
         if (nc > 0)
           for (int m0 = 0; m0 < nq; m0 += BM) {
             WorkItem w;
@@ -191,10 +191,11 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
     q_off.back() = qo;
     if (nq_chunk > 0) {
       if (!d_cand.alloc((size_t)nq_chunk * KC) || !d_bj.alloc((size_t)nq_chunk) || !d_bd.alloc((size_t)nq_chunk) || !d_sd.alloc((size_t)nq_chunk) ||
-          !d_qrow.alloc((size_t)nq_chunk) || !d_brow0.alloc((size_t)nq_chunk)) return -3;
+          !d_qrow.alloc((size_t)nq_chunk) || !d_brow0.alloc((size_t)nq_chunk) || !d_brows.alloc((size_t)nq_chunk)) return -3;
       if (cudaMemset(d_cand.p, 0xFF, (size_t)nq_chunk * KC * sizeof(int)) != cudaSuccess) return -3;  // -1: no candidate (empty other image)
       if (cudaMemcpy(d_qrow.p, h_qrow.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
-          cudaMemcpy(d_brow0.p, h_brow0.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+          cudaMemcpy(d_brow0.p, h_brow0.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(d_brows.p, h_brows.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
       if (!items.empty()) {
         if (d_items.n < items.size()) { if (d_items.p) cudaFree(d_items.p); d_items.p = nullptr; d_items.n = 0;
           if (cudaMalloc(&d_items.p, items.size() * sizeof(WorkItem)) != cudaSuccess) return -3; d_items.n = items.size(); }
@@ -206,7 +207,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
         cudaEventRecord(ev[3]);
       }
       cudaEventRecord(ev[4]);
-      k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256>>>(d_desc.p, d_qrow.p, d_brow0.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p);
+      k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p);
       if (cudaPeekAtLastError() != cudaSuccess) return -3;
       cudaEventRecord(ev[5]);
       h_bj.resize((size_t)nq_chunk); h_bd.resize((size_t)nq_chunk); h_sd.resize((size_t)nq_chunk);

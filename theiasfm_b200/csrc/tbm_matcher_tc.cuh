@@ -8,14 +8,15 @@
 //   1. k_nn_candidates (this file): ||x - y||^2 = ||x||^2 + ||y||^2 - 2 x.y with the 128-dimensional dot products as a TF32
 //      tcgen05.mma GEMM -- a 128-query block of image A (resident in shared memory) against 128-candidate tiles of image B
 //      streamed by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32 accumulators double-buffered in TMEM -- and a fused
-//      epilogue that reads the accumulator tile back with tcgen05.ld and keeps, per query row, the KC smallest scores
-//      ||y||^2 - 2 x.y in registers across all candidate tiles.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected
-//      lane) + TMEM allocation, 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs over a list of work items.
+//      epilogue that reads the accumulator tile back with tcgen05.ld and keeps, per query row, the candidates whose score
+//      ||y||^2 - 2 x.y lies within the TF32 error margin of the running runner-up (branch-free, lists in shared memory).
+//      Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane) + TMEM allocation, 2..9 = epilogue (TMEM lane quarter
+//      warp % 4, column half (warp - 2) / 4).  Persistent CTAs over a list of work items.
 //   2. k_exact_top2: the KC candidates of every query are re-evaluated EXACTLY -- float, term by term in the reference's
 //      order without fused multiply-add, like the round-1 kernel k_nn2 -- and the best two (ties: lower index) are kept.
 // TF32 only ranks candidates; every distance that leaves the GPU, every ratio test and every tie-break is computed from
 // the exact values, so the match lists equal the CPU oracle's unless the true nearest / second-nearest neighbour is not
-// among the KC = 8 best TF32 scores (tests/test_xx_matcher_gpu.py counts such cases: none).
+// within the TF32 error margin of the running runner-up when it is seen (impossible by construction: see the epilogue comment).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -29,11 +30,15 @@ namespace tbm_tc {
 constexpr int BM = 128;        // query rows per work item (= TMEM lanes)
 constexpr int BN = 128;        // candidate rows per tile (= accumulator columns)
 constexpr int DIM = 128;       // descriptor length (SIFT); 4 swizzle atoms of 32 floats
-constexpr int KC = 8;          // candidates kept per query
+constexpr int KC = 16;         // candidate slots per query handed to the exact pass (-1 = empty; typically 2..4 are filled)
+constexpr int ET = 8;          // threads per query in the exact pass
+constexpr int CAP = 12;        // provisional candidates per (query, column half) in shared memory (overflow => exact full scan of that query)
+constexpr int kOverflow = -2;  // cand[q*KC] marker: the exact pass scans every candidate of this query
 constexpr int ATOM_BYTES = BM * 128;              // one 128-row x 128-byte swizzle-atom panel
 constexpr int TILE_BYTES = 4 * ATOM_BYTES;        // 64 KB: a 128 x 128 float tile
 constexpr int NSTAGE = 2;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quarter: each scans one 64-column half of the tile
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 struct WorkItem {
   int a_row0;    // global row of the first query of this block
@@ -111,16 +116,6 @@ struct __align__(8) Ctl {
   uint32_t tmem_base;
 };
 
-// sorted insertion into the KC smallest (value, index) pairs of this thread
-__device__ __forceinline__ void keep_smallest(float (&v)[KC], int (&id)[KC], float s, int j) {
-  if (!(s < v[KC - 1])) return;
-  v[KC - 1] = s; id[KC - 1] = j;
-#pragma unroll
-  for (int k = KC - 1; k > 0; --k) {
-    if (v[k] < v[k - 1]) { const float tv = v[k]; v[k] = v[k - 1]; v[k - 1] = tv; const int ti = id[k]; id[k] = id[k - 1]; id[k - 1] = ti; }
-  }
-}
-
 // ------------------------------------------------------------------ pass 1: TF32 candidates
 // desc_map: the concatenated descriptor matrix [total_rows][128] float as a 2-D tensor map, box = 32 floats x 128 rows, SWIZZLE_128B.
 // nrm[r] = ||descriptor r||^2 (float).  cand[(out_row0 + m) * KC + k] = global row of the k-th best candidate of query m (-1: none).
@@ -132,12 +127,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
   uint8_t* sA = smem;                                  // 4 atom panels of the query block
   uint8_t* sB = smem + TILE_BYTES;                     // NSTAGE x 4 atom panels of candidate tiles
   float* sN = reinterpret_cast<float*>(smem + TILE_BYTES * (1 + NSTAGE));  // [2][BN] squared norms of the tile being drained
-  Ctl* ctl = reinterpret_cast<Ctl*>(smem + TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float));
+  uint2* sC = reinterpret_cast<uint2*>(smem + TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float));  // [CAP][256] provisional candidates (score bits, row)
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float) + (size_t)CAP * 2 * BM * sizeof(uint2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     bar_init(&ctl->a_full, 1); bar_init(&ctl->a_empty, 1);
     for (int s = 0; s < NSTAGE; ++s) { bar_init(&ctl->b_full[s], 1); bar_init(&ctl->b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { bar_init(&ctl->acc_full[a], 1); bar_init(&ctl->acc_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { bar_init(&ctl->acc_full[a], 1); bar_init(&ctl->acc_empty[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
@@ -193,39 +189,98 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, TMEM lane quarter (warp % 4) =====================
-    const int q = warp & 3;                 // warps 2,3,4,5 -> quarters 2,3,0,1
+    // ===================== epilogue: 8 warps = 4 TMEM lane quarters (warp % 4) x 2 column halves =====================
+    // Branch-free streaming selection.  A thread owns one query row and one 64-column half of every candidate tile; it keeps the
+    // running two smallest scores m1 <= m2 of  score(n) = ||y_n||^2 - 2 x.y_n  over ITS columns (three min/max per element) and
+    // appends an element to its candidate list in shared memory -- one predicated 8-byte store, no branch, no divergence -- whenever
+    //     score(n) < m2 + margin(n),  margin(n) = 2^-8 (||x||^2 + ||y_n||^2)
+    // i.e. at least twice the worst-case TF32 error of a score (operands truncated to 10 mantissa bits:
+    // |d score| <= 2 * 2^-9 ||x|| ||y|| <= 2^-9 (||x||^2 + ||y||^2)).  An element that is among the two nearest of the whole image in
+    // exact arithmetic is a fortiori among the two nearest of its half: it passes the test when it is seen (m2 only decreases) and
+    // stays below every later m2 + margin, so it survives the compactions (a list that grows past 8 drops the entries above the
+    // current limit) and reaches the exact pass, which re-evaluates the union of the two halves' lists.  A list that fills up
+    // (a dense cluster of near-identical candidates) flags the row: the exact pass then scans every candidate of that query.
+    // The first tile is scanned twice: once only to establish m1, m2 (otherwise every element of it would be appended).
+    const int q = warp & 3;                 // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;       // column half: warps 2..5 -> 0, warps 6..9 -> 1
     const int row = q * 32 + lane;          // query row of this thread inside the block
-    const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;        // 0..255 among the epilogue threads
+    const float kInf = __int_as_float(0x7f800000);
+    uint2* myC = sC + et;                   // list entries of this thread: myC[k * 2 * BM]
+    constexpr int kStride = 2 * BM * (int)sizeof(uint2);   // bytes between consecutive entries of one list
     uint32_t bt = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
-      float v[KC]; int id[KC];
-#pragma unroll
-      for (int k = 0; k < KC; ++k) { v[k] = __int_as_float(0x7f800000); id[k] = -1; }
+      float m1 = kInf, m2 = kInf;
+      const float nx8 = row < w.a_rows ? 0.00390625f * __ldg(nrm + w.a_row0 + row) : 0.0f;  // 2^-8 ||x||^2
+      int cnt = 0, ovf = 0, woff = 0;       // woff = min(cnt, CAP - 1) * kStride: where the next append goes
       const int n_tiles = (w.b_rows + BN - 1) / BN;
       for (int t = 0; t < n_tiles; ++t, ++bt) {
         const int acc = bt & 1;
-        // squared norms of this tile's candidates (one per epilogue thread), double-buffered in shared memory
-        const int col_row = t * BN + et;
-        sN[acc * BN + et] = col_row < w.b_rows ? __ldg(nrm + w.b_row0 + col_row) : __int_as_float(0x7f800000);
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        // squared norms of this tile's candidates, double-buffered in shared memory
+        if (et < BN) {
+          const int col_row = t * BN + et;
+          sN[acc * BN + et] = col_row < w.b_rows ? __ldg(nrm + w.b_row0 + col_row) : kInf;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
         bar_wait(&ctl->acc_full[acc], (bt >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN + half * 64;
+        const float* nt = sN + acc * BN + half * 64;
+        const int jt = w.b_row0 + t * BN + half * 64;
+        if (t == 0) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float sc = fmaf(-2.0f, __uint_as_float(r[c]), nt[c0 + c]);
+              m2 = fminf(m2, fmaxf(m1, sc));
+              m1 = fminf(m1, sc);
+            }
+          }
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
-          const float4* n4 = reinterpret_cast<const float4*>(sN + acc * BN + c0);
+          if (t == 0) {  // (tile 0 is already in m1, m2: counting an element twice would turn the best into its own runner-up)
+            const float lim = m2 + nx8;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float4 nn = n4[c >> 2];
-            const int j = w.b_row0 + t * BN + c0 + c;
-            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c]), nn.x), j);
-            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c + 1]), nn.y), j + 1);
-            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c + 2]), nn.z), j + 2);
-            keep_smallest(v, id, fmaf(-2.0f, __uint_as_float(r[c + 3]), nn.w), j + 3);
+            for (int c = 0; c < 32; ++c) {
+              const float ny = nt[c0 + c];
+              const float val = fmaf(ny, -0.00390625f, fmaf(-2.0f, __uint_as_float(r[c]), ny));
+              if (val < lim) {
+                *reinterpret_cast<uint2*>(reinterpret_cast<char*>(myC) + woff) = make_uint2(__float_as_uint(val), (uint32_t)(jt + c0 + c));
+                ++cnt; woff = min(woff + kStride, (CAP - 1) * kStride);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float ny = nt[c0 + c];
+              const float sc = fmaf(-2.0f, __uint_as_float(r[c]), ny);
+              const float val = fmaf(ny, -0.00390625f, sc);   // score minus the candidate's share of the margin
+              if (val < m2 + nx8) {
+                *reinterpret_cast<uint2*>(reinterpret_cast<char*>(myC) + woff) = make_uint2(__float_as_uint(val), (uint32_t)(jt + c0 + c));
+                ++cnt; woff = min(woff + kStride, (CAP - 1) * kStride);
+              }
+              m2 = fminf(m2, fmaxf(m1, sc));
+              m1 = fminf(m1, sc);
+            }
+          }
+          // list maintenance, once per 32-column chunk (rare per lane; divergent, but cheap)
+          ovf |= cnt > CAP;
+          if (cnt > 8) {
+            const float lim = m2 + nx8;
+            int k = 0;
+            for (int e = 0; e < min(cnt, CAP); ++e) {
+              const uint2 ce = myC[e * 2 * BM];
+              if (__uint_as_float(ce.x) < lim) { myC[k * 2 * BM] = ce; ++k; }
+            }
+            cnt = k; woff = min(cnt, CAP - 1) * kStride;
+            ovf |= cnt > 10;  // a dense cluster around the runner-up: hand the row to the exhaustive scan
           }
         }
         tc_fence_before();
@@ -233,9 +288,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
         if (lane == 0) bar_arrive(&ctl->acc_empty[acc]);
       }
       if (row < w.a_rows) {
-        int* o = cand + (size_t)(w.out_row0 + row) * KC;
-#pragma unroll
-        for (int k = 0; k < KC; ++k) o[k] = id[k];
+        int* o = cand + (size_t)(w.out_row0 + row) * KC + half * (KC / 2);   // slots [0, 8): columns half 0, [8, 16): half 1
+        const float lim = m2 + nx8;   // the final runner-up of this half: only entries within its margin can matter
+#pragma unroll 1
+        for (int k = 0; k < KC / 2; ++k) {
+          int j = -1;
+          if (k < min(cnt, CAP)) { const uint2 ce = myC[k * 2 * BM]; if (__uint_as_float(ce.x) < lim) j = (int)ce.y; }
+          o[k] = (ovf || cnt > KC / 2) ? kOverflow : j;
+        }
       }
     }
   }
@@ -258,41 +318,50 @@ __global__ void k_row_norms(const float* __restrict__ d, long long n_rows, float
 // ------------------------------------------------------------------ pass 2: exact top-2 among the candidates
 // One thread per (query, candidate): the exact squared distance -- float, term by term, no fused multiply-add: L2::operator()
 // (distance.h:52-56) as the oracle and k_nn2 evaluate it; then thread 0 of the query picks the best two (ties: lower index).
-// q_row[i] = global descriptor row of query i, b_row0[i] = first row of the candidate image (indices are reported relative to it).
+// q_row[i] = global descriptor row of query i, b_row0[i] / b_rows[i] = first row / number of rows of the candidate image (indices are
+// reported relative to b_row0).  A query whose candidate ring overflowed in pass 1 (cand[i*KC] == kOverflow) is scanned exhaustively.
+__device__ __forceinline__ float exact_sqdist(const float* __restrict__ a, const float* __restrict__ b) {
+  float s = 0.0f;
+  for (int k = 0; k < DIM; ++k) {
+    const float df = __fsub_rn(a[k], b[k]);
+    s = __fadd_rn(s, __fmul_rn(df, df));
+  }
+  return s;
+}
+// lexicographic (distance, index) order: what MatchImagePair's partial_sort over index-ordered candidates yields
+__device__ __forceinline__ void top2_take(int& bj, float& bd, int& sj, float& sd, int jj, float dd) {
+  if (jj < 0) return;
+  if (bj < 0 || dd < bd || (dd == bd && jj < bj)) { sj = bj; sd = bd; bj = jj; bd = dd; }
+  else if (sj < 0 || dd < sd || (dd == sd && jj < sj)) { sj = jj; sd = dd; }
+}
 __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
-                                                    const int* __restrict__ cand, long long n_q, int* __restrict__ best_j,
-                                                    float* __restrict__ best_d, float* __restrict__ second_d) {
-  __shared__ float s_d[32][KC];
-  __shared__ int s_j[32][KC];
-  const int ql = threadIdx.x / KC, c = threadIdx.x % KC;
+                                                    const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
+                                                    int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d) {
+  __shared__ float s_d[32][ET], s_d2[32][ET];
+  __shared__ int s_j[32][ET], s_j2[32][ET];
+  const int ql = threadIdx.x / ET, c = threadIdx.x % ET;
   const long long qi = (long long)blockIdx.x * 32 + ql;
-  float dist = 0.0f;
-  int j = -1;
+  int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
   if (qi < n_q) {
-    j = cand[qi * KC + c];
-    if (j >= 0) {
-      const float* a = d + (size_t)q_row[qi] * DIM;
-      const float* b = d + (size_t)j * DIM;
-      float s = 0.0f;
-      for (int k = 0; k < DIM; ++k) {
-        const float df = __fsub_rn(a[k], b[k]);
-        s = __fadd_rn(s, __fmul_rn(df, df));
+    const float* a = d + (size_t)q_row[qi] * DIM;
+    const int base = b_row0[qi];
+    if (cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow) {
+      // the candidate list of this query overflowed: exhaustive scan, thread c takes candidates c, c + ET, ...
+      const int nb = b_rows[qi];
+      for (int j = c; j < nb; j += ET) top2_take(bj, bd, sj, sd, j, exact_sqdist(a, d + (size_t)(base + j) * DIM));
+    } else {
+      for (int k = c; k < KC; k += ET) {
+        const int j = cand[qi * KC + k];
+        if (j >= 0) top2_take(bj, bd, sj, sd, j - base, exact_sqdist(a, d + (size_t)j * DIM));
       }
-      dist = s;
-      j -= b_row0[qi];
     }
   }
-  s_d[ql][c] = dist; s_j[ql][c] = j;
+  s_d[ql][c] = bd; s_j[ql][c] = bj; s_d2[ql][c] = sd; s_j2[ql][c] = sj;
   __syncthreads();
   if (c == 0 && qi < n_q) {
-    int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
-    for (int k = 0; k < KC; ++k) {
-      const int jj = s_j[ql][k]; const float dd = s_d[ql][k];
-      if (jj < 0) continue;
-      if (bj < 0 || dd < bd || (dd == bd && jj < bj)) { sj = bj; sd = bd; bj = jj; bd = dd; }
-      else if (sj < 0 || dd < sd || (dd == sd && jj < sj)) { sj = jj; sd = dd; }
-    }
-    best_j[qi] = bj; best_d[qi] = bd; second_d[qi] = sj >= 0 ? sd : 0.0f;
+    int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
+    for (int k = 0; k < ET; ++k) { top2_take(fj, fd, gj, gd, s_j[ql][k], s_d[ql][k]); top2_take(fj, fd, gj, gd, s_j2[ql][k], s_d2[ql][k]); }
+    best_j[qi] = fj; best_d[qi] = fd; second_d[qi] = gj >= 0 ? gd : 0.0f;
   }
 }
 
@@ -313,6 +382,6 @@ inline bool make_desc_map(CUtensorMap* map, const float* d_desc, long long n_row
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-constexpr size_t kSmemBytes = (size_t)TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float) + sizeof(Ctl) + 1024;
+constexpr size_t kSmemBytes = (size_t)TILE_BYTES * (1 + NSTAGE) + 2 * BN * sizeof(float) + (size_t)CAP * 2 * BM * sizeof(uint2) + sizeof(Ctl) + 1024;
 
 }  // namespace tbm_tc
