@@ -411,6 +411,7 @@ def matcher_main(args):
         call()
         tm = matcher.last_timing()
         gemm_ms += tm["gemm_ms"]; exact_ms += tm["exact_ms"]; h2d_ms += tm["h2d_ms"]
+        n_exh = tm["exhaustive_queries"]
         n_matches = int(moff[len(pr)])
     torch.cuda.synchronize()
     if world > 1:
@@ -444,7 +445,7 @@ def matcher_main(args):
                              "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "note": "algorithmic flops 2*n1*n2*128 per direction on the TF32 path (nominal dense TF32 = half the bf16 rate the peak is quoted for); per GPU",
                              "gemm_seconds": gemm_s, "exact_seconds": allred(1e-3 * exact_ms, dist.ReduceOp.MAX if world > 1 else None)},
-                "cpu_baseline": cb, "matches_per_step": n_matches, "distance_evaluations_per_s": 2.0 * n_desc * n_desc * pairs_total / dev_s if dev_s > 0 else 0.0}
+                "cpu_baseline": cb, "matches_per_step": n_matches, "exhaustive_queries_per_step_rank0": n_exh, "queries_per_step": 2 * n_desc * len(all_pairs), "distance_evaluations_per_s": 2.0 * n_desc * n_desc * pairs_total / dev_s if dev_s > 0 else 0.0}
         print(json.dumps(line))
     elif world > 1:
         allred(1e-3 * exact_ms, dist.ReduceOp.MAX)

@@ -52,7 +52,8 @@ int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const 
                           const tbm_options* options, tbm_match* matches /* capacity n1 */, int32_t* n_matches);
 
 /* Device times (CUDA events, ms) of the last tbm_match_all on the tensor-core path: {candidate GEMM kernel (tcgen05), exact
- * re-evaluation kernel, host-to-device copy of the descriptors, 0}.  All zero after a call that took the CUDA-core path. */
+ * re-evaluation kernel, host-to-device copy of the descriptors}; out4[3] = number of queries whose candidate list overflowed
+ * and were scanned exhaustively by the exact pass.  All zero after a call that took the CUDA-core path. */
 void tbm_debug_last_timing(double* out4);
 
 #ifdef __cplusplus

@@ -14,7 +14,7 @@
 #endif
 #include <cstdlib>
 
-static double g_last_timing[4] = {0, 0, 0, 0};  // ms: candidate GEMM kernel, exact re-evaluation kernel, H2D of the descriptors, unused
+static double g_last_timing[4] = {0, 0, 0, 0};  // ms: candidate GEMM kernel, exact re-evaluation kernel, H2D of the descriptors; [3] = queries scanned exhaustively
 
 namespace {
 
@@ -141,13 +141,21 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   if (!d_desc.alloc((size_t)(total > 0 ? total : 1) * DIM) || !d_nrm.alloc((size_t)(total > 0 ? total : 1))) return -3;
   if (total > 0 && cudaMemcpy(d_desc.p, descriptors, (size_t)total * DIM * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
   cudaEventRecord(ev[1]);
+  int any_negative = 0;
   if (total > 0) {
-    k_row_norms<<<(unsigned)((total + 255) / 256), 256>>>(d_desc.p, total, d_nrm.p);
+    DevI d_neg;
+    if (!d_neg.alloc(1) || cudaMemset(d_neg.p, 0, sizeof(int)) != cudaSuccess) return -3;
+    k_row_norms<<<(unsigned)((total + 255) / 256), 256>>>(d_desc.p, total, d_nrm.p, d_neg.p);
     if (cudaPeekAtLastError() != cudaSuccess) return -3;
+    if (cudaMemcpy(&any_negative, d_neg.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
   }
   CUtensorMap map;
   if (total > 0 && !make_desc_map(&map, d_desc.p, total)) return -3;
-  if (cudaFuncSetAttribute(k_nn_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
+  unsigned long long* d_nex = nullptr;  // queries handed to the exhaustive exact scan (diagnostics: tbm_debug_last_timing)
+  if (cudaMalloc(&d_nex, 8) != cudaSuccess || cudaMemset(d_nex, 0, 8) != cudaSuccess) return -3;
+  struct NexGuard { unsigned long long* p; ~NexGuard() { cudaFree(p); } } nex_guard{d_nex};
+  if (cudaFuncSetAttribute(k_nn_candidates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_nn_candidates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
   struct DevItems { WorkItem* p = nullptr; size_t n = 0; ~DevItems() { if (p) cudaFree(p); } } d_items;
   std::vector<WorkItem> items;
   std::vector<int> h_qrow, h_brow0, h_brows, h_bj;
@@ -202,12 +210,13 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
         if (cudaMemcpy(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
         const int grid = (int)(items.size() < (size_t)n_sm ? items.size() : (size_t)n_sm);
         cudaEventRecord(ev[2]);
-        k_nn_candidates<<<grid, THREADS, kSmemBytes>>>(map, d_items.p, (int)items.size(), d_nrm.p, d_cand.p);
+        if (any_negative) k_nn_candidates<false><<<grid, THREADS, kSmemBytes>>>(map, d_items.p, (int)items.size(), d_nrm.p, d_cand.p);
+        else k_nn_candidates<true><<<grid, THREADS, kSmemBytes>>>(map, d_items.p, (int)items.size(), d_nrm.p, d_cand.p);
         if (cudaPeekAtLastError() != cudaSuccess) return -3;
         cudaEventRecord(ev[3]);
       }
       cudaEventRecord(ev[4]);
-      k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p);
+      k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
       if (cudaPeekAtLastError() != cudaSuccess) return -3;
       cudaEventRecord(ev[5]);
       h_bj.resize((size_t)nq_chunk); h_bd.resize((size_t)nq_chunk); h_sd.resize((size_t)nq_chunk);
@@ -239,6 +248,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return -3;
   { float ms = 0; if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) g_last_timing[2] = ms; }
+  { unsigned long long h = 0; if (cudaMemcpy(&h, d_nex, 8, cudaMemcpyDeviceToHost) == cudaSuccess) g_last_timing[3] = (double)h; }
   match_off[n_pairs] = written;
   return overflow ? -1 : 0;
 }

@@ -119,6 +119,7 @@ struct __align__(8) Ctl {
 // ------------------------------------------------------------------ pass 1: TF32 candidates
 // desc_map: the concatenated descriptor matrix [total_rows][128] float as a 2-D tensor map, box = 32 floats x 128 rows, SWIZZLE_128B.
 // nrm[r] = ||descriptor r||^2 (float).  cand[(out_row0 + m) * KC + k] = global row of the k-th best candidate of query m (-1: none).
+template <bool NONNEG>
 __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_constant__ CUtensorMap desc_map, const WorkItem* __restrict__ items,
                                                               int n_items, const float* __restrict__ nrm, int* __restrict__ cand) {
   extern __shared__ uint8_t smem_raw[];
@@ -193,9 +194,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
     // Branch-free streaming selection.  A thread owns one query row and one 64-column half of every candidate tile; it keeps the
     // running two smallest scores m1 <= m2 of  score(n) = ||y_n||^2 - 2 x.y_n  over ITS columns (three min/max per element) and
     // appends an element to its candidate list in shared memory -- one predicated 8-byte store, no branch, no divergence -- whenever
-    //     score(n) < m2 + margin(n),  margin(n) = 2^-8 (||x||^2 + ||y_n||^2)
-    // i.e. at least twice the worst-case TF32 error of a score (operands truncated to 10 mantissa bits:
-    // |d score| <= 2 * 2^-9 ||x|| ||y|| <= 2^-9 (||x||^2 + ||y||^2)).  An element that is among the two nearest of the whole image in
+    //     score(n) < m2 + margin(n),
+    // where margin(n) is at least twice the worst-case TF32 error of a score.  tcgen05 kind::tf32 uses 10 mantissa bits of each
+    // operand (relative operand error < 2^-10 truncating, <= 2^-11 rounding), so |d score| <= 2 * 2^-9 sum_k |x_k y_k|:
+    //   * NONNEG (every descriptor component >= 0: SIFT, RootSIFT, any histogram descriptor): sum_k |x_k y_k| = x.y, read off the
+    //     accumulator itself: margin(n) = 2^-8 x.y_n (1 + 2^-6)  (truncation errors are one-sided there, so 1 x the bound suffices;
+    //     with rounding the bound halves and 2 x it is the same number);
+    //   * otherwise: sum_k |x_k y_k| <= ||x|| ||y|| <= (||x||^2 + ||y||^2) / 2:  margin(n) = 2^-8 (||x||^2 + ||y_n||^2).
+    // An element that is among the two nearest of the whole image in
     // exact arithmetic is a fortiori among the two nearest of its half: it passes the test when it is seen (m2 only decreases) and
     // stays below every later m2 + margin, so it survives the compactions (a list that grows past 8 drops the entries above the
     // current limit) and reaches the exact pass, which re-evaluates the union of the two halves' lists.  A list that fills up
@@ -207,13 +213,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
     const int et = threadIdx.x - 64;        // 0..255 among the epilogue threads
     const float kInf = __int_as_float(0x7f800000);
     uint2* myC = sC + et;                   // list entries of this thread: myC[k * 2 * BM]
-    constexpr int kStride = 2 * BM * (int)sizeof(uint2);   // bytes between consecutive entries of one list
+    constexpr uint32_t kStride = 2 * BM * (uint32_t)sizeof(uint2);   // bytes between consecutive entries of one list
+    const uint32_t c_base = smem_addr(myC), c_last = c_base + (CAP - 1) * kStride;
     uint32_t bt = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       float m1 = kInf, m2 = kInf;
-      const float nx8 = row < w.a_rows ? 0.00390625f * __ldg(nrm + w.a_row0 + row) : 0.0f;  // 2^-8 ||x||^2
-      int cnt = 0, ovf = 0, woff = 0;       // woff = min(cnt, CAP - 1) * kStride: where the next append goes
+      const float nx8 = (!NONNEG && row < w.a_rows) ? 0.00390625f * __ldg(nrm + w.a_row0 + row) : 0.0f;  // 2^-8 ||x||^2 (general margin only)
+      // wp = shared-memory address of the next append; it saturates at the last slot, and a list that reaches the last slot
+      // counts as overflowed (capacity CAP - 1 entries between two maintenance points)
+      uint32_t wp = c_base;
+      int ovf = 0;
       const int n_tiles = (w.b_rows + BN - 1) / BN;
       for (int t = 0; t < n_tiles; ++t, ++bt) {
         const int acc = bt & 1;
@@ -226,18 +236,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
         bar_wait(&ctl->acc_full[acc], (bt >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN + half * 64;
-        const float* nt = sN + acc * BN + half * 64;
+        const float4* nt4 = reinterpret_cast<const float4*>(sN + acc * BN + half * 64);
         const int jt = w.b_row0 + t * BN + half * 64;
+#define TBM_APPEND(VAL, J)                                                                                              \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p st.shared.v2.b32 [%0], {%3, %4};\n\t@p add.u32 %0, %0, %5;\n\t"        \
+               "@p min.u32 %0, %0, %6;\n\t}"                                                                            \
+               : "+r"(wp) : "f"(VAL), "f"(lim), "r"(__float_as_uint(VAL)), "r"(J), "n"(kStride), "r"(c_last) : "memory")
         if (t == 0) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + c0, r);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float sc = fmaf(-2.0f, __uint_as_float(r[c]), nt[c0 + c]);
-              m2 = fminf(m2, fmaxf(m1, sc));
-              m1 = fminf(m1, sc);
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 n4 = nt4[(c0 >> 2) + c4];
+              const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float sc = fmaf(-2.0f, __uint_as_float(r[4 * c4 + u]), nn[u]);
+                m2 = fminf(m2, fmaxf(m1, sc));
+                m1 = fminf(m1, sc);
+              }
             }
           }
         }
@@ -248,54 +267,62 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
           if (t == 0) {  // (tile 0 is already in m1, m2: counting an element twice would turn the best into its own runner-up)
             const float lim = m2 + nx8;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float ny = nt[c0 + c];
-              const float val = fmaf(ny, -0.00390625f, fmaf(-2.0f, __uint_as_float(r[c]), ny));
-              if (val < lim) {
-                *reinterpret_cast<uint2*>(reinterpret_cast<char*>(myC) + woff) = make_uint2(__float_as_uint(val), (uint32_t)(jt + c0 + c));
-                ++cnt; woff = min(woff + kStride, (CAP - 1) * kStride);
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 n4 = nt4[(c0 >> 2) + c4];
+              const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float dotv = __uint_as_float(r[4 * c4 + u]);
+                const float val = fmaf(NONNEG ? dotv : nn[u], NONNEG ? -0.00396728515625f : -0.00390625f, fmaf(-2.0f, dotv, nn[u]));
+                TBM_APPEND(val, jt + c0 + 4 * c4 + u);
               }
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float ny = nt[c0 + c];
-              const float sc = fmaf(-2.0f, __uint_as_float(r[c]), ny);
-              const float val = fmaf(ny, -0.00390625f, sc);   // score minus the candidate's share of the margin
-              if (val < m2 + nx8) {
-                *reinterpret_cast<uint2*>(reinterpret_cast<char*>(myC) + woff) = make_uint2(__float_as_uint(val), (uint32_t)(jt + c0 + c));
-                ++cnt; woff = min(woff + kStride, (CAP - 1) * kStride);
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 n4 = nt4[(c0 >> 2) + c4];
+              const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float dotv = __uint_as_float(r[4 * c4 + u]);
+                const float sc = fmaf(-2.0f, dotv, nn[u]);
+                const float val = fmaf(NONNEG ? dotv : nn[u], NONNEG ? -0.00396728515625f : -0.00390625f, sc);   // score minus the candidate's margin
+                const float lim = m2 + nx8;
+                TBM_APPEND(val, jt + c0 + 4 * c4 + u);
+                m2 = fminf(m2, fmaxf(m1, sc));
+                m1 = fminf(m1, sc);
               }
-              m2 = fminf(m2, fmaxf(m1, sc));
-              m1 = fminf(m1, sc);
             }
           }
+#undef TBM_APPEND
           // list maintenance, once per 32-column chunk (rare per lane; divergent, but cheap)
-          ovf |= cnt > CAP;
-          if (cnt > 8) {
+          ovf |= wp == c_last;
+          if (wp > c_base + 8 * kStride) {
+            const int cnt = (int)((wp - c_base) / kStride);
             const float lim = m2 + nx8;
             int k = 0;
-            for (int e = 0; e < min(cnt, CAP); ++e) {
+            for (int e = 0; e < cnt; ++e) {
               const uint2 ce = myC[e * 2 * BM];
               if (__uint_as_float(ce.x) < lim) { myC[k * 2 * BM] = ce; ++k; }
             }
-            cnt = k; woff = min(cnt, CAP - 1) * kStride;
-            ovf |= cnt > 10;  // a dense cluster around the runner-up: hand the row to the exhaustive scan
+            wp = c_base + (uint32_t)k * kStride;
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(&ctl->acc_empty[acc]);
       }
+      const int cnt = (int)((wp - c_base) / kStride);
       if (row < w.a_rows) {
         int* o = cand + (size_t)(w.out_row0 + row) * KC + half * (KC / 2);   // slots [0, 8): columns half 0, [8, 16): half 1
         const float lim = m2 + nx8;   // the final runner-up of this half: only entries within its margin can matter
-#pragma unroll 1
-        for (int k = 0; k < KC / 2; ++k) {
-          int j = -1;
-          if (k < min(cnt, CAP)) { const uint2 ce = myC[k * 2 * BM]; if (__uint_as_float(ce.x) < lim) j = (int)ce.y; }
-          o[k] = (ovf || cnt > KC / 2) ? kOverflow : j;
+        int k = 0;
+        for (int e = 0; e < cnt; ++e) {
+          const uint2 ce = myC[e * 2 * BM];
+          if (__uint_as_float(ce.x) < lim) { if (k < KC / 2) o[k] = (int)ce.y; ++k; }
         }
+        if (ovf || k > KC / 2) o[0] = kOverflow;
+        else for (; k < KC / 2; ++k) o[k] = -1;
       }
     }
   }
@@ -304,15 +331,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
 }
 
-// ||d||^2 of every descriptor row (float, plain left-to-right sum: only used to RANK candidates)
-__global__ void k_row_norms(const float* __restrict__ d, long long n_rows, float* __restrict__ nrm) {
+// ||d||^2 of every descriptor row (float, plain left-to-right sum: only used to RANK candidates); *any_negative is set when a
+// component < 0 exists anywhere (selects the general TF32 error margin instead of the tighter one of non-negative descriptors)
+__global__ void k_row_norms(const float* __restrict__ d, long long n_rows, float* __restrict__ nrm, int* __restrict__ any_negative) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const float4* p = reinterpret_cast<const float4*>(d + r * DIM);
-  float s = 0.0f;
+  float s = 0.0f, mn = 0.0f;
 #pragma unroll 8
-  for (int k = 0; k < DIM / 4; ++k) { const float4 x = __ldg(p + k); s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
+  for (int k = 0; k < DIM / 4; ++k) {
+    const float4 x = __ldg(p + k);
+    s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    mn = fminf(mn, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
+  }
   nrm[r] = s;
+  if (mn < 0.0f) *any_negative = 1;
 }
 
 // ------------------------------------------------------------------ pass 2: exact top-2 among the candidates
@@ -336,7 +369,8 @@ __device__ __forceinline__ void top2_take(int& bj, float& bd, int& sj, float& sd
 }
 __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
                                                     const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
-                                                    int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d) {
+                                                    int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
+                                                    unsigned long long* __restrict__ n_exhaustive) {
   __shared__ float s_d[32][ET], s_d2[32][ET];
   __shared__ int s_j[32][ET], s_j2[32][ET];
   const int ql = threadIdx.x / ET, c = threadIdx.x % ET;
@@ -346,9 +380,27 @@ __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d,
     const float* a = d + (size_t)q_row[qi] * DIM;
     const int base = b_row0[qi];
     if (cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow) {
-      // the candidate list of this query overflowed: exhaustive scan, thread c takes candidates c, c + ET, ...
+      // the candidate list of this query overflowed: exhaustive scan, thread c takes candidates c, c + ET, ...; four independent
+      // summation chains per thread (each in the reference's term order), 128-bit loads of the candidate rows
       const int nb = b_rows[qi];
-      for (int j = c; j < nb; j += ET) top2_take(bj, bd, sj, sd, j, exact_sqdist(a, d + (size_t)(base + j) * DIM));
+      if (c == 0 && n_exhaustive) atomicAdd(n_exhaustive, 1ull);
+      const float4* a4 = reinterpret_cast<const float4*>(a);
+      int j = c;
+      for (; j + 3 * ET < nb; j += 4 * ET) {
+        const float4* b0 = reinterpret_cast<const float4*>(d + (size_t)(base + j) * DIM);
+        const float4* b1 = b0 + (size_t)ET * (DIM / 4); const float4* b2 = b1 + (size_t)ET * (DIM / 4); const float4* b3 = b2 + (size_t)ET * (DIM / 4);
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < DIM / 4; ++k) {
+          const float4 av = __ldg(a4 + k), v0 = __ldg(b0 + k), v1 = __ldg(b1 + k), v2 = __ldg(b2 + k), v3 = __ldg(b3 + k);
+#define TBM_STEP(S, V) { float df = __fsub_rn(av.x, V.x); S = __fadd_rn(S, __fmul_rn(df, df)); df = __fsub_rn(av.y, V.y); S = __fadd_rn(S, __fmul_rn(df, df)); \
+                         df = __fsub_rn(av.z, V.z); S = __fadd_rn(S, __fmul_rn(df, df)); df = __fsub_rn(av.w, V.w); S = __fadd_rn(S, __fmul_rn(df, df)); }
+          TBM_STEP(s0, v0) TBM_STEP(s1, v1) TBM_STEP(s2, v2) TBM_STEP(s3, v3)
+#undef TBM_STEP
+        }
+        top2_take(bj, bd, sj, sd, j, s0); top2_take(bj, bd, sj, sd, j + ET, s1); top2_take(bj, bd, sj, sd, j + 2 * ET, s2); top2_take(bj, bd, sj, sd, j + 3 * ET, s3);
+      }
+      for (; j < nb; j += ET) top2_take(bj, bd, sj, sd, j, exact_sqdist(a, d + (size_t)(base + j) * DIM));
     } else {
       for (int k = c; k < KC; k += ET) {
         const int j = cand[qi * KC + k];

@@ -42,7 +42,7 @@ def last_timing():
     """{gemm_ms, exact_ms, h2d_ms} of the last match_all on the tensor-core path (CUDA events)."""
     out = (C.c_double * 4)()
     lib().tbm_debug_last_timing(out)
-    return {"gemm_ms": out[0], "exact_ms": out[1], "h2d_ms": out[2]}
+    return {"gemm_ms": out[0], "exact_ms": out[1], "h2d_ms": out[2], "exhaustive_queries": out[3]}
 
 
 def default_options(**kw):
