@@ -374,14 +374,14 @@ int p2p_setup(tba_context* c, int ncs) {
   int ok = 1;
   if (cudaMalloc(&c->p2p_inbox, 2 * (size_t)W * cap * sizeof(double)) != cudaSuccess) { c->p2p_inbox = nullptr; ok = 0; }
   if (cudaMalloc(&c->p2p_flags, (size_t)W * sizeof(unsigned long long)) != cudaSuccess) { c->p2p_flags = nullptr; ok = 0; }
-  if (cudaMalloc(&c->p2p_ctr, sizeof(int)) != cudaSuccess) { c->p2p_ctr = nullptr; ok = 0; }
+  if (cudaMalloc(&c->p2p_ctr, 2 * sizeof(int)) != cudaSuccess) { c->p2p_ctr = nullptr; ok = 0; }
   cudaGetLastError();
   P2pInfo mine;
   memset(&mine, 0, sizeof mine);
   mine.pid = (long long)getpid(); mine.device = c->device; mine.inbox = c->p2p_inbox; mine.flags = c->p2p_flags;
   if (ok) {
     CUDA_OK(c, cudaMemsetAsync(c->p2p_flags, 0, (size_t)W * sizeof(unsigned long long), c->stream));
-    CUDA_OK(c, cudaMemsetAsync(c->p2p_ctr, 0, sizeof(int), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(c->p2p_ctr, 0, 2 * sizeof(int), c->stream));
     if (cudaIpcGetMemHandle(&mine.h_inbox, c->p2p_inbox) != cudaSuccess || cudaIpcGetMemHandle(&mine.h_flags, c->p2p_flags) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
   mine.ok = ok;

@@ -894,10 +894,10 @@ __global__ void __launch_bounds__(TILE, (14 + 2 * popcount10(IMASK)) <= 20 ? 4 :
 }
 
 // --------------------------------------------- fused matvec + all-reduce over NVLink peer memory (multi-GPU)
-// Every rank owns an "inbox" [2][world][cap] in its own HBM that all peers can write (CUDA IPC / peer access).  The CTA of
-// k_schur_stream<., 0> that finishes LAST on a rank folds the replica rows and then STORES the rank's complete partial y into
-// slot `rank` of every peer's inbox (buffer seq & 1) -- 16-byte stores over NVLink, no separate collective launch -- and
-// releases flags[rank] = seq on every peer.  The consumer (k_pcg_a / k_pcg_reset_bz) acquires the `world` flags of its own
+// Every rank owns an "inbox" [2][world][cap] in its own HBM that all peers can write (CUDA IPC / peer access).  After a grid
+// barrier inside k_schur_stream<., 0> (its persistent CTAs are co-resident) every CTA STORES its slice of the rank's complete
+// partial y into slot `rank` of every peer's inbox (buffer seq & 1) -- 16-byte stores over NVLink from all SMs, no separate
+// collective launch -- and the CTA that finishes last releases flags[rank] = seq on every peer.  The consumer (k_pcg_a / k_pcg_reset_bz) acquires the `world` flags of its own
 // inbox and sums the slots in rank order: the same bits on every rank (the replicated PCG state stays in lockstep) and
 // run-to-run reproducible for a given world size.  Two buffers suffice: a rank can be at most one exchange ahead of a peer,
 // because exchange k+1 needs the sums of exchange k, to which every peer contributed after it consumed exchange k-1.
@@ -907,7 +907,7 @@ struct P2pDev {
   size_t cap = 0;                        // doubles per slot
   double* const* inbox = nullptr;        // [world] base pointers of the ranks' inboxes (inbox[rank] is the local one)
   unsigned long long* const* flags = nullptr;  // [world] base pointers of the ranks' flag arrays ([world] each)
-  int* ctr = nullptr;                    // local count of finished CTAs (zeroed before every matvec by k_pcg_c / k_pcg_reset_a)
+  int* ctr = nullptr;                    // local counters [2]: CTAs at the grid barrier / CTAs done pushing (zeroed before every matvec by k_pcg_c / k_pcg_reset_a)
 };
 #ifdef TBA_EMULATE
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
@@ -1224,32 +1224,46 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
       if (lane == 0) red_add(rr + nth_bit(IMASK, j), v);
     }
   }
-  // ---- multi-GPU: the CTA that finishes last on this rank folds and pushes the rank's complete partial y to every peer
+  // ---- multi-GPU: grid barrier (the persistent CTAs are co-resident: one per SM), then EVERY CTA stores its slice of the
+  // rank's complete partial y into slot `rank` of every peer's inbox; the CTA that finishes its stores last releases the flags
   if (MODE == 0 && pp.world > 1) {
     __shared__ int s_last;
     __threadfence();  // this thread's REDs are performed before its CTA is counted
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(pp.ctr, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) {
+      atomicAdd(pp.ctr, 1);
+#ifndef TBA_EMULATE
+      const long long t0 = clock64();
+      while (atomicAdd(pp.ctr, 0) < (int)gridDim.x) {
+        if (clock64() - t0 > 4000000000ll) { printf("tba: grid barrier of the matvec timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+      }
+#endif
+    }
+    __syncthreads();
+    __threadfence();
+    const size_t slot = ((size_t)(pp.seq & 1ull) * pp.world + pp.rank) * pp.cap;
+    const bool fold = NI > 0 && P.single_group;
+    if (fold && blockIdx.x == 0 && threadIdx.x < 10) {  // k_fold: replica columns 0..9 -> y[ne ..] (and to the peers), replicas re-zeroed
+      double v = ld_cg(y + P.ne + threadIdx.x);
+      for (int r = 0; r < NREP; ++r) { v += ld_cg(rep + (size_t)r * REPW + threadIdx.x); rep[(size_t)r * REPW + threadIdx.x] = 0.0; }
+      y[P.ne + threadIdx.x] = v;
+      for (int q = 0; q < pp.world; ++q) pp.inbox[q][slot + P.ne + threadIdx.x] = v;
+    }
+    // 16-byte stores of the extrinsics part (ne is even) and, with per-camera groups, of the intrinsics part
+    const int n_push = fold ? P.ne : P.ncs;
+    const int n2 = (n_push + 1) / 2;
+    const int per = (n2 + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int i0 = (int)blockIdx.x * per, i1 = (i0 + per < n2) ? i0 + per : n2;
+    for (int i = i0 + (int)threadIdx.x; i < i1; i += (int)blockDim.x) {
+      const double a = ld_cg(y + 2 * i), b = 2 * i + 1 < n_push ? ld_cg(y + 2 * i + 1) : 0.0;
+      for (int q = 0; q < pp.world; ++q) reinterpret_cast<double2*>(pp.inbox[q] + slot)[i] = make_double2(a, b);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(pp.ctr + 1, 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (s_last) {
-      __threadfence();
-      if (NI > 0 && P.single_group && threadIdx.x < 10) {  // k_fold: replica columns 0..9 -> y[ne ..], replicas re-zeroed
-        double v = ld_cg(y + P.ne + threadIdx.x);
-        for (int r = 0; r < NREP; ++r) { v += ld_cg(rep + (size_t)r * REPW + threadIdx.x); rep[(size_t)r * REPW + threadIdx.x] = 0.0; }
-        y[P.ne + threadIdx.x] = v;
-      }
-      __syncthreads();
-      const size_t slot = ((size_t)(pp.seq & 1ull) * pp.world + pp.rank) * pp.cap;
-      const int n2 = (P.ncs + 1) / 2;  // 16-byte stores; cap is even and the slot is padded
-      for (int q = 0; q < pp.world; ++q) {
-        double2* dst = reinterpret_cast<double2*>(pp.inbox[q] + slot);
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-          const double a = ld_cg(y + 2 * i), b = 2 * i + 1 < P.ncs ? ld_cg(y + 2 * i + 1) : 0.0;
-          dst[i] = make_double2(a, b);
-        }
-      }
       __threadfence_system();
-      __syncthreads();
       if ((int)threadIdx.x < pp.world) st_release_sys(pp.flags[threadIdx.x] + pp.rank, pp.seq);
     }
   }
@@ -1915,7 +1929,7 @@ __global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restric
                                               double* __restrict__ xs, double* __restrict__ y, int* __restrict__ done_flag, int* __restrict__ zero_ctr) {
   __shared__ double s_red[32];
   PcgState st = *in;
-  if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_ctr = 0;  // finished-CTA counter of the next matvec
+  if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { zero_ctr[0] = 0; zero_ctr[1] = 0; }  // barrier / completion counters of the next matvec
   pcg_q_test(st, part_Q, s_red);
   if (!st.done) {
     const double rho = sum_partials(part_rho, s_red);
@@ -2056,7 +2070,7 @@ __global__ void k_zero_rep_cols(double* __restrict__ rep) {  // re-zero the 10 f
 __global__ void __launch_bounds__(VT) k_pcg_reset_a(int ncs, const PcgState* __restrict__ in, const double* __restrict__ x,
                                                     const double* __restrict__ sm, double* __restrict__ xs, double* __restrict__ y,
                                                     int* __restrict__ zero_ctr) {
-  if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_ctr = 0;
+  if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { zero_ctr[0] = 0; zero_ctr[1] = 0; }
   if (in->done) return;
   for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) { xs[i] = sm[i] * x[i]; y[i] = 0.0; }
 }

@@ -353,11 +353,18 @@ __global__ void k_row_norms(const float* __restrict__ d, long long n_rows, float
 // (distance.h:52-56) as the oracle and k_nn2 evaluate it; then thread 0 of the query picks the best two (ties: lower index).
 // q_row[i] = global descriptor row of query i, b_row0[i] / b_rows[i] = first row / number of rows of the candidate image (indices are
 // reported relative to b_row0).  A query whose candidate ring overflowed in pass 1 (cand[i*KC] == kOverflow) is scanned exhaustively.
+// exact squared distance, float, term by term in index order without fused multiply-add (128-bit loads, same arithmetic)
 __device__ __forceinline__ float exact_sqdist(const float* __restrict__ a, const float* __restrict__ b) {
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
   float s = 0.0f;
-  for (int k = 0; k < DIM; ++k) {
-    const float df = __fsub_rn(a[k], b[k]);
-    s = __fadd_rn(s, __fmul_rn(df, df));
+#pragma unroll 8
+  for (int k = 0; k < DIM / 4; ++k) {
+    const float4 x = __ldg(a4 + k), y = __ldg(b4 + k);
+    float df = __fsub_rn(x.x, y.x); s = __fadd_rn(s, __fmul_rn(df, df));
+    df = __fsub_rn(x.y, y.y); s = __fadd_rn(s, __fmul_rn(df, df));
+    df = __fsub_rn(x.z, y.z); s = __fadd_rn(s, __fmul_rn(df, df));
+    df = __fsub_rn(x.w, y.w); s = __fadd_rn(s, __fmul_rn(df, df));
   }
   return s;
 }
