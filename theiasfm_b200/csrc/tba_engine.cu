@@ -536,17 +536,19 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
     if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
   }
   if (precond) {
-    int rc = allreduce_sum(c, c->Sblk.p, nS);
+    // the not-positive-definite flag of k_point_blocks rides in the extra slot behind the blocks: one all-reduce less
+    CUDA_OK(c, cudaMemcpyAsync(c->Sblk.p + nS, c->flag.p, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    int rc = allreduce_sum(c, c->Sblk.p, nS + 1);
     if (rc) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(c->flag.p, c->Sblk.p + nS, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     LAUNCH(c, k_precond_finish, (P.n_cam + P.n_group + 63) / 64, 64, 0, P, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->sm.p,
            c->D2.p, c->Minv_c.p, c->Minv_i.p, c->flag.p);
   }
   int rc = allreduce_sum(c, c->y.p, P.ncs);
   if (rc) return rc;
   LAUNCH(c, k_pcg_init, VB, VT, 0, P.ncs, c->y.p, c->sm.p, c->b.p, c->x.p, c->r.p, c->part.p);
-  // the PD flag is summed over ranks so that every rank takes the same branch
-  rc = allreduce_sum(c, c->flag.p, 1);
-  if (rc) return rc;
+  // the PD flag is summed over ranks so that every rank takes the same branch (with the preconditioner: done above)
+  if (!precond) { rc = allreduce_sum(c, c->flag.p, 1); if (rc) return rc; }
   double f;
   rc = read_scal(c, c->flag.p, 1, &f);
   if (rc) return rc;
@@ -661,7 +663,7 @@ int stage_backsub(tba_context* c) {
 
 // Cost at the candidate; scal2 then holds [cost, fixed, failed, mcc, |d_cs|^2, |d_pt|^2].
 int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, double* step_norm, bool* ok, double elapsed_s = 0.0,
-                             double* elapsed_collective = nullptr) {
+                             double* elapsed_collective = nullptr, double* cand_xnorm = nullptr) {
   DevProblem& P = c->P;
   // multi-GPU: every branch of the LM loop must be taken by all ranks alike, the time-out included.  Rank 0's clock is the
   // clock: its elapsed time rides in slot 8 of this all-reduce (the other ranks add 0), so every rank reads the same value.
@@ -674,6 +676,9 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
     prof_end(c, 6, pb_cost);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, nullptr, nullptr, c->scal2.p);
   }
+  // ||candidate|| over the non-constant blocks rides along (slots 6, 7): if the step is accepted it is the ||x|| the next
+  // parameter-tolerance test needs -- no separate kernel + all-reduce + host round trip after the acceptance
+  if (cand_xnorm) LAUNCH(c, k_xnorm, 256, 256, 0, P, P.ext_c, P.intr_c, P.pt_c, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
   int rc = allreduce_sum(c, c->scal2.p, 9);
   if (rc) return rc;
   double s[9];
@@ -683,6 +688,7 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
   *cand_cost = s[0];
   *mcc = s[3];
   *step_norm = std::sqrt(s[4] + s[5]);
+  if (cand_xnorm) *cand_xnorm = std::sqrt(s[6] + s[7]);
   if (elapsed_collective) *elapsed_collective = c->world > 1 ? s[8] : elapsed_s;
   return TBA_OK;
 }
@@ -1099,7 +1105,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(slot_run, (size_t)n_slots); ALLOC(pt_const, (size_t)npd); ALLOC(tile_flags, (size_t)n_tiles);
   ALLOC(pt_slot, (size_t)npd); ALLOC(pt_len, (size_t)npd); ALLOC(pt_stat, (size_t)npd);
   ALLOC(lin, 2 * (size_t)ncs + 16); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
-  ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
+  ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55 + 1); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
   ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(z2, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
   ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(rep, (size_t)NREP * REPW);
 #undef ALLOC
@@ -1297,7 +1303,7 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     // ComputeTrustRegionStep
     bool valid = true;
     int cg_iters = 0, cg_status = 0;
-    double mcc = 0, cand = 0, step_norm = 0;
+    double mcc = 0, cand = 0, step_norm = 0, cand_xn = -1.0;
     bool cand_ok = true;
     RC(stage_prepare(c, radius, &valid));
     if (valid) {
@@ -1308,7 +1314,7 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     s->num_linear_solver_iterations += cg_iters;
     if (valid) {
       RC(stage_backsub(c));
-      RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok, now_s() - t1, &elapsed));
+      RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok, now_s() - t1, &elapsed, &cand_xn));
       if (!std::isfinite(mcc) || !std::isfinite(step_norm)) valid = false;
       else valid = mcc > 0.0;
     }
@@ -1322,8 +1328,9 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     consecutive_invalid = 0;
     if (!cand_ok) cand = 1.7976931348623157e308;
     // DoInnerIterationsIfNeeded (N4)
-    bool inner_useful = false;
+    bool inner_useful = false, inner_ran = false;
     if (inner_enabled && cand_ok) {
+      inner_ran = true;
       double inner_cost = 0;
       bool inner_ok = true;
       RC(stage_inner_iterations(c, &inner_cost, &inner_ok));
@@ -1346,7 +1353,7 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     it.relative_decrease = it.cost_change / mcc;
     if (inner_useful || it.relative_decrease > opt.min_relative_decrease) {  // IsStepSuccessful / HandleSuccessfulStep
       accept_candidate(c);
-      RC(stage_xnorm(c, &xn));
+      if (cand_xn >= 0.0 && !inner_ran) xn = cand_xn; else RC(stage_xnorm(c, &xn));  // (the inner iterations move the candidate)
       RC(stage_linearize(c, &x_cost, &fixed, &ok));
       if (!ok) { term = TBA_FAILURE; msg = "Residual and Jacobian evaluation failed."; break; }
       it.cost = x_cost + fixed;

@@ -1258,9 +1258,10 @@ k_schur_stream(DevProblem P, const double* __restrict__ xs, double* __restrict__
       const double a = ld_cg(y + 2 * i), b = 2 * i + 1 < n_push ? ld_cg(y + 2 * i + 1) : 0.0;
       for (int q = 0; q < pp.world; ++q) reinterpret_cast<double2*>(pp.inbox[q] + slot)[i] = make_double2(a, b);
     }
-    __threadfence_system();
+    // one system-scope fence per CTA, by the thread that counts the CTA in: the stores of the other threads happen before it
+    // through the block barrier (fences are cumulative)
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(pp.ctr + 1, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(pp.ctr + 1, 1) == (int)gridDim.x - 1; }
     __syncthreads();
     if (s_last) {
       __threadfence_system();
