@@ -109,7 +109,7 @@ bench.experiments_child("c1_50cam", 1, 0)
     lines = [json.loads(ln) for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
     main, child = lines[0], lines[1:]
     assert main["steps"] == 1 and main["gpu_launches"] > 0 and set(main["stage_ms_per_step"]) == set(__import__("bench").VARIANTS and
-                                                                                                      ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost"))
+                                                                                                      ("matvec", "linearize", "precond_ext", "precond_intr", "rhs", "backsub", "candidate_cost", "prepare_fused"))
     assert [d["variant"] for d in child] == [v[0] for v in __import__("bench").VARIANTS] + ["matcher_sample"]
     for d in child:
         assert "error" not in d and d["rc"] == 0, d

@@ -124,27 +124,3 @@ def test_pack_column_set_selection_and_limits():
     assert engine.debug_pack(bad)["rc"] == _abi.ERR_INVALID_ARGUMENT
     long_ = synthetic.make_scene(n_cam=600, n_pt=3, obs_per_pt=290, seed=1)
     assert engine.debug_pack(long_)["rc"] == _abi.ERR_UNSUPPORTED
-
-
-def test_experimental_locality_order_is_a_valid_packing(monkeypatch):
-    """TBA_PACK_SORT=1 (round-2 experiment, default off) only permutes the short-track points: still a bijection, still
-    warp-contained, anchors (lowest camera index of a point) non-decreasing."""
-    p = _ragged_scene(seed=9, n_groups_mode="shared")
-    base = engine.debug_pack(p)
-    monkeypatch.setenv("TBA_PACK_SORT", "1")
-    k = engine.debug_pack(p)
-    assert k["rc"] == 0 and k["n_slots"] > 0 and k["n_long_points"] == base["n_long_points"]
-    valid = k["slot_cam"] >= 0
-    assert valid.sum() == p.n_obs and np.array_equal(np.sort(k["slot_orig"][valid]), np.arange(p.n_obs))
-    assert sorted(k["pk2caller"].tolist()) == sorted(base["pk2caller"].tolist())
-    counts = np.bincount(p.obs_pt, minlength=p.n_pt)
-    anchor = np.full(p.n_pt, 10 ** 9)
-    np.minimum.at(anchor, p.obs_pt, p.obs_cam)
-    n_short = int(((counts > 0) & (counts <= 32)).sum())
-    a = anchor[k["pk2caller"][:n_short]]
-    assert (np.diff(a) >= 0).all() and not np.array_equal(k["pk2caller"], base["pk2caller"])
-    for kp in range(len(k["pk2caller"])):
-        sl = np.nonzero(valid & (k["slot_pt"] == kp))[0]
-        assert len(sl) == counts[k["pk2caller"][kp]] and (np.diff(sl) == 1).all()
-        if len(sl) <= 32:
-            assert sl[0] // 32 == sl[-1] // 32

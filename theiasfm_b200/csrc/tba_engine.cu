@@ -1004,10 +1004,21 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   }
   for (int i = 0; i < nc; ++i) if (p->cam_group[i] < 0 || p->cam_group[i] >= ng) { set_err(c, "cam_group out of range"); return TBA_ERR_INVALID_ARGUMENT; }
   // ---- host packing (tba_pack.h: phases A-E, multi-threaded), into pinned staging memory
-  const int T = std::max(1, std::min<int>(32, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
+  // host threads of the pack: all hardware threads shared between the ranks of the box, at most 64 per rank
+  const int T = std::max(1, std::min<int>(64, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
   HostPack& H = c->pack;
   c->slot_orig.clear();
+  // TBA_UPLOAD_TRACE=1: host wall-clock of the phases of this call on stderr (where the end-to-end time of a solve goes)
+  const bool trace = getenv("TBA_UPLOAD_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tba_upload r%d] %-28s %8.2f ms\n", c->rank, what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   pack_count_and_sort(p, T, &H);  // A, B, C
+  lap("count_and_sort (A-C)");
   // rank-local validation errors (they depend on this rank's shard of the observations): in process-per-rank mode the
   // failing rank must still take part in the first collective below, where every rank learns about the failure and all
   // return together -- an early return here would leave the other ranks blocked in that all-reduce
@@ -1017,6 +1028,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   const bool collective_upload = c->world > 1 && c->preset_cnt_cam == nullptr;
   if (local_err != TBA_OK && !collective_upload) return local_err;
   if (local_err == TBA_OK) pack_points(p, &H);
+  lap("pack_points");
   // ---- which blocks take part (blocks without residuals are not in the Ceres program)
   std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
   if (local_err == TBA_OK) for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[p->cam_group[i]] += H.cnt_cam[i]; }
@@ -1050,6 +1062,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
     c->n_free_pt_global = (int64_t)tmp[tmp.size() - 2];
   }
   pack_masks_and_tiles(p, cnt_c, cnt_g, &H);  // masks, D
+  lap("masks_and_tiles (D)");
   const int ne = nc * 6, ncs = ne + ng * 10;
   const std::vector<double>& mask = H.mask;
   const std::vector<double>& blk_free = H.blk_free;
@@ -1068,7 +1081,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   const int n_tiles = H.n_tiles;
   const int64_t n_slots = H.n_slots;
   // E: fill the slot arrays (pinned staging), parallel over packed points
-  const size_t stage_bytes = (size_t)n_slots * (4 + 4 + 2 + 1 + 16) + (size_t)npk * (32 + 1) + 8 * 256;
+  const size_t stage_bytes = (size_t)n_slots * (4 + 4 + 2 + 1 + 16) + (size_t)npk * (32 + 1 + 8 + 4) + 10 * 256;
   if (c->stage_cap < stage_bytes) {
     if (c->stage) cudaFreeHost(c->stage);
     c->stage = nullptr; c->stage_cap = 0;
@@ -1084,12 +1097,12 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   int16_t* h_slot_run = (int16_t*)carve((size_t)n_slots * 2);
   uint8_t* h_slot_flags = carve((size_t)n_slots);
   uint8_t* h_pt_const = carve((size_t)npk);
-  {
-    PackDest d;
-    d.xy = h_xy; d.pt = h_pt; d.slot_cam = h_slot_cam; d.slot_pt = h_slot_pt; d.slot_run = h_slot_run; d.slot_flags = h_slot_flags;
-    d.pt_const = h_pt_const; d.slot_orig = nullptr;  // not part of the upload (see TBA_VEC_RESIDUALS in tba_debug_read)
-    pack_fill(p, H, T, d);
-  }
+  long long* h_pt_slot = (long long*)carve((size_t)npk * 8);
+  int* h_pt_len = (int*)carve((size_t)npk * 4);
+  lap("staging");
+  PackDest d;
+  d.xy = h_xy; d.pt = h_pt; d.slot_cam = h_slot_cam; d.slot_pt = h_slot_pt; d.slot_run = h_slot_run; d.slot_flags = h_slot_flags;
+  d.pt_const = h_pt_const; d.slot_orig = nullptr;  // not part of the upload (see TBA_VEC_RESIDUALS in tba_debug_read)
   c->n_long_points = n_long;
   // ---- device allocation + H2D
   c->n_cam = nc; c->n_group = ng; c->n_pt = npk; c->n_pt_caller = np; c->n_tiles = n_tiles; c->n_obs = no; c->n_slots = n_slots;
@@ -1109,25 +1122,47 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(z2, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
   ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(rep, (size_t)NREP * REPW);
 #undef ALLOC
+  lap("device alloc");
 #define H2D(buf, src, n)                                                                                      \
   do {                                                                                                        \
     CUDA_OK(c, cudaMemcpyAsync(c->buf.p, (src), (n) * sizeof(*c->buf.p), cudaMemcpyHostToDevice, c->stream)); \
     c->h2d_bytes += (double)((n) * sizeof(*c->buf.p));                                                        \
   } while (0)
-  H2D(ext, p->ext, (size_t)ne); H2D(intr, p->intr, (size_t)ng * 10); H2D(pt, h_pt, (size_t)npd * 4);
-  H2D(ext_c, p->ext, (size_t)ne); H2D(intr_c, p->intr, (size_t)ng * 10); H2D(pt_c, h_pt, (size_t)npd * 4);
+  H2D(ext, p->ext, (size_t)ne); H2D(intr, p->intr, (size_t)ng * 10);
+  H2D(ext_c, p->ext, (size_t)ne); H2D(intr_c, p->intr, (size_t)ng * 10);
   H2D(cam_group, p->cam_group, (size_t)nc); H2D(group_model, p->group_model, (size_t)ng);
-  H2D(slot_cam, h_slot_cam, (size_t)n_slots); H2D(slot_pt, h_slot_pt, (size_t)n_slots);
-  H2D(slot_flags, h_slot_flags, (size_t)n_slots); H2D(slot_run, h_slot_run, (size_t)n_slots);
   H2D(tile_pt_begin, tile_pt_begin.data(), (size_t)n_tiles + 1); H2D(tile_nruns, tile_nruns.data(), (size_t)n_tiles);
-  H2D(xy, h_xy, (size_t)n_slots * 2); H2D(pt_const, h_pt_const, (size_t)npd);
   H2D(tile_flags, tile_flags.data(), (size_t)n_tiles);
   {
-    std::vector<long long> h_pt_slot((size_t)npd);
-    std::vector<int> h_pt_len((size_t)npd);
-    for (int k = 0; k < npd; ++k) { h_pt_slot[k] = (long long)H.pt_slot[k]; h_pt_len[k] = H.cnt_pt[H.pk2caller[k]]; }
-    H2D(pt_slot, h_pt_slot.data(), (size_t)npd); H2D(pt_len, h_pt_len.data(), (size_t)npd);
+    // E: fill the slot arrays in pinned staging memory chunk by chunk (all host threads per chunk) and send every chunk on its
+    // way as soon as it is filled: the copy of chunk k overlaps the filling of chunk k + 1
+    int n_chunks = n_tiles >= 8192 ? 8 : 1;
+    if (const char* e = getenv("TBA_UPLOAD_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), std::max(1, n_tiles)));  // tests: small scenes too
+#define H2D_RANGE(buf, src, off, n)                                                                                              \
+  do {                                                                                                                           \
+    if ((n) > 0) {                                                                                                               \
+      CUDA_OK(c, cudaMemcpyAsync(c->buf.p + (off), (src) + (off), (n) * sizeof(*c->buf.p), cudaMemcpyHostToDevice, c->stream));  \
+      c->h2d_bytes += (double)((n) * sizeof(*c->buf.p));                                                                         \
+    }                                                                                                                            \
+  } while (0)
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int64_t t0 = (int64_t)n_tiles * ch / n_chunks, t1 = (int64_t)n_tiles * (ch + 1) / n_chunks;
+      if (t1 <= t0) continue;
+      pack_fill(p, H, T, d, t0, t1);
+      const size_t s0 = (size_t)t0 * TILE, ns = (size_t)(t1 - t0) * TILE;
+      const size_t q0 = (size_t)tile_pt_begin[t0], nq = (size_t)tile_pt_begin[t1] - q0;
+      H2D_RANGE(slot_cam, h_slot_cam, s0, ns); H2D_RANGE(slot_pt, h_slot_pt, s0, ns);
+      H2D_RANGE(slot_flags, h_slot_flags, s0, ns); H2D_RANGE(slot_run, h_slot_run, s0, ns);
+      H2D_RANGE(xy, h_xy, s0 * 2, ns * 2);
+      H2D_RANGE(pt, h_pt, q0 * 4, nq * 4); H2D_RANGE(pt_c, h_pt, q0 * 4, nq * 4); H2D_RANGE(pt_const, h_pt_const, q0, nq);
+    }
+#undef H2D_RANGE
   }
+  lap("fill (E) + H2D enqueue");
+  parallel_for(npd, T, [&](int64_t k0, int64_t k1, int) {
+    for (int64_t k = k0; k < k1; ++k) { h_pt_slot[k] = (long long)H.pt_slot[k]; h_pt_len[k] = H.cnt_pt[H.pk2caller[k]]; }
+  });
+  H2D(pt_slot, h_pt_slot, (size_t)npd); H2D(pt_len, h_pt_len, (size_t)npd);
   H2D(mask, mask.data(), (size_t)ncs); H2D(blk_free, blk_free.data(), (size_t)nc + ng);
 #undef H2D
   CUDA_OK(c, cudaMemsetAsync(c->rep.p, 0, (size_t)NREP * REPW * sizeof(double), c->stream));
@@ -1139,6 +1174,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   CUDA_OK(c, cudaMemsetAsync(c->Minv_c.p, 0, (size_t)nc * 36 * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->Minv_i.p, 0, (size_t)ng * 100 * sizeof(double), c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  lap("tail + stream sync");
   DevProblem& P = c->P;
   P.n_cam = nc; P.n_group = ng; P.n_pt = npd; P.n_tiles = n_tiles; P.ne = ne; P.ncs = ncs; P.single_group = ng == 1;
   P.loss_type = options->loss_function_type; P.loss_width = options->robust_loss_width;

@@ -247,9 +247,13 @@ inline void pack_slot_orig(const HostPack& H, int T, int64_t* slot_orig) {
 }
 
 // E: fill the slot arrays, parallel over tiles (each tile is cleared and filled while it is in cache).
-inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const PackDest& d) {
+// tile_begin / tile_end: fill only that range of tiles (the upload fills and copies chunk by chunk so that the host-to-device
+// copy of one chunk overlaps the filling of the next); default: everything.
+inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const PackDest& d, int64_t tile_begin = 0, int64_t tile_end = -1) {
   const int nc = p->n_cam;
-  parallel_for(H.n_tiles, T, [&](int64_t t0, int64_t t1, int) {
+  if (tile_end < 0) tile_end = H.n_tiles;
+  parallel_for(tile_end - tile_begin, T, [&](int64_t r0, int64_t r1, int) {
+    const int64_t t0 = tile_begin + r0, t1 = tile_begin + r1;
     for (int64_t t = t0; t < t1; ++t) {
       const int64_t sb = t * kPackTile;
       memset(d.slot_cam + sb, 0xFF, (size_t)kPackTile * 4);
@@ -278,7 +282,7 @@ inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const Pack
       }
     }
   });
-  if (d.slot_orig) pack_slot_orig(H, T, d.slot_orig);
+  if (d.slot_orig && tile_begin == 0 && tile_end == H.n_tiles) pack_slot_orig(H, T, d.slot_orig);
 }
 
 }  // namespace tba
