@@ -301,3 +301,21 @@ def test_schur_operator_properties_at_scale(eng):
     assert s.success and s.final_cost < 0.01 * s.initial_cost
     costs = [i["cost"] for i in s.iterations if i["step_is_successful"]]
     assert all(y <= x for x, y in zip(costs, costs[1:]))
+
+
+def test_not_positive_definite_system_is_an_invalid_step(oracle):
+    """LM diagonal clamped to zero: the 4x4 block of a homogeneous point is singular, the Cholesky factorisation fails and every step
+    is invalid (trust_region_minimizer.cc HandleInvalidStep) until max_num_consecutive_invalid_steps ends the solve with FAILURE.  The
+    engine learns about the failed factorisation only together with the PCG's termination state (deferred flag, stage_pcg): the
+    iterations that ran on the unusable system must leave no trace -- same log as the oracle, parameters untouched."""
+    p = synthetic.make_scene(n_cam=12, n_pt=300, obs_per_pt=10, seed=4)
+    kw = dict(use_inner_iterations=0, linear_solver_type=_abi.ITERATIVE_SCHUR, min_lm_diagonal=0.0, max_lm_diagonal=0.0, max_num_iterations=10)
+    po, pg = p.copy(), p.copy()
+    so = oracle.solve(po, oracle.default_options(**kw))
+    eng = engine.Engine()
+    sg = eng.solve(pg, engine.default_options(**kw))
+    eng.close()
+    assert so.termination_type == _abi.FAILURE and sg.termination_type == _abi.FAILURE
+    assert sg.num_iterations == so.num_iterations and np.allclose(sg.costs, so.costs, rtol=1e-12)
+    assert all(it["linear_solver_iterations"] == 0 and not it["step_is_valid"] for it in sg.iterations[1:])
+    assert np.array_equal(pg.ext, p.ext) and np.array_equal(pg.pt, p.pt) and np.array_equal(pg.intr, p.intr)

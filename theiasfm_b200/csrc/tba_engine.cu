@@ -259,17 +259,14 @@ int allreduce_sum(tba_context* c, double* buf, size_t n) {
   NCCL_OK(c, g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, c->stream));
   return TBA_OK;
 }
-int allreduce_max(tba_context* c, double* buf, size_t n) {
-  if (c->world == 1) return TBA_OK;
-  NCCL_OK(c, g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclMax, c->comm, c->stream));
-  return TBA_OK;
-}
-
 size_t schur_smem(const tba_context* c) { return (size_t)(c->NJ + 2) * TILE * sizeof(double); }
 
 double* lin_g(tba_context* c) { return c->lin.p; }
 double* lin_cn(tba_context* c) { return c->lin.p + c->P.ncs; }
 double* lin_scal(tba_context* c) { return c->lin.p + 2 * (size_t)c->P.ncs; }
+// grid of the per-point / per-element streaming kernels (256 threads per CTA): enough CTAs to cover the latency of a dependent
+// load chain (8 per SM), not more than the work
+int small_grid(const tba_context* c, int64_t n_items) { return (int)std::max<int64_t>(1, std::min<int64_t>((n_items + 255) / 256, (int64_t)c->n_sm * 8)); }
 
 // scal layout: 0 cost, 1 fixed cost, 2 failed evals, 3 model cost change, 4 |delta_cs|^2, 5 |delta_pt|^2,
 //              6 |x_cs|^2, 7 |x_pt|^2
@@ -282,9 +279,12 @@ int read_scal(tba_context* c, const double* dev, int n, double* out) {
 
 // ---- stages ---------------------------------------------------------------------------------
 // Evaluate cost / residuals / compact Jacobian / gradient / column norms at x (and Jacobi scale at iteration 0).
-int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
+// gmax != nullptr: also the gradient max norm (max |g| over the non-constant parameters), in the same all-reduce and the same
+// device->host read as the cost -- one collective and one host synchronisation per linearisation instead of two each.
+int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok, double* gmax = nullptr) {
   DevProblem& P = c->P;
-  CUDA_OK(c, cudaMemsetAsync(c->lin.p, 0, (2 * (size_t)P.ncs + 16) * sizeof(double), c->stream));
+  const size_t n_lin = 2 * (size_t)P.ncs + 16 + (size_t)c->world;  // [gradient | column norms | 16 scalars | one slot per rank]
+  CUDA_OK(c, cudaMemsetAsync(c->lin.p, 0, n_lin * sizeof(double), c->stream));
   LAUNCH(c, k_cam_prep, (P.n_cam + 127) / 128, 128, 0, P.n_cam, P.ext, P.cam_rec, P.cam_s4);
   if (P.n_tiles > 0) {
     const int pb = prof_begin(c);
@@ -311,30 +311,20 @@ int stage_linearize(tba_context* c, double* cost, double* fixed, bool* ok) {
     prof_end(c, 1, pb);
     LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, lin_g(c) + P.ne, lin_cn(c) + P.ne, lin_scal(c));
   }
-  int rc = allreduce_sum(c, c->lin.p, 2 * (size_t)P.ncs + 16);
+  if (gmax && P.n_pt > 0) LAUNCH(c, k_gradmax_pt, small_grid(c, P.n_pt), 256, 0, P, lin_scal(c) + 16 + c->rank);
+  int rc = allreduce_sum(c, c->lin.p, n_lin);
   if (rc) return rc;
+  if (gmax) LAUNCH(c, k_gradmax_cs, VB, VT, 0, P.ncs, lin_g(c), c->mask.p, lin_scal(c) + 16, c->world, lin_scal(c) + 3);
   if (!c->have_scale) {
     LAUNCH(c, k_cs_scale, VB, VT, 0, P.ncs, lin_cn(c), c->mask.p, c->opt.jacobi_scaling, c->sm.p);
     if (P.n_pt > 0) LAUNCH(c, k_point_scale, (P.n_pt + 255) / 256, 256, 0, P, c->opt.jacobi_scaling);
     c->have_scale = true;
   }
-  double s[3];
-  rc = read_scal(c, lin_scal(c), 3, s);
+  double s[4];
+  rc = read_scal(c, lin_scal(c), 4, s);
   if (rc) return rc;
   *cost = s[0]; *fixed = s[1]; *ok = s[2] == 0.0;
-  return TBA_OK;
-}
-
-int stage_gradient_max_norm(tba_context* c, double* gmax) {
-  DevProblem& P = c->P;
-  CUDA_OK(c, cudaMemsetAsync(c->gmax.p, 0, 2 * sizeof(double), c->stream));
-  LAUNCH(c, k_gradmax, 128, 256, 0, P, lin_g(c), c->mask.p, c->gmax.p);
-  int rc = allreduce_max(c, c->gmax.p, 2);
-  if (rc) return rc;
-  double g[2];
-  rc = read_scal(c, c->gmax.p, 2, g);
-  if (rc) return rc;
-  *gmax = std::max(g[0], g[1]);
+  if (gmax) *gmax = s[3];
   return TBA_OK;
 }
 
@@ -476,7 +466,9 @@ int launch_schur(tba_context* c, const double* xs, double* y, const int* done, c
 }
 
 // LM diagonal, per-point (E'E + D^2)^-1, SCHUR_JACOBI blocks, reduced rhs.  *ok=false if a block is not PD.
-int stage_prepare(tba_context* c, double radius, bool* ok) {
+// defer_flag: do not wait for the "a point block / preconditioner block is not positive definite" flag here; stage_pcg reads it
+// together with its own termination state (one host synchronisation less per LM iteration).
+int stage_prepare(tba_context* c, double radius, bool* ok, bool defer_flag = false) {
   DevProblem& P = c->P;
   const tba_options& o = c->opt;
   CUDA_OK(c, cudaMemsetAsync(c->flag.p, 0, sizeof(double), c->stream));
@@ -484,8 +476,12 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
   if (P.n_pt > 0) LAUNCH(c, k_point_blocks, (P.n_pt + 255) / 256, 256, 0, P, radius, o.min_lm_diagonal, o.max_lm_diagonal, c->flag.p);
   const size_t nS = (size_t)P.n_cam * 21 + (size_t)P.n_group * 55;
   const bool precond = o.preconditioner_type != TBA_PRECOND_IDENTITY;
-  if (precond) CUDA_OK(c, cudaMemsetAsync(c->Sblk.p, 0, nS * sizeof(double), c->stream));
-  CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
+  // with a preconditioner the reduced rhs is accumulated behind the blocks ([blocks | flag | pad | rhs]): one memset and, on several
+  // GPUs, ONE all-reduce for all of it
+  const size_t y_off = (nS + 2) & ~(size_t)1;
+  double* const yr = precond ? c->Sblk.p + y_off : c->y.p;
+  if (precond) CUDA_OK(c, cudaMemsetAsync(c->Sblk.p, 0, (y_off + (size_t)P.ncs) * sizeof(double), c->stream));
+  else CUDA_OK(c, cudaMemsetAsync(c->y.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
   if (P.n_tiles > 0) {
     // normal tiles: ONE streaming pass over J for the reduced rhs and both families of SCHUR_JACOBI blocks (k_prepare_stream);
     // long tiles (and TBA_MATVEC=tile / IDENTITY preconditioner): the three tile kernels
@@ -495,7 +491,7 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
       const int pb = prof_begin(c);
 #define F(M) { using Cfg = PrepCfg<M>; auto kfn = k_prepare_stream<M>; \
                const int grid = std::max(1, std::min(c->n_sm, (n_slices + Cfg::NW - 1) / Cfg::NW)); \
-               LAUNCH(c, kfn, grid, Cfg::NW * 32, Cfg::SMEM, P, c->y.p, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->rep.p, n_slices); }
+               LAUNCH(c, kfn, grid, Cfg::NW * 32, Cfg::SMEM, P, yr, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->rep.p, n_slices); }
       DISPATCH_IMASK(c->imask, F)
 #undef F
       prof_end(c, 7, pb);
@@ -525,30 +521,31 @@ int stage_prepare(tba_context* c, double radius, bool* ok) {
     }
     if (rest > 0) {
       const int pb_rhs = prof_begin(c);
-      if (first_tile == 0) { const int rc1 = launch_schur<1>(c, nullptr, c->y.p, nullptr); if (rc1) return rc1; }
+      if (first_tile == 0) { const int rc1 = launch_schur<1>(c, nullptr, yr, nullptr); if (rc1) return rc1; }
       else {
-#define F(M) { auto kfn = k_schur<M, 1, true>; LAUNCH(c, kfn, rest, TILE, schur_smem(c), P, nullptr, c->y.p, c->rep.p, nullptr, first_tile); }
+#define F(M) { auto kfn = k_schur<M, 1, true>; LAUNCH(c, kfn, rest, TILE, schur_smem(c), P, nullptr, yr, c->rep.p, nullptr, first_tile); }
         DISPATCH_IMASK(c->imask, F)
 #undef F
       }
       prof_end(c, 4, pb_rhs);
     }
-    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, c->y.p + P.ne, nullptr, nullptr);
+    if (P.single_group) LAUNCH(c, k_fold, 1, REPW, 0, c->rep.p, yr + P.ne, nullptr, nullptr);
   }
   if (precond) {
     // the not-positive-definite flag of k_point_blocks rides in the extra slot behind the blocks: one all-reduce less
     CUDA_OK(c, cudaMemcpyAsync(c->Sblk.p + nS, c->flag.p, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    int rc = allreduce_sum(c, c->Sblk.p, nS + 1);
+    int rc = allreduce_sum(c, c->Sblk.p, y_off + (size_t)P.ncs);
     if (rc) return rc;
     CUDA_OK(c, cudaMemcpyAsync(c->flag.p, c->Sblk.p + nS, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     LAUNCH(c, k_precond_finish, (P.n_cam + P.n_group + 63) / 64, 64, 0, P, c->Sblk.p, c->Sblk.p + (size_t)P.n_cam * 21, c->sm.p,
            c->D2.p, c->Minv_c.p, c->Minv_i.p, c->flag.p);
   }
-  int rc = allreduce_sum(c, c->y.p, P.ncs);
+  int rc = precond ? TBA_OK : allreduce_sum(c, c->y.p, P.ncs);
   if (rc) return rc;
-  LAUNCH(c, k_pcg_init, VB, VT, 0, P.ncs, c->y.p, c->sm.p, c->b.p, c->x.p, c->r.p, c->part.p);
+  LAUNCH(c, k_pcg_init, VB, VT, 0, P.ncs, yr, c->sm.p, c->b.p, c->x.p, c->r.p, c->part.p);
   // the PD flag is summed over ranks so that every rank takes the same branch (with the preconditioner: done above)
   if (!precond) { rc = allreduce_sum(c, c->flag.p, 1); if (rc) return rc; }
+  if (defer_flag) { *ok = true; return TBA_OK; }
   double f;
   rc = read_scal(c, c->flag.p, 1, &f);
   if (rc) return rc;
@@ -578,7 +575,8 @@ int launch_matvec(tba_context* c, const int* done, bool defer_fold = false, cons
 
 // ConjugateGradientsSolver::Solve on the reduced system; control flow on the device (PcgState),
 // the host enqueues iterations in batches and polls the done flag.
-int stage_pcg(tba_context* c, int* iters, int* status) {
+// system_ok != nullptr: also fetch stage_prepare's deferred flag (false: the linear system was not usable, the result is void).
+int stage_pcg(tba_context* c, int* iters, int* status, bool* system_ok = nullptr) {
   DevProblem& P = c->P;
   const tba_options& o = c->opt;
   double* part_rho = c->part.p;
@@ -590,6 +588,7 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
   if (c->n_free_cs == 0) {  // no reduced system: back-substitution only
     *iters = 0; *status = 0;
     CUDA_OK(c, cudaMemsetAsync(c->x.p, 0, (size_t)P.ncs * sizeof(double), c->stream));
+    if (system_ok) { double f; const int rc = read_scal(c, c->flag.p, 1, &f); if (rc) return rc; *system_ok = f == 0.0; }
     return TBA_OK;
   }
   const int ident = o.preconditioner_type == TBA_PRECOND_IDENTITY;
@@ -632,7 +631,12 @@ int stage_pcg(tba_context* c, int* iters, int* status) {
     LAUNCH(c, k_pcg_finalize, 1, 32, 0, st + cur, st + (cur ^ 1), part_Q, c->done_flag.p);
     cur ^= 1;
     CUDA_OK(c, cudaMemcpyAsync(c->h_st, st + cur, sizeof(PcgState), cudaMemcpyDeviceToHost, c->stream));
+    if (system_ok) CUDA_OK(c, cudaMemcpyAsync(c->h_scal, c->flag.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (system_ok) {
+      *system_ok = c->h_scal[0] == 0.0;
+      if (!*system_ok) { *iters = 0; *status = 0; return TBA_OK; }  // not positive definite: whatever the iterations did is discarded
+    }
     if (c->h_st->done) break;
     if (it > o.max_linear_solver_iterations + batch) { set_err(c, "PCG did not terminate"); return TBA_ERR_CUDA; }
     batch = 4;
@@ -657,7 +661,7 @@ int stage_backsub(tba_context* c) {
   }
   // candidate = x + delta, step norm
   LAUNCH(c, k_candidate_cs, VB, VT, 0, P, c->xs.p, c->scal2.p, c->rank == 0 ? 1 : 0);
-  if (P.n_pt > 0) LAUNCH(c, k_candidate_pt, 256, 256, 0, P, c->scal2.p);
+  if (P.n_pt > 0) LAUNCH(c, k_candidate_pt, small_grid(c, P.n_pt), 256, 0, P, c->scal2.p);
   return TBA_OK;
 }
 
@@ -678,7 +682,7 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
   }
   // ||candidate|| over the non-constant blocks rides along (slots 6, 7): if the step is accepted it is the ||x|| the next
   // parameter-tolerance test needs -- no separate kernel + all-reduce + host round trip after the acceptance
-  if (cand_xnorm) LAUNCH(c, k_xnorm, 256, 256, 0, P, P.ext_c, P.intr_c, P.pt_c, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
+  if (cand_xnorm) LAUNCH(c, k_xnorm, small_grid(c, std::max(P.n_pt, P.ne)), 256, 0, P, P.ext_c, P.intr_c, P.pt_c, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
   int rc = allreduce_sum(c, c->scal2.p, 9);
   if (rc) return rc;
   double s[9];
@@ -696,7 +700,7 @@ int stage_evaluate_candidate(tba_context* c, double* cand_cost, double* mcc, dou
 int stage_xnorm(tba_context* c, double* xn) {
   DevProblem& P = c->P;
   CUDA_OK(c, cudaMemsetAsync(c->scal2.p, 0, 16 * sizeof(double), c->stream));
-  LAUNCH(c, k_xnorm, 256, 256, 0, P, P.ext, P.intr, P.pt, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
+  LAUNCH(c, k_xnorm, small_grid(c, std::max(P.n_pt, P.ne)), 256, 0, P, P.ext, P.intr, P.pt, c->blk_free.p, c->scal2.p, c->rank == 0 ? 1 : 0);
   int rc = allreduce_sum(c, c->scal2.p + 6, 2);
   if (rc) return rc;
   double s[2];
@@ -1117,8 +1121,8 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(tile_pt_begin, (size_t)n_tiles + 1); ALLOC(tile_nruns, (size_t)n_tiles); ALLOC(slot_flags, (size_t)n_slots);
   ALLOC(slot_run, (size_t)n_slots); ALLOC(pt_const, (size_t)npd); ALLOC(tile_flags, (size_t)n_tiles);
   ALLOC(pt_slot, (size_t)npd); ALLOC(pt_len, (size_t)npd); ALLOC(pt_stat, (size_t)npd);
-  ALLOC(lin, 2 * (size_t)ncs + 16); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
-  ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55 + 1); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
+  ALLOC(lin, 2 * (size_t)ncs + 16 + (size_t)std::max(1, c->world)); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
+  ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55 + 2 + (size_t)ncs); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
   ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(z2, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
   ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(rep, (size_t)NREP * REPW);
 #undef ALLOC
@@ -1297,9 +1301,16 @@ int tba_minimize(tba_context* c, tba_summary* s) {
   double elapsed = 0.0;  // collective view of the solver time (see the time-out test below)
   bool inner_enabled = opt.use_inner_iterations != 0;
   const double kInnerIterationTolerance = 1e-3;  // ceres::Solver::Options::inner_iteration_tolerance
-#define RC(expr) do { rc = (expr); if (rc) goto fail; } while (0)
+  // TBA_TRACE_LM=1: host wall clock per stage (stream synchronised after each stage, which costs a little itself) on stderr at the
+  // end of the call -- against the device times of tba_get_profile_stages this shows the launch / synchronisation / collective
+  // overhead of each stage
+  const bool trace = getenv("TBA_TRACE_LM") != nullptr;
+  static const char* const kStageName[8] = {"linearize", "prepare", "pcg", "backsub", "evaluate", "accept+xnorm", "inner", "bookkeeping"};
+  double tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double t_prev = now_s();
+#define RCT(k, expr) do { rc = (expr); if (rc) goto fail; if (trace) { cudaStreamSynchronize(c->stream); const double t_now = now_s(); tr[k] += t_now - t_prev; t_prev = t_now; } } while (0)
   cudaEventRecord(ev0, c->stream);
-  RC(stage_linearize(c, &x_cost, &fixed, &ok));
+  RCT(0, stage_linearize(c, &x_cost, &fixed, &ok, &it.gradient_max_norm));
   if (!ok) { term = TBA_FAILURE; msg = "Residual and Jacobian evaluation failed."; s->initial_cost = s->final_cost = -1; goto done; }
   s->initial_cost = x_cost + fixed;
   if (c->n_free_cs == 0 && c->n_free_pt_global == 0) {
@@ -1310,9 +1321,8 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     s->final_cost = x_cost + fixed;
     goto done;
   }
-  RC(stage_xnorm(c, &xn));
+  RCT(5, stage_xnorm(c, &xn));
   it.iteration = 0; it.step_is_valid = 1; it.step_is_successful = 1; it.cost = x_cost + fixed; it.trust_region_radius = radius;
-  RC(stage_gradient_max_norm(c, &it.gradient_max_norm));
   for (;;) {
     // FinalizeIterationAndCheckIfMinimizerCanContinue
     if (it.step_is_successful) s->num_successful_steps++; else s->num_unsuccessful_steps++;
@@ -1341,16 +1351,16 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     int cg_iters = 0, cg_status = 0;
     double mcc = 0, cand = 0, step_norm = 0, cand_xn = -1.0;
     bool cand_ok = true;
-    RC(stage_prepare(c, radius, &valid));
+    RCT(1, stage_prepare(c, radius, &valid, true));
     if (valid) {
-      RC(stage_pcg(c, &cg_iters, &cg_status));
+      RCT(2, stage_pcg(c, &cg_iters, &cg_status, &valid));
       if (cg_status == 2) valid = false;
     }
     it.linear_solver_iterations = cg_iters;
     s->num_linear_solver_iterations += cg_iters;
     if (valid) {
-      RC(stage_backsub(c));
-      RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok, now_s() - t1, &elapsed, &cand_xn));
+      RCT(3, stage_backsub(c));
+      RCT(4, stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok, now_s() - t1, &elapsed, &cand_xn));
       if (!std::isfinite(mcc) || !std::isfinite(step_norm)) valid = false;
       else valid = mcc > 0.0;
     }
@@ -1369,17 +1379,17 @@ int tba_minimize(tba_context* c, tba_summary* s) {
       inner_ran = true;
       double inner_cost = 0;
       bool inner_ok = true;
-      RC(stage_inner_iterations(c, &inner_cost, &inner_ok));
+      RCT(6, stage_inner_iterations(c, &inner_cost, &inner_ok));
       if (inner_ok) {
         mcc += cand - inner_cost;                       // the inner iterations' share is not credited to the trust-region step
         inner_useful = inner_cost < x_cost;
         inner_enabled = (1.0 - inner_cost / cand) > kInnerIterationTolerance;
         cand = inner_cost;
-        RC(stage_step_norm(c, &step_norm));
+        RCT(6, stage_step_norm(c, &step_norm));
       } else {
         // Ceres returns before adopting inner_iteration_x_: restore the trust-region candidate
-        RC(stage_backsub(c));
-        RC(stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok));
+        RCT(3, stage_backsub(c));
+        RCT(4, stage_evaluate_candidate(c, &cand, &mcc, &step_norm, &cand_ok));
       }
     }
     it.step_norm = step_norm;
@@ -1388,12 +1398,12 @@ int tba_minimize(tba_context* c, tba_summary* s) {
     if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) { term = TBA_CONVERGENCE; msg = "Function tolerance reached."; break; }
     it.relative_decrease = it.cost_change / mcc;
     if (inner_useful || it.relative_decrease > opt.min_relative_decrease) {  // IsStepSuccessful / HandleSuccessfulStep
+      if (trace) { const double t_now = now_s(); tr[7] += t_now - t_prev; t_prev = t_now; }
       accept_candidate(c);
-      if (cand_xn >= 0.0 && !inner_ran) xn = cand_xn; else RC(stage_xnorm(c, &xn));  // (the inner iterations move the candidate)
-      RC(stage_linearize(c, &x_cost, &fixed, &ok));
+      if (cand_xn >= 0.0 && !inner_ran) xn = cand_xn; else RCT(5, stage_xnorm(c, &xn));  // (the inner iterations move the candidate)
+      RCT(0, stage_linearize(c, &x_cost, &fixed, &ok, &it.gradient_max_norm));
       if (!ok) { term = TBA_FAILURE; msg = "Residual and Jacobian evaluation failed."; break; }
       it.cost = x_cost + fixed;
-      RC(stage_gradient_max_norm(c, &it.gradient_max_norm));
       it.step_is_successful = 1;
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
       radius = std::min(opt.max_trust_region_radius, radius);
@@ -1407,6 +1417,12 @@ int tba_minimize(tba_context* c, tba_summary* s) {
   s->final_cost = x_cost + fixed;
 done:
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (trace) {
+    tr[7] += now_s() - t_prev;
+    double total = 0;
+    for (double v : tr) total += v;
+    for (int k = 0; k < 8; ++k) fprintf(stderr, "[tba_minimize r%d] %-14s %9.3f ms  (%5.1f %%)\n", c->rank, kStageName[k], tr[k] * 1e3, 100.0 * tr[k] / std::max(total, 1e-30));
+  }
   s->termination_type = term;
   s->success = term != TBA_FAILURE;
   snprintf(s->message, sizeof s->message, "%s", msg);

@@ -2119,11 +2119,17 @@ __global__ void k_candidate_cs(DevProblem P, const double* __restrict__ xs, doub
 __global__ void k_candidate_pt(DevProblem P, double* __restrict__ scal) {
   __shared__ double s_red[32];
   double acc = 0.0;
-  const size_t n = (size_t)P.n_pt * 4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const double d = P.pt_const[i >> 2] ? 0.0 : P.dpt[i];
-    P.pt_c[i] = P.pt[i] + d;
-    acc += d * d;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < (size_t)P.n_pt; q += (size_t)gridDim.x * blockDim.x) {  // one point per thread
+    const bool cst = P.pt_const[q] != 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double2 d = *reinterpret_cast<const double2*>(P.dpt + q * 4 + 2 * h);
+      const double2 x = *reinterpret_cast<const double2*>(P.pt + q * 4 + 2 * h);
+      if (cst) d = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(P.pt_c + q * 4 + 2 * h) = make_double2(x.x + d.x, x.y + d.y);
+      acc += d.x * d.x;
+      acc += d.y * d.y;
+    }
   }
   const double s = block_sum(acc, s_red);
   if (threadIdx.x == 0) red_add(scal + 5, s);
@@ -2138,7 +2144,10 @@ __global__ void k_xnorm(DevProblem P, const double* __restrict__ ext, const doub
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   for (size_t i = t0; i < (size_t)P.ne; i += stride) if (blk_free[i / 6] != 0.0) a_cs += ext[i] * ext[i];
   for (size_t i = t0; i < (size_t)P.n_group * 10; i += stride) if (blk_free[P.n_cam + i / 10] != 0.0) a_cs += intr[i] * intr[i];
-  for (size_t i = t0; i < (size_t)P.n_pt * 4; i += stride) if (!P.pt_const[i >> 2]) a_pt += pt[i] * pt[i];
+  for (size_t q = t0; q < (size_t)P.n_pt; q += stride) {
+    const double2 a = *reinterpret_cast<const double2*>(pt + q * 4), b = *reinterpret_cast<const double2*>(pt + q * 4 + 2);
+    if (!P.pt_const[q]) { a_pt += a.x * a.x; a_pt += a.y * a.y; a_pt += b.x * b.x; a_pt += b.y * b.y; }
+  }
   const double s1 = block_sum(a_cs, s_red);
   const double s2 = block_sum(a_pt, s_red);
   if (threadIdx.x == 0) { if (count_cs) red_add(scal + 6, s1); red_add(scal + 7, s2); }
@@ -2149,17 +2158,29 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   // v >= 0: the IEEE bit pattern is monotone
   atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
-__global__ void k_gradmax(DevProblem P, const double* __restrict__ g_cs, const double* __restrict__ mask, double* __restrict__ gmax) {
-  double m_cs = 0.0, m_pt = 0.0;
-  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  for (size_t i = t0; i < (size_t)P.ncs; i += stride) if (mask[i] != 0.0) m_cs = fmax(m_cs, fabs(g_cs[i]));
-  for (size_t i = t0; i < (size_t)P.n_pt * 4; i += stride) if (!P.pt_const[i >> 2]) m_pt = fmax(m_pt, fabs(P.gp[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m_cs = fmax(m_cs, __shfl_down_sync(0xffffffffu, m_cs, o));
-    m_pt = fmax(m_pt, __shfl_down_sync(0xffffffffu, m_pt, o));
+// Gradient max norm in two steps around the all-reduce of the camera-side gradient: (1) this rank's points -> slot[0] (one slot per
+// rank behind the linearisation scalars: after the SUM all-reduce every rank holds every rank's maximum), (2) the reduced camera-side
+// gradient and the per-rank slots -> out[0].  Both by atomicMax on the bit pattern (targets zeroed by stage_linearize's memset).
+__global__ void k_gradmax_pt(DevProblem P, double* __restrict__ slot) {
+  double m = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < (size_t)P.n_pt; q += stride) {
+    const double2 a = *reinterpret_cast<const double2*>(P.gp + q * 4), b = *reinterpret_cast<const double2*>(P.gp + q * 4 + 2);
+    if (!P.pt_const[q]) m = fmax(fmax(m, fmax(fabs(a.x), fabs(a.y))), fmax(fabs(b.x), fabs(b.y)));
   }
-  if ((threadIdx.x & 31) == 0) { atomic_max_double(gmax + 0, m_cs); atomic_max_double(gmax + 1, m_pt); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_double(slot, m);
+}
+__global__ void k_gradmax_cs(int ncs, const double* __restrict__ g_cs, const double* __restrict__ mask, const double* __restrict__ slots,
+                             int world, double* __restrict__ out) {
+  double m = 0.0;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < ncs; i += gridDim.x * blockDim.x) if (mask[i] != 0.0) m = fmax(m, fabs(g_cs[i]));
+  if (t0 < world) m = fmax(m, slots[t0]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_double(out, m);
 }
 
 }  // namespace tba
