@@ -114,12 +114,14 @@ def main():
     ap.add_argument("--cpu-tracks", type=int, default=100_000)
     ap.add_argument("--pairs", type=int, default=20_000)
     ap.add_argument("--cpu-pairs", type=int, default=400)
+    ap.add_argument("--only-big", action="store_true", help="under ncu: only the large track case and the two-view batch")
     a = ap.parse_args()
     res = {"threads": oracle_py.num_threads(), "cases": []}
-    res["cases"].append(tracks_case("fountain_sized (11 cameras' worth of tracks: 8k)", 50, 8_000, 8_000, a.repeat))
+    if not a.only_big:
+        res["cases"].append(tracks_case("fountain_sized (8k tracks)", 50, 8_000, 8_000, a.repeat))
     res["cases"].append(tracks_case("config3_sized", 10_000, a.big, a.cpu_tracks, a.repeat))
     res["cases"].append(two_view_case(a.pairs, a.cpu_pairs, a.repeat))
-    for m, nm in ((_abi.MODEL_PINHOLE, "pinhole"), (_abi.MODEL_PINHOLE_RADIAL_TANGENTIAL, "radtan"), (_abi.MODEL_FISHEYE, "fisheye"),
+    for m, nm in () if a.only_big else ((_abi.MODEL_PINHOLE, "pinhole"), (_abi.MODEL_PINHOLE_RADIAL_TANGENTIAL, "radtan"), (_abi.MODEL_FISHEYE, "fisheye"),
                   (_abi.MODEL_FOV, "fov"), (_abi.MODEL_DIVISION_UNDISTORTION, "division_undistortion")):
         res["cases"].append(linearize_case(m, nm, 1000, 500_000, 5))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
