@@ -351,7 +351,7 @@ def matcher_main(args):
     config = {"workload": "c5_matcher: %d-image sample of config 5 (10k images x 5k SIFT-128): all %d image pairs, %d x %d descriptors per pair, "
                           "ratio 0.8, symmetric, min 30 matches" % (n_img, n_img * (n_img - 1) // 2, n_desc, n_desc),
               "parallelism": "image pairs sharded round-robin over %d GPU(s), descriptors replicated, no collective" % world,
-              "l2_policy": "every step re-uploads the descriptors and streams %d candidate tiles per query block; the distance matrices are never stored" % ((n_desc + 127) // 128)}
+              "l2_policy": "every step re-uploads the descriptors and streams %d candidate tiles per query block; the distance matrices are never stored; ratio test / symmetric filter on the device, only the kept matches are copied back" % ((n_desc + 127) // 128)}
     sets = matcher_scene(n_img, n_desc)
     if args.impl == "reference":
         if rank != 0:
@@ -439,8 +439,9 @@ def matcher_main(args):
                 "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core ranking, exact f32 decision)",
                 "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": pairs_total / wall, "unit": "pairs/s", "h2d_bytes_per_step": float(n_img * n_desc * MATCHER_DIM * 4) * world,
-                        "d2h_bytes_per_step": float(len(all_pairs) * 2 * n_desc * 12), "seconds": wall},
-                "gpu_launches": int(K * 3 * max(1, (len(mine) * 2 * n_desc + (4 << 20) - 1) // (4 << 20))) * world,
+                        "d2h_bytes_per_step": float(n_matches * 12 + len(all_pairs) * 5), "seconds": wall},
+                # per call: k_row_norms once; per chunk of <= 4M queries: k_expand_segments, k_nn_candidates, k_exact_top2, k_pair_decide, k_gather_matches
+                "gpu_launches": int(K * (1 + 5 * max(1, (len(mine) * 2 * n_desc + (4 << 20) - 1) // (4 << 20)))) * world,
                 "roofline": {"kernel": "k_nn_candidates (TF32 tcgen05.mma distance GEMM + fused top-8 epilogue from TMEM)", "bound": "tensor", "achieved": achieved,
                              "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "note": "algorithmic flops 2*n1*n2*128 per direction on the TF32 path (nominal dense TF32 = half the bf16 rate the peak is quoted for); per GPU",

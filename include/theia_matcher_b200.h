@@ -44,8 +44,9 @@ int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, 
                   const int32_t* pairs, int64_t n_pairs, const tbm_options* options, tbm_match* matches,
                   int64_t matches_capacity, int64_t* match_off /*[n_pairs+1]*/, uint8_t* pair_ok /*[n_pairs]*/);
 
-/* Host-only post-processing of the nearest-neighbour results of one pair (ratio test, early exits, intersection):
- * exposed so that the CPU test suite can check it without a GPU.  best_j / best_d / second_d: forward [n1] and
+/* Host restatement of the per-pair decisions (ratio test, early exits, intersection) that tbm_match_all takes on the device
+ * (theiasfm_b200/csrc/tbm_decide.cuh: one CTA per pair, only the kept matches are copied back): exposed so that the CPU test
+ * suite can pin the logic against the oracle without a GPU.  best_j / best_d / second_d: forward [n1] and
  * reverse [n2] results; second_valid = 0 when the other image has a single descriptor.  Returns MatchImagePair's bool. */
 int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const float* f_second_d, int32_t n1, int f_second_valid,
                           const int32_t* r_best_j, const float* r_best_d, const float* r_second_d, int32_t n2, int r_second_valid,

@@ -9,6 +9,7 @@
 
 #include "../../include/theia_matcher_b200.h"
 #include "tbm_top2.h"
+#include "tbm_decide.cuh"       // MatchImagePair's decisions on the device (ratio test, early exits, IntersectMatches)
 #ifndef TBA_EMULATE
 #include "tbm_matcher_tc.cuh"   // tcgen05 / TMA path (sm_100a); the SIMT emulation build keeps the exact CUDA-core kernel only
 #endif
@@ -79,8 +80,95 @@ __global__ void __launch_bounds__(ROWS* SLICES) k_nn2(const float* __restrict__ 
   }
 }
 
-struct DevF { float* p = nullptr; size_t n = 0; ~DevF() { if (p) cudaFree(p); } bool alloc(size_t c) { if (c <= n && p) return true; if (p) cudaFree(p); p = nullptr; n = 0; if (cudaMalloc(&p, (c ? c : 1) * sizeof(float)) != cudaSuccess) return false; n = c; return true; } };
-struct DevI { int* p = nullptr; size_t n = 0; ~DevI() { if (p) cudaFree(p); } bool alloc(size_t c) { if (c <= n && p) return true; if (p) cudaFree(p); p = nullptr; n = 0; if (cudaMalloc(&p, (c ? c : 1) * sizeof(int)) != cudaSuccess) return false; n = c; return true; } };
+template <class T>
+struct Dev {
+  T* p = nullptr; size_t n = 0;
+  Dev() = default;
+  Dev(const Dev&) = delete;
+  Dev& operator=(const Dev&) = delete;
+  ~Dev() { if (p) cudaFree(p); }
+  bool alloc(size_t c) {
+    if (c <= n && p) return true;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (cudaMalloc(&p, (c ? c : 1) * sizeof(T)) != cudaSuccess) return false;
+    n = c;
+    return true;
+  }
+};
+using DevF = Dev<float>;
+using DevI = Dev<int>;
+
+#ifdef TBA_EMULATE
+#define TBM_LAUNCH(kern, grid, block, smem, ...) emu::launch((const void*)(kern), (unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); })
+#else
+#define TBM_LAUNCH(kern, grid, block, smem, ...) kern<<<(grid), (block), (smem)>>>(__VA_ARGS__)
+#endif
+
+static_assert(sizeof(tbm_match) == 12, "k_gather_matches copies a match as three 32-bit words");
+
+// Device buffers of the decision stage, kept for the whole call (grown on demand).
+struct DecideBuffers {
+  Dev<tbm::PairSeg> segs;
+  Dev<tbm_match> staged, packed;
+  Dev<int> count;
+  Dev<uint8_t> ok;
+  Dev<long long> dst_off;
+  std::vector<int> h_count;
+  std::vector<uint8_t> h_ok;
+  std::vector<long long> h_off;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double kernel_ms = 0.0;  // device time of k_pair_decide + k_gather_matches, summed over the chunks of a call
+  ~DecideBuffers() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
+
+// The pairs `segs` (results of both directions in best_j / best_d / second_d on the device, `n_fwd_queries` forward queries in
+// all): decisions on the device, kept matches packed and copied to matches[*written ...], match_off / pair_ok filled for pairs
+// [p0, p0 + segs.size()).  Returns 0 or a negative tbm code; *overflow is set when the caller's capacity is too small.
+int decide_and_fetch(DecideBuffers& B, const std::vector<tbm::PairSeg>& segs, long long n_queries, const int* best_j, const float* best_d,
+                     const float* second_d, const tbm_options* options, int64_t p0, tbm_match* matches, int64_t cap, int64_t* written,
+                     int64_t* match_off, uint8_t* pair_ok, bool* overflow) {
+  const int np = (int)segs.size();
+  if (np == 0) return 0;
+  tbm::DecideOptions o;
+  o.symmetric = options->keep_only_symmetric_matches != 0; o.use_ratio = options->use_lowes_ratio != 0; o.min_matches = options->min_num_feature_matches;
+  o.ratio_sq = options->lowes_ratio * options->lowes_ratio;
+  const size_t nq = (size_t)(n_queries > 0 ? n_queries : 1);
+  if (!B.segs.alloc((size_t)np) || !B.staged.alloc(nq) || !B.packed.alloc(nq) || !B.count.alloc((size_t)np) || !B.ok.alloc((size_t)np) || !B.dst_off.alloc((size_t)np)) return -3;
+  if (cudaMemcpy(B.segs.p, segs.data(), (size_t)np * sizeof(tbm::PairSeg), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+  const int grid = np < 4096 ? np : 4096;
+  for (auto& e : B.ev) if (!e && cudaEventCreate(&e) != cudaSuccess) return -3;
+  cudaEventRecord(B.ev[0]);
+  TBM_LAUNCH(tbm::k_pair_decide, grid, tbm::kDecideThreads, 0, B.segs.p, np, best_j, best_d, second_d, o, B.staged.p, B.count.p, B.ok.p);
+  if (cudaPeekAtLastError() != cudaSuccess) return -3;
+  cudaEventRecord(B.ev[1]);
+  B.h_count.resize((size_t)np); B.h_ok.resize((size_t)np); B.h_off.resize((size_t)np);
+  if (cudaMemcpy(B.h_count.data(), B.count.p, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(B.h_ok.data(), B.ok.p, (size_t)np, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+  { float ms = 0; if (cudaEventElapsedTime(&ms, B.ev[0], B.ev[1]) == cudaSuccess) B.kernel_ms += ms; }
+  long long total = 0;
+  for (int k = 0; k < np; ++k) {
+    B.h_off[(size_t)k] = total;
+    match_off[p0 + k] = *written + total;
+    pair_ok[p0 + k] = B.h_ok[(size_t)k];
+    total += B.h_count[(size_t)k];
+  }
+  if (total > 0) {
+    if (*written + total > cap || !matches) *overflow = true;
+    else {
+      if (cudaMemcpy(B.dst_off.p, B.h_off.data(), (size_t)np * sizeof(long long), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+      cudaEventRecord(B.ev[2]);
+      TBM_LAUNCH(tbm::k_gather_matches, grid, 256, 0, B.segs.p, np, B.count.p, B.dst_off.p, B.staged.p, B.packed.p);
+      if (cudaPeekAtLastError() != cudaSuccess) return -3;
+      cudaEventRecord(B.ev[3]);
+      if (cudaMemcpy(matches + *written, B.packed.p, (size_t)total * sizeof(tbm_match), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, B.ev[2], B.ev[3]) == cudaSuccess) B.kernel_ms += ms;
+    }
+  }
+  *written += total;
+  return 0;
+}
 
 // :58-59, :78-81: keep the best match when the ratio test is off, there is no second candidate, or it passes
 inline bool passes(const tbm_options* o, float best, float second, int second_valid) {
@@ -138,6 +226,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   DevF d_desc, d_nrm, d_bd, d_sd;
   DevI d_cand, d_bj, d_qrow, d_brow0, d_brows;
+  if (!d_bj.alloc(1) || !d_bd.alloc(1) || !d_sd.alloc(1)) return -3;  // (never null: chunks of pairs between empty images)
   if (!d_desc.alloc((size_t)(total > 0 ? total : 1) * DIM) || !d_nrm.alloc((size_t)(total > 0 ? total : 1))) return -3;
   if (total > 0 && cudaMemcpy(d_desc.p, descriptors, (size_t)total * DIM * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
   cudaEventRecord(ev[1]);
@@ -156,37 +245,37 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   struct NexGuard { unsigned long long* p; ~NexGuard() { cudaFree(p); } } nex_guard{d_nex};
   if (cudaFuncSetAttribute(k_nn_candidates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(k_nn_candidates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
-  struct DevItems { WorkItem* p = nullptr; size_t n = 0; ~DevItems() { if (p) cudaFree(p); } } d_items;
+  Dev<WorkItem> d_items;
+  Dev<tbm::QuerySeg> d_qsegs;
+  DecideBuffers dec;
   std::vector<WorkItem> items;
-  std::vector<int> h_qrow, h_brow0, h_brows, h_bj;
-  std::vector<float> h_bd, h_sd;
-  std::vector<tbm_match> tmp;
+  std::vector<tbm::QuerySeg> qsegs;
+  std::vector<tbm::PairSeg> psegs;
   const bool sym = options->keep_only_symmetric_matches != 0;
   int64_t written = 0;
   bool overflow = false;
-  const int64_t kChunkQueries = (int64_t)4 << 20;  // queries per chunk (both directions): bounds the device / host staging
+  const int64_t kChunkQueries = (int64_t)4 << 20;  // queries per chunk (both directions): bounds the device staging
   for (int64_t p0 = 0; p0 < n_pairs;) {
-    // ---- chunk [p0, p1): as many pairs as fit the query budget
-    int64_t p1 = p0, nq_chunk = 0;
+    // ---- chunk [p0, p1): as many pairs as fit the query budget; one (pair, direction) segment table instead of per-query host arrays
+    items.clear(); qsegs.clear(); psegs.clear();
+    int64_t p1 = p0, qo = 0;
     while (p1 < n_pairs) {
       const int a = pairs[2 * p1], b = pairs[2 * p1 + 1];
       if (a < 0 || a >= n_img || b < 0 || b >= n_img) return -1;
-      const int64_t n1 = img_off[a + 1] - img_off[a], n2 = img_off[b + 1] - img_off[b];
-      const int64_t add = n1 + (sym ? n2 : 0);
-      if (p1 > p0 && nq_chunk + add > kChunkQueries) break;
-      nq_chunk += add; ++p1;
-    }
-    items.clear(); h_qrow.resize((size_t)nq_chunk); h_brow0.resize((size_t)nq_chunk); h_brows.resize((size_t)nq_chunk);
-    std::vector<int64_t> q_off((size_t)(p1 - p0) * 2 + 1, 0);
-    int64_t qo = 0;
-    for (int64_t p = p0; p < p1; ++p) {
-      const int a = pairs[2 * p], b = pairs[2 * p + 1];
-      for (int dir = 0; dir < 2; ++dir) {
-        q_off[(size_t)(p - p0) * 2 + dir] = qo;
-        if (dir == 1 && !sym) continue;
+      const int n1 = (int)(img_off[a + 1] - img_off[a]), n2 = (int)(img_off[b + 1] - img_off[b]);
+      const int64_t add = (int64_t)n1 + (sym ? n2 : 0);
+      if (p1 > p0 && qo + add > kChunkQueries) break;
+      tbm::PairSeg ps;
+      ps.f0 = qo; ps.r0 = qo + n1; ps.n1 = n1; ps.n2 = n2; ps.n_rev = sym ? n2 : 0;
+      psegs.push_back(ps);
+      for (int dir = 0; dir < (sym ? 2 : 1); ++dir) {
         const int qa = dir == 0 ? a : b, cb = dir == 0 ? b : a;
-        const int nq = (int)(img_off[qa + 1] - img_off[qa]), nc = (int)(img_off[cb + 1] - img_off[cb]);
-        for (int i = 0; i < nq; ++i) { h_qrow[(size_t)qo + i] = (int)img_off[qa] + i; h_brow0[(size_t)qo + i] = (int)img_off[cb]; h_brows[(size_t)qo + i] = nc; }
+        const int nq = dir == 0 ? n1 : n2, nc = dir == 0 ? n2 : n1;
+        if (nq > 0) {
+          tbm::QuerySeg g;
+          g.out0 = qo; g.nq = nq; g.q_row0 = (int)img_off[qa]; g.b_row0 = (int)img_off[cb]; g.b_rows = nc;
+          qsegs.push_back(g);
+        }
         if (nc > 0)
           for (int m0 = 0; m0 < nq; m0 += BM) {
             WorkItem w;
@@ -195,18 +284,18 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
           }
         qo += nq;
       }
+      ++p1;
     }
-    q_off.back() = qo;
+    const int64_t nq_chunk = qo;
     if (nq_chunk > 0) {
       if (!d_cand.alloc((size_t)nq_chunk * KC) || !d_bj.alloc((size_t)nq_chunk) || !d_bd.alloc((size_t)nq_chunk) || !d_sd.alloc((size_t)nq_chunk) ||
-          !d_qrow.alloc((size_t)nq_chunk) || !d_brow0.alloc((size_t)nq_chunk) || !d_brows.alloc((size_t)nq_chunk)) return -3;
+          !d_qrow.alloc((size_t)nq_chunk) || !d_brow0.alloc((size_t)nq_chunk) || !d_brows.alloc((size_t)nq_chunk) || !d_qsegs.alloc(qsegs.size())) return -3;
       if (cudaMemset(d_cand.p, 0xFF, (size_t)nq_chunk * KC * sizeof(int)) != cudaSuccess) return -3;  // -1: no candidate (empty other image)
-      if (cudaMemcpy(d_qrow.p, h_qrow.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
-          cudaMemcpy(d_brow0.p, h_brow0.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
-          cudaMemcpy(d_brows.p, h_brows.data(), (size_t)nq_chunk * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+      if (cudaMemcpy(d_qsegs.p, qsegs.data(), qsegs.size() * sizeof(tbm::QuerySeg), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+      tbm::k_expand_segments<<<(unsigned)(qsegs.size() < 8192 ? qsegs.size() : 8192), 256>>>(d_qsegs.p, (int)qsegs.size(), d_qrow.p, d_brow0.p, d_brows.p);
+      if (cudaPeekAtLastError() != cudaSuccess) return -3;
       if (!items.empty()) {
-        if (d_items.n < items.size()) { if (d_items.p) cudaFree(d_items.p); d_items.p = nullptr; d_items.n = 0;
-          if (cudaMalloc(&d_items.p, items.size() * sizeof(WorkItem)) != cudaSuccess) return -3; d_items.n = items.size(); }
+        if (!d_items.alloc(items.size())) return -3;
         if (cudaMemcpy(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
         const int grid = (int)(items.size() < (size_t)n_sm ? items.size() : (size_t)n_sm);
         cudaEventRecord(ev[2]);
@@ -219,34 +308,19 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
       k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
       if (cudaPeekAtLastError() != cudaSuccess) return -3;
       cudaEventRecord(ev[5]);
-      h_bj.resize((size_t)nq_chunk); h_bd.resize((size_t)nq_chunk); h_sd.resize((size_t)nq_chunk);
-      if (cudaMemcpy(h_bj.data(), d_bj.p, (size_t)nq_chunk * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
-          cudaMemcpy(h_bd.data(), d_bd.p, (size_t)nq_chunk * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
-          cudaMemcpy(h_sd.data(), d_sd.p, (size_t)nq_chunk * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    }
+    // ---- MatchImagePair's decisions per pair, on the device (tbm_decide.cuh); only the kept matches are copied back
+    const int rc = decide_and_fetch(dec, psegs, nq_chunk, d_bj.p, d_bd.p, d_sd.p, options, p0, matches, cap, &written, match_off, pair_ok, &overflow);
+    if (rc) return rc;
+    if (nq_chunk > 0) {
       float ms = 0;
       if (!items.empty() && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) g_last_timing[0] += ms;
       if (cudaEventElapsedTime(&ms, ev[4], ev[5]) == cudaSuccess) g_last_timing[1] += ms;
     }
-    // ---- MatchImagePair's decisions, per pair
-    static const int kNone = -1; static const float kZero = 0.0f;
-    for (int64_t p = p0; p < p1; ++p) {
-      const int a = pairs[2 * p], b = pairs[2 * p + 1];
-      const int n1 = (int)(img_off[a + 1] - img_off[a]), n2 = (int)(img_off[b + 1] - img_off[b]);
-      const int64_t f0 = q_off[(size_t)(p - p0) * 2], r0 = q_off[(size_t)(p - p0) * 2 + 1];
-      tmp.resize((size_t)(n1 > 0 ? n1 : 1));
-      int32_t nm = 0;
-      const int* fbj = n1 > 0 ? h_bj.data() + f0 : &kNone; const float* fbd = n1 > 0 ? h_bd.data() + f0 : &kZero; const float* fsd = n1 > 0 ? h_sd.data() + f0 : &kZero;
-      const bool have_r = sym && n2 > 0;
-      const int* rbj = have_r ? h_bj.data() + r0 : &kNone; const float* rbd = have_r ? h_bd.data() + r0 : &kZero; const float* rsd = have_r ? h_sd.data() + r0 : &kZero;
-      pair_ok[p] = (uint8_t)tbm_debug_postprocess(fbj, fbd, fsd, n1, n2 >= 2, rbj, rbd, rsd, have_r ? n2 : 0, n1 >= 2, options, tmp.data(), &nm);
-      match_off[p] = written;
-      if (written + nm > cap || !matches) overflow = true;
-      else memcpy(matches + written, tmp.data(), (size_t)nm * sizeof(tbm_match));
-      written += nm;
-    }
     p0 = p1;
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+  g_last_timing[1] += dec.kernel_ms;  // the decision kernels count as device time of the "exact" stage
   { float ms = 0; if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) g_last_timing[2] = ms; }
   { unsigned long long h = 0; if (cudaMemcpy(&h, d_nex, 8, cudaMemcpyDeviceToHost) == cudaSuccess) g_last_timing[3] = (double)h; }
   match_off[n_pairs] = written;
@@ -271,48 +345,35 @@ int tbm_match_all(int device, const float* descriptors, const int64_t* img_off, 
   const int64_t total = img_off[n_img];
   int64_t max_n = 0;
   for (int i = 0; i < n_img; ++i) { if (img_off[i + 1] < img_off[i]) return -1; max_n = img_off[i + 1] - img_off[i] > max_n ? img_off[i + 1] - img_off[i] : max_n; }
-  DevF d_desc, d_bd[2], d_sd[2];
-  DevI d_bj[2];
+  DevF d_desc, d_bd, d_sd;
+  DevI d_bj;  // results of one pair: forward queries [0, n1), reverse queries [n1, n1 + n2)
   if (!d_desc.alloc((size_t)total * dim)) return -3;
-  for (int s = 0; s < 2; ++s) if (!d_bd[s].alloc((size_t)max_n) || !d_sd[s].alloc((size_t)max_n) || !d_bj[s].alloc((size_t)max_n)) return -3;
+  if (!d_bd.alloc((size_t)max_n * 2) || !d_sd.alloc((size_t)max_n * 2) || !d_bj.alloc((size_t)max_n * 2)) return -3;
   if (cudaMemcpy(d_desc.p, descriptors, (size_t)total * dim * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
   const size_t smem = ((size_t)ROWS * (dim + 1) + (size_t)TJ * dim) * sizeof(float);
   if (smem > 48 * 1024 && cudaFuncSetAttribute(k_nn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-  std::vector<int32_t> bj[2];
-  std::vector<float> bd[2], sd[2];
-  std::vector<tbm_match> tmp;
+  DecideBuffers dec;
+  std::vector<tbm::PairSeg> one(1);
   int64_t written = 0;
   bool overflow = false;
+  const bool sym = options->keep_only_symmetric_matches != 0;
   for (int64_t p = 0; p < n_pairs; ++p) {
     const int a = pairs[2 * p], b = pairs[2 * p + 1];
     if (a < 0 || a >= n_img || b < 0 || b >= n_img) return -1;
     const int n1 = (int)(img_off[a + 1] - img_off[a]), n2 = (int)(img_off[b + 1] - img_off[b]);
     const float* A = d_desc.p + (size_t)img_off[a] * dim;
     const float* B = d_desc.p + (size_t)img_off[b] * dim;
-    for (int dir = 0; dir < 2; ++dir) {
+    if (n1 + n2 > 0 && cudaMemset(d_bj.p, 0xFF, (size_t)(n1 + n2) * sizeof(int)) != cudaSuccess) return -3;  // -1: no match (empty other image)
+    for (int dir = 0; dir < (sym ? 2 : 1); ++dir) {
       const int nq = dir == 0 ? n1 : n2, nc = dir == 0 ? n2 : n1;
-      bj[dir].assign((size_t)nq, -1); bd[dir].assign((size_t)nq, 0.0f); sd[dir].assign((size_t)nq, 0.0f);
       if (nq == 0 || nc == 0) continue;
-      if (dir == 1 && !options->keep_only_symmetric_matches) continue;
-#ifdef TBA_EMULATE
-      emu::launch((const void*)k_nn2, (unsigned)((nq + ROWS - 1) / ROWS), (unsigned)(ROWS * SLICES), smem,
-                  [&] { k_nn2(dir == 0 ? A : B, nq, dir == 0 ? B : A, nc, dim, d_bj[dir].p, d_bd[dir].p, d_sd[dir].p); });
-#else
-      k_nn2<<<(nq + ROWS - 1) / ROWS, ROWS * SLICES, smem>>>(dir == 0 ? A : B, nq, dir == 0 ? B : A, nc, dim, d_bj[dir].p, d_bd[dir].p, d_sd[dir].p);
-#endif
+      const size_t o = dir == 0 ? 0 : (size_t)n1;
+      TBM_LAUNCH(k_nn2, (nq + ROWS - 1) / ROWS, ROWS * SLICES, smem, dir == 0 ? A : B, nq, dir == 0 ? B : A, nc, dim, d_bj.p + o, d_bd.p + o, d_sd.p + o);
       if (cudaPeekAtLastError() != cudaSuccess) return -3;
-      if (cudaMemcpy(bj[dir].data(), d_bj[dir].p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
-          cudaMemcpy(bd[dir].data(), d_bd[dir].p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
-          cudaMemcpy(sd[dir].data(), d_sd[dir].p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
     }
-    tmp.resize((size_t)(n1 > 0 ? n1 : 1));
-    int32_t nm = 0;
-    pair_ok[p] = (uint8_t)tbm_debug_postprocess(bj[0].data(), bd[0].data(), sd[0].data(), n1, n2 >= 2, bj[1].data(), bd[1].data(), sd[1].data(), n2,
-                                                n1 >= 2, options, tmp.data(), &nm);
-    match_off[p] = written;
-    if (written + nm > cap || !matches) overflow = true;
-    else memcpy(matches + written, tmp.data(), (size_t)nm * sizeof(tbm_match));
-    written += nm;
+    one[0].f0 = 0; one[0].r0 = n1; one[0].n1 = n1; one[0].n2 = n2; one[0].n_rev = sym ? n2 : 0;
+    const int rc = decide_and_fetch(dec, one, (long long)n1 + n2, d_bj.p, d_bd.p, d_sd.p, options, p, matches, cap, &written, match_off, pair_ok, &overflow);
+    if (rc) return rc;
   }
   match_off[n_pairs] = written;
   return overflow ? -1 : 0;
