@@ -32,7 +32,7 @@ constexpr int BN = 128;        // candidate rows per tile (= accumulator columns
 constexpr int DIM = 128;       // descriptor length (SIFT); 4 swizzle atoms of 32 floats
 constexpr int KC = 16;         // candidate slots per query handed to the exact pass (-1 = empty; typically 2..4 are filled)
 constexpr int ET = 8;          // threads per query in the exact pass
-constexpr int CAP = 12;        // provisional candidates per (query, column half) in shared memory (overflow => exact full scan of that query)
+constexpr int CAP = 15;        // list slots per (query, column half) in shared memory: 12 usable (a list that reaches slot 11 => exact full scan of that query) + 3 spare behind them (pointer clamped once per four appends)
 constexpr int kOverflow = -2;  // cand[q*KC] marker: the exact pass scans every candidate of this query
 constexpr int ATOM_BYTES = BM * 128;              // one 128-row x 128-byte swizzle-atom panel
 constexpr int TILE_BYTES = 4 * ATOM_BYTES;        // 64 KB: a 128 x 128 float tile
@@ -214,14 +214,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
     const float kInf = __int_as_float(0x7f800000);
     uint2* myC = sC + et;                   // list entries of this thread: myC[k * 2 * BM]
     constexpr uint32_t kStride = 2 * BM * (uint32_t)sizeof(uint2);   // bytes between consecutive entries of one list
-    const uint32_t c_base = smem_addr(myC), c_last = c_base + (CAP - 1) * kStride;
+    const uint32_t c_base = smem_addr(myC), c_last = c_base + (CAP - 4) * kStride;
     uint32_t bt = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const WorkItem w = items[it];
       float m1 = kInf, m2 = kInf;
       const float nx8 = (!NONNEG && row < w.a_rows) ? 0.00390625f * __ldg(nrm + w.a_row0 + row) : 0.0f;  // 2^-8 ||x||^2 (general margin only)
       // wp = shared-memory address of the next append; it saturates at the last slot, and a list that reaches the last slot
-      // counts as overflowed (capacity CAP - 1 entries between two maintenance points)
+      // counts as overflowed (capacity CAP - 4 entries between two maintenance points)
       uint32_t wp = c_base;
       int ovf = 0;
       const int n_tiles = (w.b_rows + BN - 1) / BN;
@@ -238,10 +238,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN + half * 64;
         const float4* nt4 = reinterpret_cast<const float4*>(sN + acc * BN + half * 64);
         const int jt = w.b_row0 + t * BN + half * 64;
+        // one predicated 8-byte store + pointer bump per element; the pointer is clamped to the last slot once per FOUR elements
+        // (TBM_CLAMP): at most four appends can happen in between, and the lists keep four spare slots behind c_last for them
 #define TBM_APPEND(VAL, J)                                                                                              \
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p st.shared.v2.b32 [%0], {%3, %4};\n\t@p add.u32 %0, %0, %5;\n\t"        \
-               "@p min.u32 %0, %0, %6;\n\t}"                                                                            \
-               : "+r"(wp) : "f"(VAL), "f"(lim), "r"(__float_as_uint(VAL)), "r"(J), "n"(kStride), "r"(c_last) : "memory")
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p st.shared.v2.b32 [%0], {%3, %4};\n\t@p add.u32 %0, %0, %5;\n\t}"      \
+               : "+r"(wp) : "f"(VAL), "f"(lim), "r"(__float_as_uint(VAL)), "r"(J), "n"(kStride) : "memory")
+#define TBM_CLAMP() wp = min(wp, c_last)
         if (t == 0) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
           if (t == 0) {  // (tile 0 is already in m1, m2: counting an element twice would turn the best into its own runner-up)
-            const float lim = m2 + nx8;
+            const float lim = NONNEG ? m2 : m2 + nx8;
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
               const float4 n4 = nt4[(c0 >> 2) + c4];
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
                 const float val = fmaf(NONNEG ? dotv : nn[u], NONNEG ? -0.00396728515625f : -0.00390625f, fmaf(-2.0f, dotv, nn[u]));
                 TBM_APPEND(val, jt + c0 + 4 * c4 + u);
               }
+              TBM_CLAMP();
             }
           } else {
 #pragma unroll
@@ -287,14 +290,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_nn_candidates(const __grid_const
                 const float dotv = __uint_as_float(r[4 * c4 + u]);
                 const float sc = fmaf(-2.0f, dotv, nn[u]);
                 const float val = fmaf(NONNEG ? dotv : nn[u], NONNEG ? -0.00396728515625f : -0.00390625f, sc);   // score minus the candidate's margin
-                const float lim = m2 + nx8;
+                const float lim = NONNEG ? m2 : m2 + nx8;
                 TBM_APPEND(val, jt + c0 + 4 * c4 + u);
                 m2 = fminf(m2, fmaxf(m1, sc));
                 m1 = fminf(m1, sc);
               }
+              TBM_CLAMP();
             }
           }
 #undef TBM_APPEND
+#undef TBM_CLAMP
           // list maintenance, once per 32-column chunk (rare per lane; divergent, but cheap)
           ovf |= wp == c_last;
           if (wp > c_base + 8 * kStride) {
