@@ -186,11 +186,11 @@ def cpu_baseline_subprocess(steps, timeout=240):
         return {"value": None, "unit": "obs/s", "cores": None, "kind": "port", "sample": "failed: %s: %s" % (type(e).__name__, e)}
 
 
-SWITCHES = ("TBA_TRED", "TBA_LIN_OCC", "TBA_ABLATE", "TBA_MATVEC")
+SWITCHES = ("TBA_TRED", "TBA_LIN_OCC", "TBA_ABLATE", "TBA_MATVEC", "TBA_PCG")
 # "default" = the shipped kernels (persistent streaming Schur kernels).  "tile_kernels" = the round-1 tile-per-CTA Schur kernels with
 # the transposed RED emission; "r1_kernels" = the round-1 defaults.  The TBA_ABLATE variants switch parts of the matvec OFF (wrong
 # results by construction, timing only): they say how much of the launch each part costs in situ.
-VARIANTS = (("default", {}), ("tile_kernels", {"TBA_MATVEC": "tile"}), ("r1_kernels", {"TBA_MATVEC": "tile", "TBA_TRED": "0", "TBA_LIN_OCC": "2"}),
+VARIANTS = (("default", {}), ("split_pcg", {"TBA_PCG": "split"}), ("tile_kernels", {"TBA_MATVEC": "tile"}), ("r1_kernels", {"TBA_MATVEC": "tile", "TBA_TRED": "0", "TBA_LIN_OCC": "2"}),
             ("ablate_no_red", {"TBA_ABLATE": "1"}), ("ablate_no_gather", {"TBA_ABLATE": "2"}),
             ("ablate_no_segreduce", {"TBA_ABLATE": "8"}), ("ablate_all", {"TBA_ABLATE": "15"}))
 

@@ -1,5 +1,6 @@
 """The kernel-selection switches against the oracle: TBA_MATVEC=tile (the tile-per-CTA Schur kernels instead of the persistent
-streaming ones; they remain the shipped path for tracks of more than 32 observations), TBA_TRED=0 (lane-per-row REDs), TBA_LIN_OCC=2.
+streaming ones; they remain the shipped path for tracks of more than 32 observations), TBA_TRED=0 (lane-per-row REDs), TBA_LIN_OCC=2,
+TBA_PCG=split (three vector kernels per CG iteration instead of the fused one with grid barriers).
 They only change the ORDER of fp64 sums, so the default tolerances of tests/test_gpu_parity.py apply unchanged."""
 import numpy as np
 import pytest
@@ -15,8 +16,9 @@ VARIANTS = {
     "tile_no_tred": {"TBA_MATVEC": "tile", "TBA_TRED": "0"},                       # lane-per-row REDs
     "r1_kernels": {"TBA_MATVEC": "tile", "TBA_TRED": "0", "TBA_LIN_OCC": "2"},     # the round-1 defaults
     "lin_occ2": {"TBA_LIN_OCC": "2"},
+    "split_pcg": {"TBA_PCG": "split"},                                             # k_pcg_c / k_pcg_a / k_pcg_b instead of k_pcg_fused
 }
-ALL = ("TBA_TRED", "TBA_MATVEC", "TBA_LIN_OCC", "TBA_ABLATE")
+ALL = ("TBA_TRED", "TBA_MATVEC", "TBA_LIN_OCC", "TBA_ABLATE", "TBA_PCG")
 
 
 @pytest.fixture

@@ -128,6 +128,7 @@ struct tba_context {
   DevBuf<double> b, x, r, p, z, xs, y, part /*3 x VB*/, gmax, flag, scal2 /*16*/, rep /*NREP x REPW*/;
   DevBuf<PcgState> st;      // [2]
   DevBuf<int> done_flag;
+  DevBuf<int> pcg_bar;         // [2] grid barrier of k_pcg_fused (arrivals, generation)
   bool have_scale = false;
   // optional per-kernel timing (CUDA events on the engine stream)
   bool profiling = false;
@@ -149,6 +150,7 @@ struct tba_context {
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_tred = true;     // transposed RED emission (warp_red_rows) in k_linearize / k_precond_ext / rhs / matvec; TBA_TRED=0: the round-1 lane-per-row REDs
   bool exp_lin_occ = true;  // k_linearize compiled for 3 CTAs/SM (80 registers, ~130 bytes of spills); TBA_LIN_OCC=2: 2 CTAs/SM, 128 registers
+  bool pcg_fused = true;    // one vector kernel per CG iteration (k_pcg_fused, grid barriers between its phases); TBA_PCG=split: k_pcg_c / k_pcg_a / k_pcg_b
   bool stream_schur = true; // persistent streaming k_schur_stream over the normal tiles; TBA_MATVEC=tile: the tile-per-CTA k_schur everywhere
   int n_normal_tiles = 0;   // tiles whose tracks fit a warp slice (they precede the long tiles)
   // fused matvec + all-reduce over peer memory (P2pDev, tba_kernels.cuh): world > 1, every peer reachable, TBA_P2P != 0
@@ -601,24 +603,48 @@ int stage_pcg(tba_context* c, int* iters, int* status, bool* system_ok = nullptr
   double* fold_rep = fold_in_a ? c->rep.p : nullptr;
   const bool p2p = p2p_matvec_possible(c);  // multi-GPU: the matvec pushes its partial sums to the peers, k_pcg_a sums the inbox
   int* zero_ctr = p2p ? c->p2p_ctr : nullptr;
-  LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
-         part_Q, part_rho, ident, 1, nullptr);
-  cur ^= 1;
+  // c->pcg_fused (default): ONE vector kernel per CG iteration -- phases A and B of iteration k and phase C of iteration k + 1 in
+  // k_pcg_fused, grid barriers in between -- i.e. two launches per iteration with the matvec; TBA_PCG=split (and the SIMT emulation
+  // build, which cannot run a grid barrier): the three kernels
+  const bool fused = c->pcg_fused;
+  PcgVectors V;
+  V.sm = c->sm.p; V.D2 = c->D2.p; V.b = c->b.p; V.Minv_c = c->Minv_c.p; V.Minv_i = c->Minv_i.p;
+  V.p = c->p.p; V.q = c->z.p; V.x = c->x.p; V.r = c->r.p; V.z = c->z2.p; V.xs = c->xs.p; V.y = c->y.p;
+  V.part_pq = part_pq; V.part_Q = part_Q; V.part_rho = part_rho; V.fold_rep = fold_rep; V.zero_ctr = zero_ctr; V.bar = c->pcg_bar.p;
+  V.identity_precond = ident;
+  if (fused) {  // z = Minv r, rho (phase B, first) and phase C of iteration 1
+    LAUNCH(c, k_pcg_fused, VB, VT, 0, P, st + cur, st + (cur ^ 1), V, 2 | 4, 1, p2p_none());
+    cur ^= 1;
+  } else {
+    LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
+           part_Q, part_rho, ident, 1, nullptr);
+    cur ^= 1;
+  }
+  bool c_pending = !fused;  // phase C of the coming iteration still to be launched (split mode: always; fused: after a residual reset)
   int batch = std::max(4, std::min(c->last_cg_iters + 2, 64));
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       ++it;
-      LAUNCH(c, k_pcg_c, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_Q, part_rho, c->z2.p, c->sm.p, c->p.p, c->xs.p, c->y.p, nullptr, zero_ctr);
-      cur ^= 1;
+      if (c_pending) {
+        LAUNCH(c, k_pcg_c, VB, VT, 0, P.ncs, st + cur, st + (cur ^ 1), part_Q, part_rho, c->z2.p, c->sm.p, c->p.p, c->xs.p, c->y.p, nullptr, zero_ctr);
+        cur ^= 1;
+      }
       // every kernel of an iteration (matvec included) early-exits through the device-side state
       const P2pDev pp = p2p ? p2p_next(c) : p2p_none();
       int rc = launch_matvec(c, st_done(st + cur), fold_in_a, pp);
       if (rc) return rc;
-      LAUNCH(c, k_pcg_a, VB, VT, 0, P.ncs, P.ne, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq, fold_rep, pp);
-      LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
-             part_Q, part_rho, ident, 0, fold_rep);
-      cur ^= 1;
-      if (o.cg_residual_reset_period > 0 && it % o.cg_residual_reset_period == 0) {
+      const bool reset_now = o.cg_residual_reset_period > 0 && it % o.cg_residual_reset_period == 0;
+      if (fused) {
+        LAUNCH(c, k_pcg_fused, VB, VT, 0, P, st + cur, st + (cur ^ 1), V, reset_now ? (1 | 2) : (1 | 2 | 4), 0, pp);
+        cur ^= 1;
+        c_pending = reset_now;
+      } else {
+        LAUNCH(c, k_pcg_a, VB, VT, 0, P.ncs, P.ne, st + cur, c->y.p, c->sm.p, c->D2.p, c->p.p, c->z.p, part_pq, fold_rep, pp);
+        LAUNCH(c, k_pcg_b, VB, VT, 0, P, st + cur, st + (cur ^ 1), part_pq, c->p.p, c->z.p, c->b.p, c->x.p, c->r.p, c->z2.p, c->Minv_c.p, c->Minv_i.p,
+               part_Q, part_rho, ident, 0, fold_rep);
+        cur ^= 1;
+      }
+      if (reset_now) {
         LAUNCH(c, k_pcg_reset_a, VB, VT, 0, P.ncs, st + cur, c->x.p, c->sm.p, c->xs.p, c->y.p, zero_ctr);
         const P2pDev pr = p2p ? p2p_next(c) : p2p_none();
         rc = launch_matvec(c, st_done(st + cur), fold_in_a, pr);
@@ -920,6 +946,10 @@ int tba_create(int device, int rank, int world_size, const void* nccl_unique_id,
   c->device = device; c->rank = rank; c->world = world_size;
   tba_options_init(&c->opt);
   { const char* e = getenv("TBA_MATVEC"); c->stream_schur = !(e != nullptr && e[0] == 't'); }
+  { const char* e = getenv("TBA_PCG"); c->pcg_fused = !(e != nullptr && e[0] == 's'); }
+#ifdef TBA_EMULATE
+  c->pcg_fused = false;  // the emulator runs the CTAs of a launch one after the other: no grid barrier (the three phases are the same device functions)
+#endif
   { const char* e = getenv("TBA_P2P"); c->p2p_enabled = !(e != nullptr && e[0] == '0'); }
   // round 2: the transposed RED emission and the 3-CTA/SM linearise are the defaults (driver-measured 28.1 vs 31.9 ms per
   // LM iteration at 20 M observations, costs equal to 2e-8); TBA_TRED=0 / TBA_LIN_OCC=2 select the round-1 kernels
@@ -1124,7 +1154,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   ALLOC(lin, 2 * (size_t)ncs + 16 + (size_t)std::max(1, c->world)); ALLOC(mask, (size_t)ncs); ALLOC(blk_free, (size_t)nc + ng); ALLOC(sm, (size_t)ncs); ALLOC(D2, (size_t)ncs);
   ALLOC(Sblk, (size_t)nc * 21 + (size_t)ng * 55 + 2 + (size_t)ncs); ALLOC(Minv_c, (size_t)nc * 36); ALLOC(Minv_i, (size_t)ng * 100);
   ALLOC(b, (size_t)ncs); ALLOC(x, (size_t)ncs); ALLOC(r, (size_t)ncs); ALLOC(p, (size_t)ncs); ALLOC(z, (size_t)ncs); ALLOC(z2, (size_t)ncs); ALLOC(xs, (size_t)ncs); ALLOC(y, (size_t)ncs);
-  ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(rep, (size_t)NREP * REPW);
+  ALLOC(part, 3 * VB); ALLOC(gmax, 2); ALLOC(flag, 1); ALLOC(scal2, std::max<size_t>(16, (size_t)nc + ng)); ALLOC(st, 2); ALLOC(done_flag, 1); ALLOC(pcg_bar, 2); ALLOC(rep, (size_t)NREP * REPW);
 #undef ALLOC
   lap("device alloc");
 #define H2D(buf, src, n)                                                                                      \
@@ -1170,6 +1200,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   H2D(mask, mask.data(), (size_t)ncs); H2D(blk_free, blk_free.data(), (size_t)nc + ng);
 #undef H2D
   CUDA_OK(c, cudaMemsetAsync(c->rep.p, 0, (size_t)NREP * REPW * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->pcg_bar.p, 0, 2 * sizeof(int), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->J.p, 0, (size_t)n_slots * c->NJ * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->dpt.p, 0, (size_t)npd * 4 * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->Mp.p, 0, (size_t)npd * 10 * sizeof(double), c->stream));

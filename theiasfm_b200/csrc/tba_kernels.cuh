@@ -1924,12 +1924,11 @@ __device__ __forceinline__ void pcg_q_test(PcgState& st, const double* __restric
   }
 }
 
-__global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
-                                              const double* __restrict__ part_Q, const double* __restrict__ part_rho,
-                                              const double* __restrict__ z, const double* __restrict__ sm, double* __restrict__ p,
-                                              double* __restrict__ xs, double* __restrict__ y, int* __restrict__ done_flag, int* __restrict__ zero_ctr) {
-  __shared__ double s_red[32];
-  PcgState st = *in;
+// The three phases as device functions on a PcgState held in registers (every CTA computes the same state from the same partial
+// sums): the kernels k_pcg_c / k_pcg_a / k_pcg_b wrap one phase each, k_pcg_fused runs them back to back with grid barriers.
+__device__ __forceinline__ void pcg_phase_c(int ncs, PcgState& st, const double* __restrict__ part_Q, const double* __restrict__ part_rho,
+                                            const double* __restrict__ z, const double* __restrict__ sm, double* __restrict__ p,
+                                            double* __restrict__ xs, double* __restrict__ y, int* __restrict__ zero_ctr, double* s_red) {
   if (zero_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { zero_ctr[0] = 0; zero_ctr[1] = 0; }  // barrier / completion counters of the next matvec
   pcg_q_test(st, part_Q, s_red);
   if (!st.done) {
@@ -1942,7 +1941,6 @@ __global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restric
       if (zero_or_inf(st.beta)) { st.done = 1; st.status = 2; }
     } else st.beta = 0.0;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *out = st; if (done_flag) *done_flag = st.done; }
   if (st.done) return;
   const bool first = st.iters == 1;
   for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
@@ -1952,16 +1950,22 @@ __global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restric
     y[i] = 0.0;
   }
 }
+__global__ void __launch_bounds__(VT) k_pcg_c(int ncs, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                              const double* __restrict__ part_Q, const double* __restrict__ part_rho,
+                                              const double* __restrict__ z, const double* __restrict__ sm, double* __restrict__ p,
+                                              double* __restrict__ xs, double* __restrict__ y, int* __restrict__ done_flag, int* __restrict__ zero_ctr) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  pcg_phase_c(ncs, st, part_Q, part_rho, z, sm, p, xs, y, zero_ctr, s_red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *out = st; if (done_flag) *done_flag = st.done; }
+}
 
 // fold_rep != nullptr (one GPU, one shared intrinsics group): the replica rows of the matvec are folded into y[ne ..] here,
 // in the fixed row order of k_fold, by every CTA (they all need the value) -- CTA 0 stores it and re-zeroes the replicas.
-__global__ void __launch_bounds__(VT) k_pcg_a(int ncs, int ne, const PcgState* __restrict__ in, double* __restrict__ y,
-                                              const double* __restrict__ sm, const double* __restrict__ D2,
-                                              const double* __restrict__ p, double* __restrict__ q, double* __restrict__ part_pq,
-                                              const double* __restrict__ fold_rep, P2pDev pp) {
-  __shared__ double s_red[32];
-  __shared__ double s_fold[10];
-  if (in->done) return;
+__device__ __forceinline__ void pcg_phase_a(int ncs, int ne, double* __restrict__ y, const double* __restrict__ sm,
+                                            const double* __restrict__ D2, const double* __restrict__ p, double* __restrict__ q,
+                                            double* __restrict__ part_pq, const double* __restrict__ fold_rep, const P2pDev& pp,
+                                            double* s_red, double* s_fold) {
   if (pp.world > 1) p2p_wait(pp);  // the matvec of every rank has pushed its partial sums into the local inbox
   if (fold_rep != nullptr) {
     if (threadIdx.x < 10) {
@@ -1981,16 +1985,23 @@ __global__ void __launch_bounds__(VT) k_pcg_a(int ncs, int ne, const PcgState* _
   const double s = block_sum(acc, s_red);
   if (threadIdx.x == 0) part_pq[blockIdx.x] = s;
 }
+__global__ void __launch_bounds__(VT) k_pcg_a(int ncs, int ne, const PcgState* __restrict__ in, double* __restrict__ y,
+                                              const double* __restrict__ sm, const double* __restrict__ D2,
+                                              const double* __restrict__ p, double* __restrict__ q, double* __restrict__ part_pq,
+                                              const double* __restrict__ fold_rep, P2pDev pp) {
+  __shared__ double s_red[32];
+  __shared__ double s_fold[10];
+  if (in->done) return;
+  pcg_phase_a(ncs, ne, y, sm, D2, p, q, part_pq, fold_rep, pp, s_red, s_fold);
+}
 // (the replicas are re-zeroed by the kernel that runs after every CTA of k_pcg_a has read them: k_pcg_b)
 
-__global__ void __launch_bounds__(VT) k_pcg_b(DevProblem P, const PcgState* __restrict__ in, PcgState* __restrict__ out,
-                                              const double* __restrict__ part_pq, const double* __restrict__ p,
-                                              const double* __restrict__ q, const double* __restrict__ b, double* __restrict__ x,
-                                              double* __restrict__ r, double* __restrict__ z, const double* __restrict__ Minv_c,
-                                              const double* __restrict__ Minv_i, double* __restrict__ part_Q,
-                                              double* __restrict__ part_rho, int identity_precond, int first, double* __restrict__ zero_rep) {
-  __shared__ double s_red[32];
-  PcgState st = *in;
+__device__ __forceinline__ void pcg_phase_b(const DevProblem& P, PcgState& st, const double* __restrict__ part_pq,
+                                            const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ b,
+                                            double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                            const double* __restrict__ Minv_c, const double* __restrict__ Minv_i,
+                                            double* __restrict__ part_Q, double* __restrict__ part_rho, int identity_precond, int first,
+                                            double* __restrict__ zero_rep, double* s_red) {
   if (!first && !st.done) {
     const double pq = sum_partials(part_pq, s_red);
     st.pq = pq;
@@ -2001,8 +2012,7 @@ __global__ void __launch_bounds__(VT) k_pcg_b(DevProblem P, const PcgState* __re
       else st.pending_q = 1;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
-  if (zero_rep != nullptr && !first) {  // the replica columns folded by k_pcg_a
+  if (zero_rep != nullptr && !first) {  // the replica columns folded by phase A
     for (int i = blockIdx.x * VT + threadIdx.x; i < NREP * 10; i += VB * VT) zero_rep[(size_t)(i / 10) * REPW + (i % 10)] = 0.0;
   }
   if (st.done) return;
@@ -2024,6 +2034,74 @@ __global__ void __launch_bounds__(VT) k_pcg_b(DevProblem P, const PcgState* __re
   const double sQ = block_sum(accQ, s_red);
   const double sR = block_sum(accR, s_red);
   if (threadIdx.x == 0) { if (!first) part_Q[blockIdx.x] = sQ; part_rho[blockIdx.x] = sR; }
+}
+__global__ void __launch_bounds__(VT) k_pcg_b(DevProblem P, const PcgState* __restrict__ in, PcgState* __restrict__ out,
+                                              const double* __restrict__ part_pq, const double* __restrict__ p,
+                                              const double* __restrict__ q, const double* __restrict__ b, double* __restrict__ x,
+                                              double* __restrict__ r, double* __restrict__ z, const double* __restrict__ Minv_c,
+                                              const double* __restrict__ Minv_i, double* __restrict__ part_Q,
+                                              double* __restrict__ part_rho, int identity_precond, int first, double* __restrict__ zero_rep) {
+  __shared__ double s_red[32];
+  PcgState st = *in;
+  pcg_phase_b(P, st, part_pq, p, q, b, x, r, z, Minv_c, Minv_i, part_Q, part_rho, identity_precond, first, zero_rep, s_red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
+}
+
+// ---- the three phases in ONE launch (one GPU kernel per CG iteration next to the matvec): A -> grid barrier -> B -> grid barrier
+// -> C of the NEXT iteration.  VB CTAs of VT threads are co-resident on any device this engine runs on (the previous kernel of the
+// stream has finished).  Sense-reversal barrier on bar[0] (arrivals) / bar[1] (generation), both zero before the first use; the
+// partial sums written before a barrier are read behind it (fence by the arriving thread, cumulative through the block barrier).
+// phase_mask: bit 0 = A, bit 1 = B, bit 2 = C (an iteration followed by a residual reset runs A|B only, the reset kernels, then C).
+__device__ __forceinline__ void pcg_grid_barrier(int* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int gen = *reinterpret_cast<volatile int*>(bar + 1);
+    __threadfence();
+    if (atomicAdd(bar, 1) == (int)gridDim.x - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1);
+    } else {
+#ifndef TBA_EMULATE
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile int*>(bar + 1) == gen) {
+        if (clock64() - t0 > 4000000000ll) { printf("tba: grid barrier of the fused PCG kernel timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+      }
+#endif
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+struct PcgVectors {
+  const double *sm, *D2, *b, *Minv_c, *Minv_i;
+  double *p, *q, *x, *r, *z, *xs, *y;
+  double *part_pq, *part_Q, *part_rho;
+  double* fold_rep;  // shared-intrinsics replica rows folded by phase A (one GPU), or nullptr
+  int* zero_ctr;     // P2P counters of the next matvec, or nullptr
+  int* bar;          // [2] grid barrier
+  int identity_precond;
+};
+__global__ void __launch_bounds__(VT) k_pcg_fused(DevProblem P, const PcgState* __restrict__ in, PcgState* __restrict__ out, PcgVectors V,
+                                                  int phase_mask, int first, P2pDev pp) {
+  __shared__ double s_red[32];
+  __shared__ double s_fold[10];
+  PcgState st = *in;
+  if (st.done) {  // the state travels on (the next kernel reads *out)
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
+    return;
+  }
+  if (phase_mask & 1) {
+    pcg_phase_a(P.ncs, P.ne, V.y, V.sm, V.D2, V.p, V.q, V.part_pq, V.fold_rep, pp, s_red, s_fold);
+    if (phase_mask & 6) pcg_grid_barrier(V.bar);
+  }
+  if (phase_mask & 2) {
+    pcg_phase_b(P, st, V.part_pq, V.p, V.q, V.b, V.x, V.r, V.z, V.Minv_c, V.Minv_i, V.part_Q, V.part_rho, V.identity_precond, first,
+                (phase_mask & 1) ? V.fold_rep : nullptr, s_red);
+    if (!st.done && (phase_mask & 4)) pcg_grid_barrier(V.bar);
+  }
+  if ((phase_mask & 4) && !st.done) pcg_phase_c(P.ncs, st, V.part_Q, V.part_rho, V.z, V.sm, V.p, V.xs, V.y, V.zero_ctr, s_red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = st;
 }
 
 // Residual reset, second half, with the preconditioner applied to the fresh residual: r = b - (sm.*y + D2.*x); partial x.(b + r);

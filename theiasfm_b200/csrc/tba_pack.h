@@ -21,10 +21,11 @@ namespace tba {
 constexpr int kPackTile = 256;
 constexpr int kPackMaxPoints = 256;
 
+// grain: least number of items worth a thread of its own (8192 for per-observation loops; per-tile loops pass a small one)
 template <class F>
-void parallel_for(int64_t n, int nthreads, F f) {
+void parallel_for(int64_t n, int nthreads, F f, int64_t grain = 8192) {
   if (n <= 0) return;
-  const int T = (int)std::min<int64_t>(nthreads, (n + 8191) / 8192);
+  const int T = (int)std::min<int64_t>(nthreads, (n + grain - 1) / grain);
   if (T <= 1) { f((int64_t)0, n, 0); return; }
   std::vector<std::thread> th;
   const int64_t chunk = (n + T - 1) / T;
@@ -281,7 +282,7 @@ inline void pack_fill(const tba_problem* p, const HostPack& H, int T, const Pack
         }
       }
     }
-  });
+  }, /*grain: tiles*/ 32);
   if (d.slot_orig && tile_begin == 0 && tile_end == H.n_tiles) pack_slot_orig(H, T, d.slot_orig);
 }
 

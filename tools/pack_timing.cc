@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     const double t0 = now();
     pack_count_and_sort(&p, T, &H);
     const double t1 = now();
-    pack_points(&p, &H, false);
+    pack_points(&p, &H);
     std::vector<double> cnt_c(nc, 0.0), cnt_g(ng, 0.0);
     for (int i = 0; i < nc; ++i) { cnt_c[i] = H.cnt_cam[i]; cnt_g[cg[i]] += H.cnt_cam[i]; }
     pack_masks_and_tiles(&p, cnt_c, cnt_g, &H);
