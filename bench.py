@@ -99,7 +99,11 @@ def run_microbench(device):
     if v is None:
         return None
     ex = _microbench_call("tba_microbench_ex", 6, device)
+    gaps = _microbench_call("tba_microbench_gaps", 5, device)
     return {"fp64_fma_tflops": v[0], "fp64_red_gops": v[1], "gather48_grows": v[2],
+            # launch gaps (us): small kernel alone; 220 KB-shared-memory kernel spinning ~20 us alone; the pair big + small; the pair with
+            # the small kernel hinted to the maximum shared-memory carve-out; the pair with the small kernel launched with 220 KB itself
+            "launch_gap_us": dict(zip(("small", "big_20us", "big_plus_small", "big_plus_small_carveout_hint", "big_plus_small_same_smem"), gaps)) if gaps else None,
             # design questions for the next kernel generation (NOTES.md section 3): REDs emitted element-major (6 lanes per
             # 48-byte row), shared-memory fp64 atomicAdd (CAS loop), global REDs confined to a 1200-camera window per CTA
             "fp64_red_rows_gops": ex[0] if ex else None, "fp64_smem_atomic_gops": ex[1] if ex else None,

@@ -53,7 +53,7 @@ enum { cudaSuccess = 0, cudaErrorEmu = 1 };
 typedef struct emu_stream* cudaStream_t;
 typedef struct emu_event* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
-enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = std::getenv("TBA_EMU_DEVICES"); *n = e ? std::atoi(e) : 1; return cudaSuccess; }
 // 256-byte aligned like the real allocator (vector accesses of the kernels rely on it), zero-filled like calloc was

@@ -1240,6 +1240,18 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
     DISPATCH_IMASK(c->imask, F)
 #undef F
   }
+  {
+    // The small kernels that alternate with the 220 KB-shared-memory streaming kernels inside the CG loop ask for the same (maximum)
+    // shared-memory carve-out, so that the SMs are not reconfigured between L1-heavy and shared-memory-heavy twice per CG iteration
+    // (launch_gap_us of bench.py's microbench measures that switch); TBA_CARVEOUT=0 leaves the driver's default.
+    const char* e = getenv("TBA_CARVEOUT");
+    const int pct = (e != nullptr && e[0] == '0') ? -1 : 100;
+#define HINT(k) CUDA_OK(c, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
+    HINT(k_pcg_fused); HINT(k_pcg_a); HINT(k_pcg_b); HINT(k_pcg_c); HINT(k_pcg_finalize); HINT(k_pcg_reset_a); HINT(k_pcg_reset_bz);
+    HINT(k_zero_rep_cols); HINT(k_fold); HINT(k_pcg_init); HINT(k_pcg_init_state); HINT(k_set_flag); HINT(k_cs_mul); HINT(k_cs_diag);
+    HINT(k_precond_finish); HINT(k_candidate_cs);
+#undef HINT
+  }
   c->n_normal_tiles = 0;
   for (int t = 0; t < n_tiles; ++t) c->n_normal_tiles += (tile_flags[t] & 1) ? 0 : 1;
   {

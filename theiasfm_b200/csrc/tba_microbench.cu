@@ -235,3 +235,63 @@ extern "C" int tba_microbench_ex(int device, double* out6) {
   for (int i = 0; i < 6; ++i) out3[i] = best[i];
   return 0;
 }
+
+// ---- launch-gap microbenchmark: what does a CG iteration pay for alternating a persistent 220 KB-shared-memory kernel (the matvec)
+// with small vector kernels?  All kernels are empty (one store by one thread), queued back to back on the default stream.
+// out[0] = us per launch, small kernel alone (64 x 256, no shared memory);  out[1] = us per launch, big kernel alone (one CTA per SM,
+// 384 threads, 220 KB dynamic shared memory, every CTA spinning for 40000 cycles ~ 20 us so that the host stays ahead);  out[2] = us per PAIR big + small;  out[3] = the same pair with the small kernel hinted
+// to the maximum shared-memory carve-out (cudaFuncAttributePreferredSharedMemoryCarveout = 100: no L1 / shared reconfiguration between
+// the two);  out[4] = the same pair with the small kernel itself launched with 220 KB of dynamic shared memory.
+namespace {
+__global__ void k_gap_small(double* out) { if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 1.0; }
+__global__ void k_gap_small_hint(double* out) { if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = 1.0; }
+__global__ void k_gap_small_dyn(double* out) { extern __shared__ double sm_dyn[]; if (blockIdx.x == 0 && threadIdx.x == 0) { sm_dyn[0] = 2.0; out[2] = sm_dyn[0]; } }
+__global__ void k_gap_big(double* out, long long spin) {  // every CTA stays for `spin` cycles: the host stays ahead of the GPU with its launches
+  extern __shared__ double sm_big[];
+  if (threadIdx.x == 0) {
+    sm_big[0] = (double)blockIdx.x;
+    const long long t0 = clock64();
+    while (clock64() - t0 < spin) {}
+    if (blockIdx.x == 0) out[3] = sm_big[0];
+  }
+}
+}  // namespace
+
+extern "C" int tba_microbench_gaps(int device, double* out5) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -5;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int big_smem = 220 * 1024;
+  if (cudaFuncSetAttribute(k_gap_big, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gap_small_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gap_small_hint, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return -3;
+  double* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return -3;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int N = 2000;
+  double best[5] = {1e30, 1e30, 1e30, 1e30, 1e30};
+  for (int rep = 0; rep < 4; ++rep) {
+    for (int mode = 0; mode < 5; ++mode) {
+      cudaEventRecord(e0);
+      for (int i = 0; i < N; ++i) {
+        if (mode != 0) k_gap_big<<<sms, 384, big_smem>>>(d, 40000);
+        if (mode == 0 || mode == 2) k_gap_small<<<64, 256>>>(d);
+        if (mode == 3) k_gap_small_hint<<<64, 256>>>(d);
+        if (mode == 4) k_gap_small_dyn<<<64, 256, big_smem>>>(d);
+      }
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      const double us = time_ms(e0, e1) * 1e3 / N;
+      if (rep > 0 && us < best[mode]) best[mode] = us;
+    }
+  }
+  const cudaError_t err = cudaDeviceSynchronize();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) return -3;
+  for (int i = 0; i < 5; ++i) out5[i] = best[i];
+  return 0;
+}
