@@ -569,7 +569,7 @@ def main():
     # from further solves restarted at the initial estimate (each pays its own initial evaluation inside the timed region).
     eng.upload(shard, engine.default_options(**solver_kwargs(K)))  # same packing, K iterations
     eng.reset_parameters(init)
-    eng.set_profiling(True)
+    eng.set_profiling(os.environ.get("TBA_BENCH_NOPROF") is None)  # (TBA_BENCH_NOPROF=1: experiment -- what do the stage events cost? no roofline then)
     barrier()
     tw0 = time.time()
     t0 = time.perf_counter()

@@ -57,6 +57,12 @@ int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const 
  * and were scanned exhaustively by the exact pass.  All zero after a call that took the CUDA-core path. */
 void tbm_debug_last_timing(double* out4);
 
+/* Test hook: the exact re-evaluation kernel of the tensor-core path alone, on caller-made candidate lists (tests): descriptors
+ * [n_rows][128]; query i = row q_row[i] against rows [b_row0[i], b_row0[i] + b_rows[i]); cand [n_q][16] global row indices
+ * (-1 = empty slot; cand[i][0] == -2 or cand[i][8] == -2: scan every candidate of query i). */
+int tbm_debug_exact_top2(int device, const float* descriptors, int64_t n_rows, const int32_t* q_row, const int32_t* b_row0,
+                         const int32_t* b_rows, const int32_t* cand, int64_t n_q, int32_t* best_j, float* best_d, float* second_d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,7 @@ inline emu_dim3 threadIdx, blockIdx, blockDim, gridDim;  // set by the scheduler
 struct alignas(16) double2 { double x, y; };
 struct alignas(16) double4 { double x, y, z, w; };  // CUDA 12: __align__(16), two 128-bit accesses
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct alignas(16) float4 { float x, y, z, w; };
 template <class T> inline T __ldg(const T* p) { return *p; }
 
 using std::atan; using std::atan2; using std::cos; using std::fabs; using std::fmax; using std::fmin; using std::isfinite; using std::isinf; using std::isnan; using std::sin;
@@ -110,6 +111,7 @@ template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int attr, int v)
 // ---------------------------------------------------------------- device intrinsics without synchronisation
 inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }  // volatile: no contraction into an FMA

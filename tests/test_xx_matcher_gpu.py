@@ -76,3 +76,41 @@ def test_tensor_core_path_equals_the_exact_kernel_at_sift_size(monkeypatch):
         for p in range(len(pairs)):
             assert res_t[p] == res_e[p], (kw, pairs[p], len(res_t[p]), len(res_e[p]))
     assert sum(len(r) for r in res_t) > 5000
+
+
+def test_exact_pass_with_overflowed_queries_equals_the_sequential_scan():
+    """k_exact_top2 alone (tbm_debug_exact_top2) on hand-made candidate lists: queries whose lists hold the true two nearest plus decoys,
+    queries flagged as overflowed in either column half (scanned exhaustively by the whole CTA through shared memory: candidate counts
+    that are not multiples of the 64-row tiles, several overflowed queries in one CTA, an image with a single descriptor), duplicate rows
+    (equal distances: the lower index wins).  Reference: float32 accumulation term by term without FMA (distance.h:52-56)."""
+    from test_matcher_host import _nn2_float32
+    rng = np.random.default_rng(11)
+    nA, nB, nC = 70, 333, 1
+    D = np.abs(rng.normal(size=(nA + nB + nC, 128))).astype(np.float32)
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    D[nA + 200] = D[nA + 17]                                 # duplicate candidate rows
+    A, B, Cc = D[:nA], D[nA:nA + nB], D[nA + nB:]
+    bj, bd, sd = _nn2_float32(A, B)
+    order = np.argsort(((A[:, None, :] - B[None, :, :]) ** 2).sum(-1), axis=1, kind="stable")
+    q_row = np.arange(nA, dtype=np.int32)
+    b_row0 = np.full(nA, nA, np.int32); b_rows = np.full(nA, nB, np.int32)
+    cand = np.full((nA, 16), -1, np.int32)
+    for i in range(nA):
+        true2 = order[i, :2] + nA
+        decoys = rng.choice(nB, 5, replace=False) + nA
+        slots = rng.permutation(16)[:7]
+        cand[i, slots] = np.concatenate([true2, decoys])
+    ovf = [3, 5, 6, 31, 32, 40, 69]                          # 3, 5, 6, 31: four overflowed queries in the first CTA
+    for k, i in enumerate(ovf):
+        cand[i, :] = -1
+        cand[i, 0 if k % 2 == 0 else 8] = -2
+    # the last query runs against the one-descriptor image
+    q_row = np.concatenate([q_row, [5]]).astype(np.int32); b_row0 = np.concatenate([b_row0, [nA + nB]]).astype(np.int32)
+    b_rows = np.concatenate([b_rows, [1]]).astype(np.int32)
+    last = np.full((1, 16), -1, np.int32); last[0, 8] = -2
+    cand = np.concatenate([cand, last])
+    rc, gj, gd, gs = matcher.exact_top2(D, q_row, b_row0, b_rows, cand)
+    assert rc == 0
+    assert np.array_equal(gj[:nA], bj) and np.array_equal(gd[:nA], bd) and np.array_equal(gs[:nA], sd)
+    j1, d1, _ = _nn2_float32(A[5:6], Cc)
+    assert gj[nA] == 0 and gd[nA] == d1[0] and gs[nA] == 0.0

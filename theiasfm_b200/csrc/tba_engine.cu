@@ -150,6 +150,7 @@ struct tba_context {
   bool has_ext_models = false;  // some group uses FISHEYE / FOV / DIVISION_UNDISTORTION: EXT kernel instantiations
   bool exp_tred = true;     // transposed RED emission (warp_red_rows) in k_linearize / k_precond_ext / rhs / matvec; TBA_TRED=0: the round-1 lane-per-row REDs
   bool exp_lin_occ = true;  // k_linearize compiled for 3 CTAs/SM (80 registers, ~130 bytes of spills); TBA_LIN_OCC=2: 2 CTAs/SM, 128 registers
+  double trace_pcg_gpu_ms = 0.0;  // TBA_TRACE_LM: device-side span of the PCG launches (first launch .. state copy), summed over a minimize
   bool pcg_fused = true;    // one vector kernel per CG iteration (k_pcg_fused, grid barriers between its phases); TBA_PCG=split: k_pcg_c / k_pcg_a / k_pcg_b
   bool stream_schur = true; // persistent streaming k_schur_stream over the normal tiles; TBA_MATVEC=tile: the tile-per-CTA k_schur everywhere
   int n_normal_tiles = 0;   // tiles whose tracks fit a warp slice (they precede the long tiles)
@@ -585,6 +586,9 @@ int stage_pcg(tba_context* c, int* iters, int* status, bool* system_ok = nullptr
   double* part_pq = c->part.p + VB;
   double* part_Q = c->part.p + 2 * VB;
   PcgState* st = c->st.p;
+  static const bool trace = getenv("TBA_TRACE_LM") != nullptr;
+  cudaEvent_t tev[2] = {nullptr, nullptr};
+  if (trace) { cudaEventCreate(&tev[0]); cudaEventCreate(&tev[1]); cudaEventRecord(tev[0], c->stream); }
   LAUNCH(c, k_pcg_init_state, 1, 1, 0, st, c->part.p, o.min_linear_solver_iterations, o.max_linear_solver_iterations, o.eta);
   LAUNCH(c, k_set_flag, 1, 1, 0, c->done_flag.p, 0);
   if (c->n_free_cs == 0) {  // no reduced system: back-substitution only
@@ -658,7 +662,9 @@ int stage_pcg(tba_context* c, int* iters, int* status, bool* system_ok = nullptr
     cur ^= 1;
     CUDA_OK(c, cudaMemcpyAsync(c->h_st, st + cur, sizeof(PcgState), cudaMemcpyDeviceToHost, c->stream));
     if (system_ok) CUDA_OK(c, cudaMemcpyAsync(c->h_scal, c->flag.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (trace) cudaEventRecord(tev[1], c->stream);
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (trace) { float ms = 0; if (cudaEventElapsedTime(&ms, tev[0], tev[1]) == cudaSuccess) c->trace_pcg_gpu_ms += ms; cudaEventRecord(tev[0], c->stream); }
     if (system_ok) {
       *system_ok = c->h_scal[0] == 0.0;
       if (!*system_ok) { *iters = 0; *status = 0; return TBA_OK; }  // not positive definite: whatever the iterations did is discarded
@@ -667,6 +673,7 @@ int stage_pcg(tba_context* c, int* iters, int* status, bool* system_ok = nullptr
     if (it > o.max_linear_solver_iterations + batch) { set_err(c, "PCG did not terminate"); return TBA_ERR_CUDA; }
     batch = 4;
   }
+  if (trace) { cudaEventDestroy(tev[0]); cudaEventDestroy(tev[1]); }
   c->last_cg_iters = c->h_st->iters;
   *iters = c->h_st->iters;
   *status = c->h_st->status;
@@ -1188,9 +1195,11 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
       H2D_RANGE(slot_cam, h_slot_cam, s0, ns); H2D_RANGE(slot_pt, h_slot_pt, s0, ns);
       H2D_RANGE(slot_flags, h_slot_flags, s0, ns); H2D_RANGE(slot_run, h_slot_run, s0, ns);
       H2D_RANGE(xy, h_xy, s0 * 2, ns * 2);
-      H2D_RANGE(pt, h_pt, q0 * 4, nq * 4); H2D_RANGE(pt_c, h_pt, q0 * 4, nq * 4); H2D_RANGE(pt_const, h_pt_const, q0, nq);
+      H2D_RANGE(pt, h_pt, q0 * 4, nq * 4); H2D_RANGE(pt_const, h_pt_const, q0, nq);
     }
 #undef H2D_RANGE
+    // the candidate copy of the points starts as a device-to-device copy (one trip over PCIe instead of two)
+    if (npd > 0) CUDA_OK(c, cudaMemcpyAsync(c->pt_c.p, c->pt.p, (size_t)npd * 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   }
   lap("fill (E) + H2D enqueue");
   parallel_for(npd, T, [&](int64_t k0, int64_t k1, int) {
@@ -1239,18 +1248,6 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   CUDA_OK(c, cudaFuncSetAttribute(k_prepare_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrepCfg<M>::SMEM));
     DISPATCH_IMASK(c->imask, F)
 #undef F
-  }
-  {
-    // The small kernels that alternate with the 220 KB-shared-memory streaming kernels inside the CG loop ask for the same (maximum)
-    // shared-memory carve-out, so that the SMs are not reconfigured between L1-heavy and shared-memory-heavy twice per CG iteration
-    // (launch_gap_us of bench.py's microbench measures that switch); TBA_CARVEOUT=0 leaves the driver's default.
-    const char* e = getenv("TBA_CARVEOUT");
-    const int pct = (e != nullptr && e[0] == '0') ? -1 : 100;
-#define HINT(k) CUDA_OK(c, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
-    HINT(k_pcg_fused); HINT(k_pcg_a); HINT(k_pcg_b); HINT(k_pcg_c); HINT(k_pcg_finalize); HINT(k_pcg_reset_a); HINT(k_pcg_reset_bz);
-    HINT(k_zero_rep_cols); HINT(k_fold); HINT(k_pcg_init); HINT(k_pcg_init_state); HINT(k_set_flag); HINT(k_cs_mul); HINT(k_cs_diag);
-    HINT(k_precond_finish); HINT(k_candidate_cs);
-#undef HINT
   }
   c->n_normal_tiles = 0;
   for (int t = 0; t < n_tiles; ++t) c->n_normal_tiles += (tile_flags[t] & 1) ? 0 : 1;
@@ -1465,6 +1462,8 @@ done:
     double total = 0;
     for (double v : tr) total += v;
     for (int k = 0; k < 8; ++k) fprintf(stderr, "[tba_minimize r%d] %-14s %9.3f ms  (%5.1f %%)\n", c->rank, kStageName[k], tr[k] * 1e3, 100.0 * tr[k] / std::max(total, 1e-30));
+    fprintf(stderr, "[tba_minimize r%d] pcg, device-side span of its launches: %9.3f ms, CG iterations %d\n", c->rank, c->trace_pcg_gpu_ms, (int)s->num_linear_solver_iterations);
+    c->trace_pcg_gpu_ms = 0.0;
   }
   s->termination_type = term;
   s->success = term != TBA_FAILURE;

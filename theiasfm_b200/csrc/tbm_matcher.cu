@@ -10,8 +10,9 @@
 #include "../../include/theia_matcher_b200.h"
 #include "tbm_top2.h"
 #include "tbm_decide.cuh"       // MatchImagePair's decisions on the device (ratio test, early exits, IntersectMatches)
+#include "tbm_exact.cuh"        // exact re-evaluation of the tensor-core path's candidates (plain CUDA: in both builds)
 #ifndef TBA_EMULATE
-#include "tbm_matcher_tc.cuh"   // tcgen05 / TMA path (sm_100a); the SIMT emulation build keeps the exact CUDA-core kernel only
+#include "tbm_matcher_tc.cuh"   // tcgen05 / TMA path (sm_100a); the SIMT emulation build keeps the exact CUDA-core kernels only
 #endif
 #include <cstdlib>
 
@@ -185,6 +186,34 @@ extern "C" {
 void tbm_options_init(tbm_options* o) { o->keep_only_symmetric_matches = 1; o->use_lowes_ratio = 1; o->lowes_ratio = 0.8f; o->min_num_feature_matches = 30; }
 
 void tbm_debug_last_timing(double* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_last_timing[i]; }
+
+// Test hook: the exact pass of the tensor-core path alone (k_exact_top2) on caller-made candidate lists.  descriptors [n_rows][128];
+// query i = row q_row[i] against rows [b_row0[i], b_row0[i] + b_rows[i]); cand [n_q][16] global row indices, -1 = empty slot,
+// cand[i][0] or cand[i][8] == -2: exhaustive scan of that query.  Returns 0 or a negative tbm code.
+int tbm_debug_exact_top2(int device, const float* descriptors, int64_t n_rows, const int32_t* q_row, const int32_t* b_row0, const int32_t* b_rows,
+                         const int32_t* cand, int64_t n_q, int32_t* best_j, float* best_d, float* second_d) {
+  if (!descriptors || !q_row || !b_row0 || !b_rows || !cand || !best_j || !best_d || !second_d || n_rows <= 0 || n_q <= 0) return -1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return -5; }
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  using namespace tbm_tc;
+  DevF d_desc, d_bd, d_sd;
+  DevI d_q, d_b0, d_bn, d_cand, d_bj;
+  if (!d_desc.alloc((size_t)n_rows * DIM) || !d_bd.alloc((size_t)n_q) || !d_sd.alloc((size_t)n_q) || !d_q.alloc((size_t)n_q) || !d_b0.alloc((size_t)n_q) ||
+      !d_bn.alloc((size_t)n_q) || !d_cand.alloc((size_t)n_q * KC) || !d_bj.alloc((size_t)n_q)) return -3;
+  if (cudaMemcpy(d_desc.p, descriptors, (size_t)n_rows * DIM * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d_q.p, q_row, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d_b0.p, b_row0, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d_bn.p, b_rows, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d_cand.p, cand, (size_t)n_q * KC * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+  TBM_LAUNCH(k_exact_top2, (unsigned)((n_q + 31) / 32), 256, 0, d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p, d_sd.p,
+             (unsigned long long*)nullptr);
+  if (cudaPeekAtLastError() != cudaSuccess) return -3;
+  if (cudaMemcpy(best_j, d_bj.p, (size_t)n_q * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(best_d, d_bd.p, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(second_d, d_sd.p, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+  return 0;
+}
 
 int tbm_debug_postprocess(const int32_t* f_best_j, const float* f_best_d, const float* f_second_d, int32_t n1, int f_second_valid,
                           const int32_t* r_best_j, const float* r_best_d, const float* r_second_d, int32_t n2, int r_second_valid,

@@ -25,15 +25,13 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "tbm_exact.cuh"  // DIM, KC, ET, kOverflow + the exact re-evaluation kernel (plain CUDA, shared with the emulation build)
+
 namespace tbm_tc {
 
 constexpr int BM = 128;        // query rows per work item (= TMEM lanes)
 constexpr int BN = 128;        // candidate rows per tile (= accumulator columns)
-constexpr int DIM = 128;       // descriptor length (SIFT); 4 swizzle atoms of 32 floats
-constexpr int KC = 16;         // candidate slots per query handed to the exact pass (-1 = empty; typically 2..4 are filled)
-constexpr int ET = 8;          // threads per query in the exact pass
 constexpr int CAP = 15;        // list slots per (query, column half) in shared memory: 12 usable (a list that reaches slot 11 => exact full scan of that query) + 3 spare behind them (pointer clamped once per four appends)
-constexpr int kOverflow = -2;  // cand[q*KC] marker: the exact pass scans every candidate of this query
 constexpr int ATOM_BYTES = BM * 128;              // one 128-row x 128-byte swizzle-atom panel
 constexpr int TILE_BYTES = 4 * ATOM_BYTES;        // 64 KB: a 128 x 128 float tile
 constexpr int NSTAGE = 2;
@@ -351,82 +349,6 @@ __global__ void k_row_norms(const float* __restrict__ d, long long n_rows, float
   }
   nrm[r] = s;
   if (mn < 0.0f) *any_negative = 1;
-}
-
-// ------------------------------------------------------------------ pass 2: exact top-2 among the candidates
-// One thread per (query, candidate): the exact squared distance -- float, term by term, no fused multiply-add: L2::operator()
-// (distance.h:52-56) as the oracle and k_nn2 evaluate it; then thread 0 of the query picks the best two (ties: lower index).
-// q_row[i] = global descriptor row of query i, b_row0[i] / b_rows[i] = first row / number of rows of the candidate image (indices are
-// reported relative to b_row0).  A query whose candidate ring overflowed in pass 1 (cand[i*KC] == kOverflow) is scanned exhaustively.
-// exact squared distance, float, term by term in index order without fused multiply-add (128-bit loads, same arithmetic)
-__device__ __forceinline__ float exact_sqdist(const float* __restrict__ a, const float* __restrict__ b) {
-  const float4* a4 = reinterpret_cast<const float4*>(a);
-  const float4* b4 = reinterpret_cast<const float4*>(b);
-  float s = 0.0f;
-#pragma unroll 8
-  for (int k = 0; k < DIM / 4; ++k) {
-    const float4 x = __ldg(a4 + k), y = __ldg(b4 + k);
-    float df = __fsub_rn(x.x, y.x); s = __fadd_rn(s, __fmul_rn(df, df));
-    df = __fsub_rn(x.y, y.y); s = __fadd_rn(s, __fmul_rn(df, df));
-    df = __fsub_rn(x.z, y.z); s = __fadd_rn(s, __fmul_rn(df, df));
-    df = __fsub_rn(x.w, y.w); s = __fadd_rn(s, __fmul_rn(df, df));
-  }
-  return s;
-}
-// lexicographic (distance, index) order: what MatchImagePair's partial_sort over index-ordered candidates yields
-__device__ __forceinline__ void top2_take(int& bj, float& bd, int& sj, float& sd, int jj, float dd) {
-  if (jj < 0) return;
-  if (bj < 0 || dd < bd || (dd == bd && jj < bj)) { sj = bj; sd = bd; bj = jj; bd = dd; }
-  else if (sj < 0 || dd < sd || (dd == sd && jj < sj)) { sj = jj; sd = dd; }
-}
-__global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
-                                                    const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
-                                                    int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
-                                                    unsigned long long* __restrict__ n_exhaustive) {
-  __shared__ float s_d[32][ET], s_d2[32][ET];
-  __shared__ int s_j[32][ET], s_j2[32][ET];
-  const int ql = threadIdx.x / ET, c = threadIdx.x % ET;
-  const long long qi = (long long)blockIdx.x * 32 + ql;
-  int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
-  if (qi < n_q) {
-    const float* a = d + (size_t)q_row[qi] * DIM;
-    const int base = b_row0[qi];
-    if (cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow) {
-      // the candidate list of this query overflowed: exhaustive scan, thread c takes candidates c, c + ET, ...; four independent
-      // summation chains per thread (each in the reference's term order), 128-bit loads of the candidate rows
-      const int nb = b_rows[qi];
-      if (c == 0 && n_exhaustive) atomicAdd(n_exhaustive, 1ull);
-      const float4* a4 = reinterpret_cast<const float4*>(a);
-      int j = c;
-      for (; j + 3 * ET < nb; j += 4 * ET) {
-        const float4* b0 = reinterpret_cast<const float4*>(d + (size_t)(base + j) * DIM);
-        const float4* b1 = b0 + (size_t)ET * (DIM / 4); const float4* b2 = b1 + (size_t)ET * (DIM / 4); const float4* b3 = b2 + (size_t)ET * (DIM / 4);
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll 4
-        for (int k = 0; k < DIM / 4; ++k) {
-          const float4 av = __ldg(a4 + k), v0 = __ldg(b0 + k), v1 = __ldg(b1 + k), v2 = __ldg(b2 + k), v3 = __ldg(b3 + k);
-#define TBM_STEP(S, V) { float df = __fsub_rn(av.x, V.x); S = __fadd_rn(S, __fmul_rn(df, df)); df = __fsub_rn(av.y, V.y); S = __fadd_rn(S, __fmul_rn(df, df)); \
-                         df = __fsub_rn(av.z, V.z); S = __fadd_rn(S, __fmul_rn(df, df)); df = __fsub_rn(av.w, V.w); S = __fadd_rn(S, __fmul_rn(df, df)); }
-          TBM_STEP(s0, v0) TBM_STEP(s1, v1) TBM_STEP(s2, v2) TBM_STEP(s3, v3)
-#undef TBM_STEP
-        }
-        top2_take(bj, bd, sj, sd, j, s0); top2_take(bj, bd, sj, sd, j + ET, s1); top2_take(bj, bd, sj, sd, j + 2 * ET, s2); top2_take(bj, bd, sj, sd, j + 3 * ET, s3);
-      }
-      for (; j < nb; j += ET) top2_take(bj, bd, sj, sd, j, exact_sqdist(a, d + (size_t)(base + j) * DIM));
-    } else {
-      for (int k = c; k < KC; k += ET) {
-        const int j = cand[qi * KC + k];
-        if (j >= 0) top2_take(bj, bd, sj, sd, j - base, exact_sqdist(a, d + (size_t)j * DIM));
-      }
-    }
-  }
-  s_d[ql][c] = bd; s_j[ql][c] = bj; s_d2[ql][c] = sd; s_j2[ql][c] = sj;
-  __syncthreads();
-  if (c == 0 && qi < n_q) {
-    int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
-    for (int k = 0; k < ET; ++k) { top2_take(fj, fd, gj, gd, s_j[ql][k], s_d[ql][k]); top2_take(fj, fd, gj, gd, s_j2[ql][k], s_d2[ql][k]); }
-    best_j[qi] = fj; best_d[qi] = fd; second_d[qi] = gj >= 0 ? gd : 0.0f;
-  }
 }
 
 // ------------------------------------------------------------------ host helpers

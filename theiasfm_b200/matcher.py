@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtheia_matcher_b200.so")
 _LIB = None
-EXPORTED_SYMBOLS = ["tbm_options_init", "tbm_match_all", "tbm_debug_postprocess", "tbm_debug_last_timing"]
+EXPORTED_SYMBOLS = ["tbm_options_init", "tbm_match_all", "tbm_debug_postprocess", "tbm_debug_last_timing", "tbm_debug_exact_top2"]
 
 
 class tbm_match(C.Structure):
@@ -34,6 +34,7 @@ def lib():
                                             C.POINTER(tbm_match), ip]
         L.tbm_debug_last_timing.argtypes = [C.POINTER(C.c_double)]
         L.tbm_debug_last_timing.restype = None
+        L.tbm_debug_exact_top2.argtypes = [C.c_int, fp, C.c_int64, ip, ip, ip, ip, C.c_int64, ip, fp, fp]
         _LIB = L
     return _LIB
 
@@ -43,6 +44,19 @@ def last_timing():
     out = (C.c_double * 4)()
     lib().tbm_debug_last_timing(out)
     return {"gemm_ms": out[0], "exact_ms": out[1], "h2d_ms": out[2], "exhaustive_queries": out[3]}
+
+
+def exact_top2(descriptors, q_row, b_row0, b_rows, cand, device=0):
+    """tbm_debug_exact_top2: the exact re-evaluation kernel of the tensor-core path on hand-made candidate lists [n_q, 16]."""
+    d = np.ascontiguousarray(descriptors, np.float32)
+    q = np.ascontiguousarray(q_row, np.int32); b0 = np.ascontiguousarray(b_row0, np.int32); bn = np.ascontiguousarray(b_rows, np.int32)
+    cd = np.ascontiguousarray(cand, np.int32)
+    n = len(q)
+    bj = np.zeros(n, np.int32); bd = np.zeros(n, np.float32); sd = np.zeros(n, np.float32)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    rc = lib().tbm_debug_exact_top2(device, d.ctypes.data_as(fp), len(d), q.ctypes.data_as(ip), b0.ctypes.data_as(ip), bn.ctypes.data_as(ip),
+                                    cd.ctypes.data_as(ip), n, bj.ctypes.data_as(ip), bd.ctypes.data_as(fp), sd.ctypes.data_as(fp))
+    return rc, bj, bd, sd
 
 
 def default_options(**kw):
