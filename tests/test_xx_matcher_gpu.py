@@ -100,6 +100,10 @@ def test_exact_pass_with_overflowed_queries_equals_the_sequential_scan():
         decoys = rng.choice(nB, 5, replace=False) + nA
         slots = rng.permutation(16)[:7]
         cand[i, slots] = np.concatenate([true2, decoys])
+    cand[10, :] = -1                                         # a query without candidates (the other image was empty in pass 1)
+    bj[10], bd[10], sd[10] = -1, 0.0, 0.0
+    cand[11, :] = -1; cand[11, 15] = order[11, 0] + nA       # a single candidate, in the last slot: no runner-up
+    bj[11], bd[11], sd[11] = order[11, 0], bd[11], 0.0
     ovf = [3, 5, 6, 31, 32, 40, 69]                          # 3, 5, 6, 31: four overflowed queries in the first CTA
     for k, i in enumerate(ovf):
         cand[i, :] = -1

@@ -1943,7 +1943,8 @@ __device__ __forceinline__ void pcg_phase_c(int ncs, PcgState& st, const double*
   }
   if (st.done) return;
   const bool first = st.iters == 1;
-  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
+#pragma unroll 4
+  for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {  // (unrolled: the loads of four trips in flight together)
     const double pv = first ? z[i] : z[i] + st.beta * p[i];
     p[i] = pv;
     xs[i] = sm[i] * pv;
@@ -1976,6 +1977,7 @@ __device__ __forceinline__ void pcg_phase_a(int ncs, int ne, double* __restrict_
     __syncthreads();
   }
   double acc = 0.0;
+#pragma unroll 4
   for (int i = blockIdx.x * VT + threadIdx.x; i < ncs; i += VB * VT) {
     const double yv = pp.world > 1 ? p2p_sum(pp, i) : ((fold_rep != nullptr && i >= ne && i < ne + 10) ? s_fold[i - ne] : y[i]);
     const double qv = sm[i] * yv + D2[i] * p[i];
