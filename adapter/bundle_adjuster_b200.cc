@@ -104,8 +104,9 @@ void BundleAdjusterB200::AddView(const ViewId view_id) {
     Track* track = reconstruction_->MutableTrack(track_id);
     B200_CHECK(track != nullptr, "track != NULL");
     if (!track->IsEstimated()) continue;                                  // :129-131
-    AddResidual(view_id, track_id);                                       // :134; the point stays constant (:137)
-  }                                                                       //       unless AddTrack makes it variable
+    AddResidual(view_id, track_id);                                       // :134
+    variable_tracks_.erase(track_id);                                     // SetTrackConstant :137 (re-freezes a track an earlier AddTrack
+  }                                                                       // made variable; a later AddTrack makes it variable again)
 }
 
 // bundle_adjuster.cc:141-180
@@ -123,6 +124,7 @@ void BundleAdjusterB200::AddTrack(const TrackId track_id) {
     constant_extrinsics_views_.emplace(view_id);                            // :168
     potentially_constant_camera_intrinsics_groups_.emplace(reconstruction_->CameraIntrinsicsGroupIdFromViewId(view_id));  // :173-175
   }
+  variable_tracks_.emplace(track_id);  // SetTrackVariable :178
 }
 
 void BundleAdjusterB200::Flatten(Flat* f, tba_options* o) const {
@@ -160,8 +162,9 @@ void BundleAdjusterB200::Flatten(Flat* f, tba_options* o) const {
       f->cam_group.push_back(git->second);
       for (int j = 0; j < Camera::kExtrinsicsSize; ++j) f->ext.push_back(camera->extrinsics()[j]);
       // SetCameraExtrinsicsParameterization, bundle_adjuster.cc:223-240; constant cameras :166-168
+      // (a view that AddTrack reached before AddView stays constant: call order, as in the reference)
       uint8_t c = 0;
-      if (!optimized_views_.count(view_id)) c = TBA_EXT_ALL_CONST;
+      if (constant_extrinsics_views_.count(view_id) || !optimized_views_.count(view_id)) c = TBA_EXT_ALL_CONST;
       else {
         if (options_.constant_camera_position) c |= TBA_EXT_POSITION_CONST;        // SubsetParameterization(6, {0,1,2})
         if (options_.constant_camera_orientation) c |= TBA_EXT_ORIENTATION_CONST;  // SubsetParameterization(6, {3,4,5})
@@ -174,7 +177,7 @@ void BundleAdjusterB200::Flatten(Flat* f, tba_options* o) const {
       pit = pt_of_track.emplace(track_id, static_cast<int32_t>(f->track_of_pt.size())).first;
       f->track_of_pt.push_back(track_id);
       for (int j = 0; j < 4; ++j) f->pt.push_back(track->MutablePoint()->data()[j]);
-      f->pt_const.push_back(optimized_tracks_.count(track_id) ? 0 : 1);  // SetTrackConstant :137 / SetTrackVariable :178
+      f->pt_const.push_back(variable_tracks_.count(track_id) ? 0 : 1);  // SetTrackConstant :137 / SetTrackVariable :178, last call wins
     }
     const Feature* feature = view->GetFeature(track_id);
     f->obs_cam.push_back(cit->second);

@@ -104,7 +104,9 @@ class BundleAdjusterB200 {
   std::unordered_set<TrackId> optimized_tracks_;
   std::unordered_set<CameraIntrinsicsGroupId> optimized_camera_intrinsics_groups_;
   std::unordered_set<CameraIntrinsicsGroupId> potentially_constant_camera_intrinsics_groups_;
-  std::unordered_set<ViewId> constant_extrinsics_views_;  // added through AddTrack only (bundle_adjuster.cc:166-168)
+  std::unordered_set<ViewId> constant_extrinsics_views_;  // reached through AddTrack before any AddView (bundle_adjuster.cc:166-168): the
+                                                          // reference's SetParameterBlockConstant is never undone, a later AddView included
+  std::unordered_set<TrackId> variable_tracks_;           // SetTrackVariable (:178) / SetTrackConstant (:137) in CALL ORDER: the last call wins
   std::vector<std::pair<ViewId, TrackId>> residuals_;     // in insertion order
   tba_summary last_summary_;
   std::vector<TrackId> resident_tracks_;  // point index -> TrackId of the problem left on the device by Optimize()

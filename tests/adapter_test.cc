@@ -152,6 +152,30 @@ static int TestFlatten() {
       }
     EXPECT(found_shared_const_cam);
   }
+  {
+    // --- call order (not how Theia's own callers use the class, but what the reference class does): AddTrack BEFORE AddView
+    BundleAdjusterB200 ba(IterativeOptions(), &sc.rec);
+    const TrackId t0 = sc.tracks[0];
+    ba.AddTrack(t0);                       // every view of t0 enters with constant extrinsics (:166-168), t0 variable (:178)
+    const ViewId v_late = *sc.rec.MutableTrack(t0)->ViewIds().begin();
+    ba.AddView(v_late);                    // the constant block stays constant; AddView re-freezes every track of the view (:137), t0 included
+    ba.AddTrack(sc.tracks[1]);             // tracks[1] variable again even if v_late observes it
+    BundleAdjusterB200::Flat f; tba_options o;
+    ba.Flatten(&f, &o);
+    bool saw_late = false;
+    for (size_t i = 0; i < f.view_of_cam.size(); ++i) if (f.view_of_cam[i] == v_late) { saw_late = true; EXPECT(f.ext_const[i] == TBA_EXT_ALL_CONST); }
+    EXPECT(saw_late);
+    size_t n_t0 = 0;
+    for (size_t q = 0; q < f.track_of_pt.size(); ++q) {
+      if (f.track_of_pt[q] == t0) { EXPECT(f.pt_const[q] == 1); ++n_t0; }
+      if (f.track_of_pt[q] == sc.tracks[1]) EXPECT(f.pt_const[q] == 0);
+    }
+    EXPECT(n_t0 == 1);
+    // the residual (v_late, t0) was added twice -- once by AddTrack, once by AddView -- exactly as the reference's problem holds it twice
+    size_t dup = 0;
+    for (size_t k = 0; k < f.obs_cam.size(); ++k) dup += f.view_of_cam[f.obs_cam[k]] == v_late && f.track_of_pt[f.obs_pt[k]] == t0;
+    EXPECT(dup == 2);
+  }
   std::printf("flatten ok\n");
   return 0;
 }
