@@ -55,18 +55,69 @@ __device__ __forceinline__ float smem_sqdist(const float* a, const float* b) {
   return s;
 }
 
-// One CTA = 32 queries.  Every descriptor row the CTA touches goes through SHARED MEMORY, fetched with coalesced 128-bit loads (32
-// consecutive threads = one 512-byte row) -- per-lane row loads (32 different rows per load instruction) made the first version of this
-// kernel LSU-bound (ncu: 93 % LSU wavefronts) and the exhaustive scans 85 % of its time:
-//   * the 32 query rows are staged once;
-//   * candidate slots are processed two per query at a time (64 rows, row stride 132 floats: conflict-free 128-bit reads by 64 threads,
-//     one row each, in the reference's term order); slot pairs that are empty for the whole CTA are skipped;
-//   * a query whose list overflowed in pass 1 (cand[q*KC] or cand[q*KC + KC/2] == kOverflow) is scanned exhaustively by the WHOLE CTA
-//     afterwards, 64 candidate rows per staged tile.
-// Dynamic shared memory: (XT + 32) * XS floats = kExactSmemBytes.
 constexpr int XT = 64;             // candidate rows per staged tile
-constexpr int XS = DIM + 4;        // padded row stride (floats)
-constexpr int kExactSmemBytes = (XT + 32) * XS * (int)sizeof(float);
+constexpr int XS = DIM + 4;        // padded row stride (floats): conflict-free 128-bit reads, one row per thread
+constexpr int kRowLoads = XT * (DIM / 4) / 256;   // 128-bit loads per thread and tile (8)
+
+// Tile staging in two steps so that the kRowLoads loads of a thread are in flight TOGETHER (a load-store loop would serialise them:
+// each store waits for its load): fetch into registers (32 consecutive threads = one 512-byte row: coalesced), then store.
+// row_of(r) -> global descriptor row of tile row r, or -1.
+template <class RowOf>
+__device__ __forceinline__ void tile_fetch(const float* __restrict__ d, RowOf row_of, float4 (&v)[kRowLoads]) {
+#pragma unroll
+  for (int u = 0; u < kRowLoads; ++u) {
+    const int e = (int)threadIdx.x + u * 256, r = e / (DIM / 4), k4 = e % (DIM / 4);
+    const long long j = row_of(r);
+    v[u] = j >= 0 ? __ldg(reinterpret_cast<const float4*>(d + (size_t)j * DIM) + k4) : float4{0.0f, 0.0f, 0.0f, 0.0f};
+  }
+}
+__device__ __forceinline__ void tile_store(float* s_rows, const float4 (&v)[kRowLoads]) {
+#pragma unroll
+  for (int u = 0; u < kRowLoads; ++u) {
+    const int e = (int)threadIdx.x + u * 256, r = e / (DIM / 4), k4 = e % (DIM / 4);
+    reinterpret_cast<float4*>(s_rows + r * XS)[k4] = v[u];
+  }
+}
+
+// Exhaustive scan of ONE query (row `a`, already in shared memory) against candidate rows [base, base + nb) by the whole CTA: tiles of
+// XT rows, the next tile's rows on their way into registers while the current tile is evaluated (one row per thread 0 .. XT-1, the
+// reference's term order), then a top-2 merge of the XT scanners.  All 256 threads must call it; m_* are [XT] scratch arrays.
+__device__ __forceinline__ void exhaustive_scan(const float* __restrict__ d, const float* s_a, float* s_rows, int base, int nb, float* m_d,
+                                                float* m_d2, int* m_j, int* m_j2, int* out_j, float* out_d, float* out_d2) {
+  const int tid = threadIdx.x;
+  int xbj = -1, xsj = -1; float xbd = 0.0f, xsd = 0.0f;
+  float4 v[kRowLoads];
+  tile_fetch(d, [&](int r) { return r < nb ? (long long)base + r : -1ll; }, v);
+  for (int r0 = 0; r0 < nb; r0 += XT) {
+    __syncthreads();  // the previous tile (or whatever used s_rows / m_* before) is consumed
+    tile_store(s_rows, v);
+    __syncthreads();
+    const int next = r0 + XT;
+    if (next < nb) tile_fetch(d, [&](int r) { return next + r < nb ? (long long)base + next + r : -1ll; }, v);
+    if (tid < XT && r0 + tid < nb) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
+  }
+  __syncthreads();
+  if (tid < XT) { m_d[tid] = xbd; m_j[tid] = xbj; m_d2[tid] = xsd; m_j2[tid] = xsj; }
+  __syncthreads();
+  if (tid == 0) {
+    int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
+    for (int k = 0; k < XT; ++k) { top2_take(fj, fd, gj, gd, m_j[k], m_d[k]); top2_take(fj, fd, gj, gd, m_j2[k], m_d2[k]); }
+    *out_j = fj; *out_d = fd; *out_d2 = gj >= 0 ? gd : 0.0f;
+  }
+}
+
+__device__ __forceinline__ bool list_overflowed(const int* __restrict__ cand, long long qi) {
+  return cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow;
+}
+
+constexpr int kExactSmemBytes = (XT + 32) * XS * (int)sizeof(float);  // dynamic shared memory of both kernels: [XT] candidate rows + [32] query rows
+
+// ---- variant "staged" (default): one CTA = 32 queries, EVERY descriptor row goes through shared memory with coalesced loads.
+// Per-lane row loads (32 different rows per load instruction) made the first version of this pass LSU-bound (ncu: 93 % LSU wavefronts):
+//   * the 32 query rows are staged once;
+//   * the listed candidates of the 32 queries are compacted into ONE dense work list (ballot / popc per query, prefix over the queries)
+//     and evaluated XT rows per tile, one row per thread; a per-query thread then picks its two best from its slice of the list;
+//   * a query whose list overflowed in pass 1 is scanned exhaustively by the whole CTA afterwards (exhaustive_scan).
 __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
                                                     const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
                                                     int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
@@ -76,96 +127,147 @@ __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d,
 #else
   extern __shared__ __align__(16) float smem[];
 #endif
-  float* s_rows = smem;             // [XT][XS] candidate rows of the current round / tile
-  float* s_q = smem + XT * XS;      // [32][XS] the CTA's query rows
+  float* s_rows = smem;             // [XT][XS]
+  float* s_q = smem + XT * XS;      // [32][XS]
   __shared__ float m_d[XT], m_d2[XT];
   __shared__ int m_j[XT], m_j2[XT];
-  __shared__ int s_rowj[XT];        // global descriptor row staged in s_rows[r], or -1
+  __shared__ int s_wj[32 * KC];     // dense work list: global descriptor row ...
+  __shared__ float s_wd[32 * KC];   // ... and its exact distance; the entries of query q are [s_off[q], s_off[q + 1]) in slot order
+  __shared__ unsigned char s_wq[32 * KC];
+  __shared__ int s_cnt[32], s_off[33];
   __shared__ int s_ovf[32];
   __shared__ int s_novf;
-  __shared__ int s_any[2];        // "this round has rows", double-buffered: a round without rows has no barrier behind the read
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const long long q0 = (long long)blockIdx.x * 32;
   const int nq_cta = (int)((n_q - q0) < 32 ? (n_q - q0) : 32);
   if (tid == 0) s_novf = 0;
-  // ---- the query rows
-  for (int e = tid; e < nq_cta * (DIM / 4); e += 256) {
-    const int r = e / (DIM / 4), k4 = e % (DIM / 4);
-    reinterpret_cast<float4*>(s_q + r * XS)[k4] = __ldg(reinterpret_cast<const float4*>(d + (size_t)q_row[q0 + r] * DIM) + k4);
+  // ---- the query rows (4 loads per thread, together in flight)
+  {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + u * 256, r = e / (DIM / 4), k4 = e % (DIM / 4);
+      v[u] = r < nq_cta ? __ldg(reinterpret_cast<const float4*>(d + (size_t)q_row[q0 + r] * DIM) + k4) : float4{0.0f, 0.0f, 0.0f, 0.0f};
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + u * 256, r = e / (DIM / 4), k4 = e % (DIM / 4);
+      reinterpret_cast<float4*>(s_q + r * XS)[k4] = v[u];
+    }
+  }
+  // ---- dense work list: entry e = (query e / 16, slot e % 16), two entries per thread; a warp covers two queries
+  int my_j[2], my_rank[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int e = it * 256 + tid, q = e >> 4, k = e & 15;
+    int j = -1;
+    if (q < nq_cta && !list_overflowed(cand, q0 + q)) j = cand[(q0 + q) * KC + k];
+    const unsigned b = __ballot_sync(0xffffffffu, j >= 0);
+    const unsigned m16 = (b >> (lane & 16)) & 0xFFFFu;
+    my_j[it] = j;
+    my_rank[it] = __popc(m16 & ((1u << (lane & 15)) - 1u));
+    if ((lane & 15) == 0) s_cnt[q] = __popc(m16);
+  }
+  __syncthreads();  // s_q, s_cnt, s_novf = 0
+  if (tid == 0) {
+    int o = 0;
+    for (int q = 0; q < 32; ++q) { s_off[q] = o; o += s_cnt[q]; }
+    s_off[32] = o;
+  }
+  if (tid < nq_cta && list_overflowed(cand, q0 + tid)) {
+    s_ovf[atomicAdd(&s_novf, 1)] = tid;
+    if (n_exhaustive) atomicAdd(n_exhaustive, 1ull);
   }
   __syncthreads();
-  if (tid < nq_cta) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int e = it * 256 + tid, q = e >> 4;
+    if (my_j[it] >= 0) { const int w = s_off[q] + my_rank[it]; s_wj[w] = my_j[it]; s_wq[w] = (unsigned char)q; }
+  }
+  __syncthreads();
+  const int n_work = s_off[32];
+  {
+    float4 v[kRowLoads];
+    if (n_work > 0) tile_fetch(d, [&](int r) { return r < n_work ? (long long)s_wj[r] : -1ll; }, v);
+    for (int w0 = 0; w0 < n_work; w0 += XT) {
+      __syncthreads();  // the previous tile is consumed
+      tile_store(s_rows, v);
+      __syncthreads();
+      const int next = w0 + XT;
+      if (next < n_work) tile_fetch(d, [&](int r) { return next + r < n_work ? (long long)s_wj[next + r] : -1ll; }, v);
+      if (tid < XT && w0 + tid < n_work) s_wd[w0 + tid] = smem_sqdist(s_q + (int)s_wq[w0 + tid] * XS, s_rows + tid * XS);
+    }
+  }
+  __syncthreads();
+  if (tid < nq_cta && !list_overflowed(cand, q0 + tid)) {
     const long long qi = q0 + tid;
-    if (cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow) {
-      s_ovf[atomicAdd(&s_novf, 1)] = tid;
-      if (n_exhaustive) atomicAdd(n_exhaustive, 1ull);
-    }
+    const int base = b_row0[qi];
+    int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
+    for (int w = s_off[tid]; w < s_off[tid + 1]; ++w) top2_take(fj, fd, gj, gd, s_wj[w] - base, s_wd[w]);
+    best_j[qi] = fj; best_d[qi] = fd; second_d[qi] = gj >= 0 ? gd : 0.0f;
   }
-  __syncthreads();
-  // ---- listed candidates: thread r < 64 owns (query r / 2, slots 2 g + (r & 1)) of every round g and keeps its own top-2
-  int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
-  int my_base = 0;
-  bool my_listed = false;
-  if (tid < XT && (tid >> 1) < nq_cta) {
-    const long long qi = q0 + (tid >> 1);
-    my_base = b_row0[qi];
-    my_listed = !(cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow);
-  }
-  for (int g = 0; g < KC / 2; ++g) {
-    if (tid == 0) s_any[g & 1] = 0;
-    __syncthreads();  // the rows of the previous round are consumed; the flag of this round reset
-    if (tid < XT) {
-      int j = -1;
-      if (my_listed) j = cand[(q0 + (tid >> 1)) * KC + 2 * g + (tid & 1)];
-      s_rowj[tid] = j;
-      if (j >= 0) s_any[g & 1] = 1;
-    }
-    __syncthreads();
-    if (!s_any[g & 1]) continue;  // (uniform: read after the barrier; the next write to this flag is two barriers away)
-    for (int e = tid; e < XT * (DIM / 4); e += 256) {
-      const int r = e / (DIM / 4), k4 = e % (DIM / 4);
-      const int j = s_rowj[r];
-      if (j >= 0) reinterpret_cast<float4*>(s_rows + r * XS)[k4] = __ldg(reinterpret_cast<const float4*>(d + (size_t)j * DIM) + k4);
-    }
-    __syncthreads();
-    if (tid < XT && s_rowj[tid] >= 0) top2_take(bj, bd, sj, sd, s_rowj[tid] - my_base, smem_sqdist(s_q + (tid >> 1) * XS, s_rows + tid * XS));
-  }
-  __syncthreads();
-  if (tid < XT) { m_d[tid] = bd; m_j[tid] = bj; m_d2[tid] = sd; m_j2[tid] = sj; }
-  __syncthreads();
-  if (tid < nq_cta) {
-    const long long qi = q0 + tid;
-    if (!(cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow)) {
-      int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
-      for (int k = 2 * tid; k < 2 * tid + 2; ++k) { top2_take(fj, fd, gj, gd, m_j[k], m_d[k]); top2_take(fj, fd, gj, gd, m_j2[k], m_d2[k]); }
-      best_j[qi] = fj; best_d[qi] = fd; second_d[qi] = gj >= 0 ? gd : 0.0f;
-    }
-  }
-  // ---- exhaustive scans, one overflowed query of this CTA after the other, all 256 threads
+  // ---- exhaustive scans, one overflowed query of this CTA after the other
   const int novf = s_novf;
   for (int o = 0; o < novf; ++o) {
     const int ql = s_ovf[o];
     const long long qx = q0 + ql;
-    const int base = b_row0[qx], nb = b_rows[qx];
-    int xbj = -1, xsj = -1; float xbd = 0.0f, xsd = 0.0f;
-    for (int r0 = 0; r0 < nb; r0 += XT) {
-      __syncthreads();  // the previous tile (or round, or merge) is consumed
-      const int rows = nb - r0 < XT ? nb - r0 : XT;
-      for (int e = tid; e < rows * (DIM / 4); e += 256) {
-        const int r = e / (DIM / 4), k4 = e % (DIM / 4);
-        reinterpret_cast<float4*>(s_rows + r * XS)[k4] = __ldg(reinterpret_cast<const float4*>(d + (size_t)(base + r0 + r) * DIM) + k4);
+    exhaustive_scan(d, s_q + ql * XS, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
+  }
+}
+
+// ---- variant "lanes" (TBM_EXACT=lanes; kept for the comparison in DESIGN.md): the listed candidates are read straight from global
+// memory, 8 threads per query, one candidate row per thread (32 different rows per load instruction: LSU-bound); exhaustive scans as above.
+constexpr int ET = 8;  // threads per query
+__global__ void __launch_bounds__(256) k_exact_top2_lanes(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
+                                                          const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
+                                                          int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
+                                                          unsigned long long* __restrict__ n_exhaustive) {
+#ifdef TBA_EMULATE
+  float* smem = emu::dyn_smem<float>();
+#else
+  extern __shared__ __align__(16) float smem[];
+#endif
+  float* s_rows = smem;
+  float* s_a = smem + XT * XS;
+  __shared__ float s_d[32][ET], s_d2[32][ET];
+  __shared__ int s_j[32][ET], s_j2[32][ET];
+  __shared__ float m_d[XT], m_d2[XT];
+  __shared__ int m_j[XT], m_j2[XT];
+  __shared__ int s_ovf[32];
+  __shared__ int s_novf;
+  const int ql = threadIdx.x / ET, c = threadIdx.x % ET;
+  const long long q0 = (long long)blockIdx.x * 32;
+  const long long qi = q0 + ql;
+  if (threadIdx.x == 0) s_novf = 0;
+  __syncthreads();
+  int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
+  bool overflowed = false;
+  if (qi < n_q) {
+    const float* a = d + (size_t)q_row[qi] * DIM;
+    const int base = b_row0[qi];
+    overflowed = list_overflowed(cand, qi);
+    if (overflowed) {
+      if (c == 0) { s_ovf[atomicAdd(&s_novf, 1)] = ql; if (n_exhaustive) atomicAdd(n_exhaustive, 1ull); }
+    } else {
+      for (int k = c; k < KC; k += ET) {
+        const int j = cand[qi * KC + k];
+        if (j >= 0) top2_take(bj, bd, sj, sd, j - base, exact_sqdist(a, d + (size_t)j * DIM));
       }
-      __syncthreads();
-      if (tid < rows) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_q + ql * XS, s_rows + tid * XS));
     }
-    __syncthreads();
-    if (tid < XT) { m_d[tid] = xbd; m_j[tid] = xbj; m_d2[tid] = xsd; m_j2[tid] = xsj; }
-    __syncthreads();
-    if (tid == 0) {
-      int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
-      for (int k = 0; k < XT; ++k) { top2_take(fj, fd, gj, gd, m_j[k], m_d[k]); top2_take(fj, fd, gj, gd, m_j2[k], m_d2[k]); }
-      best_j[qx] = fj; best_d[qx] = fd; second_d[qx] = gj >= 0 ? gd : 0.0f;
-    }
+  }
+  s_d[ql][c] = bd; s_j[ql][c] = bj; s_d2[ql][c] = sd; s_j2[ql][c] = sj;
+  __syncthreads();
+  if (c == 0 && qi < n_q && !overflowed) {
+    int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
+    for (int k = 0; k < ET; ++k) { top2_take(fj, fd, gj, gd, s_j[ql][k], s_d[ql][k]); top2_take(fj, fd, gj, gd, s_j2[ql][k], s_d2[ql][k]); }
+    best_j[qi] = fj; best_d[qi] = fd; second_d[qi] = gj >= 0 ? gd : 0.0f;
+  }
+  const int novf = s_novf;
+  for (int o = 0; o < novf; ++o) {
+    __syncthreads();  // s_a of the previous round consumed
+    const long long qx = q0 + s_ovf[o];
+    if (threadIdx.x < DIM / 4) reinterpret_cast<float4*>(s_a)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(d + (size_t)q_row[qx] * DIM) + threadIdx.x);
+    exhaustive_scan(d, s_a, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
   }
 }
 

@@ -171,6 +171,9 @@ int decide_and_fetch(DecideBuffers& B, const std::vector<tbm::PairSeg>& segs, lo
   return 0;
 }
 
+// TBM_EXACT=lanes: the exact pass reads the listed candidates with per-lane row loads (k_exact_top2_lanes) instead of staging them
+inline bool exact_variant_lanes() { const char* e = getenv("TBM_EXACT"); return e != nullptr && e[0] == 'l'; }
+
 // :58-59, :78-81: keep the best match when the ratio test is off, there is no second candidate, or it passes
 inline bool passes(const tbm_options* o, float best, float second, int second_valid) {
   if (!o->use_lowes_ratio || !second_valid) return true;
@@ -206,9 +209,14 @@ int tbm_debug_exact_top2(int device, const float* descriptors, int64_t n_rows, c
       cudaMemcpy(d_b0.p, b_row0, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d_bn.p, b_rows, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d_cand.p, cand, (size_t)n_q * KC * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
-  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
-  TBM_LAUNCH(k_exact_top2, (unsigned)((n_q + 31) / 32), 256, kExactSmemBytes, d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p, d_sd.p,
-             (unsigned long long*)nullptr);
+  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_exact_top2_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
+  if (exact_variant_lanes())
+    TBM_LAUNCH(k_exact_top2_lanes, (unsigned)((n_q + 31) / 32), 256, kExactSmemBytes, d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p,
+               d_sd.p, (unsigned long long*)nullptr);
+  else
+    TBM_LAUNCH(k_exact_top2, (unsigned)((n_q + 31) / 32), 256, kExactSmemBytes, d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p, d_sd.p,
+               (unsigned long long*)nullptr);
   if (cudaPeekAtLastError() != cudaSuccess) return -3;
   if (cudaMemcpy(best_j, d_bj.p, (size_t)n_q * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
       cudaMemcpy(best_d, d_bd.p, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -273,7 +281,8 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   unsigned long long* d_nex = nullptr;  // queries handed to the exhaustive exact scan (diagnostics: tbm_debug_last_timing)
   if (cudaMalloc(&d_nex, 8) != cudaSuccess || cudaMemset(d_nex, 0, 8) != cudaSuccess) return -3;
   struct NexGuard { unsigned long long* p; ~NexGuard() { cudaFree(p); } } nex_guard{d_nex};
-  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_exact_top2_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_nn_candidates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(k_nn_candidates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
   Dev<WorkItem> d_items;
@@ -336,7 +345,10 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
         cudaEventRecord(ev[3]);
       }
       cudaEventRecord(ev[4]);
-      k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256, kExactSmemBytes>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
+      if (exact_variant_lanes())
+        k_exact_top2_lanes<<<(unsigned)((nq_chunk + 31) / 32), 256, kExactSmemBytes>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
+      else
+        k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256, kExactSmemBytes>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
       if (cudaPeekAtLastError() != cudaSuccess) return -3;
       cudaEventRecord(ev[5]);
     }
