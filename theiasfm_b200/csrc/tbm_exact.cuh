@@ -82,19 +82,34 @@ __device__ __forceinline__ void tile_store(float* s_rows, const float4 (&v)[kRow
 // Exhaustive scan of ONE query (row `a`, already in shared memory) against candidate rows [base, base + nb) by the whole CTA: tiles of
 // XT rows, the next tile's rows on their way into registers while the current tile is evaluated (one row per thread 0 .. XT-1, the
 // reference's term order), then a top-2 merge of the XT scanners.  All 256 threads must call it; m_* are [XT] scratch arrays.
+// PIPE = false: the plain version (load-store loop per tile, no prefetch) -- kept selectable (TBM_EXH=simple) while the two are compared.
+template <bool PIPE>
 __device__ __forceinline__ void exhaustive_scan(const float* __restrict__ d, const float* s_a, float* s_rows, int base, int nb, float* m_d,
                                                 float* m_d2, int* m_j, int* m_j2, int* out_j, float* out_d, float* out_d2) {
   const int tid = threadIdx.x;
   int xbj = -1, xsj = -1; float xbd = 0.0f, xsd = 0.0f;
-  float4 v[kRowLoads];
-  tile_fetch(d, [&](int r) { return r < nb ? (long long)base + r : -1ll; }, v);
-  for (int r0 = 0; r0 < nb; r0 += XT) {
-    __syncthreads();  // the previous tile (or whatever used s_rows / m_* before) is consumed
-    tile_store(s_rows, v);
-    __syncthreads();
-    const int next = r0 + XT;
-    if (next < nb) tile_fetch(d, [&](int r) { return next + r < nb ? (long long)base + next + r : -1ll; }, v);
-    if (tid < XT && r0 + tid < nb) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
+  if (PIPE) {
+    float4 v[kRowLoads];
+    tile_fetch(d, [&](int r) { return r < nb ? (long long)base + r : -1ll; }, v);
+    for (int r0 = 0; r0 < nb; r0 += XT) {
+      __syncthreads();  // the previous tile (or whatever used s_rows / m_* before) is consumed
+      tile_store(s_rows, v);
+      __syncthreads();
+      const int next = r0 + XT;
+      if (next < nb) tile_fetch(d, [&](int r) { return next + r < nb ? (long long)base + next + r : -1ll; }, v);
+      if (tid < XT && r0 + tid < nb) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
+    }
+  } else {
+    for (int r0 = 0; r0 < nb; r0 += XT) {
+      __syncthreads();
+      const int rows = nb - r0 < XT ? nb - r0 : XT;
+      for (int e = tid; e < rows * (DIM / 4); e += 256) {
+        const int r = e / (DIM / 4), k4 = e % (DIM / 4);
+        reinterpret_cast<float4*>(s_rows + r * XS)[k4] = __ldg(reinterpret_cast<const float4*>(d + (size_t)(base + r0 + r) * DIM) + k4);
+      }
+      __syncthreads();
+      if (tid < rows) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
+    }
   }
   __syncthreads();
   if (tid < XT) { m_d[tid] = xbd; m_j[tid] = xbj; m_d2[tid] = xsd; m_j2[tid] = xsj; }
@@ -118,6 +133,7 @@ constexpr int kExactSmemBytes = (XT + 32) * XS * (int)sizeof(float);  // dynamic
 //   * the listed candidates of the 32 queries are compacted into ONE dense work list (ballot / popc per query, prefix over the queries)
 //     and evaluated XT rows per tile, one row per thread; a per-query thread then picks its two best from its slice of the list;
 //   * a query whose list overflowed in pass 1 is scanned exhaustively by the whole CTA afterwards (exhaustive_scan).
+template <bool PIPE>
 __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
                                                     const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
                                                     int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
@@ -211,13 +227,15 @@ __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d,
   for (int o = 0; o < novf; ++o) {
     const int ql = s_ovf[o];
     const long long qx = q0 + ql;
-    exhaustive_scan(d, s_q + ql * XS, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
+    exhaustive_scan<PIPE>(d, s_q + ql * XS, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
   }
 }
 
 // ---- variant "lanes" (TBM_EXACT=lanes; kept for the comparison in DESIGN.md): the listed candidates are read straight from global
 // memory, 8 threads per query, one candidate row per thread (32 different rows per load instruction: LSU-bound); exhaustive scans as above.
 constexpr int ET = 8;  // threads per query
+constexpr int kLanesSmemBytes = (XT * XS + DIM) * (int)sizeof(float);  // candidate tile + one query row
+template <bool PIPE>
 __global__ void __launch_bounds__(256) k_exact_top2_lanes(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
                                                           const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
                                                           int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(256) k_exact_top2_lanes(const float* __restric
     __syncthreads();  // s_a of the previous round consumed
     const long long qx = q0 + s_ovf[o];
     if (threadIdx.x < DIM / 4) reinterpret_cast<float4*>(s_a)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(d + (size_t)q_row[qx] * DIM) + threadIdx.x);
-    exhaustive_scan(d, s_a, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
+    exhaustive_scan<PIPE>(d, s_a, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
   }
 }
 

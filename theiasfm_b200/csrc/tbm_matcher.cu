@@ -173,6 +173,32 @@ int decide_and_fetch(DecideBuffers& B, const std::vector<tbm::PairSeg>& segs, lo
 
 // TBM_EXACT=lanes: the exact pass reads the listed candidates with per-lane row loads (k_exact_top2_lanes) instead of staging them
 inline bool exact_variant_lanes() { const char* e = getenv("TBM_EXACT"); return e != nullptr && e[0] == 'l'; }
+// TBM_EXH=simple: exhaustive scans with the plain load-store loop per tile instead of the register-staged, prefetching one
+inline bool exhaustive_simple() { const char* e = getenv("TBM_EXH"); return e != nullptr && e[0] == 's'; }
+
+// launches the selected variant of the exact pass on the current stream
+#ifdef TBA_EMULATE
+#define TBM_EXACT_LAUNCH(K, SMEM, ...) emu::launch((const void*)(K), grid, 256u, (size_t)(SMEM), [&] { K(__VA_ARGS__); })
+#else
+#define TBM_EXACT_LAUNCH(K, SMEM, ...) K<<<grid, 256, (SMEM)>>>(__VA_ARGS__)
+#endif
+inline int launch_exact_top2(const float* d, const int* q_row, const int* b_row0, const int* b_rows, const int* cand, long long n_q, int* best_j,
+                             float* best_d, float* second_d, unsigned long long* n_exhaustive) {
+  using namespace tbm_tc;
+  static bool attr_done = false;  // (per process; the attribute is per device function)
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_exact_top2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_exact_top2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
+    attr_done = true;
+  }
+  const unsigned grid = (unsigned)((n_q + 31) / 32);
+  const bool lanes = exact_variant_lanes(), simple = exhaustive_simple();
+  if (lanes && simple) TBM_EXACT_LAUNCH(k_exact_top2_lanes<false>, kLanesSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
+  else if (lanes) TBM_EXACT_LAUNCH(k_exact_top2_lanes<true>, kLanesSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
+  else if (simple) TBM_EXACT_LAUNCH(k_exact_top2<false>, kExactSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
+  else TBM_EXACT_LAUNCH(k_exact_top2<true>, kExactSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
 
 // :58-59, :78-81: keep the best match when the ratio test is off, there is no second candidate, or it passes
 inline bool passes(const tbm_options* o, float best, float second, int second_valid) {
@@ -209,14 +235,7 @@ int tbm_debug_exact_top2(int device, const float* descriptors, int64_t n_rows, c
       cudaMemcpy(d_b0.p, b_row0, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d_bn.p, b_rows, (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d_cand.p, cand, (size_t)n_q * KC * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
-  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(k_exact_top2_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
-  if (exact_variant_lanes())
-    TBM_LAUNCH(k_exact_top2_lanes, (unsigned)((n_q + 31) / 32), 256, kExactSmemBytes, d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p,
-               d_sd.p, (unsigned long long*)nullptr);
-  else
-    TBM_LAUNCH(k_exact_top2, (unsigned)((n_q + 31) / 32), 256, kExactSmemBytes, d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p, d_sd.p,
-               (unsigned long long*)nullptr);
+  if (launch_exact_top2(d_desc.p, d_q.p, d_b0.p, d_bn.p, d_cand.p, (long long)n_q, d_bj.p, d_bd.p, d_sd.p, nullptr) != 0) return -3;
   if (cudaPeekAtLastError() != cudaSuccess) return -3;
   if (cudaMemcpy(best_j, d_bj.p, (size_t)n_q * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
       cudaMemcpy(best_d, d_bd.p, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -281,8 +300,6 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
   unsigned long long* d_nex = nullptr;  // queries handed to the exhaustive exact scan (diagnostics: tbm_debug_last_timing)
   if (cudaMalloc(&d_nex, 8) != cudaSuccess || cudaMemset(d_nex, 0, 8) != cudaSuccess) return -3;
   struct NexGuard { unsigned long long* p; ~NexGuard() { cudaFree(p); } } nex_guard{d_nex};
-  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(k_exact_top2_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_nn_candidates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(k_nn_candidates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
   Dev<WorkItem> d_items;
@@ -345,11 +362,7 @@ static int match_all_tc(const float* descriptors, const int64_t* img_off, int32_
         cudaEventRecord(ev[3]);
       }
       cudaEventRecord(ev[4]);
-      if (exact_variant_lanes())
-        k_exact_top2_lanes<<<(unsigned)((nq_chunk + 31) / 32), 256, kExactSmemBytes>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
-      else
-        k_exact_top2<<<(unsigned)((nq_chunk + 31) / 32), 256, kExactSmemBytes>>>(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex);
-      if (cudaPeekAtLastError() != cudaSuccess) return -3;
+      if (launch_exact_top2(d_desc.p, d_qrow.p, d_brow0.p, d_brows.p, d_cand.p, nq_chunk, d_bj.p, d_bd.p, d_sd.p, d_nex) != 0) return -3;
       cudaEventRecord(ev[5]);
     }
     // ---- MatchImagePair's decisions per pair, on the device (tbm_decide.cuh); only the kept matches are copied back
