@@ -80,36 +80,24 @@ __device__ __forceinline__ void tile_store(float* s_rows, const float4 (&v)[kRow
 }
 
 // Exhaustive scan of ONE query (row `a`, already in shared memory) against candidate rows [base, base + nb) by the whole CTA: tiles of
-// XT rows, the next tile's rows on their way into registers while the current tile is evaluated (one row per thread 0 .. XT-1, the
-// reference's term order), then a top-2 merge of the XT scanners.  All 256 threads must call it; m_* are [XT] scratch arrays.
-// PIPE = false: the plain version (load-store loop per tile, no prefetch) -- kept selectable (TBM_EXH=simple) while the two are compared.
-template <bool PIPE>
+// XT rows staged with coalesced loads, one row per thread 0 .. XT-1 in the reference's term order, then a top-2 merge of the XT
+// scanners.  All 256 threads must call it; m_* are [XT] scratch arrays.
+// (A register-staged, prefetching version of this loop and per-lane loads for the listed candidates were measured against this one on
+// the bench scene: 30.8 - 34.0 ms per step for all four combinations, i.e. no difference -- the scan is bound by its LSU wavefronts
+// (load + store + row read = 12 per row), not by load latency.  The plain loop stayed.)
 __device__ __forceinline__ void exhaustive_scan(const float* __restrict__ d, const float* s_a, float* s_rows, int base, int nb, float* m_d,
                                                 float* m_d2, int* m_j, int* m_j2, int* out_j, float* out_d, float* out_d2) {
   const int tid = threadIdx.x;
   int xbj = -1, xsj = -1; float xbd = 0.0f, xsd = 0.0f;
-  if (PIPE) {
-    float4 v[kRowLoads];
-    tile_fetch(d, [&](int r) { return r < nb ? (long long)base + r : -1ll; }, v);
-    for (int r0 = 0; r0 < nb; r0 += XT) {
-      __syncthreads();  // the previous tile (or whatever used s_rows / m_* before) is consumed
-      tile_store(s_rows, v);
-      __syncthreads();
-      const int next = r0 + XT;
-      if (next < nb) tile_fetch(d, [&](int r) { return next + r < nb ? (long long)base + next + r : -1ll; }, v);
-      if (tid < XT && r0 + tid < nb) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
+  for (int r0 = 0; r0 < nb; r0 += XT) {
+    __syncthreads();  // the previous tile (or whatever used s_rows / m_* before) is consumed
+    const int rows = nb - r0 < XT ? nb - r0 : XT;
+    for (int e = tid; e < rows * (DIM / 4); e += 256) {
+      const int r = e / (DIM / 4), k4 = e % (DIM / 4);
+      reinterpret_cast<float4*>(s_rows + r * XS)[k4] = __ldg(reinterpret_cast<const float4*>(d + (size_t)(base + r0 + r) * DIM) + k4);
     }
-  } else {
-    for (int r0 = 0; r0 < nb; r0 += XT) {
-      __syncthreads();
-      const int rows = nb - r0 < XT ? nb - r0 : XT;
-      for (int e = tid; e < rows * (DIM / 4); e += 256) {
-        const int r = e / (DIM / 4), k4 = e % (DIM / 4);
-        reinterpret_cast<float4*>(s_rows + r * XS)[k4] = __ldg(reinterpret_cast<const float4*>(d + (size_t)(base + r0 + r) * DIM) + k4);
-      }
-      __syncthreads();
-      if (tid < rows) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
-    }
+    __syncthreads();
+    if (tid < rows) top2_take(xbj, xbd, xsj, xsd, r0 + tid, smem_sqdist(s_a, s_rows + tid * XS));
   }
   __syncthreads();
   if (tid < XT) { m_d[tid] = xbd; m_j[tid] = xbj; m_d2[tid] = xsd; m_j2[tid] = xsj; }
@@ -125,15 +113,14 @@ __device__ __forceinline__ bool list_overflowed(const int* __restrict__ cand, lo
   return cand[qi * KC] == kOverflow || cand[qi * KC + KC / 2] == kOverflow;
 }
 
-constexpr int kExactSmemBytes = (XT + 32) * XS * (int)sizeof(float);  // dynamic shared memory of both kernels: [XT] candidate rows + [32] query rows
+constexpr int kExactSmemBytes = (XT + 32) * XS * (int)sizeof(float);  // dynamic shared memory: [XT] candidate rows + [32] query rows
 
-// ---- variant "staged" (default): one CTA = 32 queries, EVERY descriptor row goes through shared memory with coalesced loads.
+// One CTA = 32 queries, EVERY descriptor row goes through shared memory with coalesced loads.
 // Per-lane row loads (32 different rows per load instruction) made the first version of this pass LSU-bound (ncu: 93 % LSU wavefronts):
 //   * the 32 query rows are staged once;
 //   * the listed candidates of the 32 queries are compacted into ONE dense work list (ballot / popc per query, prefix over the queries)
 //     and evaluated XT rows per tile, one row per thread; a per-query thread then picks its two best from its slice of the list;
 //   * a query whose list overflowed in pass 1 is scanned exhaustively by the whole CTA afterwards (exhaustive_scan).
-template <bool PIPE>
 __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
                                                     const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
                                                     int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
@@ -227,65 +214,7 @@ __global__ void __launch_bounds__(256) k_exact_top2(const float* __restrict__ d,
   for (int o = 0; o < novf; ++o) {
     const int ql = s_ovf[o];
     const long long qx = q0 + ql;
-    exhaustive_scan<PIPE>(d, s_q + ql * XS, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
-  }
-}
-
-// ---- variant "lanes" (TBM_EXACT=lanes; kept for the comparison in DESIGN.md): the listed candidates are read straight from global
-// memory, 8 threads per query, one candidate row per thread (32 different rows per load instruction: LSU-bound); exhaustive scans as above.
-constexpr int ET = 8;  // threads per query
-constexpr int kLanesSmemBytes = (XT * XS + DIM) * (int)sizeof(float);  // candidate tile + one query row
-template <bool PIPE>
-__global__ void __launch_bounds__(256) k_exact_top2_lanes(const float* __restrict__ d, const int* __restrict__ q_row, const int* __restrict__ b_row0,
-                                                          const int* __restrict__ b_rows, const int* __restrict__ cand, long long n_q,
-                                                          int* __restrict__ best_j, float* __restrict__ best_d, float* __restrict__ second_d,
-                                                          unsigned long long* __restrict__ n_exhaustive) {
-#ifdef TBA_EMULATE
-  float* smem = emu::dyn_smem<float>();
-#else
-  extern __shared__ __align__(16) float smem[];
-#endif
-  float* s_rows = smem;
-  float* s_a = smem + XT * XS;
-  __shared__ float s_d[32][ET], s_d2[32][ET];
-  __shared__ int s_j[32][ET], s_j2[32][ET];
-  __shared__ float m_d[XT], m_d2[XT];
-  __shared__ int m_j[XT], m_j2[XT];
-  __shared__ int s_ovf[32];
-  __shared__ int s_novf;
-  const int ql = threadIdx.x / ET, c = threadIdx.x % ET;
-  const long long q0 = (long long)blockIdx.x * 32;
-  const long long qi = q0 + ql;
-  if (threadIdx.x == 0) s_novf = 0;
-  __syncthreads();
-  int bj = -1, sj = -1; float bd = 0.0f, sd = 0.0f;
-  bool overflowed = false;
-  if (qi < n_q) {
-    const float* a = d + (size_t)q_row[qi] * DIM;
-    const int base = b_row0[qi];
-    overflowed = list_overflowed(cand, qi);
-    if (overflowed) {
-      if (c == 0) { s_ovf[atomicAdd(&s_novf, 1)] = ql; if (n_exhaustive) atomicAdd(n_exhaustive, 1ull); }
-    } else {
-      for (int k = c; k < KC; k += ET) {
-        const int j = cand[qi * KC + k];
-        if (j >= 0) top2_take(bj, bd, sj, sd, j - base, exact_sqdist(a, d + (size_t)j * DIM));
-      }
-    }
-  }
-  s_d[ql][c] = bd; s_j[ql][c] = bj; s_d2[ql][c] = sd; s_j2[ql][c] = sj;
-  __syncthreads();
-  if (c == 0 && qi < n_q && !overflowed) {
-    int fj = -1, gj = -1; float fd = 0.0f, gd = 0.0f;
-    for (int k = 0; k < ET; ++k) { top2_take(fj, fd, gj, gd, s_j[ql][k], s_d[ql][k]); top2_take(fj, fd, gj, gd, s_j2[ql][k], s_d2[ql][k]); }
-    best_j[qi] = fj; best_d[qi] = fd; second_d[qi] = gj >= 0 ? gd : 0.0f;
-  }
-  const int novf = s_novf;
-  for (int o = 0; o < novf; ++o) {
-    __syncthreads();  // s_a of the previous round consumed
-    const long long qx = q0 + s_ovf[o];
-    if (threadIdx.x < DIM / 4) reinterpret_cast<float4*>(s_a)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(d + (size_t)q_row[qx] * DIM) + threadIdx.x);
-    exhaustive_scan<PIPE>(d, s_a, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
+    exhaustive_scan(d, s_q + ql * XS, s_rows, b_row0[qx], b_rows[qx], m_d, m_d2, m_j, m_j2, best_j + qx, best_d + qx, second_d + qx);
   }
 }
 

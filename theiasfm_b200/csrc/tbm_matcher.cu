@@ -171,32 +171,12 @@ int decide_and_fetch(DecideBuffers& B, const std::vector<tbm::PairSeg>& segs, lo
   return 0;
 }
 
-// TBM_EXACT=lanes: the exact pass reads the listed candidates with per-lane row loads (k_exact_top2_lanes) instead of staging them
-inline bool exact_variant_lanes() { const char* e = getenv("TBM_EXACT"); return e != nullptr && e[0] == 'l'; }
-// TBM_EXH=simple: exhaustive scans with the plain load-store loop per tile instead of the register-staged, prefetching one
-inline bool exhaustive_simple() { const char* e = getenv("TBM_EXH"); return e != nullptr && e[0] == 's'; }
-
-// launches the selected variant of the exact pass on the current stream
-#ifdef TBA_EMULATE
-#define TBM_EXACT_LAUNCH(K, SMEM, ...) emu::launch((const void*)(K), grid, 256u, (size_t)(SMEM), [&] { K(__VA_ARGS__); })
-#else
-#define TBM_EXACT_LAUNCH(K, SMEM, ...) K<<<grid, 256, (SMEM)>>>(__VA_ARGS__)
-#endif
+// launches the exact pass of the tensor-core path on the current stream
 inline int launch_exact_top2(const float* d, const int* q_row, const int* b_row0, const int* b_rows, const int* cand, long long n_q, int* best_j,
                              float* best_d, float* second_d, unsigned long long* n_exhaustive) {
   using namespace tbm_tc;
-  static bool attr_done = false;  // (per process; the attribute is per device function)
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(k_exact_top2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_exact_top2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
-    attr_done = true;
-  }
-  const unsigned grid = (unsigned)((n_q + 31) / 32);
-  const bool lanes = exact_variant_lanes(), simple = exhaustive_simple();
-  if (lanes && simple) TBM_EXACT_LAUNCH(k_exact_top2_lanes<false>, kLanesSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
-  else if (lanes) TBM_EXACT_LAUNCH(k_exact_top2_lanes<true>, kLanesSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
-  else if (simple) TBM_EXACT_LAUNCH(k_exact_top2<false>, kExactSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
-  else TBM_EXACT_LAUNCH(k_exact_top2<true>, kExactSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
+  if (cudaFuncSetAttribute(k_exact_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmemBytes) != cudaSuccess) return -3;
+  TBM_LAUNCH(k_exact_top2, (unsigned)((n_q + 31) / 32), 256, kExactSmemBytes, d, q_row, b_row0, b_rows, cand, n_q, best_j, best_d, second_d, n_exhaustive);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 
