@@ -486,7 +486,8 @@ def main():
     config = {"workload": "%s: %d cameras / %d points / ~%d observations, %s, %s, TRIVIAL loss, default intrinsics mask "
                           "(FOCAL_LENGTH|RADIAL_DISTORTION free), use_inner_iterations=false" %
                           (args.workload, cfg["n_cam"], cfg["n_pt"], cfg["n_pt"] * cfg["obs_per_pt"], model_name, groups),
-              "parallelism": "points+observations sharded over %d GPU(s), cameras replicated, NCCL allreduce per PCG iteration" % world,
+              "parallelism": ("points+observations sharded over %d GPU(s), cameras replicated; per PCG iteration the matvec kernel itself exchanges the partial sums over NVLink peer memory "
+                               "(TBA_P2P=0: NCCL all-reduce), three NCCL all-reduces per LM iteration" % world) if world > 1 else "one GPU",
               "l2_policy": ("inputs larger than L2: the stored linearisation streamed by every kernel is %.2f GB at N=1 "
                             "(L2 = 0.126 GB), no flush needed" if cfg["n_pt"] * cfg["obs_per_pt"] * 160 > 2 * 126e6 * world else
                             "WARNING: the stored linearisation (%.2f GB at N=1) is not larger than L2 per GPU at this N: "
@@ -616,7 +617,7 @@ def main():
             traffic = json.load(f).get("k_schur_matvec_dram_bytes_per_launch")
     lin_ms = prof["linearize_ms"] / max(prof["linearize_launches"], 1)
     lin_bytes = prof["observations"] * (8 + 16 + 8 * nj + 16) + prof["points"] * (32 + 112) + shard.n_cam * (48 + 160 + 96)
-    roofline = {"kernel": "k_schur<IMASK,0> (implicit Schur-complement matvec, one launch per PCG iteration)", "bound": "hbm",
+    roofline = {"kernel": "k_schur_stream<IMASK,0> (implicit Schur-complement matvec, persistent streaming kernel, one launch per PCG iteration)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": mv_ms,
                 "launches_timed": prof["matvec_launches"], "share_of_step": prof["matvec_ms"] * 1e-3 / dev_s if dev_s > 0 else None,
