@@ -124,3 +124,28 @@ def test_pack_column_set_selection_and_limits():
     assert engine.debug_pack(bad)["rc"] == _abi.ERR_INVALID_ARGUMENT
     long_ = synthetic.make_scene(n_cam=600, n_pt=3, obs_per_pt=290, seed=1)
     assert engine.debug_pack(long_)["rc"] == _abi.ERR_UNSUPPORTED
+
+
+def test_scattered_observation_order_packs_like_the_grouped_one():
+    """Observations that are NOT grouped by point (the adapter flattens per view: bundle_adjuster.cc:125-134) take the two-level counting
+    sort of pack_count_and_sort (buckets of points, no contended atomics) instead of the run-based path: the packed problem -- tiles,
+    slot cameras / points / measurements -- must be the same as for the point-grouped order of the same observations, and every slot must
+    still name its caller observation."""
+    p = synthetic.make_scene(n_cam=40, n_pt=6000, obs_per_pt=7, seed=21, shared_intrinsics=False)
+    p.pt_const[::9] = 1
+    rng = np.random.default_rng(5)
+    by_view = np.argsort(p.obs_cam, kind="stable")
+    shuffled = rng.permutation(p.n_obs)
+    base = engine.debug_pack(p)
+    assert base["rc"] == 0
+    for perm in (by_view, shuffled):
+        q = _abi.Problem(p.ext, p.ext_const, p.cam_group, p.group_model, p.intr, p.group_const_mask, p.pt, p.pt_const,
+                         p.obs_cam[perm].copy(), p.obs_pt[perm].copy(), p.obs_xy[perm].copy())
+        k = engine.debug_pack(q)
+        assert k["rc"] == 0 and k["n_slots"] == base["n_slots"] and k["n_tiles"] == base["n_tiles"]
+        for name in ("slot_cam", "slot_pt", "slot_run", "slot_flags", "xy", "pk2caller", "tile_pt_begin", "tile_nruns", "tile_flags", "mask"):
+            assert np.array_equal(k[name], base[name]), name
+        valid = k["slot_cam"] >= 0
+        orig = k["slot_orig"][valid]
+        assert np.array_equal(np.sort(orig), np.arange(p.n_obs))
+        assert np.array_equal(q.obs_cam[orig], k["slot_cam"][valid]) and np.array_equal(perm[orig], base["slot_orig"][valid])
