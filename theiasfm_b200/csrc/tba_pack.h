@@ -225,9 +225,30 @@ inline void pack_count_and_sort(const tba_problem* p, int T, HostPack* H) {
         for (int64_t i = b0; i < e0; ++i) cnt_cam[i] += hist[i];
       }
     });
-  H->off.assign((size_t)np + 1, 0);
+  H->off.resize((size_t)np + 1);
   H->maxlen = 0;
-  for (int q = 0; q < np; ++q) { H->maxlen = std::max(H->maxlen, cnt_pt[q]); H->off[(size_t)q + 1] = H->off[q] + cnt_pt[q]; }
+  {
+    // exclusive prefix sum of the per-point counts in two parallel passes (chunk sums, then the chunks with their bases)
+    const int PC = std::max(1, std::min(T, (np + 65535) / 65536));
+    const int64_t pchunk = ((int64_t)np + PC - 1) / PC;
+    std::vector<int64_t> csum((size_t)PC + 1, 0);
+    std::vector<int> cmax((size_t)PC, 0);
+    parallel_for(PC, PC, [&](int64_t c0, int64_t c1, int) {
+      for (int64_t c = c0; c < c1; ++c) {
+        int64_t sum = 0; int mx = 0;
+        for (int64_t q = c * pchunk, e = std::min<int64_t>(np, q + pchunk); q < e; ++q) { sum += cnt_pt[q]; mx = std::max(mx, cnt_pt[q]); }
+        csum[(size_t)c + 1] = sum; cmax[(size_t)c] = mx;
+      }
+    }, 1);
+    for (int c = 0; c < PC; ++c) { csum[(size_t)c + 1] += csum[c]; H->maxlen = std::max(H->maxlen, cmax[c]); }
+    parallel_for(PC, PC, [&](int64_t c0, int64_t c1, int) {
+      for (int64_t c = c0; c < c1; ++c) {
+        int64_t run = csum[(size_t)c];
+        for (int64_t q = c * pchunk, e = std::min<int64_t>(np, q + pchunk); q < e; ++q) { H->off[(size_t)q] = run; run += cnt_pt[q]; }
+      }
+    }, 1);
+    H->off[(size_t)np] = csum[(size_t)PC];
+  }
   lap("hist merge + prefix");
   if (H->maxlen > kPackTile) return;
   H->order.resize((size_t)no);
@@ -285,19 +306,38 @@ inline void pack_count_and_sort(const tba_problem* p, int T, HostPack* H) {
 // track fits one warp slice (<= 32 observations) in caller order, then the long tracks.
 inline void pack_points(const tba_problem* p, HostPack* H) {
   const int np = p->n_pt;
-  H->pk2caller.clear();
-  H->pk2caller.reserve((size_t)np);
-  H->n_long = 0;
+  // two parallel passes over fixed chunks of points: count (short, long, free) per chunk, then write at the chunk's offsets
+  const int T = std::max(1, std::min<int>(16, (int)std::thread::hardware_concurrency()));
+  const int PC = std::max(1, std::min(T, (np + 65535) / 65536));
+  const int64_t pchunk = ((int64_t)np + PC - 1) / PC;
+  std::vector<int64_t> n_short((size_t)PC + 1, 0), n_lng((size_t)PC + 1, 0), n_free((size_t)PC, 0);
+  parallel_for(PC, PC, [&](int64_t c0, int64_t c1, int) {
+    for (int64_t c = c0; c < c1; ++c) {
+      int64_t a = 0, b = 0, f = 0;
+      for (int64_t q = c * pchunk, e = std::min<int64_t>(np, q + pchunk); q < e; ++q) {
+        const int n = H->cnt_pt[q];
+        if (n == 0) continue;
+        if (n <= 32) ++a; else ++b;
+        f += p->pt_const[q] ? 0 : 1;
+      }
+      n_short[(size_t)c + 1] = a; n_lng[(size_t)c + 1] = b; n_free[(size_t)c] = f;
+    }
+  }, 1);
   H->n_free_pt = 0;
-  std::vector<int> long_pts;
-  for (int q = 0; q < np; ++q) {
-    const int n = H->cnt_pt[q];
-    if (n == 0) continue;
-    if (n <= 32) H->pk2caller.push_back(q); else long_pts.push_back(q);
-    H->n_free_pt += p->pt_const[q] ? 0 : 1;
-  }
-  H->n_long = (int)long_pts.size();
-  H->pk2caller.insert(H->pk2caller.end(), long_pts.begin(), long_pts.end());
+  for (int c = 0; c < PC; ++c) { n_short[(size_t)c + 1] += n_short[c]; n_lng[(size_t)c + 1] += n_lng[c]; H->n_free_pt += n_free[c]; }
+  const int64_t total_short = n_short[(size_t)PC];
+  H->n_long = (int)n_lng[(size_t)PC];
+  H->pk2caller.resize((size_t)(total_short + H->n_long));
+  parallel_for(PC, PC, [&](int64_t c0, int64_t c1, int) {
+    for (int64_t c = c0; c < c1; ++c) {
+      int64_t a = n_short[(size_t)c], b = total_short + n_lng[(size_t)c];
+      for (int64_t q = c * pchunk, e = std::min<int64_t>(np, q + pchunk); q < e; ++q) {
+        const int n = H->cnt_pt[q];
+        if (n == 0) continue;
+        if (n <= 32) H->pk2caller[(size_t)a++] = (int)q; else H->pk2caller[(size_t)b++] = (int)q;
+      }
+    }
+  }, 1);
 }
 
 // Free-coordinate masks (cnt_c / cnt_g are the GLOBAL observation counts per camera / group) and phase D: tiles.
