@@ -131,7 +131,15 @@ def test_scattered_observation_order_packs_like_the_grouped_one():
     sort of pack_count_and_sort (buckets of points, no contended atomics) instead of the run-based path: the packed problem -- tiles,
     slot cameras / points / measurements -- must be the same as for the point-grouped order of the same observations, and every slot must
     still name its caller observation."""
-    p = synthetic.make_scene(n_cam=40, n_pt=6000, obs_per_pt=7, seed=21, shared_intrinsics=False)
+    _check_scattered_equals_grouped(synthetic.make_scene(n_cam=40, n_pt=6000, obs_per_pt=7, seed=21, shared_intrinsics=False))
+
+
+def test_scattered_order_with_many_points_and_parallel_prefix():
+    """150 k points: several chunks in the parallel prefix sum / packed-point list, point buckets of more than one point (shift > 0)."""
+    _check_scattered_equals_grouped(synthetic.make_scene(n_cam=12, n_pt=150_000, obs_per_pt=3, seed=22))
+
+
+def _check_scattered_equals_grouped(p):
     p.pt_const[::9] = 1
     rng = np.random.default_rng(5)
     by_view = np.argsort(p.obs_cam, kind="stable")
