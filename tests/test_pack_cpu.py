@@ -157,3 +157,16 @@ def _check_scattered_equals_grouped(p):
         orig = k["slot_orig"][valid]
         assert np.array_equal(np.sort(orig), np.arange(p.n_obs))
         assert np.array_equal(q.obs_cam[orig], k["slot_cam"][valid]) and np.array_equal(perm[orig], base["slot_orig"][valid])
+
+
+def test_worker_pool_stress(tmp_path):
+    """tests/host_pack_pool.cc: concurrent callers, nested loops, exact results through the pack's worker pool and its fall-back."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_pack_pool")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(root, "include"), "-o", exe, os.path.join(root, "tests", "host_pack_pool.cc")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "pack pool ok" in out.stdout, out.stdout + out.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TBA_PACK_POOL="0"))
+    assert out.returncode == 0 and "pack pool ok" in out.stdout

@@ -10,12 +10,18 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/theia_ba_b200.h"
 
@@ -24,18 +30,114 @@ namespace tba {
 constexpr int kPackTile = 256;
 constexpr int kPackMaxPoints = 256;
 
+// ---- worker pool of the host pack.  Creating and joining 64 threads costs 1 - 2 ms per parallel loop, and an upload runs about
+// twenty of them (eight for the chunked fill alone): a quarter of the upload time of a 20 M-observation problem was thread creation.
+// One process-wide pool of detached workers (grown on demand, never destroyed: the process exit ends them), one job at a time; a
+// caller that finds the pool busy (the rank threads of tba_solve_multi pack concurrently) or that IS a worker falls back to plain
+// std::thread's.  After a fork() the child starts a fresh pool (the parent's workers do not exist there).
+class PackPool {
+ public:
+  // runs task(0 .. n_tasks-1), the caller included, and returns when all are done; false = pool busy, nothing was run
+  template <class Task>
+  bool try_run(int n_tasks, Task&& task) {
+    PackPool* p = instance();
+    if (p == nullptr) return false;
+    return p->run_impl(n_tasks, std::function<void(int)>(std::forward<Task>(task)));
+  }
+  static PackPool& get() { static PackPool front; return front; }  // (stateless front end; the state lives in instance())
+
+ private:
+  struct Job {
+    std::function<void(int)> fn;
+    int n = 0;
+    std::atomic<int> next{0}, remaining{0};
+  };
+  std::mutex job_mu_;                  // one job at a time (try_lock by callers)
+  std::mutex m_;                       // guards current_ / gen_ / n_workers_
+  std::condition_variable cv_work_, cv_done_;
+  std::shared_ptr<Job> current_;
+  unsigned long long gen_ = 0;
+  int n_workers_ = 0;
+  long long pid_ = 0;
+  static constexpr int kMaxWorkers = 255;
+
+  static PackPool* instance() {
+    static std::mutex im;
+    static PackPool* inst = nullptr;
+    std::lock_guard<std::mutex> lk(im);
+    const long long pid = (long long)getpid();
+    if (inst == nullptr || inst->pid_ != pid) { inst = new PackPool(); inst->pid_ = pid; }  // (a forked child leaks the parent's object on purpose)
+    return inst;
+  }
+  static bool& is_worker() { static thread_local bool w = false; return w; }
+
+  void worker_loop() {
+    is_worker() = true;
+    unsigned long long seen = 0;
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        job = current_;
+      }
+      if (job) drain(*job);
+    }
+  }
+  void drain(Job& job) {
+    for (;;) {
+      const int i = job.next.fetch_add(1, std::memory_order_relaxed);
+      if (i >= job.n) return;
+      job.fn(i);
+      if (job.remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> lk(m_);
+        cv_done_.notify_all();
+      }
+    }
+  }
+  bool run_impl(int n_tasks, std::function<void(int)> fn) {
+    if (n_tasks <= 0) return true;
+    if (is_worker()) return false;                 // nested use: the caller runs its loop with its own threads
+    std::unique_lock<std::mutex> job_lk(job_mu_, std::try_to_lock);
+    if (!job_lk.owns_lock()) return false;
+    auto job = std::make_shared<Job>();
+    job->fn = std::move(fn); job->n = n_tasks; job->remaining.store(n_tasks);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      const int want = std::min(kMaxWorkers, n_tasks - 1);
+      while (n_workers_ < want) { std::thread([this] { worker_loop(); }).detach(); ++n_workers_; }
+      current_ = job;
+      ++gen_;
+    }
+    cv_work_.notify_all();
+    drain(*job);
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_done_.wait(lk, [&] { return job->remaining.load(std::memory_order_acquire) == 0; });
+      current_.reset();
+    }
+    return true;
+  }
+};
+
 // grain: least number of items worth a thread of its own (8192 for per-observation loops; per-tile loops pass a small one)
 template <class F>
 void parallel_for(int64_t n, int nthreads, F f, int64_t grain = 8192) {
   if (n <= 0) return;
   const int T = (int)std::min<int64_t>(nthreads, (n + grain - 1) / grain);
   if (T <= 1) { f((int64_t)0, n, 0); return; }
-  std::vector<std::thread> th;
   const int64_t chunk = (n + T - 1) / T;
-  for (int t = 0; t < T; ++t) {
+  auto task = [&](int t) {
     const int64_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([=, &f] { f(b, e, t); });
+    if (b < e) f(b, e, t);
+  };
+  static const bool use_pool = getenv("TBA_PACK_POOL") == nullptr || getenv("TBA_PACK_POOL")[0] != '0';  // TBA_PACK_POOL=0: threads per loop
+  if (use_pool && PackPool::get().try_run(T, task)) return;
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) {
+    if ((int64_t)t * chunk >= n) break;
+    th.emplace_back([=, &task] { task(t); });
   }
   for (auto& x : th) x.join();
 }
