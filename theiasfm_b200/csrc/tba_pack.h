@@ -465,8 +465,8 @@ inline void pack_masks_and_tiles(const tba_problem* p, const std::vector<double>
   }
   const int npk = (int)H->pk2caller.size();
   H->tile_pt_begin.clear(); H->tile_nruns.clear(); H->tile_flags.clear();
-  H->pt_slot.assign((size_t)npk, 0);
-  H->pt_runbase.assign((size_t)npk, 0);
+  H->pt_slot.resize((size_t)npk);      // (every entry is written below: no zero fill of 24 MB per upload)
+  H->pt_runbase.resize((size_t)npk);
   {
     int used = kPackTile, npts_in_tile = kPackMaxPoints, run = 0;
     bool in_long = false;
