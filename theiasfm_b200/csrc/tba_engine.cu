@@ -1187,7 +1187,7 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   {
     // E: fill the slot arrays in pinned staging memory chunk by chunk (all host threads per chunk) and send every chunk on its
     // way as soon as it is filled: the copy of chunk k overlaps the filling of chunk k + 1
-    int n_chunks = n_tiles >= 8192 ? 8 : 1;
+    int n_chunks = n_tiles >= 32768 ? 16 : n_tiles >= 8192 ? 8 : 1;  // (the last chunk's copy is what the final synchronisation waits for)
     if (const char* e = getenv("TBA_UPLOAD_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), std::max(1, n_tiles)));  // tests: small scenes too
 #define H2D_RANGE(buf, src, off, n)                                                                                              \
   do {                                                                                                                           \
