@@ -108,7 +108,6 @@ struct tba_context {
   int64_t n_free_pt = 0;  // free points on this rank
   int64_t n_free_pt_global = 0;
   int n_pt_caller = 0;
-  std::vector<int> pk2caller;  // packed point -> caller point id
   // parameters and packed problem
   DevBuf<double> ext, intr, pt, ext_c, intr_c, pt_c, cam_rec, cam_rec_c, cam_s4, cam_s4_c, xy, J, res, Hpp, gp, Mp, sp, dpt;
   DevBuf<int> cam_group, group_model, slot_cam, slot_pt, tile_pt_begin, tile_nruns;
@@ -1110,7 +1109,6 @@ int tba_upload(tba_context* c, const tba_options* options, const tba_problem* p)
   std::vector<int>& tile_pt_begin = H.tile_pt_begin;
   std::vector<int>& tile_nruns = H.tile_nruns;
   std::vector<uint8_t>& tile_flags = H.tile_flags;
-  c->pk2caller = H.pk2caller;
   c->n_free_cs = H.n_free_cs;
   c->imask = 0x3FFu;
   for (uint32_t m : kMasks) if ((H.union_free & ~m) == 0) { c->imask = m; break; }
@@ -1305,7 +1303,7 @@ int tba_download(tba_context* c, tba_problem* p) {
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   {
     const int T = std::max(1, std::min<int>(16, (int)std::thread::hardware_concurrency() / std::max(1, c->world)));
-    const int* pk2caller = c->pk2caller.data();
+    const int* pk2caller = c->pack.pk2caller.data();
     double* dst = p->pt;
     parallel_for(c->n_pt, T, [=](int64_t b0, int64_t e0, int) {
       for (int64_t k = b0; k < e0; ++k) memcpy(dst + (size_t)pk2caller[k] * 4, ptk + (size_t)k * 4, 32);
@@ -1501,7 +1499,7 @@ int tba_reset_parameters(tba_context* c, const tba_problem* p) {
   CUDA_OK(c, cudaSetDevice(c->device));
   if (p->n_cam != c->n_cam || p->n_group != c->n_group || p->n_pt != c->n_pt_caller) { set_err(c, "reset: problem shape differs from the uploaded one"); return TBA_ERR_INVALID_ARGUMENT; }
   std::vector<double> ptk((size_t)c->n_pt * 4);
-  for (int k = 0; k < c->n_pt; ++k) memcpy(&ptk[(size_t)k * 4], p->pt + (size_t)c->pk2caller[k] * 4, 32);
+  for (int k = 0; k < c->n_pt; ++k) memcpy(&ptk[(size_t)k * 4], p->pt + (size_t)c->pack.pk2caller[k] * 4, 32);
   CUDA_OK(c, cudaMemcpyAsync(c->P.ext, p->ext, (size_t)c->n_cam * 48, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaMemcpyAsync(c->P.intr, p->intr, (size_t)c->n_group * 80, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaMemcpyAsync(c->P.pt, ptk.data(), (size_t)c->n_pt * 32, cudaMemcpyHostToDevice, c->stream));
@@ -1590,7 +1588,7 @@ int tba_filter_tracks(tba_context* c, double max_inlier_reprojection_error, doub
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   int nb = 0, ni = 0;
   for (int q = 0; q < c->n_pt_caller; ++q) { status[q] = 2; if (mean_sq_error) mean_sq_error[q] = std::nan(""); }
-  for (int k = 0; k < P.n_pt; ++k) { status[c->pk2caller[k]] = hs[k]; if (mean_sq_error) mean_sq_error[c->pk2caller[k]] = hm[k]; }
+  for (int k = 0; k < P.n_pt; ++k) { status[c->pack.pk2caller[k]] = hs[k]; if (mean_sq_error) mean_sq_error[c->pack.pk2caller[k]] = hm[k]; }
   for (int q = 0; q < c->n_pt_caller; ++q) { nb += status[q] == 1; ni += status[q] == 2; }
   if (num_bad_reprojections) *num_bad_reprojections = nb;
   if (num_insufficient_angles) *num_insufficient_angles = ni;
@@ -1627,7 +1625,7 @@ int gather_track_outputs(tba_context* c, const uint8_t* d_status, const double* 
     if (final_cost) final_cost[q] = -1.0;
   }
   for (int k = 0; k < npk; ++k) {
-    const int q = c->pk2caller[k];
+    const int q = c->pack.pk2caller[k];
     status[q] = hs[k];
     if (initial_cost) initial_cost[q] = hc[(size_t)2 * k];
     if (final_cost) final_cost[q] = hc[(size_t)2 * k + 1];
@@ -2069,10 +2067,10 @@ int tba_debug_read(tba_context* c, int which, double* out, int64_t n) {
       if (which == TBA_VEC_COLNORM2_PT) {
         if ((rc = fetch(P.Hpp, (int64_t)P.n_pt * 10, tmp))) return rc;
         const int dg[4] = {0, 4, 7, 9};
-        for (int64_t k = 0; k < P.n_pt; ++k) for (int j = 0; j < 4; ++j) out[(int64_t)c->pk2caller[k] * 4 + j] = pc[k] ? 0.0 : tmp[k * 10 + dg[j]];
+        for (int64_t k = 0; k < P.n_pt; ++k) for (int j = 0; j < 4; ++j) out[(int64_t)c->pack.pk2caller[k] * 4 + j] = pc[k] ? 0.0 : tmp[k * 10 + dg[j]];
       } else {
         if ((rc = fetch(which == TBA_VEC_GRADIENT_PT ? P.gp : P.dpt, np4, tmp))) return rc;
-        for (int64_t k = 0; k < P.n_pt; ++k) for (int j = 0; j < 4; ++j) out[(int64_t)c->pk2caller[k] * 4 + j] = pc[k] ? 0.0 : tmp[k * 4 + j];
+        for (int64_t k = 0; k < P.n_pt; ++k) for (int j = 0; j < 4; ++j) out[(int64_t)c->pack.pk2caller[k] * 4 + j] = pc[k] ? 0.0 : tmp[k * 4 + j];
       }
       return TBA_OK; }
     case TBA_VEC_RESIDUALS: {
